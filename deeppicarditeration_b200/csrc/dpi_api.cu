@@ -1,0 +1,451 @@
+// C ABI (include/dpi_b200.h): handle, problem/network packing and the label-generation driver.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "dpi_common.cuh"
+#include "dpi_kernels.h"
+
+namespace dpi {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+}  // namespace dpi
+
+using namespace dpi;
+
+struct dpi_handle {
+  int device = 0;
+  bool has_problem = false;
+  bool has_net = false;
+  ProblemDev P{};
+  int net_kind = DPI_NET_ZERO;
+  MlpDev mlp{};
+  TcNetDev tc{};
+  bool tc_ready = false;
+  std::vector<void*> prob_bufs;  // device allocations owned by the problem
+  std::vector<void*> net_bufs;   // device allocations owned by the packed network
+  // per-point scratch: control variate f_b [n], first-layer constant c0 [n][HP]
+  float* fb = nullptr;
+  float* c0 = nullptr;
+  int64_t scratch_points = 0;
+  int scratch_hp = 0;
+  // staging for the *_host entry points
+  float* stage_tx = nullptr;
+  float* stage_y = nullptr;
+  int64_t stage_floats = 0;
+  int64_t launches = 0;
+};
+
+namespace {
+
+int free_all(std::vector<void*>& v) {
+  for (void* p : v) cudaFree(p);
+  v.clear();
+  return 0;
+}
+
+template <typename T>
+int dev_alloc(std::vector<void*>& owner, size_t count, T** out) {
+  void* p = nullptr;
+  DPI_CUDA_CHECK(cudaMalloc(&p, sizeof(T) * (count ? count : 1)));
+  owner.push_back(p);
+  *out = reinterpret_cast<T*>(p);
+  return DPI_OK;
+}
+
+int upload_f32(std::vector<void*>& owner, const std::vector<float>& host, float** out) {
+  int rc = dev_alloc(owner, host.size(), out);
+  if (rc) return rc;
+  DPI_CUDA_CHECK(cudaMemcpy(*out, host.data(), sizeof(float) * host.size(), cudaMemcpyHostToDevice));
+  return DPI_OK;
+}
+
+int ensure_scratch(dpi_handle* h, int64_t n, int hp) {
+  if (n <= h->scratch_points && hp <= h->scratch_hp) return DPI_OK;
+  if (h->fb) cudaFree(h->fb);
+  if (h->c0) cudaFree(h->c0);
+  h->fb = h->c0 = nullptr;
+  h->scratch_points = 0;
+  const int64_t cap = n > h->scratch_points ? n : h->scratch_points;
+  const int chp = hp > h->scratch_hp ? hp : h->scratch_hp;
+  DPI_CUDA_CHECK(cudaMalloc((void**)&h->fb, sizeof(float) * cap));
+  DPI_CUDA_CHECK(cudaMalloc((void**)&h->c0, sizeof(float) * cap * chp));
+  h->scratch_points = cap;
+  h->scratch_hp = chp;
+  return DPI_OK;
+}
+
+int ensure_stage(dpi_handle* h, int64_t floats) {
+  if (floats <= h->stage_floats) return DPI_OK;
+  if (h->stage_tx) cudaFree(h->stage_tx);
+  if (h->stage_y) cudaFree(h->stage_y);
+  h->stage_tx = h->stage_y = nullptr;
+  h->stage_floats = 0;
+  DPI_CUDA_CHECK(cudaMalloc((void**)&h->stage_tx, sizeof(float) * floats));
+  DPI_CUDA_CHECK(cudaMalloc((void**)&h->stage_y, sizeof(float) * floats));
+  h->stage_floats = floats;
+  return DPI_OK;
+}
+
+int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+}  // namespace
+
+extern "C" {
+
+int dpi_version(void) { return DPI_B200_VERSION; }
+const char* dpi_last_error(void) { return g_err; }
+
+int dpi_create(int device, dpi_handle** out) {
+  if (!out) {
+    set_error("dpi_create: out is NULL");
+    return DPI_ERR_INVALID;
+  }
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    set_error("dpi_create: no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+    return DPI_ERR_CUDA;
+  }
+  if (device < 0 || device >= count) {
+    set_error("dpi_create: device %d out of range (%d devices)", device, count);
+    return DPI_ERR_INVALID;
+  }
+  cudaDeviceProp prop;
+  DPI_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("dpi_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major,
+              prop.minor);
+    return DPI_ERR_CUDA;
+  }
+  DPI_CUDA_CHECK(cudaSetDevice(device));
+  dpi_handle* h = new dpi_handle();
+  h->device = device;
+  *out = h;
+  return DPI_OK;
+}
+
+int dpi_destroy(dpi_handle* h) {
+  if (!h) return DPI_OK;
+  cudaSetDevice(h->device);
+  free_all(h->prob_bufs);
+  free_all(h->net_bufs);
+  if (h->fb) cudaFree(h->fb);
+  if (h->c0) cudaFree(h->c0);
+  if (h->stage_tx) cudaFree(h->stage_tx);
+  if (h->stage_y) cudaFree(h->stage_y);
+  delete h;
+  return DPI_OK;
+}
+
+int dpi_set_problem(dpi_handle* h, const dpi_problem* p) {
+  if (!h || !p) {
+    set_error("dpi_set_problem: NULL argument");
+    return DPI_ERR_INVALID;
+  }
+  if (p->nx < 1 || !(p->alpha > 0.f) || !(p->T > 0.f)) {
+    set_error("dpi_set_problem: need nx>=1, alpha>0, T>0 (got nx=%d alpha=%g T=%g)", p->nx, p->alpha, p->T);
+    return DPI_ERR_INVALID;
+  }
+  DPI_CUDA_CHECK(cudaSetDevice(h->device));
+  DPI_CUDA_CHECK(cudaDeviceSynchronize());  // nothing in flight may still read the old problem buffers
+  free_all(h->prob_bufs);
+  h->has_problem = false;
+  ProblemDev P{};
+  P.eq = p->kind;
+  P.nx = p->nx;
+  P.T = p->T;
+  P.alpha = p->alpha;
+  P.sigma = std::sqrt(p->alpha);
+  P.sdgd_v = p->sdgd_v;
+  const int d = p->nx;
+  if (p->kind == DPI_EQ_CHA) {
+    // equations.py:283-289: k = k_cfg/sqrt(nx); c = (2 + k^2 alpha d) / (2 k alpha d)
+    const double k = (double)p->cha_k / std::sqrt((double)d);
+    const double kad = k * (double)p->alpha * d;
+    P.cha_k = (float)k;
+    P.cha_c = (float)((2.0 + k * kad) / (2.0 * kad));
+  } else if (p->kind == DPI_EQ_GBM) {
+    if (p->gbm_nodes < 1 || p->gbm_nodes > kMaxGbmNodes || !p->gbm_w || !p->gbm_v) {
+      set_error("dpi_set_problem: GBM needs 1..%d nodes with w and v", kMaxGbmNodes);
+      return DPI_ERR_INVALID;
+    }
+    P.gbm_nodes = p->gbm_nodes;
+    std::vector<float> w((size_t)p->gbm_nodes * (1 + d));
+    for (size_t i = 0; i < w.size(); ++i) w[i] = (float)p->gbm_w[i];
+    for (int k = 0; k < p->gbm_nodes; ++k) P.gbm_v[k] = (float)p->gbm_v[k];
+    float* dw = nullptr;
+    int rc = upload_f32(h->prob_bufs, w, &dw);
+    if (rc) return rc;
+    P.gbm_w = dw;
+  } else if (p->kind == DPI_EQ_OU) {
+    if (p->ou_K < 1 || p->ou_K > kMaxOuK || !p->ou_mean || !p->ou_diagvar || !p->ou_pi) {
+      set_error("dpi_set_problem: OU needs 1..%d mixture components with mean, diagvar, pi", kMaxOuK);
+      return DPI_ERR_INVALID;
+    }
+    P.ou_K = p->ou_K;
+    P.ou_theta = p->ou_theta;
+    P.ou_mu = p->ou_mu;
+    P.ou_x0_std = std::sqrt(p->ou_alpha_init);
+    std::vector<float> mean((size_t)p->ou_K * d), ivar((size_t)p->ou_K * d);
+    for (int k = 0; k < p->ou_K; ++k) {
+      double logdet = 0.0;
+      for (int j = 0; j < d; ++j) {
+        mean[(size_t)k * d + j] = (float)p->ou_mean[(size_t)k * d + j];
+        ivar[(size_t)k * d + j] = (float)(1.0 / p->ou_diagvar[(size_t)k * d + j]);
+        logdet += std::log(p->ou_diagvar[(size_t)k * d + j]);
+      }
+      // utils.py:866-874: log pi_k - 0.5 (d log 2pi + log det Sigma_k)
+      P.ou_lognorm[k] = (float)(std::log(p->ou_pi[k]) - 0.5 * (d * std::log(2.0 * M_PI) + logdet));
+    }
+    float *dm = nullptr, *di = nullptr;
+    int rc = upload_f32(h->prob_bufs, mean, &dm);
+    if (rc) return rc;
+    rc = upload_f32(h->prob_bufs, ivar, &di);
+    if (rc) return rc;
+    P.ou_mean = dm;
+    P.ou_ivar = di;
+  } else {
+    set_error("dpi_set_problem: unknown equation kind %d", p->kind);
+    return DPI_ERR_INVALID;
+  }
+  h->P = P;
+  h->has_problem = true;
+  return DPI_OK;
+}
+
+int dpi_set_network(dpi_handle* h, const dpi_network* net, void* stream) {
+  if (!h || !net) {
+    set_error("dpi_set_network: NULL argument");
+    return DPI_ERR_INVALID;
+  }
+  if (!h->has_problem) {
+    set_error("dpi_set_network: call dpi_set_problem first");
+    return DPI_ERR_STATE;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  DPI_CUDA_CHECK(cudaSetDevice(h->device));
+  DPI_CUDA_CHECK(cudaDeviceSynchronize());
+  free_all(h->net_bufs);
+  h->has_net = false;
+  h->tc_ready = false;
+  h->net_kind = net->kind;
+  const int nx = h->P.nx;
+  if (net->kind == DPI_NET_ZERO) {
+    h->has_net = true;
+    return DPI_OK;
+  }
+  if (net->kind == DPI_NET_MLP) {
+    const int L = net->n_main;
+    if (L < 2 || L > DPI_MAX_LINEAR) {
+      set_error("dpi_set_network: MLP needs 2..%d Linear layers (got %d)", DPI_MAX_LINEAR, L);
+      return DPI_ERR_INVALID;
+    }
+    int maxw = 0;
+    for (int l = 0; l < L; ++l) {
+      const dpi_linear& ll = net->main[l];
+      const int want_in = (l == 0) ? 1 + nx : net->main[l - 1].n_out;
+      if (!ll.W || !ll.b || ll.n_in != want_in || ll.n_out < 1) {
+        set_error("dpi_set_network: layer %d has shape [%d,%d], expected n_in=%d", l, ll.n_out, ll.n_in, want_in);
+        return DPI_ERR_INVALID;
+      }
+      if (l < L - 1 && ll.n_out > maxw) maxw = ll.n_out;
+    }
+    if (net->main[L - 1].n_out != 1) {
+      // TYPE "ValueGradient"/"OnlyGradient" nets (solution.py:300-307) are not used by any BASELINE config
+      set_error("dpi_set_network: output dim %d != 1 (only NETWORK.TYPE=Value is built)", net->main[L - 1].n_out);
+      return DPI_ERR_UNSUPPORTED;
+    }
+    if (maxw > 128) {
+      set_error("dpi_set_network: hidden width %d > 128 is not built for the plain-MLP kernels", maxw);
+      return DPI_ERR_UNSUPPORTED;
+    }
+    MlpDev M{};
+    M.n_linear = L;
+    M.nx = nx;
+    M.HP = maxw <= 64 ? 64 : 128;
+    M.d_pad = round_up(nx, 128);
+    float *Wt1, *wt, *b1, *wsum, *wout, *bout;
+    float* Wth[DPI_MAX_LINEAR] = {nullptr};
+    float* bh[DPI_MAX_LINEAR] = {nullptr};
+    int rc;
+    if ((rc = dev_alloc(h->net_bufs, (size_t)M.d_pad * M.HP, &Wt1))) return rc;
+    if ((rc = dev_alloc(h->net_bufs, M.HP, &wt))) return rc;
+    if ((rc = dev_alloc(h->net_bufs, M.HP, &b1))) return rc;
+    if ((rc = dev_alloc(h->net_bufs, M.HP, &wsum))) return rc;
+    if ((rc = dev_alloc(h->net_bufs, M.HP, &wout))) return rc;
+    if ((rc = dev_alloc(h->net_bufs, 1, &bout))) return rc;
+    for (int l = 0; l < L - 2; ++l) {
+      if ((rc = dev_alloc(h->net_bufs, (size_t)M.HP * M.HP, &Wth[l]))) return rc;
+      if ((rc = dev_alloc(h->net_bufs, M.HP, &bh[l]))) return rc;
+    }
+    if ((rc = launch_pack_mlp(*net, nx, M.HP, M.d_pad, Wt1, wt, b1, wsum, Wth, bh, wout, bout, st))) return rc;
+    h->launches += 6 + 2 * (L - 2);
+    M.Wt1 = Wt1;
+    M.wt = wt;
+    M.b1 = b1;
+    M.wsum = wsum;
+    M.wout = wout;
+    M.bout = bout;
+    for (int l = 0; l < L - 2; ++l) {
+      M.Wth[l] = Wth[l];
+      M.bh[l] = bh[l];
+    }
+    h->mlp = M;
+    // bf16 tensor-core packing (tcgen05 path) when the shape qualifies
+    rc = tc_pack_network(*net, h->P, M, h->net_bufs, &h->tc, &h->tc_ready, &h->launches, st);
+    if (rc) return rc;
+    h->has_net = true;
+    return DPI_OK;
+  }
+  if (net->kind == DPI_NET_PISGRAD) {
+    set_error("dpi_set_network: PISGradNet path not built yet");
+    return DPI_ERR_UNSUPPORTED;
+  }
+  set_error("dpi_set_network: unknown network kind %d", net->kind);
+  return DPI_ERR_INVALID;
+}
+
+int dpi_sample_tx(dpi_handle* h, int64_t n, int64_t point_index_base, uint64_t seed, float* tx, void* stream) {
+  if (!h || !h->has_problem) {
+    set_error("dpi_sample_tx: problem not set");
+    return DPI_ERR_STATE;
+  }
+  if (n < 0 || (n > 0 && !tx)) {
+    set_error("dpi_sample_tx: bad n/tx");
+    return DPI_ERR_INVALID;
+  }
+  DPI_CUDA_CHECK(cudaSetDevice(h->device));
+  // eps = 0.01: default ESTIMATE_TERMINAL "OU_ByGx" (config.py:100, data.py:134-137)
+  int rc = launch_sample_tx(h->P, n, point_index_base, seed, 0.01f, tx, reinterpret_cast<cudaStream_t>(stream));
+  if (!rc && n > 0) h->launches += 1;
+  return rc;
+}
+
+int dpi_label_gen(dpi_handle* h, const float* tx, int64_t n, const dpi_label_config* cfg, const dpi_draws* draws,
+                  float* y, void* stream) {
+  if (!h || !cfg) {
+    set_error("dpi_label_gen: NULL argument");
+    return DPI_ERR_INVALID;
+  }
+  if (!h->has_problem || !h->has_net) {
+    set_error("dpi_label_gen: problem/network not set");
+    return DPI_ERR_STATE;
+  }
+  if (n < 0 || (n > 0 && (!tx || !y)) || cfg->M_T < 1 || cfg->M_I < 1) {
+    set_error("dpi_label_gen: bad arguments (n=%lld M_T=%d M_I=%d)", (long long)n, cfg->M_T, cfg->M_I);
+    return DPI_ERR_INVALID;
+  }
+  if (n == 0) return DPI_OK;
+  if (n > 0x7fffffffLL) {
+    set_error("dpi_label_gen: n=%lld exceeds the grid limit; shard the call", (long long)n);
+    return DPI_ERR_INVALID;
+  }
+  if (draws && (!draws->zT || !draws->u_s || !draws->zS)) {
+    set_error("dpi_label_gen: deterministic mode needs zT, u_s and zS");
+    return DPI_ERR_INVALID;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  DPI_CUDA_CHECK(cudaSetDevice(h->device));
+  const ProblemDev& P = h->P;
+  const float bound = cfg->sample_bound;
+  int rc;
+
+  // 1) terminal estimator -> y
+  rc = launch_terminal(P, tx, n, cfg->M_T, cfg->seed, cfg->point_index_base, draws ? draws->zT : nullptr, y, st);
+  if (rc) return rc;
+  h->launches += 1;
+
+  // 2) integral estimator: y += ..., then clip
+  if (h->net_kind == DPI_NET_ZERO) {
+    if (P.eq == DPI_EQ_GBM) {
+      set_error("dpi_label_gen: GBM path not built yet");
+      return DPI_ERR_UNSUPPORTED;
+    }
+    rc = launch_finish_zero(P, tx, n, bound, y, st);
+    if (!rc) h->launches += 1;
+    return rc;
+  }
+  if (h->net_kind == DPI_NET_MLP && P.eq == DPI_EQ_CHA) {
+    if ((rc = ensure_scratch(h, n, h->mlp.HP))) return rc;
+    rc = launch_cha_simt_base(P, h->mlp, tx, n, h->fb, h->c0, nullptr, nullptr, st);
+    if (rc) return rc;
+    h->launches += 1;
+    if (cfg->precision == DPI_PREC_BF16) {
+      if (!h->tc_ready) {
+        set_error("dpi_label_gen: bf16 tensor-core path needs hidden widths == 128 and nx <= 1024 multiple of 4");
+        return DPI_ERR_UNSUPPORTED;
+      }
+      rc = launch_cha_tc_path(P, h->tc, tx, n, cfg->M_I, cfg->seed, cfg->point_index_base, draws ? draws->u_s : nullptr,
+                              draws ? draws->zS : nullptr, h->fb, h->c0, bound, y, st);
+    } else {
+      rc = launch_cha_simt_path(P, h->mlp, tx, n, cfg->M_I, cfg->seed, cfg->point_index_base,
+                                draws ? draws->u_s : nullptr, draws ? draws->zS : nullptr, h->fb, h->c0, bound, y, st);
+    }
+    if (!rc) h->launches += 1;
+    return rc;
+  }
+  set_error("dpi_label_gen: equation %d with network kind %d is not built yet", P.eq, h->net_kind);
+  return DPI_ERR_UNSUPPORTED;
+}
+
+int dpi_label_gen_host(dpi_handle* h, const float* tx_in_host, int64_t n, const dpi_label_config* cfg,
+                       float* tx_out_host, float* y_host, void* stream) {
+  if (!h || !cfg || !y_host || n < 0) {
+    set_error("dpi_label_gen_host: bad arguments");
+    return DPI_ERR_INVALID;
+  }
+  if (!h->has_problem) {
+    set_error("dpi_label_gen_host: problem not set");
+    return DPI_ERR_STATE;
+  }
+  if (n == 0) return DPI_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  DPI_CUDA_CHECK(cudaSetDevice(h->device));
+  const int64_t floats = n * (1 + h->P.nx);
+  int rc = ensure_stage(h, floats);
+  if (rc) return rc;
+  if (tx_in_host) {
+    DPI_CUDA_CHECK(cudaMemcpyAsync(h->stage_tx, tx_in_host, sizeof(float) * floats, cudaMemcpyHostToDevice, st));
+  } else {
+    rc = dpi_sample_tx(h, n, cfg->point_index_base, cfg->seed, h->stage_tx, stream);
+    if (rc) return rc;
+  }
+  rc = dpi_label_gen(h, h->stage_tx, n, cfg, nullptr, h->stage_y, stream);
+  if (rc) return rc;
+  DPI_CUDA_CHECK(cudaMemcpyAsync(y_host, h->stage_y, sizeof(float) * floats, cudaMemcpyDeviceToHost, st));
+  if (tx_out_host)
+    DPI_CUDA_CHECK(cudaMemcpyAsync(tx_out_host, h->stage_tx, sizeof(float) * floats, cudaMemcpyDeviceToHost, st));
+  DPI_CUDA_CHECK(cudaStreamSynchronize(st));
+  return DPI_OK;
+}
+
+int dpi_net_eval(dpi_handle* h, const float* tx, int64_t n, float* u, float* du, void* stream) {
+  if (!h || !h->has_problem || !h->has_net) {
+    set_error("dpi_net_eval: problem/network not set");
+    return DPI_ERR_STATE;
+  }
+  if (n <= 0) return DPI_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  DPI_CUDA_CHECK(cudaSetDevice(h->device));
+  if (h->net_kind == DPI_NET_MLP && h->P.eq == DPI_EQ_CHA && du == nullptr) {
+    int rc = ensure_scratch(h, n, h->mlp.HP);
+    if (rc) return rc;
+    rc = launch_cha_simt_base(h->P, h->mlp, tx, n, h->fb, h->c0, u, nullptr, st);
+    if (!rc) h->launches += 1;
+    return rc;
+  }
+  set_error("dpi_net_eval: full input gradient not built yet");
+  return DPI_ERR_UNSUPPORTED;
+}
+
+int64_t dpi_launch_count(const dpi_handle* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

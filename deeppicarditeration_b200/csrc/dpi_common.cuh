@@ -1,0 +1,135 @@
+// Shared device/host definitions for the DPI label-generator kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/dpi_b200.h"
+
+namespace dpi {
+
+constexpr int kMaxGbmNodes = 4;
+constexpr int kMaxOuK = 8;
+constexpr float kTwoPi = 6.283185307179586f;
+
+// Philox stream ids (word 3 of the counter): one independent stream per reference draw site.
+enum Stream : uint32_t {
+  kStreamT = 0,         // data.py:166     rand[n,1]
+  kStreamX0 = 1,        // utils.py:785    randn[n,nx]   (OU only)
+  kStreamX = 2,         // equations.py:225 randn[n,nx]
+  kStreamTerminal = 3,  // data.py:914     randn[n*M_T,nx]
+  kStreamS = 4,         // data.py:359     rand[n*M_I,1]
+  kStreamIntegral = 5,  // data.py:360     randn[n*M_I,nx]
+  kStreamIdx = 6        // data.py:501     randint[n*M_I,v]
+};
+
+// Device-side view of the equation (small arrays live in handle-owned device memory).
+struct ProblemDev {
+  int eq;
+  int nx;
+  float T, alpha, sigma;  // sigma = sqrt(alpha)
+  // Cha: k = k_cfg/sqrt(nx); c = (2+k^2 alpha d)/(2 k alpha d)   (equations.py:283-302)
+  float cha_k, cha_c;
+  // GBM: w [nodes][1+nx], v [nodes], w2v[nodes] = v_k * sum_j w_kj^2 (for the Laplacian of u*)
+  int gbm_nodes;
+  const float* gbm_w;
+  float gbm_v[kMaxGbmNodes];
+  // OU: mean [K][nx], ivar [K][nx] = 1/var, lognorm[k] = log pi_k - 0.5 (d log 2pi + log det Sigma_k)
+  int ou_K;
+  const float* ou_mean;
+  const float* ou_ivar;
+  float ou_lognorm[kMaxOuK];
+  float ou_theta, ou_mu, ou_x0_std;
+  int sdgd_v;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011), counter-based: every (point, stream, sample, dim-block) has its own
+// counter, so labels are independent of launch geometry, shard size and GPU count.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+    const uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += W0;
+    k.y += W1;
+  }
+  return c;
+}
+
+__device__ __forceinline__ uint4 philox_at(uint64_t seed, uint64_t point, uint32_t stream, uint32_t sample,
+                                           uint32_t block) {
+  // counter = {dim block, sample, point[31:0], point[47:32] | stream<<16}
+  const uint4 c = make_uint4(block, sample, (uint32_t)point, ((uint32_t)(point >> 32) & 0xFFFFu) | (stream << 16));
+  return philox4x32_10(c, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+}
+
+// uniform in the OPEN interval (0,1): (x>>8 + 0.5) * 2^-24
+__device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * 5.9604644775390625e-8f; }
+
+// Box-Muller on the MUFU pipe: 2 uniforms -> 2 normals (lg2, sqrt, sin, cos).
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
+  const float r = sqrtf(-1.3862943611198906f * __log2f(u01(a)));  // sqrt(-2 ln u) = sqrt(-2 ln2 log2 u)
+  float s, c;
+  __sincosf(kTwoPi * u01(b), &s, &c);
+  z0 = r * c;
+  z1 = r * s;
+}
+
+__device__ __forceinline__ float4 normal4(uint64_t seed, uint64_t point, uint32_t stream, uint32_t sample,
+                                          uint32_t block) {
+  const uint4 r = philox_at(seed, point, stream, sample, block);
+  float4 z;
+  box_muller(r.x, r.y, z.x, z.y);
+  box_muller(r.z, r.w, z.z, z.w);
+  return z;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+
+// ELU and its derivative (alpha = 1): h = z>0 ? z : e^z-1 ; h' = z>0 ? 1 : e^z
+__device__ __forceinline__ void elu_d1(float z, float& h, float& d1) {
+  const float e = __expf(fminf(z, 0.f));
+  const bool pos = z > 0.f;
+  h = pos ? z : e - 1.f;
+  d1 = pos ? 1.f : e;
+}
+
+// Load 4 consecutive dims [j0, j0+4) of a row of a [rows, d] fp32 matrix; zero beyond d.
+__device__ __forceinline__ float4 load_row4(const float* __restrict__ row, int j0, int d, bool vec_ok) {
+  float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (vec_ok && j0 + 3 < d) {
+    z = __ldg(reinterpret_cast<const float4*>(row + j0));
+  } else {
+    if (j0 + 0 < d) z.x = __ldg(row + j0 + 0);
+    if (j0 + 1 < d) z.y = __ldg(row + j0 + 1);
+    if (j0 + 2 < d) z.z = __ldg(row + j0 + 2);
+    if (j0 + 3 < d) z.w = __ldg(row + j0 + 3);
+  }
+  return z;
+}
+
+}  // namespace dpi
+
+// ---------------------------------------------------------------------------------------------
+// host-side error plumbing (definitions in dpi_api.cu)
+// ---------------------------------------------------------------------------------------------
+namespace dpi {
+void set_error(const char* fmt, ...);
+}
+#define DPI_CUDA_CHECK(expr)                                                                  \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      dpi::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return DPI_ERR_CUDA;                                                                    \
+    }                                                                                         \
+  } while (0)

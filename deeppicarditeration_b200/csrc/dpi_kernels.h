@@ -1,0 +1,62 @@
+// Internal launch interface between the C ABI (dpi_api.cu) and the kernel translation units.
+#pragma once
+#include <vector>
+
+#include "dpi_common.cuh"
+
+namespace dpi {
+
+// ---- fp32 packed MLP (SIMT path): k-major, zero-padded to HP columns --------------------------------
+struct MlpDev {
+  int n_linear;  // L: Linear(1+nx,H) , L-2 x Linear(H,H), Linear(H,1)
+  int nx;
+  int HP;     // padded hidden width: 64 or 128
+  int d_pad;  // nx rounded up to a multiple of 128
+  const float* Wt1;   // [d_pad][HP]  Wt1[j][h] = W1[h][1+j]
+  const float* wt;    // [HP]         W1[:,0]   (time column)
+  const float* b1;    // [HP]
+  const float* wsum;  // [HP]         sum_j W1[:,1+j]  == tangent of layer 1 along (0,1,...,1)
+  const float* Wth[DPI_MAX_LINEAR];  // hidden layer l: [HP][HP]  Wth[k][h] = W_l[h][k]
+  const float* bh[DPI_MAX_LINEAR];   // [HP]
+  const float* wout;  // [HP]
+  const float* bout;  // [1] device
+};
+
+int launch_sample_tx(const ProblemDev& P, int64_t n, int64_t base, uint64_t seed, float eps, float* tx,
+                     cudaStream_t st);
+int launch_terminal(const ProblemDev& P, const float* tx, int64_t n, int M_T, uint64_t seed, int64_t base,
+                    const float* zT, float* y, cudaStream_t st);
+
+// Pack torch-layout weights into MlpDev buffers (buffers preallocated by the handle; `bout` read back by caller).
+int launch_pack_mlp(const dpi_network& net, int nx, int HP, int d_pad, float* Wt1, float* wt, float* b1, float* wsum,
+                    float* const* Wth, float* const* bh, float* wout, float* bout_dev, cudaStream_t st);
+
+// Burgers (Cha) integral estimator, fp32 SIMT.  base pass: fb[n], c0[n][HP]; path pass: y += integral part, then clip.
+int launch_cha_simt_base(const ProblemDev& P, const MlpDev& net, const float* tx, int64_t n, float* fb, float* c0,
+                         float* u_out, float* dsum_out, cudaStream_t st);
+int launch_cha_simt_path(const ProblemDev& P, const MlpDev& net, const float* tx, int64_t n, int M_I, uint64_t seed,
+                         int64_t base, const float* u_s, const float* zS, const float* fb, const float* c0,
+                         float bound, float* y, cudaStream_t st);
+
+// ---- bf16 tcgen05 path (dpi_mlp_tc.cu) ---------------------------------------------------------------
+struct TcNetDev {
+  int n_hidden;               // number of H x H hidden GEMM layers (L-2)
+  int nx, d_pad;              // d_pad: nx rounded up to a multiple of 64 (K of the first GEMM)
+  const void* W1;             // bf16 [128][d_pad]   UMMA canonical K-major, 128B swizzle, 64-column K panels
+  const void* Wh[DPI_MAX_LINEAR];  // bf16 [128][128] per hidden layer, same layout
+  const float* wt;            // fp32 vectors shared with the SIMT packing
+  const float* wsum;
+  const float* bh[DPI_MAX_LINEAR];
+  const float* wout;
+  const float* bout;
+};
+int tc_pack_network(const dpi_network& net, const ProblemDev& P, const MlpDev& M, std::vector<void*>& owner,
+                    TcNetDev* out, bool* ready, int64_t* launches, cudaStream_t st);
+int launch_cha_tc_path(const ProblemDev& P, const TcNetDev& net, const float* tx, int64_t n, int M_I, uint64_t seed,
+                       int64_t base, const float* u_s, const float* zS, const float* fb, const float* c0, float bound,
+                       float* y, cudaStream_t st);
+
+// y = clip(y + add, +-bound) elementwise helpers used by the Zero-network shortcuts
+int launch_finish_zero(const ProblemDev& P, const float* tx, int64_t n, float bound, float* y, cudaStream_t st);
+
+}  // namespace dpi

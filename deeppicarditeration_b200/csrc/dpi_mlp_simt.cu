@@ -1,0 +1,465 @@
+// fp32 (CUDA-core FMA) integral estimator for the Burgers-type equation `Cha`:
+//   yI[0]   = mean_m (T-t) f_m ,  yI[1+j] = mean_m (T-t)(f_m - f_b) Z_mj / (sqrt(s_m-t) sigma)
+//   f = sigma (k u - c) sigma D,  u = u_k(s, X_s),  D = sum_j du_k/dx_j  (one forward-mode tangent)
+//
+// Restates picard/data.py:471-527 (estimator), :350-366 (s, X_s), :1226-1325 (get_f) and
+// picard/equations.py:297-302 (f), picard/solution.py:123-135 (MLP).  The reference materialises
+// [n*M, 1+nx] fp64 tensors and runs forward + reverse-mode autograd; here one CTA owns one collocation point,
+// generates the increments of a 64/128-sample tile from Philox straight into shared memory, pushes value and
+// tangent through the MLP as one register-tiled GEMM chain whose activations never leave shared memory, and
+// accumulates the Bismut-weighted sums in registers.  First layer trick: z1 = (W_x x + b) + s w_t + a (W_x Z),
+// so the GEMM runs on the unit-variance increments Z and the point-dependent part c0 is computed once per point
+// (by the baseline pass, which also yields the control variate f_b = f(t, x)).
+#include "dpi_common.cuh"
+#include "dpi_kernels.h"
+
+namespace dpi {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+
+template <int HP>
+struct Geo {
+  static constexpr int TX = HP / 8;       // column groups (8 columns per thread)
+  static constexpr int TY = kThreads / TX;  // row groups (8 GEMM rows per thread)
+  static constexpr int ROWS = TY * 8;     // GEMM rows per tile: value/tangent interleaved
+  static constexpr int RT = TY * 4;       // path rows (MC samples) per tile
+  static constexpr int LDA = ROWS + 4;
+  static constexpr int LDZ = RT + 4;
+  static constexpr int KC = 128;          // layer-1 K chunk (input dims)
+  static constexpr int kActFloats = HP * LDA;
+  static constexpr int kWsFloats = KC * HP;
+  static constexpr int kZsFloats = KC * LDZ;
+  static constexpr int kVecFloats = 4 * HP + (DPI_MAX_LINEAR)*HP + 3 * RT + 16;
+  static constexpr size_t kSmemBytes = sizeof(float) * (kActFloats + kWsFloats + kZsFloats + kVecFloats);
+};
+
+enum Mode : int { kModeBase = 0, kModePath = 1 };
+
+template <int HP, int NSLOT>
+__global__ void __launch_bounds__(kThreads, 1)
+cha_simt_kernel(const ProblemDev P, const MlpDev N, const float* __restrict__ tx, int64_t n, int M_I, uint64_t seed,
+                int64_t point_base, const float* __restrict__ u_s, const float* __restrict__ zS,
+                const float* __restrict__ fb_in, const float* __restrict__ c0_in, float bound, float* __restrict__ y,
+                float* __restrict__ fb_out, float* __restrict__ c0_out, float* __restrict__ u_out,
+                float* __restrict__ d_out, int mode) {
+  using G = Geo<HP>;
+  extern __shared__ __align__(16) float smem[];
+  float* act = smem;
+  float* Ws = act + G::kActFloats;
+  float* Zs = Ws + G::kWsFloats;
+  float* c0_s = Zs + G::kZsFloats;
+  float* wt_s = c0_s + HP;
+  float* wsum_s = wt_s + HP;
+  float* wout_s = wsum_s + HP;
+  float* bias_s = wout_s + HP;  // [DPI_MAX_LINEAR][HP]
+  float* s_s = bias_s + DPI_MAX_LINEAR * HP;
+  float* a_s = s_s + G::RT;
+  float* coef_s = a_s + G::RT;
+  float* red_v = coef_s + G::RT;  // [kWarps]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ty = tid % G::TY, txg = tid / G::TY;
+  const int d = P.nx;
+  const bool det = (zS != nullptr);
+  const bool vec_ok = (d & 3) == 0;
+  const int n_hidden = N.n_linear - 2;
+  const int nchunk = N.d_pad / G::KC;
+
+  const int64_t p = blockIdx.x;  // PATH: point index; BASE: tile index
+  float t = 0.f, dT = 0.f, fbp = 0.f;
+  int ntiles = 1;
+  if (mode == kModePath) {
+    t = __ldg(tx + p * (int64_t)(1 + d));
+    dT = P.T - t;
+    fbp = __ldg(fb_in + p);
+    ntiles = (M_I + G::RT - 1) / G::RT;
+  }
+  const uint64_t gp = (uint64_t)(point_base + p);
+
+  for (int i = tid; i < HP; i += kThreads) {
+    wt_s[i] = N.wt[i];
+    wsum_s[i] = N.wsum[i];
+    wout_s[i] = N.wout[i];
+    c0_s[i] = (mode == kModePath) ? c0_in[p * HP + i] : N.b1[i];
+  }
+  for (int l = 0; l < n_hidden; ++l)
+    for (int i = tid; i < HP; i += kThreads) bias_s[l * HP + i] = N.bh[l][i];
+  const float bout = __ldg(N.bout);
+
+  float4 Gacc[NSLOT];
+#pragma unroll
+  for (int q = 0; q < NSLOT; ++q) Gacc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float fsum = 0.f;
+
+  for (int tile = 0; tile < ntiles; ++tile) {
+    // ---- per-row scalars: s (time fed to the net) and a (scale of the increment) --------------
+    if (tid < G::RT) {
+      const int r = tid;
+      float s, a;
+      if (mode == kModePath) {
+        const int m = tile * G::RT + r;
+        float u = 0.5f;
+        if (m < M_I) u = det ? __ldg(u_s + p * M_I + m) : u01(philox_at(seed, gp, kStreamS, (uint32_t)m, 0u).x);
+        s = u * dT + t;
+        a = sqrtf(u * dT) * P.sigma;
+      } else {
+        const int64_t pt = p * G::RT + r;
+        s = (pt < n) ? __ldg(tx + pt * (int64_t)(1 + d)) : 0.f;
+        a = 1.f;
+      }
+      s_s[r] = s;
+      a_s[r] = a;
+    }
+
+    // ---- layer 1: acc1 = V . W_x^T over K chunks of 128 input dims ----------------------------
+    float acc1[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc1[i][c] = 0.f;
+
+    for (int q = 0; q < nchunk; ++q) {
+      const int j0 = 4 * lane + G::KC * q;
+      for (int r = warp; r < G::RT; r += kWarps) {
+        float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j0 < d) {
+          if (mode == kModePath) {
+            const int m = tile * G::RT + r;
+            if (m < M_I) {
+              if (det) {
+                z = load_row4(zS + ((int64_t)p * M_I + m) * d, j0, d, vec_ok);
+              } else {
+                z = normal4(seed, gp, kStreamIntegral, (uint32_t)m, (uint32_t)(j0 >> 2));
+                if (j0 + 1 >= d) z.y = 0.f;
+                if (j0 + 2 >= d) z.z = 0.f;
+                if (j0 + 3 >= d) z.w = 0.f;
+              }
+            }
+          } else {
+            const int64_t pt = p * G::RT + r;
+            if (pt < n) z = load_row4(tx + pt * (int64_t)(1 + d) + 1, j0, d, false);
+          }
+        }
+        float* zc = Zs + (4 * lane) * G::LDZ + r;
+        zc[0] = z.x;
+        zc[G::LDZ] = z.y;
+        zc[2 * G::LDZ] = z.z;
+        zc[3 * G::LDZ] = z.w;
+      }
+      {
+        const float4* src = reinterpret_cast<const float4*>(N.Wt1 + (size_t)q * G::KC * HP);
+        float4* dst = reinterpret_cast<float4*>(Ws);
+        for (int i = tid; i < G::KC * HP / 4; i += kThreads) dst[i] = __ldg(src + i);
+      }
+      __syncthreads();
+#pragma unroll 4
+      for (int jj = 0; jj < G::KC; ++jj) {
+        const float4 a4 = *reinterpret_cast<const float4*>(Zs + jj * G::LDZ + ty * 4);
+        const float4 w0 = *reinterpret_cast<const float4*>(Ws + jj * HP + txg * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(Ws + jj * HP + txg * 8 + 4);
+        const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc1[i][c] = fmaf(av[i], wv[c], acc1[i][c]);
+      }
+      __syncthreads();
+    }
+
+    // ---- epilogue 1: z = c0 + s w_t + a acc ; (h, h') ; tangent of layer 1 is the constant wsum ----
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int col = txg * 8 + c;
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = ty * 4 + i;
+        const float lin = c0_s[col] + a_s[r] * acc1[i][c];
+        if (mode == kModeBase && c0_out != nullptr) {
+          const int64_t pt = p * G::RT + r;
+          if (pt < n) c0_out[pt * HP + col] = lin;
+        }
+        float h, e1;
+        elu_d1(lin + s_s[r] * wt_s[col], h, e1);
+        o[2 * i] = h;
+        o[2 * i + 1] = e1 * wsum_s[col];
+      }
+      float4* dst = reinterpret_cast<float4*>(act + col * G::LDA + ty * 8);
+      dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+      dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+    }
+
+    // ---- hidden layers: [value;tangent] rows x HP cols, K = HP ---------------------------------
+    for (int l = 0; l < n_hidden; ++l) {
+      {
+        const float4* src = reinterpret_cast<const float4*>(N.Wth[l]);
+        float4* dst = reinterpret_cast<float4*>(Ws);
+        for (int i = tid; i < HP * HP / 4; i += kThreads) dst[i] = __ldg(src + i);
+      }
+      __syncthreads();
+      float acc[8][8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[i][c] = 0.f;
+#pragma unroll 4
+      for (int k = 0; k < HP; ++k) {
+        const float4 a0 = *reinterpret_cast<const float4*>(act + k * G::LDA + ty * 8);
+        const float4 a1 = *reinterpret_cast<const float4*>(act + k * G::LDA + ty * 8 + 4);
+        const float4 w0 = *reinterpret_cast<const float4*>(Ws + k * HP + txg * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(Ws + k * HP + txg * 8 + 4);
+        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[i][c] = fmaf(av[i], wv[c], acc[i][c]);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int col = txg * 8 + c;
+        const float b = bias_s[l * HP + col];
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float h, e1;
+          elu_d1(acc[2 * i][c] + b, h, e1);
+          o[2 * i] = h;
+          o[2 * i + 1] = e1 * acc[2 * i + 1][c];
+        }
+        float4* dst = reinterpret_cast<float4*>(act + col * G::LDA + ty * 8);
+        dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+        dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+      }
+    }
+    __syncthreads();
+
+    // ---- output layer (a dot product per GEMM row), f, Bismut coefficient ------------------------
+    if (tid < G::ROWS) {
+      const int R = tid;
+      float val = 0.f;
+#pragma unroll 8
+      for (int k = 0; k < HP; ++k) val = fmaf(act[k * G::LDA + R], wout_s[k], val);
+      const float other = __shfl_down_sync(0xffffffffu, val, 1);
+      if ((R & 1) == 0) {
+        const int r = R >> 1;
+        const float u = val + bout, D = other;
+        const float f = P.sigma * (P.cha_k * u - P.cha_c) * (P.sigma * D);
+        if (mode == kModePath) {
+          const bool valid = (tile * G::RT + r) < M_I;
+          if (valid) fsum += dT * f;
+          coef_s[r] = valid ? dT * (f - fbp) / a_s[r] : 0.f;
+        } else {
+          const int64_t pt = p * G::RT + r;
+          if (pt < n) {
+            fb_out[pt] = f;
+            if (u_out) u_out[pt] = u;
+            if (d_out) d_out[pt] = D;
+          }
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- gradient label: G_j += coef_m Z_mj (warp <-> sample, lane <-> 4 dims per slot) -----------
+    if (mode == kModePath) {
+      for (int r = warp; r < G::RT; r += kWarps) {
+        const float cf = coef_s[r];
+        const int m = tile * G::RT + r;
+        if (m >= M_I) continue;
+#pragma unroll
+        for (int q = 0; q < NSLOT; ++q) {
+          const int j0 = 4 * lane + G::KC * q;
+          float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (NSLOT == 1) {
+            const float* zc = Zs + (4 * lane) * G::LDZ + r;  // the single K chunk is still resident
+            z = make_float4(zc[0], zc[G::LDZ], zc[2 * G::LDZ], zc[3 * G::LDZ]);
+          } else if (j0 < d) {
+            if (det) {
+              z = load_row4(zS + ((int64_t)p * M_I + m) * d, j0, d, vec_ok);
+            } else {
+              z = normal4(seed, gp, kStreamIntegral, (uint32_t)m, (uint32_t)(j0 >> 2));
+              if (j0 + 1 >= d) z.y = 0.f;
+              if (j0 + 2 >= d) z.z = 0.f;
+              if (j0 + 3 >= d) z.w = 0.f;
+            }
+          }
+          Gacc[q].x = fmaf(cf, z.x, Gacc[q].x);
+          Gacc[q].y = fmaf(cf, z.y, Gacc[q].y);
+          Gacc[q].z = fmaf(cf, z.z, Gacc[q].z);
+          Gacc[q].w = fmaf(cf, z.w, Gacc[q].w);
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  if (mode != kModePath) return;
+
+  // ---- cross-warp reduction; y += integral part; clip (data.py:222) ------------------------------
+  constexpr int LDR = NSLOT * 128 + 8;
+  float* red = act;
+#pragma unroll
+  for (int q = 0; q < NSLOT; ++q) *reinterpret_cast<float4*>(red + warp * LDR + 4 * lane + 128 * q) = Gacc[q];
+  fsum = warp_sum(fsum);
+  if (lane == 0) red_v[warp] = fsum;
+  __syncthreads();
+  float* yp = y + p * (int64_t)(1 + d);
+  const float invM = 1.f / (float)M_I;
+  const bool clip = bound > 0.f && isfinite(bound);
+  for (int j = tid; j < d; j += kThreads) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) s += red[w * LDR + j];
+    float v = yp[1 + j] + s * invM;
+    if (clip) v = fminf(fmaxf(v, -bound), bound);
+    yp[1 + j] = v;
+  }
+  if (tid == 0) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) s += red_v[w];
+    float v = yp[0] + s * invM;
+    if (clip) v = fminf(fmaxf(v, -bound), bound);
+    yp[0] = v;
+  }
+}
+
+// ---- weight packing ---------------------------------------------------------------------------
+// dst[k][h] (k < K_pad, h < HP) = W[h][col_off + k] for k < k_valid, h < out_valid, else 0.   W is [out, ld] row-major.
+__global__ void pack_transpose_kernel(const float* __restrict__ W, int ld, int col_off, int k_valid, int out_valid,
+                                      float* __restrict__ dst, int K_pad, int HP) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K_pad * HP) return;
+  const int k = i / HP, h = i - k * HP;
+  dst[i] = (k < k_valid && h < out_valid) ? W[(size_t)h * ld + col_off + k] : 0.f;
+}
+// dst[h] = h < n_valid ? src[h*stride] : 0
+__global__ void pack_vec_kernel(const float* __restrict__ src, int stride, int n_valid, float* __restrict__ dst, int HP) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= HP) return;
+  dst[h] = (h < n_valid && src != nullptr) ? src[(size_t)h * stride] : 0.f;
+}
+// dst[h] = sum_{j<nx} W1[h][1+j]
+__global__ void pack_wsum_kernel(const float* __restrict__ W1, int nx, int out_valid, float* __restrict__ dst, int HP) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= HP) return;
+  float s = 0.f;
+  if (h < out_valid)
+    for (int j = 0; j < nx; ++j) s += W1[(size_t)h * (1 + nx) + 1 + j];
+  dst[h] = s;
+}
+
+template <int HP, int NSLOT>
+int launch_cha_t(const ProblemDev& P, const MlpDev& N, const float* tx, int64_t n, int M_I, uint64_t seed, int64_t base,
+                 const float* u_s, const float* zS, const float* fb_in, const float* c0_in, float bound, float* y,
+                 float* fb_out, float* c0_out, float* u_out, float* d_out, int mode, cudaStream_t st) {
+  using G = Geo<HP>;
+  auto k = cha_simt_kernel<HP, NSLOT>;
+  DPI_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::kSmemBytes));
+  const int64_t grid = (mode == kModePath) ? n : (n + G::RT - 1) / G::RT;
+  k<<<(unsigned)grid, kThreads, G::kSmemBytes, st>>>(P, N, tx, n, M_I, seed, base, u_s, zS, fb_in, c0_in, bound, y,
+                                                     fb_out, c0_out, u_out, d_out, mode);
+  DPI_CUDA_CHECK(cudaGetLastError());
+  return DPI_OK;
+}
+
+template <int HP>
+int launch_cha_hp(const ProblemDev& P, const MlpDev& N, const float* tx, int64_t n, int M_I, uint64_t seed,
+                  int64_t base, const float* u_s, const float* zS, const float* fb_in, const float* c0_in, float bound,
+                  float* y, float* fb_out, float* c0_out, float* u_out, float* d_out, int mode, cudaStream_t st) {
+#define DPI_ARGS P, N, tx, n, M_I, seed, base, u_s, zS, fb_in, c0_in, bound, y, fb_out, c0_out, u_out, d_out, mode, st
+  switch (N.d_pad / 128) {
+    case 1: return launch_cha_t<HP, 1>(DPI_ARGS);
+    case 2: return launch_cha_t<HP, 2>(DPI_ARGS);
+    case 3:
+    case 4: return launch_cha_t<HP, 4>(DPI_ARGS);
+    case 5:
+    case 6:
+    case 7:
+    case 8: return launch_cha_t<HP, 8>(DPI_ARGS);
+  }
+#undef DPI_ARGS
+  set_error("nx=%d > 1024 is not supported by the fp32 MLP kernel", N.nx);
+  return DPI_ERR_UNSUPPORTED;
+}
+
+int launch_cha(const ProblemDev& P, const MlpDev& N, const float* tx, int64_t n, int M_I, uint64_t seed, int64_t base,
+               const float* u_s, const float* zS, const float* fb_in, const float* c0_in, float bound, float* y,
+               float* fb_out, float* c0_out, float* u_out, float* d_out, int mode, cudaStream_t st) {
+  if (n <= 0) return DPI_OK;
+  if (N.HP == 64)
+    return launch_cha_hp<64>(P, N, tx, n, M_I, seed, base, u_s, zS, fb_in, c0_in, bound, y, fb_out, c0_out, u_out,
+                             d_out, mode, st);
+  if (N.HP == 128)
+    return launch_cha_hp<128>(P, N, tx, n, M_I, seed, base, u_s, zS, fb_in, c0_in, bound, y, fb_out, c0_out, u_out,
+                              d_out, mode, st);
+  set_error("padded hidden width %d not supported (64 or 128)", N.HP);
+  return DPI_ERR_UNSUPPORTED;
+}
+
+__global__ void finish_zero_kernel(const ProblemDev P, const float* __restrict__ tx, int64_t n, float bound,
+                                   float* __restrict__ y) {
+  // ZeroSolution (u_k == 0, grad == 0; picard/solution.py:330-337, data.py:1316):
+  //   Cha: f = 0                      -> y = yT
+  //   OU : f = -d theta (constant)    -> yI[0] = -(T-t) d theta, gradient part vanishes (f - f_b == 0)
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int ld = 1 + P.nx;
+  if (i >= n * ld) return;
+  const int64_t p = i / ld;
+  const int c = (int)(i - p * ld);
+  float v = y[i];
+  if (c == 0 && P.eq == DPI_EQ_OU) v += -(P.T - tx[p * ld]) * (float)P.nx * P.ou_theta;
+  if (bound > 0.f && isfinite(bound)) v = fminf(fmaxf(v, -bound), bound);
+  y[i] = v;
+}
+
+}  // namespace
+
+int launch_pack_mlp(const dpi_network& net, int nx, int HP, int d_pad, float* Wt1, float* wt, float* b1, float* wsum,
+                    float* const* Wth, float* const* bh, float* wout, float* bout_dev, cudaStream_t st) {
+  const int L = net.n_main;
+  const dpi_linear& l1 = net.main[0];
+  const int T = 256;
+  pack_transpose_kernel<<<(d_pad * HP + T - 1) / T, T, 0, st>>>(l1.W, 1 + nx, 1, nx, l1.n_out, Wt1, d_pad, HP);
+  pack_vec_kernel<<<(HP + T - 1) / T, T, 0, st>>>(l1.W, 1 + nx, l1.n_out, wt, HP);
+  pack_vec_kernel<<<(HP + T - 1) / T, T, 0, st>>>(l1.b, 1, l1.n_out, b1, HP);
+  pack_wsum_kernel<<<(HP + T - 1) / T, T, 0, st>>>(l1.W, nx, l1.n_out, wsum, HP);
+  for (int l = 1; l < L - 1; ++l) {
+    const dpi_linear& ll = net.main[l];
+    pack_transpose_kernel<<<(HP * HP + T - 1) / T, T, 0, st>>>(ll.W, ll.n_in, 0, ll.n_in, ll.n_out, Wth[l - 1], HP, HP);
+    pack_vec_kernel<<<(HP + T - 1) / T, T, 0, st>>>(ll.b, 1, ll.n_out, bh[l - 1], HP);
+  }
+  const dpi_linear& lo = net.main[L - 1];
+  pack_vec_kernel<<<(HP + T - 1) / T, T, 0, st>>>(lo.W, 1, lo.n_in, wout, HP);
+  pack_vec_kernel<<<1, 32, 0, st>>>(lo.b, 1, 1, bout_dev, 1);
+  DPI_CUDA_CHECK(cudaGetLastError());
+  return DPI_OK;
+}
+
+int launch_cha_simt_base(const ProblemDev& P, const MlpDev& N, const float* tx, int64_t n, float* fb, float* c0,
+                         float* u_out, float* dsum_out, cudaStream_t st) {
+  return launch_cha(P, N, tx, n, 0, 0, 0, nullptr, nullptr, nullptr, nullptr, 0.f, nullptr, fb, c0, u_out, dsum_out,
+                    kModeBase, st);
+}
+
+int launch_cha_simt_path(const ProblemDev& P, const MlpDev& N, const float* tx, int64_t n, int M_I, uint64_t seed,
+                         int64_t base, const float* u_s, const float* zS, const float* fb, const float* c0, float bound,
+                         float* y, cudaStream_t st) {
+  return launch_cha(P, N, tx, n, M_I, seed, base, u_s, zS, fb, c0, bound, y, nullptr, nullptr, nullptr, nullptr,
+                    kModePath, st);
+}
+
+int launch_finish_zero(const ProblemDev& P, const float* tx, int64_t n, float bound, float* y, cudaStream_t st) {
+  if (n <= 0) return DPI_OK;
+  const int64_t tot = n * (1 + P.nx);
+  finish_zero_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(P, tx, n, bound, y);
+  DPI_CUDA_CHECK(cudaGetLastError());
+  return DPI_OK;
+}
+
+}  // namespace dpi

@@ -1,0 +1,300 @@
+// Collocation-point sampling and the terminal estimator E[(g(X_T)-g(x)) (1, Z/(sqrt(T-t) sigma))] + (g(x), 0).
+//
+// Restates (not ports) picard/data.py:161-167 (t), picard/equations.py:118-119,217-230 (x) and
+// picard/data.py:899-926 (terminal estimator with Bismut weights).  The reference materialises five
+// [n*M_T, nx] fp64 tensors in HBM; here a warp owns one MC sample at a time, each lane generates its 4 Brownian
+// increments per 128-dim slot from Philox in registers (or streams them with one coalesced 16-byte load in
+// deterministic mode), the payoff statistics are warp-shuffle reduced, and the Bismut-weighted sums stay in
+// registers until one label row per point is written.  HBM traffic: (1+nx) floats in, (1+nx) floats out per point.
+#include "dpi_common.cuh"
+#include "dpi_kernels.h"
+
+namespace dpi {
+
+namespace {
+
+constexpr int kTermThreads = 256;
+constexpr int kTermWarps = kTermThreads / 32;
+
+// ---- per-equation payoff g from per-row sufficient statistics ------------------------------------
+// Cha:  1 statistic  S   = sum_j Z_j                       g = sigmoid(T + k (sum x + a S))
+// GBM:  nodes stats  P_k = sum_j w_kj Z_j                  g = sum_k v_k sin(w_k0 T + w_k.x + a P_k)
+// OU :  K stats      Q_k = sum_j (x_j - m_kj + a Z_j)^2/var_kj   g = -logsumexp_k(lognorm_k - Q_k/2)
+template <int EQ>
+struct Payoff;
+
+template <>
+struct Payoff<DPI_EQ_CHA> {
+  static constexpr int NS = 1;
+  static constexpr int NCH = 0;  // per-dim constant channels in shared memory
+  __device__ static void accumulate(float (&st)[NS], const float4 z, const float* cst, int ldc, int j0, float a) {
+    st[0] += (z.x + z.y) + (z.z + z.w);
+  }
+  __device__ static float eval(const ProblemDev& P, const float (&st)[NS], const float* base, float a) {
+    return sigmoidf_(P.T + P.cha_k * (base[0] + a * st[0]));
+  }
+};
+
+template <>
+struct Payoff<DPI_EQ_GBM> {
+  static constexpr int NS = kMaxGbmNodes;
+  static constexpr int NCH = kMaxGbmNodes;  // w_k[j]
+  __device__ static void accumulate(float (&st)[NS], const float4 z, const float* cst, int ldc, int j0, float a) {
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+      const float4 w = *reinterpret_cast<const float4*>(cst + k * ldc + j0);
+      st[k] += (w.x * z.x + w.y * z.y) + (w.z * z.z + w.w * z.w);
+    }
+  }
+  __device__ static float eval(const ProblemDev& P, const float (&st)[NS], const float* base, float a) {
+    float g = 0.f;
+#pragma unroll
+    for (int k = 0; k < NS; ++k)
+      if (k < P.gbm_nodes) g += P.gbm_v[k] * sinf(base[k] + a * st[k]);  // base[k] = w_k0 T + w_k . x
+    return g;
+  }
+};
+
+template <>
+struct Payoff<DPI_EQ_OU> {
+  static constexpr int NS = kMaxOuK;
+  static constexpr int NCH = 2 * kMaxOuK;  // (x - m_k)[j], ivar_k[j]
+  __device__ static void accumulate(float (&st)[NS], const float4 z, const float* cst, int ldc, int j0, float a) {
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+      const float4 dm = *reinterpret_cast<const float4*>(cst + (2 * k) * ldc + j0);
+      const float4 iv = *reinterpret_cast<const float4*>(cst + (2 * k + 1) * ldc + j0);
+      const float e0 = dm.x + a * z.x, e1 = dm.y + a * z.y, e2 = dm.z + a * z.z, e3 = dm.w + a * z.w;
+      st[k] += (e0 * e0 * iv.x + e1 * e1 * iv.y) + (e2 * e2 * iv.z + e3 * e3 * iv.w);
+    }
+  }
+  __device__ static float eval(const ProblemDev& P, const float (&st)[NS], const float* base, float a) {
+    float l[NS], mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+      l[k] = (k < P.ou_K) ? P.ou_lognorm[k] - 0.5f * st[k] : -INFINITY;
+      mx = fmaxf(mx, l[k]);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < NS; ++k) s += __expf(l[k] - mx);
+    return -(mx + __logf(s));
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+template <int EQ, int NSLOT, bool DET>
+__global__ void __launch_bounds__(kTermThreads)
+terminal_kernel(const ProblemDev P, const float* __restrict__ tx, int M_T, uint64_t seed, int64_t point_base,
+                const float* __restrict__ zT, float* __restrict__ y) {
+  using PO = Payoff<EQ>;
+  constexpr int NS = PO::NS;
+  constexpr int LDC = NSLOT * 128;  // padded dim count
+  extern __shared__ __align__(16) float smem[];
+  float* cst = smem;                          // [NCH][LDC]
+  float* red = smem + PO::NCH * LDC;          // [kTermWarps][LDC + 8]
+  __shared__ float base[NS > 1 ? NS : 1];     // x-dependent scalars of g
+  __shared__ float red_v[kTermWarps];
+
+  const int d = P.nx;
+  const int64_t p = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* txp = tx + p * (int64_t)(1 + d);
+  const float t = __ldg(txp);
+  const float a = sqrtf(P.T - t) * P.sigma;
+  const bool vec_ok = (d & 3) == 0;
+
+  // ---- per-point constants -----------------------------------------------------------------
+  for (int i = threadIdx.x; i < PO::NCH * LDC; i += kTermThreads) {
+    const int ch = i / LDC, j = i - ch * LDC;
+    float v = 0.f;
+    if (j < d) {
+      if (EQ == DPI_EQ_GBM) {
+        if (ch < P.gbm_nodes) v = P.gbm_w[ch * (1 + d) + 1 + j];
+      } else if (EQ == DPI_EQ_OU) {
+        const int k = ch >> 1;
+        if (k < P.ou_K) v = (ch & 1) ? P.ou_ivar[k * d + j] : (__ldg(txp + 1 + j) - P.ou_mean[k * d + j]);
+      }
+    }
+    cst[i] = v;
+  }
+  if (warp == 0) {
+    if (EQ == DPI_EQ_CHA) {
+      float s = 0.f;
+      for (int j = lane; j < d; j += 32) s += __ldg(txp + 1 + j);
+      s = warp_sum(s);
+      if (lane == 0) base[0] = s;
+    } else if (EQ == DPI_EQ_GBM) {
+      for (int k = 0; k < P.gbm_nodes; ++k) {
+        float s = 0.f;
+        for (int j = lane; j < d; j += 32) s += P.gbm_w[k * (1 + d) + 1 + j] * __ldg(txp + 1 + j);
+        s = warp_sum(s);
+        if (lane == 0) base[k] = s + P.gbm_w[k * (1 + d)] * P.T;
+      }
+    }
+  }
+  __syncthreads();
+
+  // g(x): the same payoff with zero increments
+  float g0;
+  {
+    float st[NS];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) st[k] = 0.f;
+    if (EQ == DPI_EQ_OU) {
+#pragma unroll
+      for (int q = 0; q < NSLOT; ++q) PO::accumulate(st, make_float4(0.f, 0.f, 0.f, 0.f), cst, LDC, 4 * lane + 128 * q, 0.f);
+#pragma unroll
+      for (int k = 0; k < NS; ++k) st[k] = warp_sum(st[k]);
+    }
+    g0 = PO::eval(P, st, base, 0.f);
+  }
+
+  // ---- MC loop: warp <-> sample, lane <-> 4 dims per 128-dim slot ------------------------------
+  float4 acc[NSLOT];
+#pragma unroll
+  for (int q = 0; q < NSLOT; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float acc_v = 0.f;
+  const uint64_t gp = (uint64_t)(point_base + p);
+
+  for (int m = warp; m < M_T; m += kTermWarps) {
+    float4 z[NSLOT];
+    float st[NS];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) st[k] = 0.f;
+#pragma unroll
+    for (int q = 0; q < NSLOT; ++q) {
+      const int j0 = 4 * lane + 128 * q;
+      if (j0 < d) {
+        if (DET) {
+          z[q] = load_row4(zT + ((int64_t)p * M_T + m) * d, j0, d, vec_ok);
+        } else {
+          z[q] = normal4(seed, gp, kStreamTerminal, (uint32_t)m, (uint32_t)(j0 >> 2));
+          if (j0 + 1 >= d) z[q].y = 0.f;
+          if (j0 + 2 >= d) z[q].z = 0.f;
+          if (j0 + 3 >= d) z[q].w = 0.f;
+        }
+        PO::accumulate(st, z[q], cst, LDC, j0, a);
+      } else {
+        z[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (EQ == DPI_EQ_OU) PO::accumulate(st, z[q], cst, LDC, j0, a);  // padded dims contribute 0 (ivar=0)
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NS; ++k) st[k] = warp_sum(st[k]);
+    const float dg = PO::eval(P, st, base, a) - g0;
+    acc_v += dg;
+#pragma unroll
+    for (int q = 0; q < NSLOT; ++q) {
+      acc[q].x = fmaf(dg, z[q].x, acc[q].x);
+      acc[q].y = fmaf(dg, z[q].y, acc[q].y);
+      acc[q].z = fmaf(dg, z[q].z, acc[q].z);
+      acc[q].w = fmaf(dg, z[q].w, acc[q].w);
+    }
+  }
+
+  // ---- cross-warp reduction, one label row per point -------------------------------------------
+  constexpr int LDR = LDC + 8;
+#pragma unroll
+  for (int q = 0; q < NSLOT; ++q) *reinterpret_cast<float4*>(red + warp * LDR + 4 * lane + 128 * q) = acc[q];
+  if (lane == 0) red_v[warp] = acc_v;
+  __syncthreads();
+  float* yp = y + p * (int64_t)(1 + d);
+  const float inv = 1.f / ((float)M_T * a);
+  for (int j = threadIdx.x; j < d; j += kTermThreads) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kTermWarps; ++w) s += red[w * LDR + j];
+    yp[1 + j] = s * inv;
+  }
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kTermWarps; ++w) s += red_v[w];
+    yp[0] = s / (float)M_T + g0;
+  }
+}
+
+// t = (T-2eps)(1-U)+eps ; x = x0 + sqrt(t) sigma Z  (one warp per point)
+__global__ void __launch_bounds__(256)
+sample_tx_kernel(const ProblemDev P, int64_t n, int64_t point_base, uint64_t seed, float eps, float* __restrict__ tx) {
+  const int lane = threadIdx.x & 31;
+  const int64_t p = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (p >= n) return;
+  const int d = P.nx;
+  const uint64_t gp = (uint64_t)(point_base + p);
+  const uint4 r = philox_at(seed, gp, kStreamT, 0u, 0u);
+  const float t = (P.T - 2.f * eps) * (1.f - u01(r.x)) + eps;
+  float* row = tx + p * (int64_t)(1 + d);
+  if (lane == 0) row[0] = t;
+  const float a = sqrtf(t) * P.sigma;
+  for (int j0 = 4 * lane; j0 < d; j0 += 128) {
+    const float4 z = normal4(seed, gp, kStreamX, 0u, (uint32_t)(j0 >> 2));
+    float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (P.ou_x0_std > 0.f && P.eq == DPI_EQ_OU) {
+      x0 = normal4(seed, gp, kStreamX0, 0u, (uint32_t)(j0 >> 2));
+      x0.x *= P.ou_x0_std; x0.y *= P.ou_x0_std; x0.z *= P.ou_x0_std; x0.w *= P.ou_x0_std;
+    }
+    const float v[4] = {x0.x + a * z.x, x0.y + a * z.y, x0.z + a * z.z, x0.w + a * z.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (j0 + q < d) row[1 + j0 + q] = v[q];
+  }
+}
+
+template <int EQ, int NSLOT>
+int launch_terminal_t(const ProblemDev& P, const float* tx, int64_t n, int M_T, uint64_t seed, int64_t base,
+                      const float* zT, float* y, cudaStream_t st) {
+  using PO = Payoff<EQ>;
+  constexpr int LDC = NSLOT * 128;
+  const size_t smem = sizeof(float) * (PO::NCH * LDC + kTermWarps * (LDC + 8));
+  auto kd = terminal_kernel<EQ, NSLOT, true>;
+  auto kp = terminal_kernel<EQ, NSLOT, false>;
+  if (smem > 48 * 1024) {
+    DPI_CUDA_CHECK(cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DPI_CUDA_CHECK(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  if (zT)
+    kd<<<(unsigned)n, kTermThreads, smem, st>>>(P, tx, M_T, seed, base, zT, y);
+  else
+    kp<<<(unsigned)n, kTermThreads, smem, st>>>(P, tx, M_T, seed, base, nullptr, y);
+  DPI_CUDA_CHECK(cudaGetLastError());
+  return DPI_OK;
+}
+
+template <int EQ>
+int launch_terminal_eq(const ProblemDev& P, const float* tx, int64_t n, int M_T, uint64_t seed, int64_t base,
+                       const float* zT, float* y, cudaStream_t st) {
+  const int d = P.nx;
+  if (d <= 128) return launch_terminal_t<EQ, 1>(P, tx, n, M_T, seed, base, zT, y, st);
+  if (d <= 256) return launch_terminal_t<EQ, 2>(P, tx, n, M_T, seed, base, zT, y, st);
+  if (d <= 512) return launch_terminal_t<EQ, 4>(P, tx, n, M_T, seed, base, zT, y, st);
+  if (d <= 1024) return launch_terminal_t<EQ, 8>(P, tx, n, M_T, seed, base, zT, y, st);
+  set_error("nx=%d > 1024 is not supported by the terminal kernel", d);
+  return DPI_ERR_UNSUPPORTED;
+}
+
+}  // namespace
+
+int launch_terminal(const ProblemDev& P, const float* tx, int64_t n, int M_T, uint64_t seed, int64_t base,
+                    const float* zT, float* y, cudaStream_t st) {
+  if (n <= 0) return DPI_OK;
+  switch (P.eq) {
+    case DPI_EQ_CHA: return launch_terminal_eq<DPI_EQ_CHA>(P, tx, n, M_T, seed, base, zT, y, st);
+    case DPI_EQ_GBM: return launch_terminal_eq<DPI_EQ_GBM>(P, tx, n, M_T, seed, base, zT, y, st);
+    case DPI_EQ_OU: return launch_terminal_eq<DPI_EQ_OU>(P, tx, n, M_T, seed, base, zT, y, st);
+  }
+  set_error("unknown equation kind %d", P.eq);
+  return DPI_ERR_INVALID;
+}
+
+int launch_sample_tx(const ProblemDev& P, int64_t n, int64_t base, uint64_t seed, float eps, float* tx,
+                     cudaStream_t st) {
+  if (n <= 0) return DPI_OK;
+  const int wpb = 8;
+  sample_tx_kernel<<<(unsigned)((n + wpb - 1) / wpb), wpb * 32, 0, st>>>(P, n, base, seed, eps, tx);
+  DPI_CUDA_CHECK(cudaGetLastError());
+  return DPI_OK;
+}
+
+}  // namespace dpi

@@ -1,0 +1,208 @@
+"""Torch-facing wrapper of the C-ABI handle, and the `picard_b200::label_gen` custom op.
+
+PyTorch is plumbing here (device memory, streams); all arithmetic happens in libdpi_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _native as nat
+
+_ENGINES: Dict[int, "LabelEngine"] = {}
+_NEXT_ID = [1]
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _f32c(t: torch.Tensor, device) -> torch.Tensor:
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+class LabelEngine:
+    """One handle per device. Holds the packed equation and frozen network u_k."""
+
+    def __init__(self, device="cuda"):
+        if not torch.cuda.is_available():
+            raise RuntimeError("deeppicarditeration_b200 needs a CUDA (sm_100a) device; there is no CPU fallback")
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError(f"LabelEngine device must be cuda, got {device}")
+        self.index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", self.index)
+        self.lib = nat.load()
+        h = C.c_void_p()
+        nat.check(self.lib.dpi_create(self.index, C.byref(h)), "dpi_create")
+        self.h = h
+        self.nx = None
+        self._keep: List[torch.Tensor] = []
+        self._prob_keep = []
+        self.id = _NEXT_ID[0]
+        _NEXT_ID[0] += 1
+        _ENGINES[self.id] = self
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.dpi_destroy(self.h)
+            self.h = None
+            _ENGINES.pop(self.id, None)
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ------------------------------------------------------------------------------------------
+    def set_problem(self, kind: str, nx: int, T: float, alpha: float, *, cha_k: float = 0.0, gbm_w=None, gbm_v=None,
+                    ou_mean=None, ou_diagvar=None, ou_pi=None, ou_theta: float = 1.0, ou_mu: float = 0.0,
+                    ou_alpha_init: float = 0.0, sdgd_v: int = 0):
+        p = nat.dpi_problem()
+        p.kind = {"Cha": nat.DPI_EQ_CHA, "GBM": nat.DPI_EQ_GBM, "OU": nat.DPI_EQ_OU}[kind]
+        p.nx, p.T, p.alpha, p.cha_k = int(nx), float(T), float(alpha), float(cha_k)
+        p.sdgd_v = int(sdgd_v)
+        keep = []
+
+        def dptr(a):
+            arr = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+            keep.append(arr)
+            return arr.ctypes.data_as(C.POINTER(C.c_double))
+
+        if kind == "GBM":
+            w = np.asarray(gbm_w, dtype=np.float64)
+            p.gbm_nodes = int(w.shape[0])
+            p.gbm_w, p.gbm_v = dptr(w), dptr(np.asarray(gbm_v, dtype=np.float64).reshape(-1))
+        if kind == "OU":
+            m = np.asarray(ou_mean, dtype=np.float64)
+            p.ou_K = int(m.shape[0])
+            p.ou_mean, p.ou_diagvar, p.ou_pi = dptr(m), dptr(ou_diagvar), dptr(ou_pi)
+            p.ou_theta, p.ou_mu, p.ou_alpha_init = float(ou_theta), float(ou_mu), float(ou_alpha_init)
+        with torch.cuda.device(self.device):
+            nat.check(self.lib.dpi_set_problem(self.h, C.byref(p)), "dpi_set_problem")
+        self.nx = int(nx)
+        self.kind = kind
+
+    def _fill_chain(self, arr, lins: Sequence[Tuple[torch.Tensor, torch.Tensor]]) -> int:
+        if len(lins) > nat.DPI_MAX_LINEAR:
+            raise NotImplementedError(f"at most {nat.DPI_MAX_LINEAR} Linear layers per chain")
+        for i, (W, b) in enumerate(lins):
+            W, b = _f32c(W, self.device), _f32c(b, self.device)
+            self._keep += [W, b]
+            arr[i].W, arr[i].b = W.data_ptr(), b.data_ptr()
+            arr[i].n_out, arr[i].n_in = int(W.shape[0]), int(W.shape[1])
+        return len(lins)
+
+    def set_network(self, kind: str, main=(), t_encoder=(), smooth_net=(), phase=None, coeff=None):
+        """kind: 'zero' | 'mlp' | 'pisgrad'; chains are lists of (W[out,in], b[out]) tensors."""
+        net = nat.dpi_network()
+        self._keep = []
+        net.kind = {"zero": nat.DPI_NET_ZERO, "mlp": nat.DPI_NET_MLP, "pisgrad": nat.DPI_NET_PISGRAD}[kind]
+        net.n_main = self._fill_chain(net.main, main)
+        net.n_t_encoder = self._fill_chain(net.t_encoder, t_encoder)
+        net.n_smooth = self._fill_chain(net.smooth_net, smooth_net)
+        if phase is not None:
+            ph, co = _f32c(phase.reshape(-1), self.device), _f32c(coeff.reshape(-1), self.device)
+            self._keep += [ph, co]
+            net.timestep_phase, net.timestep_coeff = ph.data_ptr(), co.data_ptr()
+        with torch.cuda.device(self.device):
+            nat.check(self.lib.dpi_set_network(self.h, C.byref(net), self._stream()), "dpi_set_network")
+        self.net_kind = kind
+
+    # ------------------------------------------------------------------------------------------
+    def sample_tx(self, n: int, seed: int = 0, point_index_base: int = 0) -> torch.Tensor:
+        tx = torch.empty(n, 1 + self.nx, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            nat.check(self.lib.dpi_sample_tx(self.h, n, point_index_base, C.c_uint64(seed & (2**64 - 1)), _ptr(tx),
+                                             self._stream()), "dpi_sample_tx")
+        return tx
+
+    @staticmethod
+    def _cfg(M_T, M_I, precision, bound, seed, base):
+        cfg = nat.dpi_label_config()
+        cfg.M_T, cfg.M_I = int(M_T), int(M_I)
+        cfg.precision = {"fp32": nat.DPI_PREC_FP32, "bf16": nat.DPI_PREC_BF16}[precision]
+        cfg.sample_bound = float(bound) if bound is not None and math.isfinite(bound) else 0.0
+        cfg.seed = seed & (2**64 - 1)
+        cfg.point_index_base = int(base)
+        return cfg
+
+    def label_gen(self, tx: torch.Tensor, M_T: int, M_I: int, *, precision: str = "fp32", sample_bound=None,
+                  seed: int = 0, point_index_base: int = 0, draws: Optional[dict] = None) -> torch.Tensor:
+        tx = _f32c(tx, self.device)
+        n = tx.shape[0]
+        assert tx.shape[1] == 1 + self.nx
+        y = torch.empty_like(tx)
+        cfg = self._cfg(M_T, M_I, precision, sample_bound, seed, point_index_base)
+        dr = None
+        keep = []
+        if draws is not None:
+            dr = nat.dpi_draws()
+            zT, u_s, zS = (_f32c(draws[k], self.device) for k in ("zT", "u_s", "zS"))
+            assert zT.numel() == n * M_T * self.nx and zS.numel() == n * M_I * self.nx and u_s.numel() == n * M_I
+            keep += [zT, u_s, zS]
+            dr.zT, dr.u_s, dr.zS = zT.data_ptr(), u_s.data_ptr(), zS.data_ptr()
+            if draws.get("idx") is not None:
+                idx = draws["idx"].to(device=self.device, dtype=torch.int32).contiguous()
+                keep.append(idx)
+                dr.idx = idx.data_ptr()
+        with torch.cuda.device(self.device):
+            nat.check(self.lib.dpi_label_gen(self.h, _ptr(tx), n, C.byref(cfg), C.byref(dr) if dr is not None else None,
+                                             _ptr(y), self._stream()), "dpi_label_gen")
+        if keep:  # draws must outlive the asynchronous launch
+            torch.cuda.current_stream(self.device).synchronize()
+        return y
+
+    def label_gen_host(self, n: int, M_T: int, M_I: int, *, tx_host: Optional[torch.Tensor] = None,
+                       y_host: Optional[torch.Tensor] = None, tx_out_host: Optional[torch.Tensor] = None,
+                       precision: str = "fp32", sample_bound=None, seed: int = 0, point_index_base: int = 0):
+        """Host-buffer entry point (H2D + kernels + D2H + sync inside the call)."""
+        ld = 1 + self.nx
+        if y_host is None:
+            y_host = torch.empty(n, ld, dtype=torch.float32, pin_memory=True)
+        if tx_host is None and tx_out_host is None:
+            tx_out_host = torch.empty(n, ld, dtype=torch.float32, pin_memory=True)
+        cfg = self._cfg(M_T, M_I, precision, sample_bound, seed, point_index_base)
+        with torch.cuda.device(self.device):
+            nat.check(self.lib.dpi_label_gen_host(
+                self.h, _ptr(tx_host), n, C.byref(cfg), _ptr(tx_out_host), _ptr(y_host), self._stream()),
+                "dpi_label_gen_host")
+        return (tx_host if tx_host is not None else tx_out_host), y_host
+
+    def net_eval(self, tx: torch.Tensor, want_grad: bool = False):
+        tx = _f32c(tx, self.device)
+        n = tx.shape[0]
+        u = torch.empty(n, device=self.device, dtype=torch.float32)
+        du = torch.empty(n, self.nx, device=self.device, dtype=torch.float32) if want_grad else None
+        with torch.cuda.device(self.device):
+            nat.check(self.lib.dpi_net_eval(self.h, _ptr(tx), n, _ptr(u), _ptr(du), self._stream()), "dpi_net_eval")
+        return u, du
+
+    def launch_count(self) -> int:
+        return int(self.lib.dpi_launch_count(self.h))
+
+
+# ------------------------------------------------------------------------------------------------
+# torch custom op: thin shim so the label generator composes with torch code (streams, graphs capture-free).
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("picard_b200::label_gen", mutates_args=(), device_types="cuda")
+def label_gen_op(tx: torch.Tensor, engine_id: int, M_T: int, M_I: int, bf16: bool, sample_bound: float, seed: int,
+                 point_index_base: int, zT: Optional[torch.Tensor] = None, u_s: Optional[torch.Tensor] = None,
+                 zS: Optional[torch.Tensor] = None, idx: Optional[torch.Tensor] = None) -> torch.Tensor:
+    eng = _ENGINES[engine_id]
+    draws = None if zT is None else {"zT": zT, "u_s": u_s, "zS": zS, "idx": idx}
+    return eng.label_gen(tx, M_T, M_I, precision="bf16" if bf16 else "fp32", sample_bound=sample_bound, seed=seed,
+                         point_index_base=point_index_base, draws=draws)
+
+
+@label_gen_op.register_fake
+def _(tx, engine_id, M_T, M_I, bf16, sample_bound, seed, point_index_base, zT=None, u_s=None, zS=None, idx=None):
+    return torch.empty_like(tx, dtype=torch.float32)

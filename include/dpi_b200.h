@@ -1,0 +1,159 @@
+/*
+ * dpi_b200.h — C ABI of the B200-native Deep-Picard-Iteration label generator.
+ *
+ * This is the drop-in boundary for ONE hot path of the reference (DeepOptimalControl/DeepPicardIteration):
+ * the per-iteration Monte Carlo label generator.  The reference has no FFI — the path sits behind a
+ * Python object protocol — so each entry point below cites the Python interface it replaces
+ * (paths relative to the reference root):
+ *
+ *   dpi_sample_tx      <- _OnlineDataGenerator.sample_t_always_uniform   picard/data.py:161-167
+ *                         + Equation.sample_x / sample_x0 / sample_x_ts   picard/equations.py:118-119,217-230,334-335,485-486,710-711
+ *   dpi_label_gen      <- OnlineDataGenerator.generate_with_gradients     picard/data.py:1208-1218
+ *                           = estimate_terminal_with_gradients            picard/data.py:899-926
+ *                           + estimate_integral_with_gradients            picard/data.py:471-527
+ *                           + get_f (u_k forward + derivative + f)        picard/data.py:1226-1325
+ *                           + clip                                        picard/data.py:222
+ *   dpi_label_gen_host <- OnlineDataGenerator.sample_with_gradients as seen by a host-memory caller
+ *                         (IterableDatasetWithInternalBatch.refresh_buffer, picard/dataset.py:107-116)
+ *   dpi_set_problem    <- Equation constructors: Cha / GBMEquationComplexExact / OUProcessEquation
+ *                         picard/equations.py:283-289,401-419,504-558,610-620
+ *   dpi_set_network    <- OnlineDataGenerator.__init__ freezing `solution`  picard/data.py:407-412
+ *                         (construct_mlp / PISGradNet / ZeroSolution, picard/solution.py:123-135,138-289,330-337)
+ *   dpi_net_eval       <- solution(tx) and autograd.grad(u.sum(), x)       picard/data.py:1230,1245-1251
+ *                         (used by the evaluation callback, picard/utils.py:362-458)
+ *
+ * Conventions: plain pointers and sizes only (no torch types).  All functions return 0 on success or a
+ * negative dpi_status; the message is available from dpi_last_error() (thread-local).  Nothing throws.
+ * Device pointers are torch-owned; the library allocates only handle-internal scratch (packed weights,
+ * per-point baseline scratch, staging for the *_host entry points).  Kernels are launched on the stream
+ * passed in (a cudaStream_t cast to void*); calls are asynchronous like torch ops, except *_host variants
+ * which synchronise the stream before returning.  One handle per device; a handle is not thread-safe.
+ *
+ * There is NO CPU fallback: every entry point fails with DPI_ERR_CUDA when no sm_100 device is present.
+ */
+#ifndef DPI_B200_H
+#define DPI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPI_B200_VERSION 100 /* major*10000 + minor*100 + patch */
+#define DPI_MAX_LINEAR 8     /* Linear layers per chain */
+
+typedef struct dpi_handle dpi_handle;
+
+typedef enum {
+  DPI_OK = 0,
+  DPI_ERR_INVALID = -1,     /* bad argument / unsupported combination */
+  DPI_ERR_CUDA = -2,        /* CUDA runtime error (message has the cudaError string) */
+  DPI_ERR_UNSUPPORTED = -3, /* valid in the reference, not built yet in this library */
+  DPI_ERR_STATE = -4        /* problem / network not set */
+} dpi_status;
+
+typedef enum { DPI_EQ_CHA = 0, DPI_EQ_GBM = 1, DPI_EQ_OU = 2 } dpi_equation_kind;
+typedef enum { DPI_NET_ZERO = 0, DPI_NET_MLP = 1, DPI_NET_PISGRAD = 2 } dpi_network_kind;
+/* arithmetic of the u_k GEMM chain: fp32 FMA (labels within 1e-4 rel of the fp64 reference) or
+ * bf16 tcgen05 tensor cores with fp32 accumulation (within 1e-2 rel). */
+typedef enum { DPI_PREC_FP32 = 0, DPI_PREC_BF16 = 1 } dpi_precision;
+
+/* Equation parameters.  All array pointers are HOST pointers (tiny), copied by dpi_set_problem. */
+typedef struct {
+  int32_t kind; /* dpi_equation_kind */
+  int32_t nx;
+  float T;
+  float alpha;
+  /* Cha (equations.py:283-289): k as configured (the library divides by sqrt(nx)) */
+  float cha_k;
+  /* GBMEquationComplexExact (equations.py:401-419): w [nodes, 1+nx] row-major, v [nodes] */
+  int32_t gbm_nodes;
+  const double* gbm_w;
+  const double* gbm_v;
+  /* OUProcessEquation (equations.py:504-558,610-620): mean [K,nx], diagvar [K,nx], pi [K] */
+  int32_t ou_K;
+  const double* ou_mean;
+  const double* ou_diagvar;
+  const double* ou_pi;
+  float ou_theta;
+  float ou_mu;
+  float ou_alpha_init; /* alpha_scale * alpha: variance of x0 ~ N(0, alpha_init I) */
+  /* SDGD (data.py:497-502): number of sampled Hessian-diagonal coordinates per path; 0 = off */
+  int32_t sdgd_v;
+} dpi_problem;
+
+/* One torch.nn.Linear: W [n_out, n_in] row-major fp32 and b [n_out], DEVICE pointers. */
+typedef struct {
+  const float* W;
+  const float* b;
+  int32_t n_in;
+  int32_t n_out;
+} dpi_linear;
+
+/* Frozen previous iterate u_k.  ELU between Linear layers (the only activation the configs use). */
+typedef struct {
+  int32_t kind; /* dpi_network_kind */
+  /* MLP: `main` = Linear(1+nx,H1) .. Linear(HL,1).  PISGradNet: `main` = nn_module (nx+64 -> .. -> nx). */
+  int32_t n_main;
+  dpi_linear main[DPI_MAX_LINEAR];
+  /* PISGradNet only (solution.py:170-207): */
+  int32_t n_t_encoder;
+  dpi_linear t_encoder[DPI_MAX_LINEAR];
+  int32_t n_smooth;
+  dpi_linear smooth_net[DPI_MAX_LINEAR];
+  const float* timestep_phase; /* [64] device */
+  const float* timestep_coeff; /* [64] device */
+} dpi_network;
+
+/* Deterministic mode: caller-supplied draws laid out exactly as the reference draws them
+ * (row = point*M + sample).  DEVICE pointers; idx may be NULL unless sdgd_v > 0. */
+typedef struct {
+  const float* zT;    /* [n*M_T, nx]  terminal increments      data.py:914  */
+  const float* u_s;   /* [n*M_I]      uniform integral times   data.py:359  */
+  const float* zS;    /* [n*M_I, nx]  integral increments      data.py:360  */
+  const int32_t* idx; /* [n*M_I, v]   SDGD coordinates         data.py:501  */
+} dpi_draws;
+
+typedef struct {
+  int32_t M_T;            /* n_estimate_terminal */
+  int32_t M_I;            /* n_estimate_integral */
+  int32_t precision;      /* dpi_precision */
+  float sample_bound;     /* clip(y, +-bound); <=0 or inf = off (data.py:123-128,222) */
+  uint64_t seed;          /* Philox key (ignored when draws != NULL) */
+  int64_t point_index_base; /* global index of tx row 0: Philox counters are keyed by the GLOBAL point
+                               index so labels do not depend on the shard size or GPU count */
+} dpi_label_config;
+
+int dpi_version(void);
+const char* dpi_last_error(void);
+
+int dpi_create(int device, dpi_handle** out);
+int dpi_destroy(dpi_handle* h);
+
+int dpi_set_problem(dpi_handle* h, const dpi_problem* p);
+/* (Re)pack the frozen network for the kernels. Reads the weight tensors on `stream`. */
+int dpi_set_network(dpi_handle* h, const dpi_network* net, void* stream);
+
+/* tx [n, 1+nx] device, written.  t ~ U[eps, T-eps] (eps=0.01), x = x0 + sqrt(t*alpha) Z. */
+int dpi_sample_tx(dpi_handle* h, int64_t n, int64_t point_index_base, uint64_t seed, float* tx, void* stream);
+
+/* y [n, 1+nx] device, written: column 0 the value label, columns 1.. the gradient label. */
+int dpi_label_gen(dpi_handle* h, const float* tx, int64_t n, const dpi_label_config* cfg,
+                  const dpi_draws* draws /* nullable: Philox mode */, float* y, void* stream);
+
+/* Same, with HOST buffers (pinned for full speed): copies tx in, y out, and synchronises. If tx_in_host is
+ * NULL the points are drawn on the device (dpi_sample_tx) and returned in tx_out_host. */
+int dpi_label_gen_host(dpi_handle* h, const float* tx_in_host, int64_t n, const dpi_label_config* cfg,
+                       float* tx_out_host /* nullable */, float* y_host, void* stream);
+
+/* u_k and its input gradient on rows of tx: u [n], du [n, nx] (either may be NULL). fp32 path. */
+int dpi_net_eval(dpi_handle* h, const float* tx, int64_t n, float* u, float* du, void* stream);
+
+/* Kernels launched by this handle since creation (for bench.py's gpu_launches). */
+int64_t dpi_launch_count(const dpi_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPI_B200_H */
