@@ -41,6 +41,10 @@ struct dpi_handle {
   float* stage_y = nullptr;
   int64_t stage_floats = 0;
   int64_t launches = 0;
+  // optional per-stage timing (dpi_set_stage_timing)
+  bool timing = false;
+  cudaEvent_t ev[DPI_STAGE_COUNT][2] = {};
+  bool ev_valid[DPI_STAGE_COUNT] = {};
 };
 
 namespace {
@@ -96,6 +100,22 @@ int ensure_stage(dpi_handle* h, int64_t floats) {
 
 int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+// RAII bracket: records the stage's start event now and its end event when it goes out of scope.
+struct StageTimer {
+  dpi_handle* h;
+  int stage;
+  cudaStream_t st;
+  StageTimer(dpi_handle* h_, int stage_, cudaStream_t st_) : h(h_), stage(stage_), st(st_) {
+    if (h->timing) cudaEventRecord(h->ev[stage][0], st);
+  }
+  ~StageTimer() {
+    if (h->timing) {
+      cudaEventRecord(h->ev[stage][1], st);
+      h->ev_valid[stage] = true;
+    }
+  }
+};
+
 }  // namespace
 
 extern "C" {
@@ -141,6 +161,9 @@ int dpi_destroy(dpi_handle* h) {
   if (h->c0) cudaFree(h->c0);
   if (h->stage_tx) cudaFree(h->stage_tx);
   if (h->stage_y) cudaFree(h->stage_y);
+  for (int s = 0; s < DPI_STAGE_COUNT; ++s)
+    for (int e = 0; e < 2; ++e)
+      if (h->ev[s][e]) cudaEventDestroy(h->ev[s][e]);
   delete h;
   return DPI_OK;
 }
@@ -358,8 +381,13 @@ int dpi_label_gen(dpi_handle* h, const float* tx, int64_t n, const dpi_label_con
   const float bound = cfg->sample_bound;
   int rc;
 
+  for (int s = 0; s < DPI_STAGE_COUNT; ++s) h->ev_valid[s] = false;
+
   // 1) terminal estimator -> y
-  rc = launch_terminal(P, tx, n, cfg->M_T, cfg->seed, cfg->point_index_base, draws ? draws->zT : nullptr, y, st);
+  {
+    StageTimer tm(h, DPI_STAGE_TERMINAL, st);
+    rc = launch_terminal(P, tx, n, cfg->M_T, cfg->seed, cfg->point_index_base, draws ? draws->zT : nullptr, y, st);
+  }
   if (rc) return rc;
   h->launches += 1;
 
@@ -375,9 +403,13 @@ int dpi_label_gen(dpi_handle* h, const float* tx, int64_t n, const dpi_label_con
   }
   if (h->net_kind == DPI_NET_MLP && P.eq == DPI_EQ_CHA) {
     if ((rc = ensure_scratch(h, n, h->mlp.HP))) return rc;
-    rc = launch_cha_simt_base(P, h->mlp, tx, n, h->fb, h->c0, nullptr, nullptr, st);
+    {
+      StageTimer tm(h, DPI_STAGE_BASELINE, st);
+      rc = launch_cha_simt_base(P, h->mlp, tx, n, h->fb, h->c0, nullptr, nullptr, st);
+    }
     if (rc) return rc;
     h->launches += 1;
+    StageTimer tm(h, DPI_STAGE_INTEGRAL, st);
     if (cfg->precision == DPI_PREC_BF16) {
       if (!h->tc_ready) {
         set_error("dpi_label_gen: bf16 tensor-core path needs hidden widths == 128 and nx <= 1024 multiple of 4");
@@ -447,5 +479,32 @@ int dpi_net_eval(dpi_handle* h, const float* tx, int64_t n, float* u, float* du,
 }
 
 int64_t dpi_launch_count(const dpi_handle* h) { return h ? h->launches : 0; }
+
+int dpi_set_stage_timing(dpi_handle* h, int enable) {
+  if (!h) {
+    set_error("dpi_set_stage_timing: NULL handle");
+    return DPI_ERR_INVALID;
+  }
+  DPI_CUDA_CHECK(cudaSetDevice(h->device));
+  if (enable && !h->ev[0][0])
+    for (int s = 0; s < DPI_STAGE_COUNT; ++s)
+      for (int e = 0; e < 2; ++e) DPI_CUDA_CHECK(cudaEventCreate(&h->ev[s][e]));
+  h->timing = enable != 0;
+  return DPI_OK;
+}
+
+int dpi_stage_ms(dpi_handle* h, int stage, float* ms) {
+  if (!h || !ms || stage < 0 || stage >= DPI_STAGE_COUNT) {
+    set_error("dpi_stage_ms: bad arguments");
+    return DPI_ERR_INVALID;
+  }
+  if (!h->timing || !h->ev_valid[stage]) {
+    set_error("dpi_stage_ms: stage %d was not timed by the last dpi_label_gen call", stage);
+    return DPI_ERR_STATE;
+  }
+  DPI_CUDA_CHECK(cudaEventSynchronize(h->ev[stage][1]));
+  DPI_CUDA_CHECK(cudaEventElapsedTime(ms, h->ev[stage][0], h->ev[stage][1]));
+  return DPI_OK;
+}
 
 }  // extern "C"

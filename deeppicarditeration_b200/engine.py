@@ -189,6 +189,17 @@ class LabelEngine:
     def launch_count(self) -> int:
         return int(self.lib.dpi_launch_count(self.h))
 
+    STAGES = {"terminal": 0, "baseline": 1, "integral": 2}
+
+    def set_stage_timing(self, enable: bool = True) -> None:
+        nat.check(self.lib.dpi_set_stage_timing(self.h, int(bool(enable))), "dpi_set_stage_timing")
+
+    def stage_ms(self, stage: str) -> float:
+        """Device time of one stage of the most recent label_gen call (CUDA events on the launching stream)."""
+        ms = C.c_float()
+        nat.check(self.lib.dpi_stage_ms(self.h, self.STAGES[stage], C.byref(ms)), "dpi_stage_ms")
+        return float(ms.value)
+
 
 # ------------------------------------------------------------------------------------------------
 # torch custom op: thin shim so the label generator composes with torch code (streams, graphs capture-free).

@@ -153,6 +153,14 @@ int dpi_net_eval(dpi_handle* h, const float* tx, int64_t n, float* u, float* du,
 /* Kernels launched by this handle since creation (for bench.py's gpu_launches). */
 int64_t dpi_launch_count(const dpi_handle* h);
 
+/* Per-stage device timing (replaces the reference's PROFILE_CUDA / count_cuda_time_wrapper switch,
+ * picard/utils.py:50-66).  When enabled, dpi_label_gen brackets each stage with CUDA events on the launching
+ * stream; dpi_stage_ms waits for the stage's end event of the most recent dpi_label_gen call and returns its
+ * duration.  Stages: the terminal estimator, the per-point baseline pass, the integral (u_k over paths) kernel. */
+typedef enum { DPI_STAGE_TERMINAL = 0, DPI_STAGE_BASELINE = 1, DPI_STAGE_INTEGRAL = 2, DPI_STAGE_COUNT = 3 } dpi_stage;
+int dpi_set_stage_timing(dpi_handle* h, int enable);
+int dpi_stage_ms(dpi_handle* h, int stage, float* ms);
+
 #ifdef __cplusplus
 }
 #endif
