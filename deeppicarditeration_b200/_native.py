@@ -19,7 +19,7 @@ DPI_PREC_FP32, DPI_PREC_BF16 = 0, 1
 EXPORTED_SYMBOLS = (
     "dpi_version", "dpi_last_error", "dpi_create", "dpi_destroy", "dpi_set_problem", "dpi_set_network",
     "dpi_sample_tx", "dpi_label_gen", "dpi_label_gen_host", "dpi_net_eval", "dpi_launch_count",
-    "dpi_set_stage_timing", "dpi_stage_ms",
+    "dpi_set_stage_timing", "dpi_stage_ms", "dpi_selftest_umma",
 )
 
 
@@ -87,6 +87,7 @@ def load() -> C.CDLL:
     lib.dpi_launch_count.restype = C.c_int64
     lib.dpi_set_stage_timing.argtypes = [H, C.c_int]
     lib.dpi_stage_ms.argtypes = [H, C.c_int, C.POINTER(C.c_float)]
+    lib.dpi_selftest_umma.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     for name in EXPORTED_SYMBOLS:
         getattr(lib, name)  # AttributeError if a declared symbol is not exported
     _lib = lib

@@ -36,6 +36,10 @@ struct dpi_handle {
   float* c0 = nullptr;
   int64_t scratch_points = 0;
   int scratch_hp = 0;
+  // unit partial sums of the tensor-core path
+  float* partG = nullptr;
+  float* partF = nullptr;
+  int64_t part_units = 0;
   // staging for the *_host entry points
   float* stage_tx = nullptr;
   float* stage_y = nullptr;
@@ -83,6 +87,18 @@ int ensure_scratch(dpi_handle* h, int64_t n, int hp) {
   DPI_CUDA_CHECK(cudaMalloc((void**)&h->c0, sizeof(float) * cap * chp));
   h->scratch_points = cap;
   h->scratch_hp = chp;
+  return DPI_OK;
+}
+
+int ensure_parts(dpi_handle* h, int64_t units) {
+  if (units <= h->part_units) return DPI_OK;
+  if (h->partG) cudaFree(h->partG);
+  if (h->partF) cudaFree(h->partF);
+  h->partG = h->partF = nullptr;
+  h->part_units = 0;
+  DPI_CUDA_CHECK(cudaMalloc((void**)&h->partG, sizeof(float) * units * kTcPartGFloatsPerUnit));
+  DPI_CUDA_CHECK(cudaMalloc((void**)&h->partF, sizeof(float) * units * kTcPartFFloatsPerUnit));
+  h->part_units = units;
   return DPI_OK;
 }
 
@@ -161,6 +177,8 @@ int dpi_destroy(dpi_handle* h) {
   if (h->c0) cudaFree(h->c0);
   if (h->stage_tx) cudaFree(h->stage_tx);
   if (h->stage_y) cudaFree(h->stage_y);
+  if (h->partG) cudaFree(h->partG);
+  if (h->partF) cudaFree(h->partF);
   for (int s = 0; s < DPI_STAGE_COUNT; ++s)
     for (int e = 0; e < 2; ++e)
       if (h->ev[s][e]) cudaEventDestroy(h->ev[s][e]);
@@ -297,6 +315,7 @@ int dpi_set_network(dpi_handle* h, const dpi_network* net, void* stream) {
     M.d_pad = round_up(nx, 128);
     float *Wt1, *wt, *b1, *wsum, *wout, *bout;
     float* Wth[DPI_MAX_LINEAR] = {nullptr};
+    float* Wth_bf[DPI_MAX_LINEAR] = {nullptr};
     float* bh[DPI_MAX_LINEAR] = {nullptr};
     int rc;
     if ((rc = dev_alloc(h->net_bufs, (size_t)M.d_pad * M.HP, &Wt1))) return rc;
@@ -307,10 +326,11 @@ int dpi_set_network(dpi_handle* h, const dpi_network* net, void* stream) {
     if ((rc = dev_alloc(h->net_bufs, 1, &bout))) return rc;
     for (int l = 0; l < L - 2; ++l) {
       if ((rc = dev_alloc(h->net_bufs, (size_t)M.HP * M.HP, &Wth[l]))) return rc;
+      if ((rc = dev_alloc(h->net_bufs, (size_t)M.HP * M.HP, &Wth_bf[l]))) return rc;
       if ((rc = dev_alloc(h->net_bufs, M.HP, &bh[l]))) return rc;
     }
-    if ((rc = launch_pack_mlp(*net, nx, M.HP, M.d_pad, Wt1, wt, b1, wsum, Wth, bh, wout, bout, st))) return rc;
-    h->launches += 6 + 2 * (L - 2);
+    if ((rc = launch_pack_mlp(*net, nx, M.HP, M.d_pad, Wt1, wt, b1, wsum, Wth, Wth_bf, bh, wout, bout, st))) return rc;
+    h->launches += 6 + 3 * (L - 2);
     M.Wt1 = Wt1;
     M.wt = wt;
     M.b1 = b1;
@@ -319,6 +339,7 @@ int dpi_set_network(dpi_handle* h, const dpi_network* net, void* stream) {
     M.bout = bout;
     for (int l = 0; l < L - 2; ++l) {
       M.Wth[l] = Wth[l];
+      M.Wth_bf[l] = Wth_bf[l];
       M.bh[l] = bh[l];
     }
     h->mlp = M;
@@ -402,25 +423,40 @@ int dpi_label_gen(dpi_handle* h, const float* tx, int64_t n, const dpi_label_con
     return rc;
   }
   if (h->net_kind == DPI_NET_MLP && P.eq == DPI_EQ_CHA) {
+    const bool bf16 = cfg->precision == DPI_PREC_BF16;
+    if (bf16 && !h->tc_ready) {
+      set_error("dpi_label_gen: the bf16 tensor-core path needs the MLP [1+d,128,128,128,128,1] with d <= 128");
+      return DPI_ERR_UNSUPPORTED;
+    }
     if ((rc = ensure_scratch(h, n, h->mlp.HP))) return rc;
     {
       StageTimer tm(h, DPI_STAGE_BASELINE, st);
-      rc = launch_cha_simt_base(P, h->mlp, tx, n, h->fb, h->c0, nullptr, nullptr, st);
+      rc = launch_cha_simt_base(P, h->mlp, tx, n, h->fb, h->c0, nullptr, nullptr, bf16, st);
     }
     if (rc) return rc;
     h->launches += 1;
     StageTimer tm(h, DPI_STAGE_INTEGRAL, st);
-    if (cfg->precision == DPI_PREC_BF16) {
-      if (!h->tc_ready) {
-        set_error("dpi_label_gen: bf16 tensor-core path needs hidden widths == 128 and nx <= 1024 multiple of 4");
-        return DPI_ERR_UNSUPPORTED;
+    if (bf16) {
+      // chunk the points so that the unit-partial scratch stays below ~256 MB
+      const int64_t upp = tc_units_per_point(cfg->M_I);
+      int64_t chunk = (int64_t)(256u << 20) / (int64_t)(sizeof(float) * kTcPartGFloatsPerUnit * upp);
+      if (chunk < 1) chunk = 1;
+      if (chunk > n) chunk = n;
+      if ((rc = ensure_parts(h, chunk * upp))) return rc;
+      const int d = P.nx;
+      for (int64_t p0 = 0; p0 < n; p0 += chunk) {
+        const int64_t np = (n - p0 < chunk) ? n - p0 : chunk;
+        rc = launch_cha_tc_path(P, h->tc, tx + p0 * (1 + d), np, cfg->M_I, cfg->seed, cfg->point_index_base + p0,
+                                draws ? draws->u_s + p0 * cfg->M_I : nullptr,
+                                draws ? draws->zS + p0 * (int64_t)cfg->M_I * d : nullptr, h->fb + p0,
+                                h->c0 + p0 * h->mlp.HP, bound, h->partG, h->partF, y + p0 * (1 + d), st);
+        if (rc) return rc;
+        h->launches += 2;
       }
-      rc = launch_cha_tc_path(P, h->tc, tx, n, cfg->M_I, cfg->seed, cfg->point_index_base, draws ? draws->u_s : nullptr,
-                              draws ? draws->zS : nullptr, h->fb, h->c0, bound, y, st);
-    } else {
-      rc = launch_cha_simt_path(P, h->mlp, tx, n, cfg->M_I, cfg->seed, cfg->point_index_base,
-                                draws ? draws->u_s : nullptr, draws ? draws->zS : nullptr, h->fb, h->c0, bound, y, st);
+      return DPI_OK;
     }
+    rc = launch_cha_simt_path(P, h->mlp, tx, n, cfg->M_I, cfg->seed, cfg->point_index_base,
+                              draws ? draws->u_s : nullptr, draws ? draws->zS : nullptr, h->fb, h->c0, bound, y, st);
     if (!rc) h->launches += 1;
     return rc;
   }
@@ -470,7 +506,7 @@ int dpi_net_eval(dpi_handle* h, const float* tx, int64_t n, float* u, float* du,
   if (h->net_kind == DPI_NET_MLP && h->P.eq == DPI_EQ_CHA && du == nullptr) {
     int rc = ensure_scratch(h, n, h->mlp.HP);
     if (rc) return rc;
-    rc = launch_cha_simt_base(h->P, h->mlp, tx, n, h->fb, h->c0, u, nullptr, st);
+    rc = launch_cha_simt_base(h->P, h->mlp, tx, n, h->fb, h->c0, u, nullptr, false, st);
     if (!rc) h->launches += 1;
     return rc;
   }
@@ -479,6 +515,15 @@ int dpi_net_eval(dpi_handle* h, const float* tx, int64_t n, float* u, float* du,
 }
 
 int64_t dpi_launch_count(const dpi_handle* h) { return h ? h->launches : 0; }
+
+int dpi_selftest_umma(dpi_handle* h, const float* A, const float* B, float* D, void* stream) {
+  if (!h || !A || !B || !D) {
+    set_error("dpi_selftest_umma: NULL argument");
+    return DPI_ERR_INVALID;
+  }
+  DPI_CUDA_CHECK(cudaSetDevice(h->device));
+  return tc_umma_selftest(A, B, D, reinterpret_cast<cudaStream_t>(stream));
+}
 
 int dpi_set_stage_timing(dpi_handle* h, int enable) {
   if (!h) {

@@ -17,6 +17,7 @@ struct MlpDev {
   const float* b1;    // [HP]
   const float* wsum;  // [HP]         sum_j W1[:,1+j]  == tangent of layer 1 along (0,1,...,1)
   const float* Wth[DPI_MAX_LINEAR];  // hidden layer l: [HP][HP]  Wth[k][h] = W_l[h][k]
+  const float* Wth_bf[DPI_MAX_LINEAR];  // same, every entry rounded to bf16 (control variate of the bf16 path)
   const float* bh[DPI_MAX_LINEAR];   // [HP]
   const float* wout;  // [HP]
   const float* bout;  // [1] device
@@ -29,32 +30,45 @@ int launch_terminal(const ProblemDev& P, const float* tx, int64_t n, int M_T, ui
 
 // Pack torch-layout weights into MlpDev buffers (buffers preallocated by the handle; `bout` read back by caller).
 int launch_pack_mlp(const dpi_network& net, int nx, int HP, int d_pad, float* Wt1, float* wt, float* b1, float* wsum,
-                    float* const* Wth, float* const* bh, float* wout, float* bout_dev, cudaStream_t st);
+                    float* const* Wth, float* const* Wth_bf, float* const* bh, float* wout, float* bout_dev,
+                    cudaStream_t st);
 
 // Burgers (Cha) integral estimator, fp32 SIMT.  base pass: fb[n], c0[n][HP]; path pass: y += integral part, then clip.
+// emulate_bf16: hidden layers use the bf16-rounded weights and round the activations between layers, i.e. the
+// arithmetic of the tensor-core path, so that f_m - f_b cancels its rounding error as s -> t.
 int launch_cha_simt_base(const ProblemDev& P, const MlpDev& net, const float* tx, int64_t n, float* fb, float* c0,
-                         float* u_out, float* dsum_out, cudaStream_t st);
+                         float* u_out, float* dsum_out, bool emulate_bf16, cudaStream_t st);
 int launch_cha_simt_path(const ProblemDev& P, const MlpDev& net, const float* tx, int64_t n, int M_I, uint64_t seed,
                          int64_t base, const float* u_s, const float* zS, const float* fb, const float* c0,
                          float bound, float* y, cudaStream_t st);
 
 // ---- bf16 tcgen05 path (dpi_mlp_tc.cu) ---------------------------------------------------------------
+constexpr int kTcGroupTiles = 8;  // 128-sample tiles per work unit (fixed: the summation order must not depend on n)
+// per-column fp32 constants of the network, passed to the kernel by value (constant bank)
+struct alignas(16) TcConsts {
+  float wt[128];    // W1[:,0]            time column
+  float wsum[128];  // sum_j W1[:,1+j]    first-layer tangent along (0,1,...,1)
+  float b[3][128];  // biases of the three hidden GEMM layers
+  float wout[128];
+  float bout;
+  float pad[3];
+};
 struct TcNetDev {
-  int n_hidden;               // number of H x H hidden GEMM layers (L-2)
-  int nx, d_pad;              // d_pad: nx rounded up to a multiple of 64 (K of the first GEMM)
-  const void* W1;             // bf16 [128][d_pad]   UMMA canonical K-major, 128B swizzle, 64-column K panels
-  const void* Wh[DPI_MAX_LINEAR];  // bf16 [128][128] per hidden layer, same layout
-  const float* wt;            // fp32 vectors shared with the SIMT packing
-  const float* wsum;
-  const float* bh[DPI_MAX_LINEAR];
-  const float* wout;
-  const float* bout;
+  const void* W;  // 4 x [128 x 128] bf16 operand images (K-major, SWIZZLE_128B): W1 x-columns, W2, W3, W4
+  TcConsts consts;
+  int nx, ksteps1, nq, cls, num_sms;
 };
 int tc_pack_network(const dpi_network& net, const ProblemDev& P, const MlpDev& M, std::vector<void*>& owner,
                     TcNetDev* out, bool* ready, int64_t* launches, cudaStream_t st);
+int64_t tc_units_per_point(int M_I);
+constexpr int64_t kTcPartGFloatsPerUnit = 2 * 8 * 128;
+constexpr int64_t kTcPartFFloatsPerUnit = 4;
+// partG [n*units][2][8][128], partF [n*units][4]: scratch for the unit partial sums
 int launch_cha_tc_path(const ProblemDev& P, const TcNetDev& net, const float* tx, int64_t n, int M_I, uint64_t seed,
                        int64_t base, const float* u_s, const float* zS, const float* fb, const float* c0, float bound,
-                       float* y, cudaStream_t st);
+                       float* partG, float* partF, float* y, cudaStream_t st);
+// D[128x128] = A[128x128] . B[128x128]^T (fp32 row-major device buffers, rounded to bf16) through tcgen05
+int tc_umma_selftest(const float* A, const float* B, float* D, cudaStream_t st);
 
 // y = clip(y + add, +-bound) elementwise helpers used by the Zero-network shortcuts
 int launch_finish_zero(const ProblemDev& P, const float* tx, int64_t n, float bound, float* y, cudaStream_t st);

@@ -11,10 +11,14 @@
 // so the GEMM runs on the unit-variance increments Z and the point-dependent part c0 is computed once per point
 // (by the baseline pass, which also yields the control variate f_b = f(t, x)).
 #include "dpi_common.cuh"
+#include <cuda_bf16.h>
+
 #include "dpi_kernels.h"
 
 namespace dpi {
 namespace {
+
+__device__ __forceinline__ float bf16r(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
@@ -43,7 +47,7 @@ cha_simt_kernel(const ProblemDev P, const MlpDev N, const float* __restrict__ tx
                 int64_t point_base, const float* __restrict__ u_s, const float* __restrict__ zS,
                 const float* __restrict__ fb_in, const float* __restrict__ c0_in, float bound, float* __restrict__ y,
                 float* __restrict__ fb_out, float* __restrict__ c0_out, float* __restrict__ u_out,
-                float* __restrict__ d_out, int mode) {
+                float* __restrict__ d_out, int mode, int emu) {
   using G = Geo<HP>;
   extern __shared__ __align__(16) float smem[];
   float* act = smem;
@@ -184,8 +188,8 @@ cha_simt_kernel(const ProblemDev P, const MlpDev N, const float* __restrict__ tx
         }
         float h, e1;
         elu_d1(lin + s_s[r] * wt_s[col], h, e1);
-        o[2 * i] = h;
-        o[2 * i + 1] = e1 * wsum_s[col];
+        o[2 * i] = emu ? bf16r(h) : h;
+        o[2 * i + 1] = emu ? bf16r(e1 * wsum_s[col]) : e1 * wsum_s[col];
       }
       float4* dst = reinterpret_cast<float4*>(act + col * G::LDA + ty * 8);
       dst[0] = make_float4(o[0], o[1], o[2], o[3]);
@@ -195,7 +199,7 @@ cha_simt_kernel(const ProblemDev P, const MlpDev N, const float* __restrict__ tx
     // ---- hidden layers: [value;tangent] rows x HP cols, K = HP ---------------------------------
     for (int l = 0; l < n_hidden; ++l) {
       {
-        const float4* src = reinterpret_cast<const float4*>(N.Wth[l]);
+        const float4* src = reinterpret_cast<const float4*>(emu ? N.Wth_bf[l] : N.Wth[l]);
         float4* dst = reinterpret_cast<float4*>(Ws);
         for (int i = tid; i < HP * HP / 4; i += kThreads) dst[i] = __ldg(src + i);
       }
@@ -228,8 +232,9 @@ cha_simt_kernel(const ProblemDev P, const MlpDev N, const float* __restrict__ tx
         for (int i = 0; i < 4; ++i) {
           float h, e1;
           elu_d1(acc[2 * i][c] + b, h, e1);
-          o[2 * i] = h;
-          o[2 * i + 1] = e1 * acc[2 * i + 1][c];
+          const bool rnd = emu && l < n_hidden - 1;  // the last hidden output feeds the fp32 output dot product
+          o[2 * i] = rnd ? bf16r(h) : h;
+          o[2 * i + 1] = rnd ? bf16r(e1 * acc[2 * i + 1][c]) : e1 * acc[2 * i + 1][c];
         }
         float4* dst = reinterpret_cast<float4*>(act + col * G::LDA + ty * 8);
         dst[0] = make_float4(o[0], o[1], o[2], o[3]);
@@ -332,11 +337,12 @@ cha_simt_kernel(const ProblemDev P, const MlpDev N, const float* __restrict__ tx
 // ---- weight packing ---------------------------------------------------------------------------
 // dst[k][h] (k < K_pad, h < HP) = W[h][col_off + k] for k < k_valid, h < out_valid, else 0.   W is [out, ld] row-major.
 __global__ void pack_transpose_kernel(const float* __restrict__ W, int ld, int col_off, int k_valid, int out_valid,
-                                      float* __restrict__ dst, int K_pad, int HP) {
+                                      float* __restrict__ dst, int K_pad, int HP, int round_bf16) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= K_pad * HP) return;
   const int k = i / HP, h = i - k * HP;
-  dst[i] = (k < k_valid && h < out_valid) ? W[(size_t)h * ld + col_off + k] : 0.f;
+  const float v = (k < k_valid && h < out_valid) ? W[(size_t)h * ld + col_off + k] : 0.f;
+  dst[i] = round_bf16 ? bf16r(v) : v;
 }
 // dst[h] = h < n_valid ? src[h*stride] : 0
 __global__ void pack_vec_kernel(const float* __restrict__ src, int stride, int n_valid, float* __restrict__ dst, int HP) {
@@ -357,13 +363,13 @@ __global__ void pack_wsum_kernel(const float* __restrict__ W1, int nx, int out_v
 template <int HP, int NSLOT>
 int launch_cha_t(const ProblemDev& P, const MlpDev& N, const float* tx, int64_t n, int M_I, uint64_t seed, int64_t base,
                  const float* u_s, const float* zS, const float* fb_in, const float* c0_in, float bound, float* y,
-                 float* fb_out, float* c0_out, float* u_out, float* d_out, int mode, cudaStream_t st) {
+                 float* fb_out, float* c0_out, float* u_out, float* d_out, int mode, int emu, cudaStream_t st) {
   using G = Geo<HP>;
   auto k = cha_simt_kernel<HP, NSLOT>;
   DPI_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::kSmemBytes));
   const int64_t grid = (mode == kModePath) ? n : (n + G::RT - 1) / G::RT;
   k<<<(unsigned)grid, kThreads, G::kSmemBytes, st>>>(P, N, tx, n, M_I, seed, base, u_s, zS, fb_in, c0_in, bound, y,
-                                                     fb_out, c0_out, u_out, d_out, mode);
+                                                     fb_out, c0_out, u_out, d_out, mode, emu);
   DPI_CUDA_CHECK(cudaGetLastError());
   return DPI_OK;
 }
@@ -371,8 +377,8 @@ int launch_cha_t(const ProblemDev& P, const MlpDev& N, const float* tx, int64_t 
 template <int HP>
 int launch_cha_hp(const ProblemDev& P, const MlpDev& N, const float* tx, int64_t n, int M_I, uint64_t seed,
                   int64_t base, const float* u_s, const float* zS, const float* fb_in, const float* c0_in, float bound,
-                  float* y, float* fb_out, float* c0_out, float* u_out, float* d_out, int mode, cudaStream_t st) {
-#define DPI_ARGS P, N, tx, n, M_I, seed, base, u_s, zS, fb_in, c0_in, bound, y, fb_out, c0_out, u_out, d_out, mode, st
+                  float* y, float* fb_out, float* c0_out, float* u_out, float* d_out, int mode, int emu, cudaStream_t st) {
+#define DPI_ARGS P, N, tx, n, M_I, seed, base, u_s, zS, fb_in, c0_in, bound, y, fb_out, c0_out, u_out, d_out, mode, emu, st
   switch (N.d_pad / 128) {
     case 1: return launch_cha_t<HP, 1>(DPI_ARGS);
     case 2: return launch_cha_t<HP, 2>(DPI_ARGS);
@@ -390,14 +396,14 @@ int launch_cha_hp(const ProblemDev& P, const MlpDev& N, const float* tx, int64_t
 
 int launch_cha(const ProblemDev& P, const MlpDev& N, const float* tx, int64_t n, int M_I, uint64_t seed, int64_t base,
                const float* u_s, const float* zS, const float* fb_in, const float* c0_in, float bound, float* y,
-               float* fb_out, float* c0_out, float* u_out, float* d_out, int mode, cudaStream_t st) {
+               float* fb_out, float* c0_out, float* u_out, float* d_out, int mode, int emu, cudaStream_t st) {
   if (n <= 0) return DPI_OK;
   if (N.HP == 64)
     return launch_cha_hp<64>(P, N, tx, n, M_I, seed, base, u_s, zS, fb_in, c0_in, bound, y, fb_out, c0_out, u_out,
-                             d_out, mode, st);
+                             d_out, mode, emu, st);
   if (N.HP == 128)
     return launch_cha_hp<128>(P, N, tx, n, M_I, seed, base, u_s, zS, fb_in, c0_in, bound, y, fb_out, c0_out, u_out,
-                              d_out, mode, st);
+                              d_out, mode, emu, st);
   set_error("padded hidden width %d not supported (64 or 128)", N.HP);
   return DPI_ERR_UNSUPPORTED;
 }
@@ -421,17 +427,21 @@ __global__ void finish_zero_kernel(const ProblemDev P, const float* __restrict__
 }  // namespace
 
 int launch_pack_mlp(const dpi_network& net, int nx, int HP, int d_pad, float* Wt1, float* wt, float* b1, float* wsum,
-                    float* const* Wth, float* const* bh, float* wout, float* bout_dev, cudaStream_t st) {
+                    float* const* Wth, float* const* Wth_bf, float* const* bh, float* wout, float* bout_dev,
+                    cudaStream_t st) {
   const int L = net.n_main;
   const dpi_linear& l1 = net.main[0];
   const int T = 256;
-  pack_transpose_kernel<<<(d_pad * HP + T - 1) / T, T, 0, st>>>(l1.W, 1 + nx, 1, nx, l1.n_out, Wt1, d_pad, HP);
+  pack_transpose_kernel<<<(d_pad * HP + T - 1) / T, T, 0, st>>>(l1.W, 1 + nx, 1, nx, l1.n_out, Wt1, d_pad, HP, 0);
   pack_vec_kernel<<<(HP + T - 1) / T, T, 0, st>>>(l1.W, 1 + nx, l1.n_out, wt, HP);
   pack_vec_kernel<<<(HP + T - 1) / T, T, 0, st>>>(l1.b, 1, l1.n_out, b1, HP);
   pack_wsum_kernel<<<(HP + T - 1) / T, T, 0, st>>>(l1.W, nx, l1.n_out, wsum, HP);
   for (int l = 1; l < L - 1; ++l) {
     const dpi_linear& ll = net.main[l];
-    pack_transpose_kernel<<<(HP * HP + T - 1) / T, T, 0, st>>>(ll.W, ll.n_in, 0, ll.n_in, ll.n_out, Wth[l - 1], HP, HP);
+    pack_transpose_kernel<<<(HP * HP + T - 1) / T, T, 0, st>>>(ll.W, ll.n_in, 0, ll.n_in, ll.n_out, Wth[l - 1], HP, HP,
+                                                               0);
+    pack_transpose_kernel<<<(HP * HP + T - 1) / T, T, 0, st>>>(ll.W, ll.n_in, 0, ll.n_in, ll.n_out, Wth_bf[l - 1], HP,
+                                                               HP, 1);
     pack_vec_kernel<<<(HP + T - 1) / T, T, 0, st>>>(ll.b, 1, ll.n_out, bh[l - 1], HP);
   }
   const dpi_linear& lo = net.main[L - 1];
@@ -442,16 +452,16 @@ int launch_pack_mlp(const dpi_network& net, int nx, int HP, int d_pad, float* Wt
 }
 
 int launch_cha_simt_base(const ProblemDev& P, const MlpDev& N, const float* tx, int64_t n, float* fb, float* c0,
-                         float* u_out, float* dsum_out, cudaStream_t st) {
+                         float* u_out, float* dsum_out, bool emulate_bf16, cudaStream_t st) {
   return launch_cha(P, N, tx, n, 0, 0, 0, nullptr, nullptr, nullptr, nullptr, 0.f, nullptr, fb, c0, u_out, dsum_out,
-                    kModeBase, st);
+                    kModeBase, emulate_bf16 ? 1 : 0, st);
 }
 
 int launch_cha_simt_path(const ProblemDev& P, const MlpDev& N, const float* tx, int64_t n, int M_I, uint64_t seed,
                          int64_t base, const float* u_s, const float* zS, const float* fb, const float* c0, float bound,
                          float* y, cudaStream_t st) {
   return launch_cha(P, N, tx, n, M_I, seed, base, u_s, zS, fb, c0, bound, y, nullptr, nullptr, nullptr, nullptr,
-                    kModePath, st);
+                    kModePath, 0, st);
 }
 
 int launch_finish_zero(const ProblemDev& P, const float* tx, int64_t n, float bound, float* y, cudaStream_t st) {

@@ -189,6 +189,16 @@ class LabelEngine:
     def launch_count(self) -> int:
         return int(self.lib.dpi_launch_count(self.h))
 
+    def selftest_umma(self, A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
+        """D = bf16(A) @ bf16(B).T on the tensor cores (128x128x128), for the hardware self-test."""
+        A, B = _f32c(A, self.device), _f32c(B, self.device)
+        assert A.shape == (128, 128) and B.shape == (128, 128)
+        D = torch.empty(128, 128, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            nat.check(self.lib.dpi_selftest_umma(self.h, _ptr(A), _ptr(B), _ptr(D), self._stream()),
+                      "dpi_selftest_umma")
+        return D
+
     STAGES = {"terminal": 0, "baseline": 1, "integral": 2}
 
     def set_stage_timing(self, enable: bool = True) -> None:

@@ -161,6 +161,11 @@ typedef enum { DPI_STAGE_TERMINAL = 0, DPI_STAGE_BASELINE = 1, DPI_STAGE_INTEGRA
 int dpi_set_stage_timing(dpi_handle* h, int enable);
 int dpi_stage_ms(dpi_handle* h, int stage, float* ms);
 
+/* Hardware self-test of the tcgen05 building blocks (shared-memory descriptors, SWIZZLE_128B operand layout,
+ * instruction descriptor, TMEM readback): D[128x128] = bf16(A[128x128]) . bf16(B[128x128])^T with fp32
+ * accumulation; A, B, D are fp32 row-major DEVICE buffers.  Synchronises the stream. */
+int dpi_selftest_umma(dpi_handle* h, const float* A, const float* B, float* D, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

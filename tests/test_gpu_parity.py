@@ -97,3 +97,85 @@ def test_philox_labels_agree_with_oracle_statistically():
     both = torch.cat([y[:, 1:], y_ref[:, 1:]])
     assert float(err.mean().abs()) < 5 * float(both.std()) / (n * eq.nx) ** 0.5 + 1e-3
     e.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# bf16 tensor-core (tcgen05) path
+# ---------------------------------------------------------------------------------------------------------
+def test_umma_selftest_matches_bf16_matmul():
+    """tcgen05 building blocks in isolation: descriptors, SWIZZLE_128B operand images, TMEM readback."""
+    from tests.gpu_util import engine_for
+    e = engine_for(orc.Cha(100, 1.0, 5.0, 1.0), orc.ZeroNet())
+    g = torch.Generator().manual_seed(0)
+    A = torch.randn(128, 128, generator=g)
+    B = torch.randn(128, 128, generator=g)
+    D = e.selftest_umma(A, B).cpu().double()
+    ref = A.bfloat16().double() @ B.bfloat16().double().t()
+    assert orc.rel_l2(D, ref) < 1e-5
+    # structured operands catch transposition / swizzle mix-ups that random data could hide statistically
+    A2 = torch.arange(128.).view(-1, 1).repeat(1, 128) / 128 + torch.eye(128)
+    B2 = torch.arange(128.).view(1, -1).repeat(128, 1) / 64 - torch.eye(128)
+    D2 = e.selftest_umma(A2, B2).cpu().double()
+    ref2 = A2.bfloat16().double() @ B2.bfloat16().double().t()
+    assert orc.rel_l2(D2, ref2) < 1e-5
+    e.close()
+
+
+TC_GOLDEN = ["burgers_100d_mlp128"]
+
+
+@pytest.mark.parametrize("name", TC_GOLDEN)
+def test_labels_match_reference_bf16(name):
+    from tests.gpu_util import draws_dict
+    g = Golden(name)
+    e = _engine(g)
+    y = e.label_gen(g.tx, g.M_T, g.M_I, precision="bf16", draws=draws_dict(g.draws)).double().cpu()
+    assert torch.isfinite(y).all()
+    assert orc.rel_l2(y, g.y) < TOL_BF16
+    assert orc.rel_l2(y[:, 1:], g.y[:, 1:]) < TOL_BF16
+    assert orc.rel_l2(y[:, :1], g.y[:, :1]) < TOL_BF16
+    # the integral estimator on its own (terminal part subtracted)
+    assert orc.rel_l2(y - g.y_terminal, g.y_integral) < 5 * TOL_BF16
+    e.close()
+
+
+@pytest.mark.parametrize("nx,M_T,M_I,n", [(100, 64, 128, 7), (100, 256, 4096, 5), (100, 32, 1100, 9), (64, 16, 300, 4),
+                                          (128, 16, 200, 3), (10, 16, 131, 6), (77, 16, 257, 3)])
+def test_bf16_path_agrees_with_fp32_path_on_the_same_philox_draws(nx, M_T, M_I, n):
+    """Both integral kernels consume identical Philox counters, so they differ only by bf16 rounding of the GEMM
+    inputs; covers ragged M_I (not a multiple of 128), several work units per point and d not a multiple of 4/16."""
+    from tests.gpu_util import engine_for
+    eq = orc.Cha(nx, 1.0, 5.0, 1.0)
+    net = orc.make_mlp(1 + nx, [128] * 4, seed=2, gain=1.3)
+    e = engine_for(eq, net)
+    tx = e.sample_tx(n, seed=3)
+    y32 = e.label_gen(tx, M_T, M_I, precision="fp32", seed=5).double().cpu()
+    y16 = e.label_gen(tx, M_T, M_I, precision="bf16", seed=5).double().cpu()
+    assert torch.isfinite(y16).all()
+    assert orc.rel_l2(y16, y32) < TOL_BF16
+    assert orc.rel_l2(y16[:, :1], y32[:, :1]) < TOL_BF16
+    e.close()
+
+
+def test_bf16_shard_invariance_and_determinism():
+    from tests.gpu_util import engine_for
+    eq = orc.Cha(100, 1.0, 5.0, 1.0)
+    net = orc.make_mlp(101, [128] * 4, seed=5)
+    e = engine_for(eq, net)
+    tx = e.sample_tx(300, seed=7)
+    y = e.label_gen(tx, 64, 1500, precision="bf16", seed=7)
+    assert torch.equal(y, e.label_gen(tx, 64, 1500, precision="bf16", seed=7))
+    y_b = torch.cat([e.label_gen(tx[:11], 64, 1500, precision="bf16", seed=7),
+                     e.label_gen(tx[11:], 64, 1500, precision="bf16", seed=7, point_index_base=11)])
+    assert torch.equal(y, y_b)
+    e.close()
+
+
+def test_bf16_rejects_unsupported_network_loudly():
+    from tests.gpu_util import engine_for
+    eq = orc.Cha(100, 1.0, 5.0, 1.0)
+    e = engine_for(eq, orc.make_mlp(101, [64, 64], seed=1))
+    tx = e.sample_tx(4, seed=0)
+    with pytest.raises(NotImplementedError):
+        e.label_gen(tx, 16, 16, precision="bf16")
+    e.close()
