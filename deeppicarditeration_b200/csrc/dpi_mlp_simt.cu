@@ -19,6 +19,10 @@ namespace dpi {
 namespace {
 
 __device__ __forceinline__ float bf16r(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+// the tensor-core path carries activations scaled by log2(e) and rounds THOSE to bf16 (dpi_mlp_tc.cu)
+__device__ __forceinline__ float bf16r_scaled(float x) {
+  return bf16r(x * 1.4426950408889634f) * 0.6931471805599453f;
+}
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
@@ -188,8 +192,8 @@ cha_simt_kernel(const ProblemDev P, const MlpDev N, const float* __restrict__ tx
         }
         float h, e1;
         elu_d1(lin + s_s[r] * wt_s[col], h, e1);
-        o[2 * i] = emu ? bf16r(h) : h;
-        o[2 * i + 1] = emu ? bf16r(e1 * wsum_s[col]) : e1 * wsum_s[col];
+        o[2 * i] = emu ? bf16r_scaled(h) : h;
+        o[2 * i + 1] = emu ? bf16r_scaled(e1 * wsum_s[col]) : e1 * wsum_s[col];
       }
       float4* dst = reinterpret_cast<float4*>(act + col * G::LDA + ty * 8);
       dst[0] = make_float4(o[0], o[1], o[2], o[3]);
@@ -233,8 +237,8 @@ cha_simt_kernel(const ProblemDev P, const MlpDev N, const float* __restrict__ tx
           float h, e1;
           elu_d1(acc[2 * i][c] + b, h, e1);
           const bool rnd = emu && l < n_hidden - 1;  // the last hidden output feeds the fp32 output dot product
-          o[2 * i] = rnd ? bf16r(h) : h;
-          o[2 * i + 1] = rnd ? bf16r(e1 * acc[2 * i + 1][c]) : e1 * acc[2 * i + 1][c];
+          o[2 * i] = rnd ? bf16r_scaled(h) : h;
+          o[2 * i + 1] = rnd ? bf16r_scaled(e1 * acc[2 * i + 1][c]) : e1 * acc[2 * i + 1][c];
         }
         float4* dst = reinterpret_cast<float4*>(act + col * G::LDA + ty * 8);
         dst[0] = make_float4(o[0], o[1], o[2], o[3]);

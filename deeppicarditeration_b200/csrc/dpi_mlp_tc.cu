@@ -66,7 +66,7 @@ struct TcArgs {
   const float* zS;
   const float* fb;  // [n] control variate f(t,x)
   const float* c0;  // [n][128]
-  float* partG;     // [units][2][8][128]
+  float* partG;     // [units][16][128]
   float* partF;     // [units][4]
   int M_I;
   int units_per_point;
@@ -76,19 +76,28 @@ struct TcArgs {
   int cls;      // row classes of the producer mapping
 };
 
-// ---- one hidden-layer epilogue for this warp's column half: TMEM -> bias/ELU/ELU' -> bf16 A operands ----------
-// L = 1: z = c0 + s w_t + a acc, tangent = ELU'(z) * wsum (constant first-layer tangent);  L = 2,3: z = acc + b.
-template <int L>
+// All activations are carried scaled by log2(e): with z' = log2e z the ELU pair needs one op less per element,
+//   e = 2^min(z',0) = ELU'(z),   h' = log2e ELU(z) = max(z', e log2e - log2e),   tangent' = e * (log2e dz),
+// and because every layer is linear in its input only the biases (x log2e), the first-layer constants and the
+// output weights (x ln2) change -- the hidden weight matrices are used as they are (TcConsts holds the scaled
+// vectors; see tc_pack_network).
+//
+// One hidden-layer epilogue for this warp's 64 columns: TMEM -> bias/ELU/ELU' -> bf16 A operands of the next layer.
+// FIRST: z' = c0' + s' w_t + a' acc, tangent' = e * wsum' (constant first-layer tangent);  else z' = acc + b'[layer].
+template <bool FIRST>
 __device__ __forceinline__ void epi_hidden(uint8_t* smem, uint32_t sbase, const TcConsts& C, uint32_t tacc, int hf,
-                                           int r, int lane, float s, float a) {
+                                           int lane, uint32_t rowbase, uint32_t rx, int layer, float s, float a) {
   const float* c0_s = reinterpret_cast<const float*>(smem + kOffC0);
+  const float* bias = C.b[layer];
 #pragma unroll 1
   for (int jj = 0; jj < 2; ++jj) {
     const int col0 = hf * 64 + jj * 32;
     uint32_t v[32], tv[32];
     tmem_ld32(tacc + col0, v);
-    if (L > 1) tmem_ld32(tacc + 128 + col0, tv);
+    if (!FIRST) tmem_ld32(tacc + 128 + col0, tv);
     tmem_ld_wait();
+    uint8_t* const hv_row = smem + kOffHV + rowbase;
+    uint8_t* const ht_row = smem + kOffHT + rowbase;
 #pragma unroll
     for (int c8 = 0; c8 < 32; c8 += 8) {
       uint32_t hv[4], ht[4];
@@ -96,7 +105,7 @@ __device__ __forceinline__ void epi_hidden(uint8_t* smem, uint32_t sbase, const 
       for (int k4 = 0; k4 < 8; k4 += 4) {
         const int col = col0 + c8 + k4;
         float zb[4], tg[4];
-        if (L == 1) {
+        if (FIRST) {
           const float4 w = *reinterpret_cast<const float4*>(&C.wt[col]);
           const float4 ws = *reinterpret_cast<const float4*>(&C.wsum[col]);
           const float4 c0 = *reinterpret_cast<const float4*>(&c0_s[col]);
@@ -106,7 +115,7 @@ __device__ __forceinline__ void epi_hidden(uint8_t* smem, uint32_t sbase, const 
           zb[3] = fmaf(a, __uint_as_float(v[c8 + k4 + 3]), fmaf(s, w.w, c0.w));
           tg[0] = ws.x, tg[1] = ws.y, tg[2] = ws.z, tg[3] = ws.w;
         } else {
-          const float4 b = *reinterpret_cast<const float4*>(&C.b[L - 2][col]);
+          const float4 b = *reinterpret_cast<const float4*>(&bias[col]);
           zb[0] = __uint_as_float(v[c8 + k4 + 0]) + b.x;
           zb[1] = __uint_as_float(v[c8 + k4 + 1]) + b.y;
           zb[2] = __uint_as_float(v[c8 + k4 + 2]) + b.z;
@@ -117,9 +126,8 @@ __device__ __forceinline__ void epi_hidden(uint8_t* smem, uint32_t sbase, const 
         float h[4], dh[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          // e = exp(min(z,0)) is ELU'(z); ELU(z) = max(z, e - 1) (for z > 0: e = 1; for z <= 0: expm1(z) >= z)
-          const float e = exp2f(fminf(zb[i], 0.f) * kLog2e);
-          h[i] = fmaxf(zb[i], e - 1.f);
+          const float e = exp2f(fminf(zb[i], 0.f));
+          h[i] = fmaxf(zb[i], fmaf(e, kLog2e, -kLog2e));
           dh[i] = e * tg[i];
         }
         hv[k4 / 2 + 0] = pack_bf16x2(h[0], h[1]);
@@ -127,9 +135,10 @@ __device__ __forceinline__ void epi_hidden(uint8_t* smem, uint32_t sbase, const 
         ht[k4 / 2 + 0] = pack_bf16x2(dh[0], dh[1]);
         ht[k4 / 2 + 1] = pack_bf16x2(dh[2], dh[3]);
       }
-      const uint32_t off = sw128_offset((uint32_t)r, (uint32_t)(col0 + c8));
-      *reinterpret_cast<uint4*>(smem + kOffHV + off) = make_uint4(hv[0], hv[1], hv[2], hv[3]);
-      *reinterpret_cast<uint4*>(smem + kOffHT + off) = make_uint4(ht[0], ht[1], ht[2], ht[3]);
+      // 16-byte chunk (jj*4 + c8/8) of this row's 128-byte line in K panel hf, XOR-swizzled with (row & 7)
+      const uint32_t off = ((uint32_t)((jj * 4 + c8 / 8) << 4)) ^ rx;
+      *reinterpret_cast<uint4*>(hv_row + off) = make_uint4(hv[0], hv[1], hv[2], hv[3]);
+      *reinterpret_cast<uint4*>(ht_row + off) = make_uint4(ht[0], ht[1], ht[2], ht[3]);
     }
     // this warp's 32 K-columns of the next A operand are written: publish them to the MMA thread
     tc_fence_before();
@@ -139,7 +148,7 @@ __device__ __forceinline__ void epi_hidden(uint8_t* smem, uint32_t sbase, const 
   }
 }
 
-template <int ITEMS>
+template <int ITEMS, bool DET>
 __global__ void __launch_bounds__(kTcThreads, 1)
 cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcConsts C,
               const __grid_constant__ TcArgs A) {
@@ -156,7 +165,7 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
       __trap();
     }
     mbar_init(bar(kBarW), 1);
-    mbar_init(bar(kBarZFull), 4);   // the 4 warps of the producing group
+    mbar_init(bar(kBarZFull), 8);   // the 8 producer warps
     mbar_init(bar(kBarZEmpty), 1);  // tcgen05.commit
     mbar_init(bar(kBarAcc0), 1);
     mbar_init(bar(kBarAcc1), 1);
@@ -185,6 +194,11 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
                  bar(kBarW));
       mbar_wait(bar(kBarW), 0, 0);
       constexpr uint32_t idesc = make_idesc_bf16(128, 128);
+      // descriptors differ only in the 14-bit start-address field: +2 per UMMA_K step inside a K panel (32 B),
+      // +1024 per panel (16 KB).  Kept as base + small offsets so the loop needs few registers (this thread runs
+      // with 32 registers and there is next to no L1 left for spills).
+      const uint64_t dZ = make_desc_sw128(sbase + kOffZ), dV = make_desc_sw128(sbase + kOffHV),
+                     dT = make_desc_sw128(sbase + kOffHT), dW = make_desc_sw128(sbase + kOffW);
       uint32_t it = 0, ph_ready = 0;
       for (int64_t u = blockIdx.x; u < A.n_units; u += gridDim.x) {
         const int g = (int)(u % UP);
@@ -194,16 +208,21 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
           // tile were published only after every epilogue warp had finished reading set 0 (layer 3).
           mbar_wait(bar(kBarZFull), it & 1u, 1);
           tc_fence_after();
-          for (int ks = 0; ks < A.ksteps1; ++ks)
-            umma_bf16(tmem, desc_kstep(sbase + kOffZ, ks), desc_kstep(sbase + kOffW, ks), idesc, ks > 0);
+#pragma unroll 1
+          for (int ks = 0; ks < A.ksteps1; ++ks) {
+            const uint64_t o = (uint64_t)((ks >> 2) * 1024 + (ks & 3) * 2);
+            umma_bf16(tmem, dZ + o, dW + o, idesc, ks > 0);
+          }
           tc_commit(bar(kBarZEmpty));
           tc_commit(bar(kBarAcc0));
           // hidden layers 2..4: weights image l, accumulator set (l & 1); K chunks in the order 0,2,1,3 (chunk 0
           // first: its completion implies every epilogue warp is past the previous tile's output layer)
+#pragma unroll 1
           for (int l = 1; l <= 3; ++l) {
             const uint32_t acc = tmem + (uint32_t)(l & 1) * 256u;
-            const uint32_t wb = sbase + kOffW + (uint32_t)l * kOperandBytes;
+            const uint64_t dWl = dW + (uint64_t)(l * (kOperandBytes >> 4));
             uint32_t accum = 0;
+#pragma unroll 1
             for (int ci = 0; ci < 4; ++ci) {
               const int c = (ci & 1) * 2 + (ci >> 1);
               mbar_wait(bar(kBarReady0 + c), ph_ready, 10 + c);
@@ -211,9 +230,9 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
 #pragma unroll
               for (int kk = 0; kk < 2; ++kk) {
                 const int ks = 2 * c + kk;
-                const uint64_t bd = desc_kstep(wb, ks);
-                umma_bf16(acc, desc_kstep(sbase + kOffHV, ks), bd, idesc, accum);
-                umma_bf16(acc + 128u, desc_kstep(sbase + kOffHT, ks), bd, idesc, accum);
+                const uint64_t o = (uint64_t)((ks >> 2) * 1024 + (ks & 3) * 2);
+                umma_bf16(acc, dV + o, dWl + o, idesc, accum);
+                umma_bf16(acc + 128u, dT + o, dWl + o, idesc, accum);
                 accum = 1;
               }
             }
@@ -230,10 +249,10 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
     const int q = warp & 3, hf = warp >> 2;
     const int r = q * 32 + lane;
     const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+    const uint32_t rowbase = (uint32_t)hf * kPanelBytes + (uint32_t)r * 128u, rx = (uint32_t)(r & 7) << 4;
     float* c0_s = reinterpret_cast<float*>(smem + kOffC0);
     float* coef_s = reinterpret_cast<float*>(smem + kOffCoef);
     float2* xch = reinterpret_cast<float2*>(smem + kOffXch);
-    const bool det = A.zS != nullptr;
     uint32_t ph0 = 0, ph1 = 0, it = 0;
     for (int64_t u = blockIdx.x; u < A.n_units; u += gridDim.x) {
       const int64_t p = u / UP;
@@ -244,31 +263,33 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
       const float fbp = __ldg(A.fb + p);
       const uint64_t gp = (uint64_t)(A.point_base + p);
       named_bar_sync(1, 256);  // everyone is done with the previous point's c0
-      if (threadIdx.x < 128) c0_s[threadIdx.x] = __ldg(A.c0 + p * 128 + threadIdx.x);
+      if (threadIdx.x < 128) c0_s[threadIdx.x] = kLog2e * __ldg(A.c0 + p * 128 + threadIdx.x);
       named_bar_sync(1, 256);
       float fsum = 0.f;
       for (int tl = 0; tl < tiles; ++tl, ++it) {
         const int m = (g * kTcGroupTiles + tl) * 128 + r;
         const bool valid = m < M_I;
         float uu = 0.5f;
-        if (valid) uu = det ? __ldg(A.u_s + p * M_I + m) : u01(philox_at(A.seed, gp, kStreamS, (uint32_t)m, 0u).x);
-        const float s = uu * dT + t;
+        if (valid) uu = DET ? __ldg(A.u_s + p * M_I + m) : u01(philox_at(A.seed, gp, kStreamS, (uint32_t)m, 0u).x);
         const float a = sqrtf(uu * dT) * P.sigma;
+        const float s2 = (uu * dT + t) * kLog2e, a2 = a * kLog2e;
 
         mbar_wait(bar(kBarAcc0), ph0, 20);
         ph0 ^= 1u;
         tc_fence_after();
-        epi_hidden<1>(smem, sbase, C, tlane, hf, r, lane, s, a);
-
-        mbar_wait(bar(kBarAcc1), ph1, 21);
-        ph1 ^= 1u;
-        tc_fence_after();
-        epi_hidden<2>(smem, sbase, C, tlane + 256u, hf, r, lane, s, a);
-
-        mbar_wait(bar(kBarAcc0), ph0, 22);
-        ph0 ^= 1u;
-        tc_fence_after();
-        epi_hidden<3>(smem, sbase, C, tlane, hf, r, lane, s, a);
+        epi_hidden<true>(smem, sbase, C, tlane, hf, lane, rowbase, rx, 0, s2, a2);
+#pragma unroll 1
+        for (int l = 0; l < 2; ++l) {  // hidden GEMM layers 2 and 3: accumulator sets 1 and 0
+          if (l == 0) {
+            mbar_wait(bar(kBarAcc1), ph1, 21);
+            ph1 ^= 1u;
+          } else {
+            mbar_wait(bar(kBarAcc0), ph0, 22);
+            ph0 ^= 1u;
+          }
+          tc_fence_after();
+          epi_hidden<false>(smem, sbase, C, tlane + (l == 0 ? 256u : 0u), hf, lane, rowbase, rx, l, 0.f, 0.f);
+        }
 
         // ---- output layer: u = w_out . h4 + b_out, D = w_out . h4' over this warp's 64 columns ----
         mbar_wait(bar(kBarAcc1), ph1, 23);
@@ -290,8 +311,8 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const float zb = __uint_as_float(v[c4 + i]) + bb[i];
-              const float e = exp2f(fminf(zb, 0.f) * kLog2e);
-              pu = fmaf(ww[i], fmaxf(zb, e - 1.f), pu);
+              const float e = exp2f(fminf(zb, 0.f));
+              pu = fmaf(ww[i], fmaxf(zb, fmaf(e, kLog2e, -kLog2e)), pu);
               pD = fmaf(ww[i], e * __uint_as_float(tv[c4 + i]), pD);
             }
           }
@@ -320,73 +341,96 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
   } else {
     // =================================== increment producers ===================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kWorkerRegs));
-    const int tw = threadIdx.x - 256;
-    const int wg = tw >> 7, tl_id = tw & 127;
+    // All 8 warps draw every tile: thread (q, c) owns the 4 dims [4q, 4q+4) of the rows r = c + cls * i.  A tile's
+    // increments are generated into registers first (no dependence on the shared Z buffer), stored once the
+    // layer-1 MMA of the previous tile has released the buffer, and kept until the tile's Bismut coefficients
+    // arrive one tile later.
+    const int tl_id = threadIdx.x - 256;
     const int nq = A.nq, cls = A.cls;
     const int q = tl_id % nq, c = tl_id / nq;
     const bool active = c < cls;
-    const bool det = A.zS != nullptr;
     const bool vec_ok = (d & 3) == 0;
-    const float* coef_s = reinterpret_cast<const float*>(smem + kOffCoef) + wg * 128;
-    uint32_t z[ITEMS][2];
+    const float* coef_s = reinterpret_cast<const float*>(smem + kOffCoef);
+    uint8_t* const zdst = smem + kOffZ + (uint32_t)(q >> 4) * kPanelBytes + (uint32_t)(q & 1) * 8u;
+    const uint32_t zchunk = (uint32_t)((q & 15) >> 1);
+    uint32_t zold[ITEMS][2], znew[ITEMS][2];
     float4 G = make_float4(0.f, 0.f, 0.f, 0.f);
     uint32_t it = 0;
+    bool prev_valid = false, prev_last = false;
+    int64_t prev_u = 0;
+    auto finish_prev = [&]() {
+      // Bismut accumulation of tile it-1: G_j += coef_m Z_mj (bf16 Z, exactly what the MLP saw)
+      const uint32_t pit = it - 1u;
+      mbar_wait(bar(kBarCoef0 + (int)(pit & 1u)), (pit >> 1) & 1u, 31);
+      if (active) {
+        const float* cf_s = coef_s + (pit & 1u) * 128u;
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+          const int r = c + cls * i;
+          if (r < 128) {
+            const float cf = cf_s[r];
+            G.x = fmaf(cf, bf16_lo(zold[i][0]), G.x);
+            G.y = fmaf(cf, bf16_hi(zold[i][0]), G.y);
+            G.z = fmaf(cf, bf16_lo(zold[i][1]), G.z);
+            G.w = fmaf(cf, bf16_hi(zold[i][1]), G.w);
+          }
+        }
+        if (prev_last) {
+          *reinterpret_cast<float4*>(A.partG + (prev_u * 16 + c) * 128 + 4 * q) = G;
+          G = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    };
     for (int64_t u = blockIdx.x; u < A.n_units; u += gridDim.x) {
       const int64_t p = u / UP;
       const int g = (int)(u % UP);
       const int tiles = min(kTcGroupTiles, TP - g * kTcGroupTiles);
       const uint64_t gp = (uint64_t)(A.point_base + p);
-      for (int tl = 0; tl < tiles; ++tl, ++it) {
-        if ((int)(it & 1u) != wg) continue;  // the other producer group draws this tile
-        if (it > 0) mbar_wait(bar(kBarZEmpty), (it - 1u) & 1u, 30);  // layer-1 MMA of the previous tile has read Z
+      for (int tl = 0; tl < tiles; ++tl) {
         const int m0 = (g * kTcGroupTiles + tl) * 128;
         if (active) {
 #pragma unroll
           for (int i = 0; i < ITEMS; ++i) {
             const int r = c + cls * i;
-            z[i][0] = z[i][1] = 0u;
-            if (r < 128) {
-              const int m = m0 + r;
-              float4 zz = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (m < M_I) {
-                if (det) {
-                  zz = load_row4(A.zS + ((int64_t)p * M_I + m) * d, 4 * q, d, vec_ok);
-                } else {
-                  zz = normal4(A.seed, gp, kStreamIntegral, (uint32_t)m, (uint32_t)q);
-                  if (4 * q + 1 >= d) zz.y = 0.f;
-                  if (4 * q + 2 >= d) zz.z = 0.f;
-                  if (4 * q + 3 >= d) zz.w = 0.f;
-                }
+            const int m = m0 + r;
+            float4 zz = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < 128 && m < M_I) {
+              if (DET) {
+                zz = load_row4(A.zS + ((int64_t)p * M_I + m) * d, 4 * q, d, vec_ok);
+              } else {
+                zz = normal4(A.seed, gp, kStreamIntegral, (uint32_t)m, (uint32_t)q);
+                if (4 * q + 1 >= d) zz.y = 0.f;
+                if (4 * q + 2 >= d) zz.z = 0.f;
+                if (4 * q + 3 >= d) zz.w = 0.f;
               }
-              z[i][0] = pack_bf16x2(zz.x, zz.y);
-              z[i][1] = pack_bf16x2(zz.z, zz.w);
-              *reinterpret_cast<uint2*>(smem + kOffZ + sw128_offset((uint32_t)r, (uint32_t)(4 * q))) =
-                  make_uint2(z[i][0], z[i][1]);
             }
+            znew[i][0] = pack_bf16x2(zz.x, zz.y);
+            znew[i][1] = pack_bf16x2(zz.z, zz.w);
+          }
+        }
+        if (it > 0) mbar_wait(bar(kBarZEmpty), (it - 1u) & 1u, 30);  // layer-1 MMA of the previous tile has read Z
+        if (active) {
+#pragma unroll
+          for (int i = 0; i < ITEMS; ++i) {
+            const int r = c + cls * i;
+            if (r < 128)
+              *reinterpret_cast<uint2*>(zdst + (uint32_t)r * 128u + ((zchunk ^ (uint32_t)(r & 7)) << 4)) =
+                  make_uint2(znew[i][0], znew[i][1]);
           }
         }
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(kBarZFull));
-        // Bismut accumulation once this tile's coefficients exist: G_j += coef_m Z_mj (bf16 Z, as the MLP saw it)
-        mbar_wait(bar(kBarCoef0 + wg), (it >> 1) & 1u, 31);
-        if (active) {
+        if (prev_valid) finish_prev();
 #pragma unroll
-          for (int i = 0; i < ITEMS; ++i) {
-            const int r = c + cls * i;
-            if (r < 128) {
-              const float cf = coef_s[r];
-              G.x = fmaf(cf, bf16_lo(z[i][0]), G.x);
-              G.y = fmaf(cf, bf16_hi(z[i][0]), G.y);
-              G.z = fmaf(cf, bf16_lo(z[i][1]), G.z);
-              G.w = fmaf(cf, bf16_hi(z[i][1]), G.w);
-            }
-          }
-        }
+        for (int i = 0; i < ITEMS; ++i) zold[i][0] = znew[i][0], zold[i][1] = znew[i][1];
+        prev_u = u;
+        prev_last = (tl == tiles - 1);
+        prev_valid = true;
+        ++it;
       }
-      if (active) *reinterpret_cast<float4*>(A.partG + ((u * 2 + wg) * 8 + c) * 128 + 4 * q) = G;
-      G = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    if (prev_valid) finish_prev();
   }
 
   tc_fence_before();
@@ -409,8 +453,7 @@ cha_tc_finish_kernel(const float* __restrict__ partG, const float* __restrict__ 
   if (j < d) {
     float s = 0.f;
     for (int g = 0; g < units_per_point; ++g)
-      for (int w = 0; w < 2; ++w)
-        for (int c = 0; c < cls; ++c) s += partG[(((p * units_per_point + g) * 2 + w) * 8 + c) * 128 + j];
+      for (int c = 0; c < cls; ++c) s += partG[((p * units_per_point + g) * 16 + c) * 128 + j];
     float v = yp[1 + j] + s * invM;
     if (clip) v = fminf(fmaxf(v, -bound), bound);
     yp[1 + j] = v;
@@ -481,9 +524,9 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const uint8_t* __
   }
 }
 
-template <int ITEMS>
+template <int ITEMS, bool DET>
 int launch_tc_t(const ProblemDev& P, const TcNetDev& N, const TcArgs& A, int grid, cudaStream_t st) {
-  auto k = cha_tc_kernel<ITEMS>;
+  auto k = cha_tc_kernel<ITEMS, DET>;
   DPI_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
   k<<<grid, kTcThreads, kTcSmemBytes, st>>>(P, N.consts, A);
   DPI_CUDA_CHECK(cudaGetLastError());
@@ -517,11 +560,18 @@ int tc_pack_network(const dpi_network& net, const ProblemDev& P, const MlpDev& M
     DPI_CUDA_CHECK(cudaMemcpy(T.consts.b[l], M.bh[l], 128 * sizeof(float), cudaMemcpyDeviceToHost));
   DPI_CUDA_CHECK(cudaMemcpy(T.consts.wout, M.wout, 128 * sizeof(float), cudaMemcpyDeviceToHost));
   DPI_CUDA_CHECK(cudaMemcpy(&T.consts.bout, M.bout, sizeof(float), cudaMemcpyDeviceToHost));
+  // activations are carried scaled by log2(e) (see epi_hidden): scale the vectors that add to / read from them
+  for (int i = 0; i < 128; ++i) {
+    T.consts.wt[i] *= kLog2e;
+    T.consts.wsum[i] *= kLog2e;
+    for (int l = 0; l < 3; ++l) T.consts.b[l][i] *= kLog2e;
+    T.consts.wout[i] *= 0.6931471805599453f;
+  }
   T.W = img;
   T.nx = P.nx;
   T.ksteps1 = (P.nx + 15) / 16;
   T.nq = (P.nx + 3) / 4;
-  T.cls = T.nq <= 16 ? 8 : (T.nq <= 25 ? 5 : 4);
+  T.cls = T.nq <= 16 ? 16 : (T.nq <= 25 ? 10 : 8);  // row classes of the 256 producer threads: cls * nq <= 256
   int dev = 0, sms = 0;
   DPI_CUDA_CHECK(cudaGetDevice(&dev));
   DPI_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -560,12 +610,13 @@ int launch_cha_tc_path(const ProblemDev& P, const TcNetDev& N, const float* tx, 
   A.cls = N.cls;
   const int grid = (int)(A.n_units < N.num_sms ? A.n_units : N.num_sms);
   int rc;
-  if (N.cls == 8)
-    rc = launch_tc_t<16>(P, N, A, grid, st);
-  else if (N.cls == 5)
-    rc = launch_tc_t<26>(P, N, A, grid, st);
+  const bool det = zS != nullptr;
+  if (N.cls == 16)
+    rc = det ? launch_tc_t<8, true>(P, N, A, grid, st) : launch_tc_t<8, false>(P, N, A, grid, st);
+  else if (N.cls == 10)
+    rc = det ? launch_tc_t<13, true>(P, N, A, grid, st) : launch_tc_t<13, false>(P, N, A, grid, st);
   else
-    rc = launch_tc_t<32>(P, N, A, grid, st);
+    rc = det ? launch_tc_t<16, true>(P, N, A, grid, st) : launch_tc_t<16, false>(P, N, A, grid, st);
   if (rc) return rc;
   cha_tc_finish_kernel<<<(unsigned)n, 128, 0, st>>>(partG, partF, A.units_per_point, N.cls, P.nx, M_I, bound, y);
   DPI_CUDA_CHECK(cudaGetLastError());

@@ -68,8 +68,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if ((++spins & 0x3FFu) == 0 && clock64() - t0 > 4000000000LL) {
+#ifdef DPI_TC_WATCHDOG_PRINTF
       printf("dpi tc watchdog: block %d thread %d stuck on barrier tag %d parity %u\n", (int)blockIdx.x,
              (int)threadIdx.x, tag, parity);
+#endif
       __trap();
     }
   }
