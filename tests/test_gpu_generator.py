@@ -28,7 +28,7 @@ def _load_mlp(net, g):
 def _generator(g, **kw):
     from deeppicarditeration_b200 import equations as eqs, solution as sol
     from deeppicarditeration_b200.data import OnlineDataGenerator
-    eq = eqs.Cha(nx=g.nx, alpha=g.alpha, k=g.k * g.nx ** 0.5, T=g.T)
+    eq = eqs.Cha(nx=g.nx, alpha=g.alpha, k=g.k, T=g.T)
     if g.net.kind == "zero":
         net = sol.ZeroSolution()
     else:
