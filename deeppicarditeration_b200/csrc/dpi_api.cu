@@ -413,11 +413,25 @@ int dpi_label_gen(dpi_handle* h, const float* tx, int64_t n, const dpi_label_con
   h->launches += 1;
 
   // 2) integral estimator: y += ..., then clip
-  if (h->net_kind == DPI_NET_ZERO) {
-    if (P.eq == DPI_EQ_GBM) {
-      set_error("dpi_label_gen: GBM path not built yet");
+  if (P.eq == DPI_EQ_GBM && (h->net_kind == DPI_NET_ZERO || h->net_kind == DPI_NET_MLP)) {
+    if (P.sdgd_v < 1) {
+      // has_hessian_term without an approximation context takes the full-Hessian branch (data.py:1262-1272),
+      // which no BASELINE config selects
+      set_error("dpi_label_gen: GBMEquationComplexExact needs HESSIAN_APPROXIMATION.method=SDGD (sdgd_v >= 1)");
       return DPI_ERR_UNSUPPORTED;
     }
+    if (cfg->precision != DPI_PREC_FP32) {
+      set_error("dpi_label_gen: the SDGD (2-jet) path is fp32 only");
+      return DPI_ERR_UNSUPPORTED;
+    }
+    StageTimer tm(h, DPI_STAGE_INTEGRAL, st);
+    rc = launch_gbm_simt(P, h->mlp, h->net_kind == DPI_NET_ZERO, tx, n, cfg->M_I, cfg->seed, cfg->point_index_base,
+                         draws ? draws->u_s : nullptr, draws ? draws->zS : nullptr, draws ? draws->idx : nullptr,
+                         bound, y, st);
+    if (!rc) h->launches += 1;
+    return rc;
+  }
+  if (h->net_kind == DPI_NET_ZERO) {
     rc = launch_finish_zero(P, tx, n, bound, y, st);
     if (!rc) h->launches += 1;
     return rc;

@@ -42,6 +42,11 @@ int launch_cha_simt_path(const ProblemDev& P, const MlpDev& net, const float* tx
                          int64_t base, const float* u_s, const float* zS, const float* fb, const float* c0,
                          float bound, float* y, cudaStream_t st);
 
+// ---- fully nonlinear equation with SDGD (dpi_gbm_simt.cu): y += integral part, then clip ------------------
+int launch_gbm_simt(const ProblemDev& P, const MlpDev& net, bool zero_net, const float* tx, int64_t n, int M_I,
+                    uint64_t seed, int64_t base, const float* u_s, const float* zS, const int32_t* idx, float bound,
+                    float* y, cudaStream_t st);
+
 // ---- bf16 tcgen05 path (dpi_mlp_tc.cu) ---------------------------------------------------------------
 constexpr int kTcGroupTiles = 8;  // 128-sample tiles per work unit (fixed: the summation order must not depend on n)
 // per-column fp32 constants of the network, passed to the kernel by value (constant bank)

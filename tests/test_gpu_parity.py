@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 TOL_FP32 = 1e-4
 TOL_BF16 = 1e-2
 
-BUILT = [n for n in golden_names() if n.startswith("burgers") or n == "hjb_100d_zero"]
+BUILT = [n for n in golden_names() if n.startswith("burgers") or n.startswith("gbm") or n == "hjb_100d_zero"]
 
 
 def _engine(g):
