@@ -1,4 +1,5 @@
 // C ABI (include/dpi_b200.h): handle, problem/network packing and the label-generation driver.
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -29,6 +30,10 @@ struct dpi_handle {
   MlpDev mlp{};
   TcNetDev tc{};
   bool tc_ready = false;
+  PisDev pis{};
+  // activations of one chunk of rows of the batched-GEMM (PISGradNet) path
+  float* hjb_scratch = nullptr;
+  int64_t hjb_scratch_floats = 0;
   std::vector<void*> prob_bufs;  // device allocations owned by the problem
   std::vector<void*> net_bufs;   // device allocations owned by the packed network
   // per-point scratch: control variate f_b [n], first-layer constant c0 [n][HP]
@@ -114,6 +119,18 @@ int ensure_stage(dpi_handle* h, int64_t floats) {
   return DPI_OK;
 }
 
+int ensure_hjb_scratch(dpi_handle* h, int64_t floats) {
+  if (floats <= h->hjb_scratch_floats) return DPI_OK;
+  if (h->hjb_scratch) cudaFree(h->hjb_scratch);
+  h->hjb_scratch = nullptr;
+  h->hjb_scratch_floats = 0;
+  DPI_CUDA_CHECK(cudaMalloc((void**)&h->hjb_scratch, sizeof(float) * floats));
+  h->hjb_scratch_floats = floats;
+  return DPI_OK;
+}
+// activation scratch of the batched-GEMM path: at most this many bytes per chunk of rows
+constexpr int64_t kHjbScratchBudget = 6LL << 30;
+
 int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 // RAII bracket: records the stage's start event now and its end event when it goes out of scope.
@@ -179,6 +196,7 @@ int dpi_destroy(dpi_handle* h) {
   if (h->stage_y) cudaFree(h->stage_y);
   if (h->partG) cudaFree(h->partG);
   if (h->partF) cudaFree(h->partF);
+  if (h->hjb_scratch) cudaFree(h->hjb_scratch);
   for (int s = 0; s < DPI_STAGE_COUNT; ++s)
     for (int e = 0; e < 2; ++e)
       if (h->ev[s][e]) cudaEventDestroy(h->ev[s][e]);
@@ -350,8 +368,40 @@ int dpi_set_network(dpi_handle* h, const dpi_network* net, void* stream) {
     return DPI_OK;
   }
   if (net->kind == DPI_NET_PISGRAD) {
-    set_error("dpi_set_network: PISGradNet path not built yet");
-    return DPI_ERR_UNSUPPORTED;
+    // solution.py:138-207: channels = 64; t_encoder 128->64->64; smooth_net 128->64->..->64->dim; nn_module (64+nx)->..->nx
+    if (h->P.eq != DPI_EQ_OU) {
+      set_error("dpi_set_network: PISGradNet is built for OUProcessEquation only (its residual uses the GMM terminal)");
+      return DPI_ERR_UNSUPPORTED;
+    }
+    auto chain_ok = [&](const dpi_linear* c, int n, int n_in, int n_out, int mid /* 0 = free */) {
+      if (n < 2 || n > DPI_MAX_LINEAR) return false;
+      for (int l = 0; l < n; ++l) {
+        const int want_in = l == 0 ? n_in : c[l - 1].n_out;
+        if (!c[l].W || !c[l].b || c[l].n_in != want_in || c[l].n_out < 1) return false;
+        if (mid && l < n - 1 && c[l].n_out != mid) return false;
+      }
+      return c[n - 1].n_out == n_out;
+    };
+    if (!chain_ok(net->t_encoder, net->n_t_encoder, 128, 64, 64) || net->n_t_encoder != 2 ||
+        !chain_ok(net->smooth_net, net->n_smooth, 128, net->smooth_net[net->n_smooth > 0 ? net->n_smooth - 1 : 0].n_out, 64) ||
+        !chain_ok(net->main, net->n_main, 64 + nx, nx, 0) || !net->timestep_phase || !net->timestep_coeff) {
+      set_error("dpi_set_network: PISGradNet chains do not have the shapes of picard/solution.py:170-207 for nx=%d", nx);
+      return DPI_ERR_INVALID;
+    }
+    PisDev N{};
+    N.n_main = net->n_main, N.n_t_encoder = net->n_t_encoder, N.n_smooth = net->n_smooth;
+    N.hmax = 0;
+    for (int l = 0; l < net->n_main; ++l) {
+      N.main[l] = net->main[l];
+      if (l < net->n_main - 1 && net->main[l].n_out > N.hmax) N.hmax = net->main[l].n_out;
+    }
+    for (int l = 0; l < net->n_t_encoder; ++l) N.t_encoder[l] = net->t_encoder[l];
+    for (int l = 0; l < net->n_smooth; ++l) N.smooth_net[l] = net->smooth_net[l];
+    N.phase = net->timestep_phase, N.coeff = net->timestep_coeff;
+    h->pis = N;
+    h->has_net = true;
+    (void)st;
+    return DPI_OK;
   }
   set_error("dpi_set_network: unknown network kind %d", net->kind);
   return DPI_ERR_INVALID;
@@ -474,6 +524,17 @@ int dpi_label_gen(dpi_handle* h, const float* tx, int64_t n, const dpi_label_con
     if (!rc) h->launches += 1;
     return rc;
   }
+  if (h->net_kind == DPI_NET_PISGRAD && P.eq == DPI_EQ_OU) {
+    if (cfg->precision != DPI_PREC_FP32) {
+      set_error("dpi_label_gen: the PISGradNet path is fp32 only");
+      return DPI_ERR_UNSUPPORTED;
+    }
+    const int64_t ppc = std::min<int64_t>(n, hjb_points_per_chunk(h->pis, P.nx, cfg->M_I, kHjbScratchBudget));
+    if ((rc = ensure_hjb_scratch(h, hjb_scratch_floats(h->pis, P.nx, ppc * (cfg->M_I + 1))))) return rc;
+    StageTimer tm(h, DPI_STAGE_INTEGRAL, st);
+    return launch_hjb_paths(P, h->pis, tx, n, cfg->M_I, cfg->seed, cfg->point_index_base, draws ? draws->u_s : nullptr,
+                            draws ? draws->zS : nullptr, bound, h->hjb_scratch, ppc, y, st, &h->launches);
+  }
   set_error("dpi_label_gen: equation %d with network kind %d is not built yet", P.eq, h->net_kind);
   return DPI_ERR_UNSUPPORTED;
 }
@@ -523,6 +584,13 @@ int dpi_net_eval(dpi_handle* h, const float* tx, int64_t n, float* u, float* du,
     rc = launch_cha_simt_base(h->P, h->mlp, tx, n, h->fb, h->c0, u, nullptr, false, st);
     if (!rc) h->launches += 1;
     return rc;
+  }
+  if (h->net_kind == DPI_NET_PISGRAD && h->P.eq == DPI_EQ_OU) {
+    const int64_t per_row = hjb_scratch_floats(h->pis, h->P.nx, 1) * (int64_t)sizeof(float);
+    const int64_t rpc = std::max<int64_t>(1, std::min<int64_t>(n, kHjbScratchBudget / per_row));
+    int rc = ensure_hjb_scratch(h, hjb_scratch_floats(h->pis, h->P.nx, rpc));
+    if (rc) return rc;
+    return launch_hjb_eval(h->P, h->pis, tx, n, h->hjb_scratch, rpc, u, du, st, &h->launches);
   }
   set_error("dpi_net_eval: full input gradient not built yet");
   return DPI_ERR_UNSUPPORTED;

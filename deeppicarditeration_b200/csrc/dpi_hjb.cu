@@ -1,0 +1,570 @@
+// fp32 integral estimator (and u_k / grad u_k evaluation) for the HJB equation `OUProcessEquation` with u_k = PISGradNet.
+//
+// Restates picard/data.py:471-527 (estimator), :350-366 (path points), :1226-1325 (get_f: u_k and its full input
+// gradient), picard/solution.py:211-289 (PISGradNet: sin/cos time embedding, t_encoder, smooth_net, nn_module,
+// output S <n, x> + (1 - S) g(gamma x)), picard/equations.py:657-666 (ff) and picard/utils.py:852-915 (GMM log-density
+// and its gradient).
+//
+// The reference back-propagates through the whole network to get grad_x u_k.  Here the gradient is the closed form
+// 
+//     grad_x u = S (n + J_n^T x) + (1 - S) gamma g_x(gamma x),      J_n^T x = one VJP through nn_module, cotangent x,
+// S and t_emb depending on the time only.  nn_module is 512 wide (1 MB of fp32 per layer), so unlike the Burgers
+// kernels the weights cannot live in shared memory: the rows (point x MC sample, plus one baseline row per point)
+// of a chunk of points go through the layers as batched GEMMs - a register-tiled 128x128x16 fp32 GEMM with the
+// bias / ELU / ELU' / VJP-mask epilogues fused - with the activations of the chunk in handle-owned scratch.  The
+// weights are read in torch layout in both directions (y = x W^T forward, c W backward), nothing is repacked.
+#include <algorithm>
+#include <cmath>
+
+#include "dpi_common.cuh"
+#include "dpi_kernels.h"
+
+namespace dpi {
+namespace {
+
+// ------------------------------------------------------------------------------------------------------------
+// C[R,N] = epilogue(A[R,K] . B), B given as W[N][K] (b_kn = 0: y = x W^T) or W[K][N] (b_kn = 1: c W)
+// ------------------------------------------------------------------------------------------------------------
+constexpr int BM = 128, BN = 128, BK = 16, kGemmThreads = 256;
+constexpr int kLds = BM + 4;  // 528-byte rows: 16-byte aligned, the +4 skews the k rows across banks
+
+enum GemmEpi : int {
+  kEpiNone = 0,      // C = acc
+  kEpiBias = 1,      // C = acc + bias
+  kEpiBiasElu = 2,   // C = ELU(acc + bias)
+  kEpiBiasEluD = 3,  // C = ELU(acc + bias), D = ELU'(acc + bias)
+  kEpiMulE = 4       // C = acc * E        (VJP through an ELU: cotangent times the stored ELU')
+};
+
+struct GemmArgs {
+  const float* A;
+  int lda;
+  const float* B;
+  int ldb;
+  int b_kn;
+  const float* bias;
+  const float* E;
+  int lde;
+  float* C;
+  int ldc;
+  float* D;
+  int ldd;
+  int64_t R;
+  int N, K, epi;
+};
+
+__device__ __forceinline__ void load8(const float* __restrict__ p, int i0, int limit, bool vec, float (&v)[8]) {
+  // elements [i0, i0+8) of a contiguous run of `limit` floats starting at p; zero beyond
+  if (vec && i0 + 7 < limit) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p + i0));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p + i0 + 4));
+    v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = (i0 + i < limit) ? __ldg(p + i0 + i) : 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 2) sgemm_kernel(const GemmArgs g) {
+  __shared__ __align__(16) float As[2][BK][kLds];
+  __shared__ __align__(16) float Bs[2][BK][kLds];
+  const int t = threadIdx.x;
+  const int64_t r0 = (int64_t)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int K = g.K, N = g.N;
+  const bool a_vec = ((g.lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0);
+  const bool b_vec = ((g.ldb & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.B) & 15) == 0);
+
+  // global -> register staging.  A (and B when b_kn == 0): thread owns 8 consecutive k of one row.
+  const int lrow = t & 127, lkq = (t >> 7) * 8;
+  // B when b_kn == 1: thread owns 8 consecutive n of one k row
+  const int bk_k = t >> 4, bk_n = (t & 15) * 8;
+  const float* arow = (r0 + lrow < g.R) ? g.A + (r0 + lrow) * (int64_t)g.lda : nullptr;
+  const float* brow = nullptr;
+  if (!g.b_kn && n0 + lrow < N) brow = g.B + (int64_t)(n0 + lrow) * g.ldb;
+
+  float ra[8], rb[8];
+  auto fetch = [&](int k0) {
+    if (arow) {
+      load8(arow, k0 + lkq, K, a_vec, ra);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ra[i] = 0.f;
+    }
+    if (!g.b_kn) {
+      if (brow) {
+        load8(brow, k0 + lkq, K, b_vec, rb);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rb[i] = 0.f;
+      }
+    } else {
+      if (k0 + bk_k < K) {
+        load8(g.B + (int64_t)(k0 + bk_k) * g.ldb, n0 + bk_n, N, b_vec, rb);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rb[i] = 0.f;
+      }
+    }
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) As[buf][lkq + i][lrow] = ra[i];
+    if (!g.b_kn) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) Bs[buf][lkq + i][lrow] = rb[i];
+    } else {
+      *reinterpret_cast<float4*>(&Bs[buf][bk_k][bk_n]) = make_float4(rb[0], rb[1], rb[2], rb[3]);
+      *reinterpret_cast<float4*>(&Bs[buf][bk_k][bk_n + 4]) = make_float4(rb[4], rb[5], rb[6], rb[7]);
+    }
+  };
+
+  const int ty = t >> 4, tx = t & 15;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  fetch(0);
+  stash(0);
+  __syncthreads();
+  const int nk = (K + BK - 1) / BK;
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) fetch((kt + 1) * BK);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) {
+      stash(buf ^ 1);  // the other buffer was last read before the previous barrier
+      __syncthreads();
+    }
+  }
+
+  // ---- epilogue ----
+  const bool c_vec = ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
+  const bool d_vec = g.D && ((g.ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.D) & 15) == 0);
+  const bool e_vec = g.E && ((g.lde & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.E) & 15) == 0);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t row = r0 + ((i < 4) ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (row >= g.R) continue;
+#pragma unroll
+    for (int jg = 0; jg < 2; ++jg) {
+      const int col = n0 + jg * 64 + tx * 4;
+      if (col >= N) continue;
+      float v[4] = {acc[i][jg * 4 + 0], acc[i][jg * 4 + 1], acc[i][jg * 4 + 2], acc[i][jg * 4 + 3]};
+      float dv[4] = {0.f, 0.f, 0.f, 0.f};
+      const bool full = col + 3 < N;
+      if (g.epi == kEpiBias || g.epi == kEpiBiasElu || g.epi == kEpiBiasEluD) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (col + j < N) v[j] += __ldg(g.bias + col + j);
+      }
+      if (g.epi == kEpiBiasElu || g.epi == kEpiBiasEluD) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) elu_d1(v[j], v[j], dv[j]);
+      }
+      if (g.epi == kEpiMulE) {
+        const float* ep = g.E + row * (int64_t)g.lde + col;
+        if (full && e_vec) {
+          const float4 e = __ldg(reinterpret_cast<const float4*>(ep));
+          v[0] *= e.x, v[1] *= e.y, v[2] *= e.z, v[3] *= e.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (col + j < N) v[j] *= __ldg(ep + j);
+        }
+      }
+      float* cp = g.C + row * (int64_t)g.ldc + col;
+      if (full && c_vec) {
+        *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (col + j < N) cp[j] = v[j];
+      }
+      if (g.epi == kEpiBiasEluD) {
+        float* dp = g.D + row * (int64_t)g.ldd + col;
+        if (full && d_vec) {
+          *reinterpret_cast<float4*>(dp) = make_float4(dv[0], dv[1], dv[2], dv[3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (col + j < N) dp[j] = dv[j];
+        }
+      }
+    }
+  }
+}
+
+int gemm(const GemmArgs& g, cudaStream_t st, int64_t* launches) {
+  if (g.R <= 0 || g.N <= 0) return DPI_OK;
+  dim3 grid((unsigned)((g.R + BM - 1) / BM), (unsigned)((g.N + BN - 1) / BN));
+  sgemm_kernel<<<grid, kGemmThreads, 0, st>>>(g);
+  DPI_CUDA_CHECK(cudaGetLastError());
+  if (launches) *launches += 1;
+  return DPI_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Row construction.  Row layout of a chunk of `np` points: r = p * rpp + m with rpp = M_I + 1; m < M_I is the MC
+// sample m (data.py:350-366), m == M_I the baseline row (t, x) (data.py:511-512).  One extra row at the very end
+// (index np * rpp) carries lambda = 0 for smooth_net(emb(0)) (solution.py:247-252).  In `points` mode (net_eval)
+// rpp == 1 and every row is (t, x) itself.  One warp per row, lane <-> 4 dims per 128-dim slot.
+// ------------------------------------------------------------------------------------------------------------
+struct RowBufs {
+  float* emb;   // [R+1][128]   sin | cos time embedding
+  float* in;    // [R+1][64+d]  nn_module input: t_emb (written by the t_encoder GEMM) | X
+  float* z;     // [R][d]       increments (paths mode)
+  float* sa;    // [R][2]       (s, a) with a = sqrt(s - t) sigma
+};
+
+__global__ void __launch_bounds__(256)
+hjb_rows_kernel(const ProblemDev P, const float* __restrict__ tx, int64_t np, int rpp, int M_I, uint64_t seed,
+                int64_t point_base, const float* __restrict__ u_s, const float* __restrict__ zS,
+                const float* __restrict__ phase, const float* __restrict__ coeff, RowBufs B) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int64_t R = np * rpp;
+  if (r > R) return;
+  const int d = P.nx, ldin = 64 + d;
+  float lam = 0.f;
+  if (r < R) {
+    const int64_t p = r / rpp;
+    const int m = (int)(r - p * rpp);
+    const float* txp = tx + p * (int64_t)(1 + d);
+    const float t = __ldg(txp);
+    const bool path = (rpp > 1) && (m < M_I);
+    float s = t, a = 0.f;
+    if (path) {
+      const uint64_t gp = (uint64_t)(point_base + p);
+      const float uu = zS ? __ldg(u_s + p * M_I + m) : u01(philox_at(seed, gp, kStreamS, (uint32_t)m, 0u).x);
+      s = uu * (P.T - t) + t;
+      a = sqrtf(uu * (P.T - t)) * P.sigma;
+      const bool vec_ok = (d & 3) == 0;
+      for (int j0 = 4 * lane; j0 < d; j0 += 128) {
+        float4 z;
+        if (zS)
+          z = load_row4(zS + (p * M_I + m) * (int64_t)d, j0, d, vec_ok);
+        else
+          z = normal4(seed, gp, kStreamIntegral, (uint32_t)m, (uint32_t)(j0 >> 2));
+        const float zz[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (j0 + q < d) {
+            B.z[r * d + j0 + q] = zz[q];
+            B.in[r * ldin + 64 + j0 + q] = fmaf(a, zz[q], __ldg(txp + 1 + j0 + q));
+          }
+      }
+    } else {
+      for (int j = lane; j < d; j += 32) {
+        B.in[r * ldin + 64 + j] = __ldg(txp + 1 + j);
+        if (rpp > 1) B.z[r * d + j] = 0.f;
+      }
+    }
+    if (lane == 0) {
+      B.sa[2 * r] = s;
+      B.sa[2 * r + 1] = a;
+    }
+    lam = P.T - s;
+  } else {
+    for (int j = lane; j < d; j += 32) B.in[r * ldin + 64 + j] = 0.f;
+  }
+  // solution.py:211-229: arg up to ~100 rad -> evaluate in double (fast-math sinf is not accurate out there)
+  for (int c = lane; c < 64; c += 32) {
+    const double arg = (double)__ldg(coeff + c) * (double)lam + (double)__ldg(phase + c);
+    double sn, cs;
+    sincos(arg, &sn, &cs);
+    B.emb[r * 128 + c] = (float)sn;
+    B.emb[r * 128 + 64 + c] = (float)cs;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Per-row combination: u, grad_x u, and f = ff(s, X, u, grad) (equations.py:657-666).  One warp per row.
+// ------------------------------------------------------------------------------------------------------------
+struct FinalArgs {
+  const float* in;     // [R+1][64+d]: X at column 64
+  const float* nout;   // [R][d]  nn_module output n
+  const float* jtx;    // [R][d]  J_n^T x
+  const float* sraw;   // [R+1]   smooth_net(emb(lambda))[0]; entry R is the lambda = 0 row
+  const float* sa;     // [R][2]
+  float* f;            // [R] or null
+  float* u;            // [R] or null
+  float* du;           // [R][d] or null
+  int64_t R;
+};
+
+__global__ void __launch_bounds__(256) hjb_final_kernel(const ProblemDev P, const FinalArgs A) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= A.R) return;
+  const int d = P.nx, ldin = 64 + d, K = P.ou_K;
+  const float S = __ldg(A.sraw + r) - __ldg(A.sraw + A.R);
+  const float s = __ldg(A.sa + 2 * r);
+  const float gamma = __expf(-0.5f * (P.T - s));
+  const float* X = A.in + r * (int64_t)ldin + 64;
+  // GMM at y = gamma X (utils.py:852-880): l_k = lognorm_k - 1/2 sum_j (y_j - m_kj)^2 / var_kj
+  float q[kMaxOuK];
+#pragma unroll
+  for (int k = 0; k < kMaxOuK; ++k) q[k] = 0.f;
+  for (int j = lane; j < d; j += 32) {
+    const float yj = gamma * __ldg(X + j);
+#pragma unroll
+    for (int k = 0; k < kMaxOuK; ++k)
+      if (k < K) {
+        const float e = yj - __ldg(P.ou_mean + k * d + j);
+        q[k] = fmaf(e * e, __ldg(P.ou_ivar + k * d + j), q[k]);
+      }
+  }
+  float l[kMaxOuK], mx = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < kMaxOuK; ++k) {
+    l[k] = (k < K) ? P.ou_lognorm[k] - 0.5f * warp_sum(q[k]) : -INFINITY;
+    mx = fmaxf(mx, l[k]);
+  }
+  float se = 0.f;
+#pragma unroll
+  for (int k = 0; k < kMaxOuK; ++k) {
+    l[k] = __expf(l[k] - mx);
+    se += l[k];
+  }
+  const float g = -(mx + __logf(se));
+  const float inv_se = 1.f / se;
+  // grad = S (n + J^T x) + (1 - S) gamma g_x(gamma X),   g_x(y) = sum_k resp_k (y - m_k) / var_k  (utils.py:882-915)
+  float dot_nx = 0.f, dot_fg = 0.f, gg = 0.f;
+  for (int j = lane; j < d; j += 32) {
+    const float xj = __ldg(X + j), yj = gamma * xj;
+    float gx = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxOuK; ++k)
+      if (k < K) gx = fmaf(l[k] * inv_se, (yj - __ldg(P.ou_mean + k * d + j)) * __ldg(P.ou_ivar + k * d + j), gx);
+    const float nj = __ldg(A.nout + r * d + j);
+    const float grad = S * (nj + __ldg(A.jtx + r * d + j)) + (1.f - S) * gamma * gx;
+    dot_nx = fmaf(nj, xj, dot_nx);
+    dot_fg = fmaf(P.ou_theta * (P.ou_mu - xj), grad, dot_fg);
+    gg = fmaf(grad, grad, gg);
+    if (A.du) A.du[r * d + j] = grad;
+  }
+  dot_nx = warp_sum(dot_nx);
+  dot_fg = warp_sum(dot_fg);
+  gg = warp_sum(gg);
+  if (lane == 0) {
+    if (A.u) A.u[r] = S * dot_nx + (1.f - S) * g;
+    if (A.f) A.f[r] = -dot_fg - 0.5f * P.alpha * gg - (float)d * P.ou_theta;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// MC reduction (data.py:514-527): y[p] += mean_m dT (f_m - f_b) (1, Z_m / (a_m)) + (dT f_b, 0); clip (data.py:222).
+// One CTA per point, thread j owns gradient component j; fixed summation order.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+hjb_reduce_kernel(const ProblemDev P, const float* __restrict__ tx, int M_I, const float* __restrict__ f,
+                  const float* __restrict__ z, const float* __restrict__ sa, float bound, float* __restrict__ y) {
+  const int64_t p = blockIdx.x;
+  const int d = P.nx, rpp = M_I + 1;
+  const float dT = P.T - __ldg(tx + p * (int64_t)(1 + d));
+  const int64_t rb = p * rpp;
+  const float fb = __ldg(f + rb + M_I);
+  const float invM = 1.f / (float)M_I;
+  const bool clip = bound > 0.f && isfinite(bound);
+  float* yp = y + p * (int64_t)(1 + d);
+  for (int j = threadIdx.x; j < d; j += blockDim.x) {
+    float G = 0.f;
+    for (int m = 0; m < M_I; ++m) {
+      const float coef = dT * (__ldg(f + rb + m) - fb) / __ldg(sa + 2 * (rb + m) + 1);
+      G = fmaf(coef, __ldg(z + (rb + m) * d + j), G);
+    }
+    float v = yp[1 + j] + G * invM;
+    if (clip) v = fminf(fmaxf(v, -bound), bound);
+    yp[1 + j] = v;
+  }
+  if (threadIdx.x < 32) {
+    float fs = 0.f;
+    for (int m = threadIdx.x; m < M_I; m += 32) fs += __ldg(f + rb + m);
+    fs = warp_sum(fs);
+    if (threadIdx.x == 0) {
+      float v = yp[0] + dT * fs * invM;
+      if (clip) v = fminf(fmaxf(v, -bound), bound);
+      yp[0] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Chunk scratch carve-up
+// ------------------------------------------------------------------------------------------------------------
+struct Scratch {
+  RowBufs rows;
+  float *t1, *sA, *sB, *sraw, *hA, *hB, *E[DPI_MAX_LINEAR], *nout, *jtx, *f;
+};
+
+int64_t floats_per_row(const PisDev& N, int d) {
+  const int nh = N.n_main - 1;
+  return 128 + (64 + d) + d + 2 + 64 + 64 + 64 + 1 + 2 * (int64_t)N.hmax + (int64_t)nh * N.hmax + d + d + 1 + 8;
+}
+
+Scratch carve(float* base, int64_t rows1 /* rows incl. the lambda = 0 row */, const PisDev& N, int d) {
+  Scratch S{};
+  float* p = base;
+  auto take = [&](int64_t per_row) {
+    float* q = p;
+    p += ((rows1 * per_row + 3) / 4) * 4;  // keep every buffer 16-byte aligned
+    return q;
+  };
+  S.rows.emb = take(128);
+  S.rows.in = take(64 + d);
+  S.rows.z = take(d);
+  S.rows.sa = take(2);
+  S.t1 = take(64);
+  S.sA = take(64);
+  S.sB = take(64);
+  S.sraw = take(1);
+  S.hA = take(N.hmax);
+  S.hB = take(N.hmax);
+  for (int l = 0; l < N.n_main - 1; ++l) S.E[l] = take(N.hmax);
+  S.nout = take(d);
+  S.jtx = take(d);
+  S.f = take(1);
+  return S;
+}
+
+// time nets + nn_module forward + VJP for `R` rows (+1 lambda = 0 row) whose emb / X are already in S.rows
+int eval_rows(const PisDev& N, int d, const Scratch& S, int64_t R, cudaStream_t st, int64_t* launches) {
+  int rc;
+  const int64_t R1 = R + 1;
+  auto G = [&](const float* A, int lda, const dpi_linear& L, int N_, float* C, int ldc, int epi, float* D = nullptr,
+               int ldd = 0) {
+    GemmArgs g{};
+    g.A = A, g.lda = lda, g.B = L.W, g.ldb = L.n_in, g.b_kn = 0, g.bias = L.b, g.C = C, g.ldc = ldc, g.D = D, g.ldd = ldd;
+    g.R = R1, g.N = N_, g.K = L.n_in, g.epi = epi;
+    return gemm(g, st, launches);
+  };
+  // t_encoder (solution.py:170-174): Linear(128,64) ELU Linear(64,64) -> columns [0,64) of the nn_module input
+  if ((rc = G(S.rows.emb, 128, N.t_encoder[0], 64, S.t1, 64, kEpiBiasElu))) return rc;
+  if ((rc = G(S.t1, 64, N.t_encoder[1], 64, S.rows.in, 64 + d, kEpiBias))) return rc;
+  // smooth_net (solution.py:180-190): only output 0 of the last Linear is used (solution.py:254)
+  {
+    const float* cur = S.rows.emb;
+    int ld = 128;
+    float* bufs[2] = {S.sA, S.sB};
+    for (int l = 0; l < N.n_smooth - 1; ++l) {
+      float* out = bufs[l & 1];
+      if ((rc = G(cur, ld, N.smooth_net[l], N.smooth_net[l].n_out, out, 64, kEpiBiasElu))) return rc;
+      cur = out, ld = 64;
+    }
+    if ((rc = G(cur, ld, N.smooth_net[N.n_smooth - 1], 1, S.sraw, 1, kEpiBias))) return rc;
+  }
+  // nn_module forward (solution.py:195-203), keeping ELU' of every hidden layer for the VJP
+  const int L = N.n_main;
+  {
+    const float* cur = S.rows.in;
+    int ld = 64 + d;
+    float* bufs[2] = {S.hA, S.hB};
+    for (int l = 0; l < L - 1; ++l) {
+      float* out = bufs[l & 1];
+      const int w = N.main[l].n_out;
+      if ((rc = G(cur, ld, N.main[l], w, out, w, kEpiBiasEluD, S.E[l], w))) return rc;
+      cur = out, ld = w;
+    }
+    if ((rc = G(cur, ld, N.main[L - 1], d, S.nout, d, kEpiBias))) return rc;
+  }
+  // VJP with cotangent x: c = x W_last; c = (c . ELU'(z_l)) W_l for l = L-2 .. 0; keep the x columns of the result
+  {
+    auto GB = [&](const float* A, int lda, int K_, const float* Bp, int ldb, int N_, const float* E, int lde, float* C,
+                  int ldc) {
+      GemmArgs g{};
+      g.A = A, g.lda = lda, g.B = Bp, g.ldb = ldb, g.b_kn = 1, g.E = E, g.lde = lde, g.C = C, g.ldc = ldc;
+      g.R = R, g.N = N_, g.K = K_, g.epi = E ? kEpiMulE : kEpiNone;
+      return gemm(g, st, launches);
+    };
+    float* bufs[2] = {S.hA, S.hB};
+    const int wl = N.main[L - 1].n_in;
+    if ((rc = GB(S.rows.in + 64, 64 + d, d, N.main[L - 1].W, wl, wl, S.E[L - 2], wl, bufs[0], wl))) return rc;
+    const float* cur = bufs[0];
+    int ld = wl, b = 1;
+    for (int l = L - 2; l >= 1; --l) {
+      const int win = N.main[l].n_in, wout = N.main[l].n_out;
+      if ((rc = GB(cur, ld, wout, N.main[l].W, win, win, S.E[l - 1], win, bufs[b], win))) return rc;
+      cur = bufs[b], ld = win, b ^= 1;
+    }
+    const int w0 = N.main[0].n_out;
+    if ((rc = GB(cur, ld, w0, N.main[0].W + 64, 64 + d, d, nullptr, 0, S.jtx, d))) return rc;
+  }
+  return DPI_OK;
+}
+
+}  // namespace
+
+int64_t hjb_scratch_floats(const PisDev& N, int d, int64_t rows) { return (rows + 1) * floats_per_row(N, d) + 64; }
+
+int64_t hjb_points_per_chunk(const PisDev& N, int d, int M_I, int64_t budget_bytes) {
+  const int64_t per_point = (int64_t)(M_I + 1) * floats_per_row(N, d) * (int64_t)sizeof(float);
+  int64_t pc = budget_bytes / per_point;
+  return pc < 1 ? 1 : pc;
+}
+
+int launch_hjb_paths(const ProblemDev& P, const PisDev& N, const float* tx, int64_t n, int M_I, uint64_t seed,
+                     int64_t base, const float* u_s, const float* zS, float bound, float* scratch,
+                     int64_t points_per_chunk, float* y, cudaStream_t st, int64_t* launches) {
+  const int d = P.nx, rpp = M_I + 1;
+  for (int64_t p0 = 0; p0 < n; p0 += points_per_chunk) {
+    const int64_t np = std::min<int64_t>(points_per_chunk, n - p0);
+    const int64_t R = np * rpp;
+    const Scratch S = carve(scratch, R + 1, N, d);
+    hjb_rows_kernel<<<(unsigned)((R + 1 + 7) / 8), 256, 0, st>>>(
+        P, tx + p0 * (1 + d), np, rpp, M_I, seed, base + p0, u_s ? u_s + p0 * M_I : nullptr,
+        zS ? zS + p0 * (int64_t)M_I * d : nullptr, N.phase, N.coeff, S.rows);
+    DPI_CUDA_CHECK(cudaGetLastError());
+    *launches += 1;
+    int rc = eval_rows(N, d, S, R, st, launches);
+    if (rc) return rc;
+    FinalArgs F{};
+    F.in = S.rows.in, F.nout = S.nout, F.jtx = S.jtx, F.sraw = S.sraw, F.sa = S.rows.sa, F.f = S.f, F.R = R;
+    hjb_final_kernel<<<(unsigned)((R + 7) / 8), 256, 0, st>>>(P, F);
+    DPI_CUDA_CHECK(cudaGetLastError());
+    hjb_reduce_kernel<<<(unsigned)np, 128, 0, st>>>(P, tx + p0 * (1 + d), M_I, S.f, S.rows.z, S.rows.sa, bound,
+                                                    y + p0 * (1 + d));
+    DPI_CUDA_CHECK(cudaGetLastError());
+    *launches += 2;
+  }
+  return DPI_OK;
+}
+
+int launch_hjb_eval(const ProblemDev& P, const PisDev& N, const float* tx, int64_t n, float* scratch,
+                    int64_t rows_per_chunk, float* u, float* du, cudaStream_t st, int64_t* launches) {
+  const int d = P.nx;
+  for (int64_t p0 = 0; p0 < n; p0 += rows_per_chunk) {
+    const int64_t R = std::min<int64_t>(rows_per_chunk, n - p0);
+    const Scratch S = carve(scratch, R + 1, N, d);
+    hjb_rows_kernel<<<(unsigned)((R + 1 + 7) / 8), 256, 0, st>>>(P, tx + p0 * (1 + d), R, 1, 0, 0, 0, nullptr, nullptr,
+                                                               N.phase, N.coeff, S.rows);
+    DPI_CUDA_CHECK(cudaGetLastError());
+    *launches += 1;
+    int rc = eval_rows(N, d, S, R, st, launches);
+    if (rc) return rc;
+    FinalArgs F{};
+    F.in = S.rows.in, F.nout = S.nout, F.jtx = S.jtx, F.sraw = S.sraw, F.sa = S.rows.sa, F.R = R;
+    F.u = u ? u + p0 : nullptr;
+    F.du = du ? du + p0 * d : nullptr;
+    hjb_final_kernel<<<(unsigned)((R + 7) / 8), 256, 0, st>>>(P, F);
+    DPI_CUDA_CHECK(cudaGetLastError());
+    *launches += 1;
+  }
+  return DPI_OK;
+}
+
+}  // namespace dpi

@@ -75,6 +75,25 @@ int launch_cha_tc_path(const ProblemDev& P, const TcNetDev& net, const float* tx
 // D[128x128] = A[128x128] . B[128x128]^T (fp32 row-major device buffers, rounded to bf16) through tcgen05
 int tc_umma_selftest(const float* A, const float* B, float* D, cudaStream_t st);
 
+// ---- HJB / PISGradNet, fp32 batched-GEMM pipeline (dpi_hjb.cu) -------------------------------------------
+// Weight pointers are the caller's torch-layout tensors (W [n_out, n_in] row-major), used in place.
+struct PisDev {
+  int n_main, n_t_encoder, n_smooth;
+  int hmax;  // widest nn_module hidden layer
+  dpi_linear main[DPI_MAX_LINEAR], t_encoder[DPI_MAX_LINEAR], smooth_net[DPI_MAX_LINEAR];
+  const float* phase;  // [64]
+  const float* coeff;  // [64]
+};
+int64_t hjb_scratch_floats(const PisDev& net, int d, int64_t rows);
+int64_t hjb_points_per_chunk(const PisDev& net, int d, int M_I, int64_t budget_bytes);
+// y += integral part (paths + baseline row per point through the network), then clip
+int launch_hjb_paths(const ProblemDev& P, const PisDev& net, const float* tx, int64_t n, int M_I, uint64_t seed,
+                     int64_t base, const float* u_s, const float* zS, float bound, float* scratch,
+                     int64_t points_per_chunk, float* y, cudaStream_t st, int64_t* launches);
+// u [n] and grad_x u [n, d] at the rows of tx (either may be null)
+int launch_hjb_eval(const ProblemDev& P, const PisDev& net, const float* tx, int64_t n, float* scratch,
+                    int64_t rows_per_chunk, float* u, float* du, cudaStream_t st, int64_t* launches);
+
 // y = clip(y + add, +-bound) elementwise helpers used by the Zero-network shortcuts
 int launch_finish_zero(const ProblemDev& P, const float* tx, int64_t n, float bound, float* y, cudaStream_t st);
 

@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 TOL_FP32 = 1e-4
 TOL_BF16 = 1e-2
 
-BUILT = [n for n in golden_names() if n.startswith("burgers") or n.startswith("gbm") or n == "hjb_100d_zero"]
+BUILT = golden_names()  # every fixture generated from the reference: Burgers / GBM+SDGD / HJB, MLP / PISGradNet / Zero
 
 
 def _engine(g):
@@ -96,6 +96,41 @@ def test_philox_labels_agree_with_oracle_statistically():
     err = (y[:, 1:] - y_ref[:, 1:])
     both = torch.cat([y[:, 1:], y_ref[:, 1:]])
     assert float(err.mean().abs()) < 5 * float(both.std()) / (n * eq.nx) ** 0.5 + 1e-3
+    e.close()
+
+
+def test_pisgradnet_value_and_gradient_match_oracle():
+    """dpi_net_eval on PISGradNet: u and the closed-form grad_x u (one VJP through nn_module) vs the fp64 oracle,
+    whose closed form is itself checked against autograd of the reference network in tests/test_oracle_golden.py."""
+    g = Golden("hjb_100d_pisgrad")
+    e = _engine(g)
+    gen = torch.Generator().manual_seed(3)
+    tx = torch.cat([torch.rand(37, 1, generator=gen, dtype=torch.float64) * 0.98 + 0.01,
+                    torch.randn(37, g.nx, generator=gen, dtype=torch.float64) * 1.5], dim=1)
+    u_ref, du_ref = g.net.value_and_grad_closed(tx, g.eq)
+    u, du = e.net_eval(tx, want_grad=True)
+    assert orc.rel_l2(u.double().cpu().view(-1, 1), u_ref) < 1e-5
+    assert orc.rel_l2(du.double().cpu(), du_ref) < 1e-5
+    e.close()
+
+
+def test_hjb_full_width_network_runs_chunked_and_is_shard_invariant():
+    """The shipped HJB shape (hidden 4 x 512, solution.py:195-203) through the batched-GEMM pipeline with Philox
+    draws: finite labels, independent of how the points are split across calls."""
+    from tests.gpu_util import engine_for
+    g = Golden("hjb_100d_pisgrad")
+    net = orc.make_pisgrad(g.nx, [512] * 4, T=g.T, seed=4, phase_scale=0.3)
+    e = engine_for(g.eq, net)
+    tx = e.sample_tx(12, seed=2)
+    y = e.label_gen(tx, 64, 200, seed=9)
+    assert torch.isfinite(y).all()
+    y_b = torch.cat([e.label_gen(tx[:5], 64, 200, seed=9), e.label_gen(tx[5:], 64, 200, seed=9, point_index_base=5)])
+    assert torch.equal(y, y_b)
+    # against the fp64 oracle on its own draws: the value column agrees within Monte Carlo error
+    gen = torch.Generator().manual_seed(0)
+    d = orc.draw(g.eq, 12, 64, 200, None, gen)
+    y_ref = orc.generate_with_gradients(g.eq, net, tx.double().cpu(), d, 64, 200)
+    assert orc.rel_l2(y[:, :1].double().cpu(), y_ref[:, :1]) < 5e-2
     e.close()
 
 
