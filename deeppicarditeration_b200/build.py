@@ -30,9 +30,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = []
     os.makedirs(os.path.join(PKG, "build"), exist_ok=True)
     procs = []
+    extra = os.environ.get("DPI_NVCC_EXTRA", "").split()
     for src in SOURCES:
         obj = os.path.join(PKG, "build", src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     log = []

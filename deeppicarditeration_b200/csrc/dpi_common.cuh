@@ -69,11 +69,14 @@ __device__ __forceinline__ uint4 philox_at(uint64_t seed, uint64_t point, uint32
 // uniform in the OPEN interval (0,1): (x>>8 + 0.5) * 2^-24
 __device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * 5.9604644775390625e-8f; }
 
-// Box-Muller on the MUFU pipe: 2 uniforms -> 2 normals (lg2, sqrt, sin, cos).
+// Box-Muller on the MUFU pipe: 2 x 32 random bits -> 2 normals (lg2, sqrt, sin, cos), 12 instructions.
+// Radius from u = (a + 0.5) 2^-32 in (0, 1] (a is rounded to 24 bits by the int->float conversion; u = 1 gives r = 0),
+// angle 2 pi b 2^-32.
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
-  const float r = sqrtf(-1.3862943611198906f * __log2f(u01(a)));  // sqrt(-2 ln u) = sqrt(-2 ln2 log2 u)
+  const float u = fmaf((float)a, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+  const float r = sqrtf(-1.3862943611198906f * __log2f(u));  // sqrt(-2 ln u) = sqrt(-2 ln2 log2 u)
   float s, c;
-  __sincosf(kTwoPi * u01(b), &s, &c);
+  __sincosf((float)b * 1.4629180792671596e-9f, &s, &c);  // 2 pi / 2^32
   z0 = r * c;
   z1 = r * s;
 }

@@ -67,8 +67,8 @@ int tc_pack_network(const dpi_network& net, const ProblemDev& P, const MlpDev& M
                     TcNetDev* out, bool* ready, int64_t* launches, cudaStream_t st);
 int64_t tc_units_per_point(int M_I);
 constexpr int64_t kTcPartGFloatsPerUnit = 16 * 128;
-constexpr int64_t kTcPartFFloatsPerUnit = 4;
-// partG [n*units][16][128], partF [n*units][4]: scratch for the unit partial sums
+constexpr int64_t kTcPartFFloatsPerUnit = 8;  // [slot][lane quarter]
+// partG [n*units][16][128], partF [n*units][8]: scratch for the unit partial sums
 int launch_cha_tc_path(const ProblemDev& P, const TcNetDev& net, const float* tx, int64_t n, int M_I, uint64_t seed,
                        int64_t base, const float* u_s, const float* zS, const float* fb, const float* c0, float bound,
                        float* partG, float* partF, float* y, cudaStream_t st);

@@ -1,27 +1,28 @@
 // bf16 tcgen05 integral estimator for the Burgers-type equation `Cha` (u_k = MLP [1+d,128,128,128,128,1], d <= 128).
 //
 // Same mathematics as dpi_mlp_simt.cu (picard/data.py:471-527,350-366,1226-1325; equations.py:297-302;
-// solution.py:123-135) with the three hidden 128x128 GEMMs (value and tangent) and the first-layer GEMM on the
+// solution.py:123-135) with the first-layer GEMM and the three hidden 128x128 GEMMs (value and tangent) on the
 // 5th-generation tensor cores:
 //
-//   * one persistent CTA per SM; the four weight matrices live in shared memory for the whole kernel as bf16
-//     K-major SWIZZLE_128B operand images (4 x 32 KB, fetched once with TMA bulk copies);
-//   * a work unit is (collocation point, group of 8 tiles); a tile is 128 MC samples = 128 TMEM lanes;
-//   * producer warpgroups (2 x 4 warps, alternating tiles) draw the Brownian increments with Philox4x32-10 +
-//     Box-Muller in registers, round them to bf16 and write the [128 x d] A-operand tile; they KEEP their
-//     increments in registers and, once the tile's Bismut coefficients are known, accumulate
-//     G_j += coef_m Z_mj there, so increments never leave the SM;
-//   * one thread issues tcgen05.mma: layer 1 (Z . W_x^T) into accumulator set 0, hidden layers alternate between the
-//     two TMEM accumulator sets (value 128 cols + tangent 128 cols each = all 512 columns);
-//   * 8 epilogue warps (TMEM lane quarter x column half) read the accumulators with tcgen05.ld, apply
-//     bias/ELU/ELU' in fp32, and write the next layer's bf16 A operands (value rows and tangent rows) straight
-//     into the swizzled shared-memory layout.  They signal the MMA thread per 32-column K chunk, so the next
-//     layer's MMAs run underneath the remaining epilogue work of the current layer;
-//   * the last layer is a dot product in the epilogue (fp32), followed by f, the Bismut coefficient and the
-//     value-label partial sum.
+//   * one persistent CTA per SM.  A work unit is (collocation point, group of 8 tiles); a tile is 128 MC samples =
+//     128 TMEM lanes.  TWO tiles are in flight per CTA, one per "slot": while the epilogue warps of one slot turn a
+//     layer's accumulators into the next layer's operands, the tensor pipe runs the other slot's layer;
+//   * shared memory: the hidden weights W2..W4 stay resident as bf16 K-major SWIZZLE_128B operand images (3 x 32 KB);
+//     each slot owns an hV and an hT buffer (value rows / tangent rows of the next A operand, 2 x 32 KB).  For layer 1
+//     the slot's hV holds the increments Z (A operand) and its hT receives the W1 image (B operand) by TMA bulk copy
+//     from L2 for every tile -- that is what makes room for the second tile in 227 KB;
+//   * TMEM: 512 columns = 2 slots x (value 128 + tangent 128) fp32 accumulator columns;
+//   * 8 producer warps draw the Brownian increments with Philox4x32-10 + Box-Muller in registers, round them to bf16,
+//     store the [128 x d] A-operand tile when the slot frees up, and KEEP them in registers: once the tile's Bismut
+//     coefficients are known they accumulate G_j += coef_m Z_mj there, so increments never leave the SM;
+//   * one thread issues tcgen05.mma for both slots in a fixed round-robin order, one thread issues the TMA copies;
+//   * 4 epilogue warps per slot (thread = sample row) read the accumulators with tcgen05.ld, apply bias/ELU/ELU' in
+//     fp32 and write the next layer's bf16 A operands straight into the swizzled shared-memory layout; the last layer
+//     is a dot product in the epilogue (fp32), followed by f, the Bismut coefficient and the value-label partial sum.
 //
-// Partial sums go to a small scratch ([unit][producer group][row class][128]) and a finish kernel adds them
-// in a fixed order, so labels are bitwise independent of the launch geometry and of how points are sharded.
+// Partial sums go to a small scratch ([unit][row class][128], [unit][slot][lane quarter]) and a finish kernel adds
+// them in a fixed order; the slot of a tile is its index inside the unit, so labels are bitwise independent of the
+// launch geometry and of how points are sharded.
 #include <cstdio>
 #include <vector>
 
@@ -33,28 +34,37 @@ namespace dpi {
 namespace {
 using namespace tc;
 
-// 8 epilogue warps + 8 producer warps + one warpgroup whose first warp issues the MMAs.  The register file is
-// per SM sub-partition (16K registers, warp w lives on sub-partition w % 4): five warps per sub-partition cap the
-// launch at 96 registers/thread, so the MMA warpgroup hands its registers back (setmaxnreg.dec 32) and the sixteen
-// worker warps grow to 112 (4 x 112 + 32 = 480 <= 512 per lane).
+// ---- roles ---------------------------------------------------------------------------------------------------
+// warps 0-3: epilogue of tile slot 0, warps 4-7: epilogue of tile slot 1 (warp & 3 = TMEM lane quarter),
+// warps 8-15: increment producers, warp 16: MMA issuer (one thread), warp 17: TMA issuer (one thread).
+// The register file is per SM sub-partition (512 registers per lane, warp w lives on sub-partition w % 4), so each
+// sub-partition holds one warp of every warpgroup.  setmaxnreg only moves registers inside the CTA's own pool (what
+// its warps have released), so the re-split must balance against the launch allocation of 96 per thread:
+// MMA/TMA warpgroup 96 -> 32, epilogue 96 -> 88, producers 96 -> 136 (2 x 88 + 2 x 136 + 32 = 480 = 5 x 96).
 constexpr int kTcThreads = 640;
-constexpr int kMmaWarp = 16;
-constexpr int kWorkerRegs = 112, kMmaRegs = 32;
+constexpr int kProdWarp0 = 8, kMmaWarp = 16, kTmaWarp = 17;
+constexpr int kEpiRegs = 88, kProdRegs = 136, kMmaRegs = 32;
 constexpr float kLog2e = 1.4426950408889634f;
 
 // shared memory map (dynamic, 1024-byte aligned)
-constexpr uint32_t kOffW = 0;                          // 4 x 32 KB weight images
-constexpr uint32_t kOffHV = 4 * kOperandBytes;         // value rows of the next layer's A operand
-constexpr uint32_t kOffHT = kOffHV + kOperandBytes;    // tangent rows
-constexpr uint32_t kOffZ = kOffHT + kOperandBytes;     // increments (A operand of layer 1)
-constexpr uint32_t kOffBars = kOffZ + kOperandBytes;   // 16 mbarriers
+constexpr uint32_t kOffW = 0;                              // W2, W3, W4 operand images (3 x 32 KB), resident
+constexpr uint32_t kOffSlot = 3 * kOperandBytes;           // tile slot s at + s * 64 KB: hV (32 KB) | hT (32 KB)
+constexpr uint32_t kSlotBytes = 2 * kOperandBytes;
+constexpr uint32_t kOffC0 = kOffSlot + 2 * kSlotBytes;     // [2 slots][128] first-layer constant of the slot's point
+constexpr uint32_t kOffCoef = kOffC0 + 1024;               // [3][128] Bismut coefficients (ring over tiles)
+constexpr uint32_t kOffBars = kOffCoef + 1536;             // 16 mbarriers
 constexpr uint32_t kOffTmemPtr = kOffBars + 128;
-constexpr uint32_t kOffC0 = kOffBars + 160;            // [128] per-point first-layer constant
-constexpr uint32_t kOffCoef = kOffC0 + 512;            // [2][128] Bismut coefficients (one buffer per producer group)
-constexpr uint32_t kOffXch = kOffCoef + 1024;          // [128] float2: output-layer partial sums of column half 1
-constexpr uint32_t kTcSmemBytes = kOffXch + 1024;      // 232,096 B <= 232,448 B
+constexpr uint32_t kTcSmemBytes = kOffTmemPtr + 16;        // 232,080 B <= 232,448 B
 
-enum Bar : int { kBarW = 0, kBarZFull = 1, kBarZEmpty = 2, kBarAcc0 = 3, kBarAcc1 = 4, kBarReady0 = 5, kBarCoef0 = 9 };
+enum Bar : int {
+  kBarW = 0,         // W2..W4 landed (TMA)
+  kBarW1Full = 1,    // [2] W1 image landed in the slot's hT buffer (TMA, once per tile)
+  kBarZFull = 3,     // [2] increments stored in the slot's hV buffer (8 producer warps)
+  kBarSlotFree = 5,  // [2] layer-4 MMAs of the slot's tile have completed: hV / hT may be overwritten (tcgen05.commit)
+  kBarAccFull = 7,   // [2] a layer's accumulators are complete (tcgen05.commit, 4 per tile)
+  kBarAReady = 9,    // [2] an epilogue pass is done: next A operand written, accumulators read (4 epilogue warps)
+  kBarCoef = 11      // [3] Bismut coefficients of a tile written (4 epilogue warps)
+};
 
 struct TcArgs {
   const void* W;  // 4 consecutive operand images: W1 (x columns), W2, W3, W4
@@ -67,13 +77,12 @@ struct TcArgs {
   const float* fb;  // [n] control variate f(t,x)
   const float* c0;  // [n][128]
   float* partG;     // [units][16][128]
-  float* partF;     // [units][4]
+  float* partF;     // [units][8]
   int M_I;
   int units_per_point;
   int tiles_per_point;
   int ksteps1;  // ceil(d/16)
   int nq;       // ceil(d/4) quads of dims
-  int cls;      // row classes of the producer mapping
 };
 
 // All activations are carried scaled by log2(e): with z' = log2e z the ELU pair needs one op less per element,
@@ -82,73 +91,112 @@ struct TcArgs {
 // output weights (x ln2) change -- the hidden weight matrices are used as they are (TcConsts holds the scaled
 // vectors; see tc_pack_network).
 //
-// One hidden-layer epilogue for this warp's 64 columns: TMEM -> bias/ELU/ELU' -> bf16 A operands of the next layer.
-// FIRST: z' = c0' + s' w_t + a' acc, tangent' = e * wsum' (constant first-layer tangent);  else z' = acc + b'[layer].
-template <bool FIRST>
-__device__ __forceinline__ void epi_hidden(uint8_t* smem, uint32_t sbase, const TcConsts& C, uint32_t tacc, int hf,
-                                           int lane, uint32_t rowbase, uint32_t rx, int layer, float s, float a) {
-  const float* c0_s = reinterpret_cast<const float*>(smem + kOffC0);
+// One epilogue pass over the 128 accumulator columns of this thread's row (TMEM lane), 8 columns at a time with the
+// next chunk's tcgen05.ld in flight under the arithmetic of the current one.  Column indices are compile-time, so
+// the per-column constants are read straight from the constant bank as instruction operands.
+//   kPassFirst : z' = c0' + s' w_t' + a' acc, tangent' = e wsum' (constant first-layer tangent)  -> bf16 A operands
+//   kPassHidden: z' = acc + b'[layer], tangent' = e acc_t                                          -> bf16 A operands
+//   kPassOut   : same ELU, then the output layer as fp32 dot products with w_out: pu = w.h, pD = w.(e acc_t)
+enum : int { kPassFirst = 0, kPassHidden = 1, kPassOut = 2 };
+
+template <int MODE>
+__device__ __forceinline__ void epi_pass(const TcConsts& C, uint32_t tacc, uint8_t* hv_row, uint8_t* ht_row,
+                                         uint32_t rx, const float* c0_s, int layer, float s2, float a2, float& pu,
+                                         float& pD) {
+  uint32_t v[2][8], tv[2][8];
+  tmem_ld8(tacc, v[0]);
+  if (MODE != kPassFirst) tmem_ld8(tacc + 128u, tv[0]);
   const float* bias = C.b[layer];
-#pragma unroll 1
-  for (int jj = 0; jj < 2; ++jj) {
-    const int col0 = hf * 64 + jj * 32;
-    uint32_t v[32], tv[32];
-    tmem_ld32(tacc + col0, v);
-    if (!FIRST) tmem_ld32(tacc + 128 + col0, tv);
+#pragma unroll
+  for (int ch = 0; ch < 16; ++ch) {
     tmem_ld_wait();
-    uint8_t* const hv_row = smem + kOffHV + rowbase;
-    uint8_t* const ht_row = smem + kOffHT + rowbase;
+    if (ch + 1 < 16) {
+      tmem_ld8(tacc + (uint32_t)((ch + 1) * 8), v[(ch + 1) & 1]);
+      if (MODE != kPassFirst) tmem_ld8(tacc + 128u + (uint32_t)((ch + 1) * 8), tv[(ch + 1) & 1]);
+    }
+    const uint32_t* vv = v[ch & 1];
+    const uint32_t* tt = tv[ch & 1];
+    uint32_t hv[4], ht[4];
 #pragma unroll
-    for (int c8 = 0; c8 < 32; c8 += 8) {
-      uint32_t hv[4], ht[4];
+    for (int k4 = 0; k4 < 8; k4 += 4) {
+      const int col = ch * 8 + k4;
+      float zb[4], tg[4];
+      if (MODE == kPassFirst) {
+        const float4 c0 = *reinterpret_cast<const float4*>(&c0_s[col]);
+        zb[0] = fmaf(a2, __uint_as_float(vv[k4 + 0]), fmaf(s2, C.wt[col + 0], c0.x));
+        zb[1] = fmaf(a2, __uint_as_float(vv[k4 + 1]), fmaf(s2, C.wt[col + 1], c0.y));
+        zb[2] = fmaf(a2, __uint_as_float(vv[k4 + 2]), fmaf(s2, C.wt[col + 2], c0.z));
+        zb[3] = fmaf(a2, __uint_as_float(vv[k4 + 3]), fmaf(s2, C.wt[col + 3], c0.w));
 #pragma unroll
-      for (int k4 = 0; k4 < 8; k4 += 4) {
-        const int col = col0 + c8 + k4;
-        float zb[4], tg[4];
-        if (FIRST) {
-          const float4 w = *reinterpret_cast<const float4*>(&C.wt[col]);
-          const float4 ws = *reinterpret_cast<const float4*>(&C.wsum[col]);
-          const float4 c0 = *reinterpret_cast<const float4*>(&c0_s[col]);
-          zb[0] = fmaf(a, __uint_as_float(v[c8 + k4 + 0]), fmaf(s, w.x, c0.x));
-          zb[1] = fmaf(a, __uint_as_float(v[c8 + k4 + 1]), fmaf(s, w.y, c0.y));
-          zb[2] = fmaf(a, __uint_as_float(v[c8 + k4 + 2]), fmaf(s, w.z, c0.z));
-          zb[3] = fmaf(a, __uint_as_float(v[c8 + k4 + 3]), fmaf(s, w.w, c0.w));
-          tg[0] = ws.x, tg[1] = ws.y, tg[2] = ws.z, tg[3] = ws.w;
-        } else {
+        for (int i = 0; i < 4; ++i) tg[i] = C.wsum[col + i];
+      } else {
+        if (MODE == kPassHidden) {
           const float4 b = *reinterpret_cast<const float4*>(&bias[col]);
-          zb[0] = __uint_as_float(v[c8 + k4 + 0]) + b.x;
-          zb[1] = __uint_as_float(v[c8 + k4 + 1]) + b.y;
-          zb[2] = __uint_as_float(v[c8 + k4 + 2]) + b.z;
-          zb[3] = __uint_as_float(v[c8 + k4 + 3]) + b.w;
+          zb[0] = __uint_as_float(vv[k4 + 0]) + b.x;
+          zb[1] = __uint_as_float(vv[k4 + 1]) + b.y;
+          zb[2] = __uint_as_float(vv[k4 + 2]) + b.z;
+          zb[3] = __uint_as_float(vv[k4 + 3]) + b.w;
+        } else {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) tg[i] = __uint_as_float(tv[c8 + k4 + i]);
+          for (int i = 0; i < 4; ++i) zb[i] = __uint_as_float(vv[k4 + i]) + C.b[2][col + i];
         }
-        float h[4], dh[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) tg[i] = __uint_as_float(tt[k4 + i]);
+      }
+      float h[4], dh[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float e = exp2f(fminf(zb[i], 0.f));
+        h[i] = fmaxf(zb[i], fmaf(e, kLog2e, -kLog2e));
+        dh[i] = e * tg[i];
+      }
+      if (MODE == kPassOut) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float e = exp2f(fminf(zb[i], 0.f));
-          h[i] = fmaxf(zb[i], fmaf(e, kLog2e, -kLog2e));
-          dh[i] = e * tg[i];
+          pu = fmaf(C.wout[col + i], h[i], pu);
+          pD = fmaf(C.wout[col + i], dh[i], pD);
         }
+      } else {
         hv[k4 / 2 + 0] = pack_bf16x2(h[0], h[1]);
         hv[k4 / 2 + 1] = pack_bf16x2(h[2], h[3]);
         ht[k4 / 2 + 0] = pack_bf16x2(dh[0], dh[1]);
         ht[k4 / 2 + 1] = pack_bf16x2(dh[2], dh[3]);
       }
-      // 16-byte chunk (jj*4 + c8/8) of this row's 128-byte line in K panel hf, XOR-swizzled with (row & 7)
-      const uint32_t off = ((uint32_t)((jj * 4 + c8 / 8) << 4)) ^ rx;
+    }
+    if (MODE != kPassOut) {
+      // 16-byte chunk ch of this row: K panel (ch >> 3), chunk index XOR-swizzled with (row & 7)
+      const uint32_t off = (uint32_t)(ch >> 3) * kPanelBytes + (((uint32_t)(ch & 7) << 4) ^ rx);
       *reinterpret_cast<uint4*>(hv_row + off) = make_uint4(hv[0], hv[1], hv[2], hv[3]);
       *reinterpret_cast<uint4*>(ht_row + off) = make_uint4(ht[0], ht[1], ht[2], ht[3]);
     }
-    // this warp's 32 K-columns of the next A operand are written: publish them to the MMA thread
-    tc_fence_before();
-    fence_proxy_async();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(sbase + kOffBars + 8u * (kBarReady0 + hf * 2 + jj));
   }
 }
 
-template <int ITEMS, bool DET>
+// flat cursor over this CTA's tiles: unit u = blockIdx.x + k gridDim.x, tile tl inside the unit; slot = tl & 1, so
+// the slot of a tile (and with it the order of every floating-point sum) does not depend on the launch geometry
+struct TileCursor {
+  int64_t u;
+  int tl, tiles;
+  __device__ __forceinline__ void init(const TcArgs& A) {
+    u = blockIdx.x;
+    tl = 0;
+    tiles = (u < A.n_units) ? tiles_of(A, u) : 0;
+  }
+  __device__ __forceinline__ static int tiles_of(const TcArgs& A, int64_t uu) {
+    const int g = (int)(uu % A.units_per_point);
+    return min(kTcGroupTiles, A.tiles_per_point - g * kTcGroupTiles);
+  }
+  __device__ __forceinline__ bool valid(const TcArgs& A) const { return u < A.n_units; }
+  __device__ __forceinline__ void next(const TcArgs& A) {
+    if (++tl == tiles) {
+      u += gridDim.x;
+      tl = 0;
+      tiles = (u < A.n_units) ? tiles_of(A, u) : 0;
+    }
+  }
+};
+
+template <int ITEMS, int CLS, bool DET>
 __global__ void __launch_bounds__(kTcThreads, 1)
 cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcConsts C,
               const __grid_constant__ TcArgs A) {
@@ -156,7 +204,7 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d = P.nx;
-  const int UP = A.units_per_point, TP = A.tiles_per_point, M_I = A.M_I;
+  const int UP = A.units_per_point, M_I = A.M_I;
   auto bar = [&](int i) -> uint32_t { return sbase + kOffBars + 8u * (uint32_t)i; };
 
   if (threadIdx.x == 0) {
@@ -165,18 +213,20 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
       __trap();
     }
     mbar_init(bar(kBarW), 1);
-    mbar_init(bar(kBarZFull), 8);   // the 8 producer warps
-    mbar_init(bar(kBarZEmpty), 1);  // tcgen05.commit
-    mbar_init(bar(kBarAcc0), 1);
-    mbar_init(bar(kBarAcc1), 1);
-    for (int c = 0; c < 4; ++c) mbar_init(bar(kBarReady0 + c), 4);  // 4 epilogue warps per K chunk
-    mbar_init(bar(kBarCoef0), 4);
-    mbar_init(bar(kBarCoef0 + 1), 4);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar(kBarW1Full + s), 1);
+      mbar_init(bar(kBarZFull + s), 8);
+      mbar_init(bar(kBarSlotFree + s), 1);
+      mbar_init(bar(kBarAccFull + s), 1);
+      mbar_init(bar(kBarAReady + s), 4);
+    }
+    for (int b = 0; b < 3; ++b) mbar_init(bar(kBarCoef + b), 4);
     fence_barrier_init();
   }
-  // the padded K columns of the increment tile must read as zero
-  for (int i = threadIdx.x; i < kOperandBytes / 16; i += kTcThreads)
-    reinterpret_cast<uint4*>(smem + kOffZ)[i] = make_uint4(0u, 0u, 0u, 0u);
+  // The layer-1 MMA reads K = 16 ceil(d/16) columns of the slot's hV buffer; the producers write the first d of them
+  // and the padded weight columns are zero, so whatever the buffer holds there only has to be finite: zero it once.
+  for (int i = threadIdx.x; i < (int)(2 * kSlotBytes / 16); i += kTcThreads)
+    reinterpret_cast<uint4*>(smem + kOffSlot)[i] = make_uint4(0u, 0u, 0u, 0u);
   fence_proxy_async();
   if (warp == kMmaWarp) tmem_alloc(sbase + kOffTmemPtr, 512);
   tc_fence_before();
@@ -185,198 +235,220 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + kOffTmemPtr);
 
   if (warp >= kMmaWarp) {
-    // =================================== MMA issuer (one thread) ===================================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kMmaRegs));
     if (warp == kMmaWarp && lane == 0) {
-      mbar_arrive_expect_tx(bar(kBarW), 4u * kOperandBytes);
-      for (int i = 0; i < 16; ++i)
-        bulk_g2s(sbase + kOffW + (uint32_t)i * 8192u, reinterpret_cast<const uint8_t*>(A.W) + (size_t)i * 8192, 8192u,
-                 bar(kBarW));
+      // =================================== MMA issuer ===================================
       mbar_wait(bar(kBarW), 0, 0);
       constexpr uint32_t idesc = make_idesc_bf16(128, 128);
-      // descriptors differ only in the 14-bit start-address field: +2 per UMMA_K step inside a K panel (32 B),
-      // +1024 per panel (16 KB).  Kept as base + small offsets so the loop needs few registers (this thread runs
-      // with 32 registers and there is next to no L1 left for spills).
-      const uint64_t dZ = make_desc_sw128(sbase + kOffZ), dV = make_desc_sw128(sbase + kOffHV),
-                     dT = make_desc_sw128(sbase + kOffHT), dW = make_desc_sw128(sbase + kOffW);
-      uint32_t it = 0, ph_ready = 0;
-      for (int64_t u = blockIdx.x; u < A.n_units; u += gridDim.x) {
-        const int g = (int)(u % UP);
-        const int tiles = min(kTcGroupTiles, TP - g * kTcGroupTiles);
-        for (int tl = 0; tl < tiles; ++tl, ++it) {
-          // layer 1: acc set 0 (value columns) = Z . W_x^T.  Set 0 is free: the chunks of layer 4 of the previous
-          // tile were published only after every epilogue warp had finished reading set 0 (layer 3).
-          mbar_wait(bar(kBarZFull), it & 1u, 1);
+      TileCursor cur;
+      cur.init(A);
+      int lay0 = 0, lay1 = 0, slt0 = 0, slt1 = 0;  // two in-flight tiles: next layer to issue (0 = none) and slot
+      uint32_t ph_z = 0, ph_w1 = 0, ph_ar = 0, used = 0;  // bit s = slot s
+      auto issue = [&](int s, int l) {
+        const uint32_t acc = tmem + (uint32_t)s * 256u;
+        const uint32_t slot = sbase + kOffSlot + (uint32_t)s * kSlotBytes;
+        const uint64_t dV = make_desc_sw128(slot), dT = make_desc_sw128(slot + kOperandBytes);
+        const uint32_t bit = 1u << s;
+        if (l == 1) {
+          // accumulators free (output pass of the slot's previous tile done), increments stored, W1 landed in hT
+          if (used & bit) {
+            mbar_wait(bar(kBarAReady + s), (ph_ar >> s) & 1u, 10);
+            ph_ar ^= bit;
+          }
+          used |= bit;
+          mbar_wait(bar(kBarZFull + s), (ph_z >> s) & 1u, 11);
+          ph_z ^= bit;
+          mbar_wait(bar(kBarW1Full + s), (ph_w1 >> s) & 1u, 12);
+          ph_w1 ^= bit;
           tc_fence_after();
 #pragma unroll 1
           for (int ks = 0; ks < A.ksteps1; ++ks) {
             const uint64_t o = (uint64_t)((ks >> 2) * 1024 + (ks & 3) * 2);
-            umma_bf16(tmem, dZ + o, dW + o, idesc, ks > 0);
+            umma_bf16(acc, dV + o, dT + o, idesc, ks > 0);
           }
-          tc_commit(bar(kBarZEmpty));
-          tc_commit(bar(kBarAcc0));
-          // hidden layers 2..4: weights image l, accumulator set (l & 1); K chunks in the order 0,2,1,3 (chunk 0
-          // first: its completion implies every epilogue warp is past the previous tile's output layer)
+          tc_commit(bar(kBarAccFull + s));
+        } else {
+          mbar_wait(bar(kBarAReady + s), (ph_ar >> s) & 1u, 13);
+          ph_ar ^= bit;
+          tc_fence_after();
+          const uint64_t dW = make_desc_sw128(sbase + kOffW + (uint32_t)(l - 2) * kOperandBytes);
 #pragma unroll 1
-          for (int l = 1; l <= 3; ++l) {
-            const uint32_t acc = tmem + (uint32_t)(l & 1) * 256u;
-            const uint64_t dWl = dW + (uint64_t)(l * (kOperandBytes >> 4));
-            uint32_t accum = 0;
-#pragma unroll 1
-            for (int ci = 0; ci < 4; ++ci) {
-              const int c = (ci & 1) * 2 + (ci >> 1);
-              mbar_wait(bar(kBarReady0 + c), ph_ready, 10 + c);
-              tc_fence_after();
-#pragma unroll
-              for (int kk = 0; kk < 2; ++kk) {
-                const int ks = 2 * c + kk;
-                const uint64_t o = (uint64_t)((ks >> 2) * 1024 + (ks & 3) * 2);
-                umma_bf16(acc, dV + o, dWl + o, idesc, accum);
-                umma_bf16(acc + 128u, dT + o, dWl + o, idesc, accum);
-                accum = 1;
-              }
-            }
-            ph_ready ^= 1u;
-            tc_commit(bar(kBarAcc0 + (l & 1)));
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t o = (uint64_t)((ks >> 2) * 1024 + (ks & 3) * 2);
+            umma_bf16(acc, dV + o, dW + o, idesc, ks > 0);
+            umma_bf16(acc + 128u, dT + o, dW + o, idesc, ks > 0);
           }
+          tc_commit(bar(kBarAccFull + s));
+          if (l == 4) tc_commit(bar(kBarSlotFree + s));
         }
+      };
+      for (;;) {
+        if (lay0 == 0 && cur.valid(A) && (lay1 == 0 || slt1 != (cur.tl & 1))) {
+          slt0 = cur.tl & 1, lay0 = 1;
+          cur.next(A);
+        }
+        if (lay1 == 0 && cur.valid(A) && (lay0 == 0 || slt0 != (cur.tl & 1))) {
+          slt1 = cur.tl & 1, lay1 = 1;
+          cur.next(A);
+        }
+        if (lay0 == 0 && lay1 == 0) break;
+        if (lay0) {
+          issue(slt0, lay0);
+          lay0 = (lay0 == 4) ? 0 : lay0 + 1;
+        }
+        if (lay1) {
+          issue(slt1, lay1);
+          lay1 = (lay1 == 4) ? 0 : lay1 + 1;
+        }
+      }
+    } else if (warp == kTmaWarp && lane == 0) {
+      // =================================== TMA issuer ===================================
+      const uint8_t* Wg = reinterpret_cast<const uint8_t*>(A.W);
+      mbar_arrive_expect_tx(bar(kBarW), 3u * kOperandBytes);
+      for (int i = 0; i < 12; ++i)
+        bulk_g2s(sbase + kOffW + (uint32_t)i * 8192u, Wg + kOperandBytes + (size_t)i * 8192, 8192u, bar(kBarW));
+      const int n_chunks = (d > 64) ? 4 : 2;  // K panels of the W1 image that layer 1 reads (16 KB each)
+      uint32_t ph_free = 0, used = 0;
+      TileCursor cur;
+      for (cur.init(A); cur.valid(A); cur.next(A)) {
+        const int s = cur.tl & 1;
+        const uint32_t bit = 1u << s;
+        if (used & bit) {
+          mbar_wait(bar(kBarSlotFree + s), (ph_free >> s) & 1u, 20);
+          ph_free ^= bit;
+        }
+        used |= bit;
+        const uint32_t dst = sbase + kOffSlot + (uint32_t)s * kSlotBytes + kOperandBytes;
+        mbar_arrive_expect_tx(bar(kBarW1Full + s), (uint32_t)n_chunks * 8192u);
+        for (int i = 0; i < n_chunks; ++i) bulk_g2s(dst + (uint32_t)i * 8192u, Wg + (size_t)i * 8192, 8192u, bar(kBarW1Full + s));
       }
     }
     __syncwarp();
-  } else if (warp < 8) {
+  } else if (warp < kProdWarp0) {
     // =================================== epilogue warps ===================================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kWorkerRegs));
-    const int q = warp & 3, hf = warp >> 2;
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
+    const int slot = warp >> 2, q = warp & 3;
     const int r = q * 32 + lane;
-    const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
-    const uint32_t rowbase = (uint32_t)hf * kPanelBytes + (uint32_t)r * 128u, rx = (uint32_t)(r & 7) << 4;
-    float* c0_s = reinterpret_cast<float*>(smem + kOffC0);
+    const uint32_t tacc = tmem + (uint32_t)slot * 256u + ((uint32_t)(q * 32) << 16);
+    uint8_t* const hv_row = smem + kOffSlot + (uint32_t)slot * kSlotBytes + (uint32_t)r * 128u;
+    uint8_t* const ht_row = hv_row + kOperandBytes;
+    const uint32_t rx = (uint32_t)(r & 7) << 4;
+    float* c0_s = reinterpret_cast<float*>(smem + kOffC0) + slot * 128;
     float* coef_s = reinterpret_cast<float*>(smem + kOffCoef);
-    float2* xch = reinterpret_cast<float2*>(smem + kOffXch);
-    uint32_t ph0 = 0, ph1 = 0, it = 0;
+    const uint32_t b_acc = bar(kBarAccFull + slot), b_ar = bar(kBarAReady + slot);
+    uint32_t ph_acc = 0, j = 0;
+    int64_t c0_point = -1;
     for (int64_t u = blockIdx.x; u < A.n_units; u += gridDim.x) {
       const int64_t p = u / UP;
       const int g = (int)(u % UP);
-      const int tiles = min(kTcGroupTiles, TP - g * kTcGroupTiles);
-      const float t = __ldg(A.tx + p * (int64_t)(1 + d));
-      const float dT = P.T - t;
-      const float fbp = __ldg(A.fb + p);
-      const uint64_t gp = (uint64_t)(A.point_base + p);
-      named_bar_sync(1, 256);  // everyone is done with the previous point's c0
-      if (threadIdx.x < 128) c0_s[threadIdx.x] = kLog2e * __ldg(A.c0 + p * 128 + threadIdx.x);
-      named_bar_sync(1, 256);
+      const int tiles = min(kTcGroupTiles, A.tiles_per_point - g * kTcGroupTiles);
       float fsum = 0.f;
-      for (int tl = 0; tl < tiles; ++tl, ++it) {
+      for (int tl = 0; tl < tiles; ++tl, ++j) {
+        if ((tl & 1) != slot) continue;
+        const float t = __ldg(A.tx + p * (int64_t)(1 + d));
+        const float dT = P.T - t;
+        const float fbp = __ldg(A.fb + p);
+        if (p != c0_point) {
+          named_bar_sync(1 + slot, 128);  // every warp of the slot is past the first pass of the previous point
+          c0_s[r] = kLog2e * __ldg(A.c0 + p * 128 + r);
+          named_bar_sync(1 + slot, 128);
+          c0_point = p;
+        }
         const int m = (g * kTcGroupTiles + tl) * 128 + r;
         const bool valid = m < M_I;
         float uu = 0.5f;
-        if (valid) uu = DET ? __ldg(A.u_s + p * M_I + m) : u01(philox_at(A.seed, gp, kStreamS, (uint32_t)m, 0u).x);
+        if (valid)
+          uu = DET ? __ldg(A.u_s + p * M_I + m)
+                   : u01(philox_at(A.seed, (uint64_t)(A.point_base + p), kStreamS, (uint32_t)m, 0u).x);
         const float a = sqrtf(uu * dT) * P.sigma;
         const float s2 = (uu * dT + t) * kLog2e, a2 = a * kLog2e;
-
-        mbar_wait(bar(kBarAcc0), ph0, 20);
-        ph0 ^= 1u;
-        tc_fence_after();
-        epi_hidden<true>(smem, sbase, C, tlane, hf, lane, rowbase, rx, 0, s2, a2);
-#pragma unroll 1
-        for (int l = 0; l < 2; ++l) {  // hidden GEMM layers 2 and 3: accumulator sets 1 and 0
-          if (l == 0) {
-            mbar_wait(bar(kBarAcc1), ph1, 21);
-            ph1 ^= 1u;
-          } else {
-            mbar_wait(bar(kBarAcc0), ph0, 22);
-            ph0 ^= 1u;
-          }
-          tc_fence_after();
-          epi_hidden<false>(smem, sbase, C, tlane + (l == 0 ? 256u : 0u), hf, lane, rowbase, rx, l, 0.f, 0.f);
-        }
-
-        // ---- output layer: u = w_out . h4 + b_out, D = w_out . h4' over this warp's 64 columns ----
-        mbar_wait(bar(kBarAcc1), ph1, 23);
-        ph1 ^= 1u;
-        tc_fence_after();
         float pu = 0.f, pD = 0.f;
-#pragma unroll 1
-        for (int jj = 0; jj < 2; ++jj) {
-          const int col0 = hf * 64 + jj * 32;
-          uint32_t v[32], tv[32];
-          tmem_ld32(tlane + 256u + col0, v);
-          tmem_ld32(tlane + 256u + 128u + col0, tv);
-          tmem_ld_wait();
-#pragma unroll
-          for (int c4 = 0; c4 < 32; c4 += 4) {
-            const float4 b = *reinterpret_cast<const float4*>(&C.b[2][col0 + c4]);
-            const float4 wo = *reinterpret_cast<const float4*>(&C.wout[col0 + c4]);
-            const float bb[4] = {b.x, b.y, b.z, b.w}, ww[4] = {wo.x, wo.y, wo.z, wo.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float zb = __uint_as_float(v[c4 + i]) + bb[i];
-              const float e = exp2f(fminf(zb, 0.f));
-              pu = fmaf(ww[i], fmaxf(zb, fmaf(e, kLog2e, -kLog2e)), pu);
-              pD = fmaf(ww[i], e * __uint_as_float(tv[c4 + i]), pD);
-            }
-          }
-        }
-        tc_fence_before();
-        if (hf == 1) {
-          xch[r] = make_float2(pu, pD);
-          __threadfence_block();
-          named_bar_arrive(2, 256);
-        } else {
-          named_bar_sync(2, 256);
-          const float2 o = xch[r];
-          const float uval = pu + o.x + C.bout, D = pD + o.y;
-          const float f = P.sigma * (P.cha_k * uval - P.cha_c) * (P.sigma * D);
-          if (valid) fsum += dT * f;
-          coef_s[(it & 1u) * 128u + r] = valid ? dT * (f - fbp) / a : 0.f;
+
+        auto pass_done = [&]() {
+          tc_fence_before();
+          fence_proxy_async();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar(kBarCoef0 + (int)(it & 1u)));
+          if (lane == 0) mbar_arrive(b_ar);
+        };
+        mbar_wait(b_acc, ph_acc, 30);
+        ph_acc ^= 1u;
+        tc_fence_after();
+        epi_pass<kPassFirst>(C, tacc, hv_row, ht_row, rx, c0_s, 0, s2, a2, pu, pD);
+        pass_done();
+#pragma unroll 1
+        for (int l = 0; l < 2; ++l) {
+          mbar_wait(b_acc, ph_acc, 31);
+          ph_acc ^= 1u;
+          tc_fence_after();
+          epi_pass<kPassHidden>(C, tacc, hv_row, ht_row, rx, c0_s, l, 0.f, 0.f, pu, pD);
+          pass_done();
+        }
+        mbar_wait(b_acc, ph_acc, 32);
+        ph_acc ^= 1u;
+        tc_fence_after();
+        epi_pass<kPassOut>(C, tacc, hv_row, ht_row, rx, c0_s, 2, 0.f, 0.f, pu, pD);
+        // output layer, f (equations.py:297-302) and the Bismut coefficient of this row
+        const float uval = pu + C.bout;
+        const float f = P.sigma * (P.cha_k * uval - P.cha_c) * (P.sigma * pD);
+        if (valid) fsum += dT * f;
+        const uint32_t cb = j % 3u;
+        coef_s[cb * 128u + r] = valid ? dT * (f - fbp) / a : 0.f;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(b_ar);                // accumulators of this slot are free for the next tile's layer 1
+          mbar_arrive(bar(kBarCoef + cb));  // (release: orders the coefficient stores of the whole warp)
         }
       }
-      if (hf == 0) {
-        const float ws = warp_sum(fsum);
-        if (lane == 0) A.partF[u * 4 + q] = ws;
-      }
+      const float ws = warp_sum(fsum);
+      if (lane == 0) A.partF[u * kTcPartFFloatsPerUnit + slot * 4 + q] = ws;
     }
   } else {
     // =================================== increment producers ===================================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kWorkerRegs));
-    // All 8 warps draw every tile: thread (q, c) owns the 4 dims [4q, 4q+4) of the rows r = c + cls * i.  A tile's
-    // increments are generated into registers first (no dependence on the shared Z buffer), stored once the
-    // layer-1 MMA of the previous tile has released the buffer, and kept until the tile's Bismut coefficients
-    // arrive one tile later.
-    const int tl_id = threadIdx.x - 256;
-    const int nq = A.nq, cls = A.cls;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kProdRegs));
+    // All 8 warps draw every tile: thread (q, c) owns the 4 dims [4q, 4q+4) of the rows r = c + CLS i.  A tile's
+    // increments are generated into registers (no dependence on shared memory), stored into the slot's hV buffer once
+    // the slot's previous tile has left it, and kept until the tile's Bismut coefficients arrive two tiles later.
+    const int tl_id = threadIdx.x - 32 * kProdWarp0;
+    const int nq = A.nq;
     const int q = tl_id % nq, c = tl_id / nq;
-    const bool active = c < cls;
+    const bool active = c < CLS;
     const bool vec_ok = (d & 3) == 0;
+    constexpr int PERIOD = (CLS % 8 == 0) ? 1 : ((CLS % 4 == 0) ? 2 : ((CLS % 2 == 0) ? 4 : 8));
+    uint32_t zoff[PERIOD];  // byte offset of item i in a slot's hV image: zoff[i % PERIOD] + (i / PERIOD) PERIOD CLS 128
+#pragma unroll
+    for (int k = 0; k < PERIOD; ++k) {
+      const uint32_t rr = (uint32_t)(c + CLS * k);
+      zoff[k] = (uint32_t)(q >> 4) * kPanelBytes + rr * 128u + (((uint32_t)((q & 15) >> 1) ^ (rr & 7u)) << 4) +
+                (uint32_t)(q & 1) * 8u;
+    }
     const float* coef_s = reinterpret_cast<const float*>(smem + kOffCoef);
-    uint8_t* const zdst = smem + kOffZ + (uint32_t)(q >> 4) * kPanelBytes + (uint32_t)(q & 1) * 8u;
-    const uint32_t zchunk = (uint32_t)((q & 15) >> 1);
-    uint32_t zold[ITEMS][2], znew[ITEMS][2];
+    uint32_t zc[ITEMS][2], z1[ITEMS][2], z2[ITEMS][2];
     float4 G = make_float4(0.f, 0.f, 0.f, 0.f);
-    uint32_t it = 0;
-    bool prev_valid = false, prev_last = false;
-    int64_t prev_u = 0;
-    auto finish_prev = [&]() {
-      // Bismut accumulation of tile it-1: G_j += coef_m Z_mj (bf16 Z, exactly what the MLP saw)
-      const uint32_t pit = it - 1u;
-      mbar_wait(bar(kBarCoef0 + (int)(pit & 1u)), (pit >> 1) & 1u, 31);
+    uint32_t ph_free = 0, used = 0, ph_coef = 0, j = 0;
+    int pending = 0;
+    int64_t u1 = 0, u2 = 0;      // units of the pending tiles (1 = newer, 2 = older)
+    bool last1 = false, last2 = false;
+    uint32_t j1 = 0, j2 = 0;
+    // Bismut accumulation of a finished tile: G_j += coef_m Z_mj (bf16 Z, exactly what the MLP saw)
+    auto bismut = [&](const uint32_t (&z)[ITEMS][2], uint32_t jt, int64_t ut, bool last) {
+      const uint32_t cb = jt % 3u;
+      mbar_wait(bar(kBarCoef + (int)cb), (ph_coef >> cb) & 1u, 40);
+      ph_coef ^= 1u << cb;
       if (active) {
-        const float* cf_s = coef_s + (pit & 1u) * 128u;
+        const float* cf_s = coef_s + cb * 128u + c;
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
-          const int r = c + cls * i;
-          if (r < 128) {
-            const float cf = cf_s[r];
-            G.x = fmaf(cf, bf16_lo(zold[i][0]), G.x);
-            G.y = fmaf(cf, bf16_hi(zold[i][0]), G.y);
-            G.z = fmaf(cf, bf16_lo(zold[i][1]), G.z);
-            G.w = fmaf(cf, bf16_hi(zold[i][1]), G.w);
+          if (CLS * i + (CLS - 1) < 128 || c + CLS * i < 128) {
+            const float cf = cf_s[CLS * i];
+            G.x = fmaf(cf, bf16_lo(z[i][0]), G.x);
+            G.y = fmaf(cf, bf16_hi(z[i][0]), G.y);
+            G.z = fmaf(cf, bf16_lo(z[i][1]), G.z);
+            G.w = fmaf(cf, bf16_hi(z[i][1]), G.w);
           }
         }
-        if (prev_last) {
-          *reinterpret_cast<float4*>(A.partG + (prev_u * 16 + c) * 128 + 4 * q) = G;
+        if (last) {
+          *reinterpret_cast<float4*>(A.partG + (ut * 16 + c) * 128 + 4 * q) = G;
           G = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
@@ -384,53 +456,63 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
     for (int64_t u = blockIdx.x; u < A.n_units; u += gridDim.x) {
       const int64_t p = u / UP;
       const int g = (int)(u % UP);
-      const int tiles = min(kTcGroupTiles, TP - g * kTcGroupTiles);
+      const int tiles = min(kTcGroupTiles, A.tiles_per_point - g * kTcGroupTiles);
       const uint64_t gp = (uint64_t)(A.point_base + p);
-      for (int tl = 0; tl < tiles; ++tl) {
+      for (int tl = 0; tl < tiles; ++tl, ++j) {
         const int m0 = (g * kTcGroupTiles + tl) * 128;
+        const int nvalid = min(128, M_I - m0);
         if (active) {
 #pragma unroll
           for (int i = 0; i < ITEMS; ++i) {
-            const int r = c + cls * i;
-            const int m = m0 + r;
+            const int rr = c + CLS * i;
             float4 zz = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r < 128 && m < M_I) {
-              if (DET) {
-                zz = load_row4(A.zS + ((int64_t)p * M_I + m) * d, 4 * q, d, vec_ok);
-              } else {
-                zz = normal4(A.seed, gp, kStreamIntegral, (uint32_t)m, (uint32_t)q);
+            if (DET) {
+              if (rr < nvalid) zz = load_row4(A.zS + ((int64_t)p * M_I + m0 + rr) * d, 4 * q, d, vec_ok);
+            } else {
+              zz = normal4(A.seed, gp, kStreamIntegral, (uint32_t)(m0 + rr), (uint32_t)q);
+              if (!vec_ok) {
                 if (4 * q + 1 >= d) zz.y = 0.f;
                 if (4 * q + 2 >= d) zz.z = 0.f;
                 if (4 * q + 3 >= d) zz.w = 0.f;
               }
             }
-            znew[i][0] = pack_bf16x2(zz.x, zz.y);
-            znew[i][1] = pack_bf16x2(zz.z, zz.w);
+            const bool ok = rr < nvalid;
+            zc[i][0] = ok ? pack_bf16x2(zz.x, zz.y) : 0u;
+            zc[i][1] = ok ? pack_bf16x2(zz.z, zz.w) : 0u;
           }
         }
-        if (it > 0) mbar_wait(bar(kBarZEmpty), (it - 1u) & 1u, 30);  // layer-1 MMA of the previous tile has read Z
+        const int s = tl & 1;
+        const uint32_t bit = 1u << s;
+        if (used & bit) {
+          mbar_wait(bar(kBarSlotFree + s), (ph_free >> s) & 1u, 41);  // the slot's previous tile has left hV / hT
+          ph_free ^= bit;
+        }
+        used |= bit;
         if (active) {
+          uint8_t* const zdst = smem + kOffSlot + (uint32_t)s * kSlotBytes;
 #pragma unroll
           for (int i = 0; i < ITEMS; ++i) {
-            const int r = c + cls * i;
-            if (r < 128)
-              *reinterpret_cast<uint2*>(zdst + (uint32_t)r * 128u + ((zchunk ^ (uint32_t)(r & 7)) << 4)) =
-                  make_uint2(znew[i][0], znew[i][1]);
+            if (CLS * i + (CLS - 1) < 128 || c + CLS * i < 128)
+              *reinterpret_cast<uint2*>(zdst + zoff[i % PERIOD] + (uint32_t)((i / PERIOD) * PERIOD * CLS * 128)) =
+                  make_uint2(zc[i][0], zc[i][1]);
           }
         }
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar(kBarZFull));
-        if (prev_valid) finish_prev();
+        if (lane == 0) mbar_arrive(bar(kBarZFull + s));
+        if (pending == 2) bismut(z2, j2, u2, last2);
 #pragma unroll
-        for (int i = 0; i < ITEMS; ++i) zold[i][0] = znew[i][0], zold[i][1] = znew[i][1];
-        prev_u = u;
-        prev_last = (tl == tiles - 1);
-        prev_valid = true;
-        ++it;
+        for (int i = 0; i < ITEMS; ++i) {
+          z2[i][0] = z1[i][0], z2[i][1] = z1[i][1];
+          z1[i][0] = zc[i][0], z1[i][1] = zc[i][1];
+        }
+        j2 = j1, u2 = u1, last2 = last1;
+        j1 = j, u1 = u, last1 = (tl == tiles - 1);
+        if (pending < 2) ++pending;
       }
     }
-    if (prev_valid) finish_prev();
+    if (pending == 2) bismut(z2, j2, u2, last2);
+    if (pending >= 1) bismut(z1, j1, u1, last1);
   }
 
   tc_fence_before();
@@ -461,7 +543,8 @@ cha_tc_finish_kernel(const float* __restrict__ partG, const float* __restrict__ 
   if (j == 0) {
     float s = 0.f;
     for (int g = 0; g < units_per_point; ++g)
-      for (int qq = 0; qq < 4; ++qq) s += partF[(p * units_per_point + g) * 4 + qq];
+      for (int qq = 0; qq < (int)kTcPartFFloatsPerUnit; ++qq)
+        s += partF[(p * units_per_point + g) * kTcPartFFloatsPerUnit + qq];
     float v = yp[0] + s * invM;
     if (clip) v = fminf(fmaxf(v, -bound), bound);
     yp[0] = v;
@@ -524,9 +607,9 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const uint8_t* __
   }
 }
 
-template <int ITEMS, bool DET>
+template <int ITEMS, int CLS, bool DET>
 int launch_tc_t(const ProblemDev& P, const TcNetDev& N, const TcArgs& A, int grid, cudaStream_t st) {
-  auto k = cha_tc_kernel<ITEMS, DET>;
+  auto k = cha_tc_kernel<ITEMS, CLS, DET>;
   DPI_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
   k<<<grid, kTcThreads, kTcSmemBytes, st>>>(P, N.consts, A);
   DPI_CUDA_CHECK(cudaGetLastError());
@@ -607,16 +690,15 @@ int launch_cha_tc_path(const ProblemDev& P, const TcNetDev& N, const float* tx, 
   A.M_I = M_I;
   A.ksteps1 = N.ksteps1;
   A.nq = N.nq;
-  A.cls = N.cls;
   const int grid = (int)(A.n_units < N.num_sms ? A.n_units : N.num_sms);
   int rc;
   const bool det = zS != nullptr;
   if (N.cls == 16)
-    rc = det ? launch_tc_t<8, true>(P, N, A, grid, st) : launch_tc_t<8, false>(P, N, A, grid, st);
+    rc = det ? launch_tc_t<8, 16, true>(P, N, A, grid, st) : launch_tc_t<8, 16, false>(P, N, A, grid, st);
   else if (N.cls == 10)
-    rc = det ? launch_tc_t<13, true>(P, N, A, grid, st) : launch_tc_t<13, false>(P, N, A, grid, st);
+    rc = det ? launch_tc_t<13, 10, true>(P, N, A, grid, st) : launch_tc_t<13, 10, false>(P, N, A, grid, st);
   else
-    rc = det ? launch_tc_t<16, true>(P, N, A, grid, st) : launch_tc_t<16, false>(P, N, A, grid, st);
+    rc = det ? launch_tc_t<16, 8, true>(P, N, A, grid, st) : launch_tc_t<16, 8, false>(P, N, A, grid, st);
   if (rc) return rc;
   cha_tc_finish_kernel<<<(unsigned)n, 128, 0, st>>>(partG, partF, A.units_per_point, N.cls, P.nx, M_I, bound, y);
   DPI_CUDA_CHECK(cudaGetLastError());
