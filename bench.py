@@ -8,7 +8,7 @@ One "step" = one pass of the hot path (terminal estimator + integral estimator w
 collective (weak scaling: every rank labels `--points` points per step; Philox counters are keyed by the global
 point index).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--precision bf16|fp32]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--precision f16|fp32]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 Prints ONE JSON line (rank 0).  `value` is device-resident throughput; `e2e` goes through the host-buffer C-ABI
@@ -89,7 +89,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -274,7 +274,7 @@ def run_b200(args, wl):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16" if prec == "bf16" else "f32", "data": "synthetic",
+        "dtype": "f16" if prec in ("f16", "bf16") else "f32", "data": "synthetic",
         "config": {"workload": args.workload, "restates": wl["config"], "equation": "Cha", "nx": nx,
                    "mlp": [1 + nx] + wl["hidden"] + [1], "M_T": M, "M_I": M, "points_per_gpu_per_step": n,
                    "global_points_per_step": world * n, "parallelism": f"points sharded x{world}, no collective",
@@ -304,11 +304,13 @@ def run_b200(args, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="burgers100d", choices=sorted(WORKLOADS))
-    ap.add_argument("--precision", default=os.environ.get("DPI_BENCH_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("DPI_BENCH_PRECISION", "f16"), choices=["fp32", "f16", "bf16"],
+                    help="f16: tcgen05 path (fp16 operands, fp32 accumulation; labels within 1e-2 of the reference); "
+                         "fp32: CUDA-core path (within 1e-4)")
     ap.add_argument("--points", type=int, default=0, help="points per GPU per step (default: workload's)")
     ap.add_argument("--cpu-points", type=int, default=32, help="points per CPU-arm step (bounded sample)")
     ap.add_argument("--cpu-steps", type=int, default=4)

@@ -9,12 +9,14 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libdpi_b200.so")
+# DPI_B200_LIB: developer override used by tools_variants.py to time experimental builds of the same library
+LIB_PATH = os.environ.get("DPI_B200_LIB") or os.path.join(_PKG, "libdpi_b200.so")
 
 DPI_MAX_LINEAR = 8
 DPI_EQ_CHA, DPI_EQ_GBM, DPI_EQ_OU = 0, 1, 2
 DPI_NET_ZERO, DPI_NET_MLP, DPI_NET_PISGRAD = 0, 1, 2
-DPI_PREC_FP32, DPI_PREC_BF16 = 0, 1
+DPI_PREC_FP32, DPI_PREC_F16 = 0, 1
+DPI_PREC_BF16 = DPI_PREC_F16  # alias: the 16-bit tensor-core path (fp16 operands)
 
 EXPORTED_SYMBOLS = (
     "dpi_version", "dpi_last_error", "dpi_create", "dpi_destroy", "dpi_set_problem", "dpi_set_network",

@@ -17,7 +17,7 @@ struct MlpDev {
   const float* b1;    // [HP]
   const float* wsum;  // [HP]         sum_j W1[:,1+j]  == tangent of layer 1 along (0,1,...,1)
   const float* Wth[DPI_MAX_LINEAR];  // hidden layer l: [HP][HP]  Wth[k][h] = W_l[h][k]
-  const float* Wth_bf[DPI_MAX_LINEAR];  // same, every entry rounded to bf16 (control variate of the bf16 path)
+  const float* Wth_bf[DPI_MAX_LINEAR];  // same, every entry rounded to fp16 (control variate of the tensor-core path)
   const float* bh[DPI_MAX_LINEAR];   // [HP]
   const float* wout;  // [HP]
   const float* bout;  // [1] device
@@ -47,19 +47,19 @@ int launch_gbm_simt(const ProblemDev& P, const MlpDev& net, bool zero_net, const
                     uint64_t seed, int64_t base, const float* u_s, const float* zS, const int32_t* idx, float bound,
                     float* y, cudaStream_t st);
 
-// ---- bf16 tcgen05 path (dpi_mlp_tc.cu) ---------------------------------------------------------------
+// ---- 16-bit tcgen05 path (dpi_mlp_tc.cu): fp16 operands, fp32 accumulation ---------------------------------------------------------------
 constexpr int kTcGroupTiles = 8;  // 128-sample tiles per work unit (fixed: the summation order must not depend on n)
 // per-column fp32 constants of the network, passed to the kernel by value (constant bank)
 struct alignas(16) TcConsts {
-  float wt[128];    // W1[:,0]            time column
-  float wsum[128];  // sum_j W1[:,1+j]    first-layer tangent along (0,1,...,1)
-  float b[3][128];  // biases of the three hidden GEMM layers
-  float wout[128];
+  float wt[128];            // log2e W1[:,0]                time column (fp32: multiplies the per-row time)
+  uint32_t wsum16[64];      // fp16x2 pairs: log2e sum_j W1[:,1+j]   first-layer tangent along (0,1,...,1)
+  uint32_t b16[3][64];      // fp16x2 pairs: log2e biases of the three hidden GEMM layers
+  uint32_t wout16[64];      // fp16x2 pairs: ln2 w_out
   float bout;
   float pad[3];
 };
 struct TcNetDev {
-  const void* W;  // 4 x [128 x 128] bf16 operand images (K-major, SWIZZLE_128B): W1 x-columns, W2, W3, W4
+  const void* W;  // 4 x [128 x 128] fp16 operand images (K-major, SWIZZLE_128B): W1 x-columns, W2, W3, W4
   TcConsts consts;
   int nx, ksteps1, nq, cls, num_sms;
 };

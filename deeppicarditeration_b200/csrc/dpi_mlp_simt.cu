@@ -11,15 +11,16 @@
 // so the GEMM runs on the unit-variance increments Z and the point-dependent part c0 is computed once per point
 // (by the baseline pass, which also yields the control variate f_b = f(t, x)).
 #include "dpi_common.cuh"
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "dpi_kernels.h"
 
 namespace dpi {
 namespace {
 
-__device__ __forceinline__ float bf16r(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
-// the tensor-core path carries activations scaled by log2(e) and rounds THOSE to bf16 (dpi_mlp_tc.cu)
+// rounding of the tensor-core path's 16-bit operands (fp16)
+__device__ __forceinline__ float bf16r(float x) { return __half2float(__float2half_rn(x)); }
+// the tensor-core path carries activations scaled by log2(e) and rounds THOSE to fp16 (dpi_mlp_tc.cu)
 __device__ __forceinline__ float bf16r_scaled(float x) {
   return bf16r(x * 1.4426950408889634f) * 0.6931471805599453f;
 }

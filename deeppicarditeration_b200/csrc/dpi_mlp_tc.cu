@@ -1,4 +1,4 @@
-// bf16 tcgen05 integral estimator for the Burgers-type equation `Cha` (u_k = MLP [1+d,128,128,128,128,1], d <= 128).
+// 16-bit (fp16 operands, fp32 accumulation) tcgen05 integral estimator for the Burgers-type equation `Cha` (u_k = MLP [1+d,128,128,128,128,1], d <= 128).
 //
 // Same mathematics as dpi_mlp_simt.cu (picard/data.py:471-527,350-366,1226-1325; equations.py:297-302;
 // solution.py:123-135) with the first-layer GEMM and the three hidden 128x128 GEMMs (value and tangent) on the
@@ -7,23 +7,26 @@
 //   * one persistent CTA per SM.  A work unit is (collocation point, group of 8 tiles); a tile is 128 MC samples =
 //     128 TMEM lanes.  TWO tiles are in flight per CTA, one per "slot": while the epilogue warps of one slot turn a
 //     layer's accumulators into the next layer's operands, the tensor pipe runs the other slot's layer;
-//   * shared memory: the hidden weights W2..W4 stay resident as bf16 K-major SWIZZLE_128B operand images (3 x 32 KB);
+//   * shared memory: the hidden weights W2..W4 stay resident as fp16 K-major SWIZZLE_128B operand images (3 x 32 KB);
 //     each slot owns an hV and an hT buffer (value rows / tangent rows of the next A operand, 2 x 32 KB).  For layer 1
 //     the slot's hV holds the increments Z (A operand) and its hT receives the W1 image (B operand) by TMA bulk copy
 //     from L2 for every tile -- that is what makes room for the second tile in 227 KB;
 //   * TMEM: 512 columns = 2 slots x (value 128 + tangent 128) fp32 accumulator columns;
-//   * 8 producer warps draw the Brownian increments with Philox4x32-10 + Box-Muller in registers, round them to bf16,
+//   * 8 producer warps draw the Brownian increments with Philox4x32-10 + Box-Muller in registers, round them to fp16,
 //     store the [128 x d] A-operand tile when the slot frees up, and KEEP them in registers: once the tile's Bismut
 //     coefficients are known they accumulate G_j += coef_m Z_mj there, so increments never leave the SM;
 //   * one thread issues tcgen05.mma for both slots in a fixed round-robin order, one thread issues the TMA copies;
 //   * 4 epilogue warps per slot (thread = sample row) read the accumulators with tcgen05.ld, apply bias/ELU/ELU' in
-//     fp32 and write the next layer's bf16 A operands straight into the swizzled shared-memory layout; the last layer
-//     is a dot product in the epilogue (fp32), followed by f, the Bismut coefficient and the value-label partial sum.
+//     packed fp16x2 arithmetic (two columns per instruction; its absolute error stays below the rounding of the
+//     16-bit operands it produces) and write the next layer's A operands straight into the swizzled shared-memory
+//     layout; the last layer is a dot product in the epilogue, followed by f, the Bismut coefficient and the
+//     value-label partial sum in fp32.
 //
 // Partial sums go to a small scratch ([unit][row class][128], [unit][slot][lane quarter]) and a finish kernel adds
 // them in a fixed order; the slot of a tile is its index inside the unit, so labels are bitwise independent of the
 // launch geometry and of how points are sharded.
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "dpi_common.cuh"
@@ -83,7 +86,26 @@ struct TcArgs {
   int tiles_per_point;
   int ksteps1;  // ceil(d/16)
   int nq;       // ceil(d/4) quads of dims
+  long long* trace;  // developer timeline (DPI_TC_TRACE builds only), else null
 };
+
+#ifdef DPI_TC_TRACE
+// Low-overhead timeline of CTA 0: every traced thread owns a region of the buffer and a register counter, an event
+// is one fire-and-forget 16-byte store {code = slot*100000 + (tile j % 1000)*100 + tag, clock64}.
+constexpr int kTraceCap = 8192;
+#define TRACE_DECL(region) long long* trace_p = (A.trace && blockIdx.x == 0) ? A.trace + (region) * 2 * kTraceCap : nullptr; int trace_n = 0
+#define TRACE(role, slot, j, tag)                                                                         \
+  do {                                                                                                    \
+    if (trace_p && trace_n < kTraceCap) {                                                                 \
+      *reinterpret_cast<longlong2*>(trace_p + 2 * trace_n) =                                              \
+          make_longlong2((long long)(slot) * 100000 + (long long)((j) % 1000u) * 100 + (tag), clock64()); \
+      ++trace_n;                                                                                          \
+    }                                                                                                     \
+  } while (0)
+#else
+#define TRACE_DECL(region)
+#define TRACE(role, slot, j, tag)
+#endif
 
 // All activations are carried scaled by log2(e): with z' = log2e z the ELU pair needs one op less per element,
 //   e = 2^min(z',0) = ELU'(z),   h' = log2e ELU(z) = max(z', e log2e - log2e),   tangent' = e * (log2e dz),
@@ -98,72 +120,76 @@ struct TcArgs {
 //   kPassHidden: z' = acc + b'[layer], tangent' = e acc_t                                          -> bf16 A operands
 //   kPassOut   : same ELU, then the output layer as fp32 dot products with w_out: pu = w.h, pD = w.(e acc_t)
 enum : int { kPassFirst = 0, kPassHidden = 1, kPassOut = 2 };
+#ifndef DPI_EPI_UNROLL
+#define DPI_EPI_UNROLL 4
+#endif
+constexpr int kEpiUnroll = DPI_EPI_UNROLL;  // chunks per loop iteration of an epilogue pass (even)
 
 template <int MODE>
 __device__ __forceinline__ void epi_pass(const TcConsts& C, uint32_t tacc, uint8_t* hv_row, uint8_t* ht_row,
                                          uint32_t rx, const float* c0_s, int layer, float s2, float a2, float& pu,
                                          float& pD) {
   uint32_t v[2][8], tv[2][8];
+  float4 cc[2][2];  // first pass: c0 of the current / next chunk (prefetched like the accumulators)
   tmem_ld8(tacc, v[0]);
   if (MODE != kPassFirst) tmem_ld8(tacc + 128u, tv[0]);
-  const float* bias = C.b[layer];
-#pragma unroll
+  if (MODE == kPassFirst) {
+    cc[0][0] = *reinterpret_cast<const float4*>(&c0_s[0]);
+    cc[0][1] = *reinterpret_cast<const float4*>(&c0_s[4]);
+  }
+  const uint32_t* bias = C.b16[layer];
+  const uint32_t kL = h2_const(kLog2e, kLog2e), kNegL = h2_const(-kLog2e, -kLog2e), kZero = 0u;
+  uint32_t accU = 0u, accD = 0u;  // output pass: fp16x2 partial dot products, flushed to fp32 every 16 columns
+  // rolled two chunks at a time (static double-buffer indices): the pass is a short loop that stays in the
+  // instruction cache; per-column constants are then fetched with indexed constant loads
+#pragma unroll kEpiUnroll
   for (int ch = 0; ch < 16; ++ch) {
     tmem_ld_wait();
     if (ch + 1 < 16) {
       tmem_ld8(tacc + (uint32_t)((ch + 1) * 8), v[(ch + 1) & 1]);
       if (MODE != kPassFirst) tmem_ld8(tacc + 128u + (uint32_t)((ch + 1) * 8), tv[(ch + 1) & 1]);
+      if (MODE == kPassFirst) {
+        cc[(ch + 1) & 1][0] = *reinterpret_cast<const float4*>(&c0_s[(ch + 1) * 8]);
+        cc[(ch + 1) & 1][1] = *reinterpret_cast<const float4*>(&c0_s[(ch + 1) * 8 + 4]);
+      }
     }
     const uint32_t* vv = v[ch & 1];
     const uint32_t* tt = tv[ch & 1];
     uint32_t hv[4], ht[4];
 #pragma unroll
-    for (int k4 = 0; k4 < 8; k4 += 4) {
-      const int col = ch * 8 + k4;
-      float zb[4], tg[4];
+    for (int k2 = 0; k2 < 8; k2 += 2) {  // two columns per packed instruction
+      const int col = ch * 8 + k2;
+      uint32_t z, tg;
       if (MODE == kPassFirst) {
-        const float4 c0 = *reinterpret_cast<const float4*>(&c0_s[col]);
-        zb[0] = fmaf(a2, __uint_as_float(vv[k4 + 0]), fmaf(s2, C.wt[col + 0], c0.x));
-        zb[1] = fmaf(a2, __uint_as_float(vv[k4 + 1]), fmaf(s2, C.wt[col + 1], c0.y));
-        zb[2] = fmaf(a2, __uint_as_float(vv[k4 + 2]), fmaf(s2, C.wt[col + 2], c0.z));
-        zb[3] = fmaf(a2, __uint_as_float(vv[k4 + 3]), fmaf(s2, C.wt[col + 3], c0.w));
-#pragma unroll
-        for (int i = 0; i < 4; ++i) tg[i] = C.wsum[col + i];
+        const float4 c0 = cc[ch & 1][k2 / 4];
+        const float c0a = (k2 & 2) ? c0.z : c0.x, c0b = (k2 & 2) ? c0.w : c0.y;
+        z = pack_f16x2(fmaf(a2, __uint_as_float(vv[k2]), fmaf(s2, C.wt[col], c0a)),
+                       fmaf(a2, __uint_as_float(vv[k2 + 1]), fmaf(s2, C.wt[col + 1], c0b)));
+        tg = C.wsum16[col / 2];
       } else {
-        if (MODE == kPassHidden) {
-          const float4 b = *reinterpret_cast<const float4*>(&bias[col]);
-          zb[0] = __uint_as_float(vv[k4 + 0]) + b.x;
-          zb[1] = __uint_as_float(vv[k4 + 1]) + b.y;
-          zb[2] = __uint_as_float(vv[k4 + 2]) + b.z;
-          zb[3] = __uint_as_float(vv[k4 + 3]) + b.w;
-        } else {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) zb[i] = __uint_as_float(vv[k4 + i]) + C.b[2][col + i];
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) tg[i] = __uint_as_float(tt[k4 + i]);
+        z = h2_add(pack_f16x2(__uint_as_float(vv[k2]), __uint_as_float(vv[k2 + 1])),
+                   MODE == kPassHidden ? bias[col / 2] : C.b16[2][col / 2]);
+        tg = pack_f16x2(__uint_as_float(tt[k2]), __uint_as_float(tt[k2 + 1]));
       }
-      float h[4], dh[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float e = exp2f(fminf(zb[i], 0.f));
-        h[i] = fmaxf(zb[i], fmaf(e, kLog2e, -kLog2e));
-        dh[i] = e * tg[i];
-      }
+      const uint32_t e = h2_ex2(h2_min(z, kZero));           // ELU'(z) = 2^min(z',0)
+      const uint32_t h = h2_max(z, h2_fma(e, kL, kNegL));    // log2e ELU(z)
+      const uint32_t dh = h2_mul(e, tg);
       if (MODE == kPassOut) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          pu = fmaf(C.wout[col + i], h[i], pu);
-          pD = fmaf(C.wout[col + i], dh[i], pD);
-        }
+        accU = h2_fma(C.wout16[col / 2], h, accU);
+        accD = h2_fma(C.wout16[col / 2], dh, accD);
       } else {
-        hv[k4 / 2 + 0] = pack_bf16x2(h[0], h[1]);
-        hv[k4 / 2 + 1] = pack_bf16x2(h[2], h[3]);
-        ht[k4 / 2 + 0] = pack_bf16x2(dh[0], dh[1]);
-        ht[k4 / 2 + 1] = pack_bf16x2(dh[2], dh[3]);
+        hv[k2 / 2] = h;
+        ht[k2 / 2] = dh;
       }
     }
-    if (MODE != kPassOut) {
+    if (MODE == kPassOut) {
+      if (ch & 1) {
+        const float2 fu = h2_unpack(accU), fd = h2_unpack(accD);
+        pu += fu.x + fu.y;
+        pD += fd.x + fd.y;
+        accU = accD = 0u;
+      }
+    } else {
       // 16-byte chunk ch of this row: K panel (ch >> 3), chunk index XOR-swizzled with (row & 7)
       const uint32_t off = (uint32_t)(ch >> 3) * kPanelBytes + (((uint32_t)(ch & 7) << 4) ^ rx);
       *reinterpret_cast<uint4*>(hv_row + off) = make_uint4(hv[0], hv[1], hv[2], hv[3]);
@@ -233,19 +259,33 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + kOffTmemPtr);
+  if (tmem != 0u) {  // all 512 columns of the SM belong to this CTA: the MMA issuer relies on base column 0
+    if (threadIdx.x == 0) printf("dpi tc: unexpected TMEM base 0x%x\n", tmem);
+    __trap();
+  }
 
   if (warp >= kMmaWarp) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kMmaRegs));
-    if (warp == kMmaWarp && lane == 0) {
+    if (warp == kMmaWarp) {
       // =================================== MMA issuer ===================================
+      // The whole warp runs this (uniform) control flow; the elected lane issues tcgen05.mma / commit.
+      const uint32_t leader = elect_one();
+      TRACE_DECL(0);
+#ifdef DPI_TC_TRACE
+      if (lane != 0) trace_p = nullptr;
+#endif
       mbar_wait(bar(kBarW), 0, 0);
-      constexpr uint32_t idesc = make_idesc_bf16(128, 128);
+      constexpr uint32_t idesc = make_idesc_f16(128, 128);
       TileCursor cur;
       cur.init(A);
       int lay0 = 0, lay1 = 0, slt0 = 0, slt1 = 0;  // two in-flight tiles: next layer to issue (0 = none) and slot
       uint32_t ph_z = 0, ph_w1 = 0, ph_ar = 0, used = 0;  // bit s = slot s
       auto issue = [&](int s, int l) {
-        const uint32_t acc = tmem + (uint32_t)s * 256u;
+        TRACE(1, s, 0, l * 10 + 0);
+        // lane-0 broadcasts mark these warp-uniform values as uniform for the compiler (uniform registers / datapath)
+        s = __shfl_sync(0xffffffffu, s, 0);
+        l = __shfl_sync(0xffffffffu, l, 0);
+        const uint32_t acc = (uint32_t)s * 256u;  // TMEM base is column 0 (checked at allocation)
         const uint32_t slot = sbase + kOffSlot + (uint32_t)s * kSlotBytes;
         const uint64_t dV = make_desc_sw128(slot), dT = make_desc_sw128(slot + kOperandBytes);
         const uint32_t bit = 1u << s;
@@ -261,25 +301,31 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
           mbar_wait(bar(kBarW1Full + s), (ph_w1 >> s) & 1u, 12);
           ph_w1 ^= bit;
           tc_fence_after();
-#pragma unroll 1
-          for (int ks = 0; ks < A.ksteps1; ++ks) {
-            const uint64_t o = (uint64_t)((ks >> 2) * 1024 + (ks & 3) * 2);
-            umma_bf16(acc, dV + o, dT + o, idesc, ks > 0);
+          TRACE(1, s, 0, l * 10 + 1);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            if (ks < A.ksteps1) {
+              const uint64_t o = (uint64_t)((ks >> 2) * 1024 + (ks & 3) * 2);
+              umma_bf16_p(acc, dV + o, dT + o, idesc, ks > 0, leader);
+            }
           }
-          tc_commit(bar(kBarAccFull + s));
+          tc_commit_p(bar(kBarAccFull + s), leader);
+          TRACE(1, s, 0, l * 10 + 2);
         } else {
           mbar_wait(bar(kBarAReady + s), (ph_ar >> s) & 1u, 13);
           ph_ar ^= bit;
           tc_fence_after();
+          TRACE(1, s, 0, l * 10 + 1);
           const uint64_t dW = make_desc_sw128(sbase + kOffW + (uint32_t)(l - 2) * kOperandBytes);
-#pragma unroll 1
+#pragma unroll
           for (int ks = 0; ks < 8; ++ks) {
             const uint64_t o = (uint64_t)((ks >> 2) * 1024 + (ks & 3) * 2);
-            umma_bf16(acc, dV + o, dW + o, idesc, ks > 0);
-            umma_bf16(acc + 128u, dT + o, dW + o, idesc, ks > 0);
+            umma_bf16_p(acc, dV + o, dW + o, idesc, ks > 0, leader);
+            umma_bf16_p(acc + 128u, dT + o, dW + o, idesc, ks > 0, leader);
           }
-          tc_commit(bar(kBarAccFull + s));
-          if (l == 4) tc_commit(bar(kBarSlotFree + s));
+          tc_commit_p(bar(kBarAccFull + s), leader);
+          if (l == 4) tc_commit_p(bar(kBarSlotFree + s), leader);
+          TRACE(1, s, 0, l * 10 + 2);
         }
       };
       for (;;) {
@@ -301,12 +347,14 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
           lay1 = (lay1 == 4) ? 0 : lay1 + 1;
         }
       }
-    } else if (warp == kTmaWarp && lane == 0) {
+    } else if (warp == kTmaWarp) {
       // =================================== TMA issuer ===================================
+      const uint32_t leader = elect_one();
       const uint8_t* Wg = reinterpret_cast<const uint8_t*>(A.W);
-      mbar_arrive_expect_tx(bar(kBarW), 3u * kOperandBytes);
+      mbar_arrive_expect_tx_p(bar(kBarW), 3u * kOperandBytes, leader);
+#pragma unroll 1
       for (int i = 0; i < 12; ++i)
-        bulk_g2s(sbase + kOffW + (uint32_t)i * 8192u, Wg + kOperandBytes + (size_t)i * 8192, 8192u, bar(kBarW));
+        bulk_g2s_p(sbase + kOffW + (uint32_t)i * 8192u, Wg + kOperandBytes + (size_t)i * 8192, 8192u, bar(kBarW), leader);
       const int n_chunks = (d > 64) ? 4 : 2;  // K panels of the W1 image that layer 1 reads (16 KB each)
       uint32_t ph_free = 0, used = 0;
       TileCursor cur;
@@ -319,8 +367,9 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
         }
         used |= bit;
         const uint32_t dst = sbase + kOffSlot + (uint32_t)s * kSlotBytes + kOperandBytes;
-        mbar_arrive_expect_tx(bar(kBarW1Full + s), (uint32_t)n_chunks * 8192u);
-        for (int i = 0; i < n_chunks; ++i) bulk_g2s(dst + (uint32_t)i * 8192u, Wg + (size_t)i * 8192, 8192u, bar(kBarW1Full + s));
+        mbar_arrive_expect_tx_p(bar(kBarW1Full + s), (uint32_t)n_chunks * 8192u, leader);
+        for (int i = 0; i < n_chunks; ++i)
+          bulk_g2s_p(dst + (uint32_t)i * 8192u, Wg + (size_t)i * 8192, 8192u, bar(kBarW1Full + s), leader);
       }
     }
     __syncwarp();
@@ -338,19 +387,36 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
     const uint32_t b_acc = bar(kBarAccFull + slot), b_ar = bar(kBarAReady + slot);
     uint32_t ph_acc = 0, j = 0;
     int64_t c0_point = -1;
+    TRACE_DECL(1 + slot);
+#ifdef DPI_TC_TRACE
+    if (q != 0 || lane != 0) trace_p = nullptr;
+#endif
+    // per-point scalars are fetched one unit ahead so that their latency is off the slot's critical path
+    float t_n = 0.f, fb_n = 0.f, c0_n = 0.f;
+    if ((int64_t)blockIdx.x < A.n_units) {
+      const int64_t pn = (int64_t)blockIdx.x / UP;
+      t_n = __ldg(A.tx + pn * (int64_t)(1 + d));
+      fb_n = __ldg(A.fb + pn);
+      c0_n = __ldg(A.c0 + pn * 128 + r);
+    }
     for (int64_t u = blockIdx.x; u < A.n_units; u += gridDim.x) {
       const int64_t p = u / UP;
       const int g = (int)(u % UP);
       const int tiles = min(kTcGroupTiles, A.tiles_per_point - g * kTcGroupTiles);
+      const float t = t_n, fbp = fb_n, c0v = kLog2e * c0_n;
+      const float dT = P.T - t;
+      if (u + gridDim.x < A.n_units) {
+        const int64_t pn = (u + gridDim.x) / UP;
+        t_n = __ldg(A.tx + pn * (int64_t)(1 + d));
+        fb_n = __ldg(A.fb + pn);
+        c0_n = __ldg(A.c0 + pn * 128 + r);
+      }
       float fsum = 0.f;
       for (int tl = 0; tl < tiles; ++tl, ++j) {
         if ((tl & 1) != slot) continue;
-        const float t = __ldg(A.tx + p * (int64_t)(1 + d));
-        const float dT = P.T - t;
-        const float fbp = __ldg(A.fb + p);
         if (p != c0_point) {
           named_bar_sync(1 + slot, 128);  // every warp of the slot is past the first pass of the previous point
-          c0_s[r] = kLog2e * __ldg(A.c0 + p * 128 + r);
+          c0_s[r] = c0v;
           named_bar_sync(1 + slot, 128);
           c0_point = p;
         }
@@ -364,15 +430,20 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
         const float s2 = (uu * dT + t) * kLog2e, a2 = a * kLog2e;
         float pu = 0.f, pD = 0.f;
 
+        int pass_no = 0;
         auto pass_done = [&]() {
           tc_fence_before();
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(b_ar);
+          TRACE(2, slot, j, pass_no * 10 + 2);
+          ++pass_no;
         };
+        TRACE(2, slot, j, 0);
         mbar_wait(b_acc, ph_acc, 30);
         ph_acc ^= 1u;
         tc_fence_after();
+        TRACE(2, slot, j, 1);
         epi_pass<kPassFirst>(C, tacc, hv_row, ht_row, rx, c0_s, 0, s2, a2, pu, pD);
         pass_done();
 #pragma unroll 1
@@ -380,12 +451,14 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
           mbar_wait(b_acc, ph_acc, 31);
           ph_acc ^= 1u;
           tc_fence_after();
+          TRACE(2, slot, j, pass_no * 10 + 1);
           epi_pass<kPassHidden>(C, tacc, hv_row, ht_row, rx, c0_s, l, 0.f, 0.f, pu, pD);
           pass_done();
         }
         mbar_wait(b_acc, ph_acc, 32);
         ph_acc ^= 1u;
         tc_fence_after();
+        TRACE(2, slot, j, 31);
         epi_pass<kPassOut>(C, tacc, hv_row, ht_row, rx, c0_s, 2, 0.f, 0.f, pu, pD);
         // output layer, f (equations.py:297-302) and the Bismut coefficient of this row
         const float uval = pu + C.bout;
@@ -396,6 +469,7 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
+          TRACE(2, slot, j, 32);
           mbar_arrive(b_ar);                // accumulators of this slot are free for the next tile's layer 1
           mbar_arrive(bar(kBarCoef + cb));  // (release: orders the coefficient stores of the whole warp)
         }
@@ -427,10 +501,14 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
     float4 G = make_float4(0.f, 0.f, 0.f, 0.f);
     uint32_t ph_free = 0, used = 0, ph_coef = 0, j = 0;
     int pending = 0;
+    TRACE_DECL(3);
+#ifdef DPI_TC_TRACE
+    if (tl_id != 0) trace_p = nullptr;
+#endif
     int64_t u1 = 0, u2 = 0;      // units of the pending tiles (1 = newer, 2 = older)
     bool last1 = false, last2 = false;
     uint32_t j1 = 0, j2 = 0;
-    // Bismut accumulation of a finished tile: G_j += coef_m Z_mj (bf16 Z, exactly what the MLP saw)
+    // Bismut accumulation of a finished tile: G_j += coef_m Z_mj (fp16 Z, exactly what the MLP saw)
     auto bismut = [&](const uint32_t (&z)[ITEMS][2], uint32_t jt, int64_t ut, bool last) {
       const uint32_t cb = jt % 3u;
       mbar_wait(bar(kBarCoef + (int)cb), (ph_coef >> cb) & 1u, 40);
@@ -441,10 +519,11 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
         for (int i = 0; i < ITEMS; ++i) {
           if (CLS * i + (CLS - 1) < 128 || c + CLS * i < 128) {
             const float cf = cf_s[CLS * i];
-            G.x = fmaf(cf, bf16_lo(z[i][0]), G.x);
-            G.y = fmaf(cf, bf16_hi(z[i][0]), G.y);
-            G.z = fmaf(cf, bf16_lo(z[i][1]), G.z);
-            G.w = fmaf(cf, bf16_hi(z[i][1]), G.w);
+            const float2 za = h2_unpack(z[i][0]), zb = h2_unpack(z[i][1]);
+            G.x = fmaf(cf, za.x, G.x);
+            G.y = fmaf(cf, za.y, G.y);
+            G.z = fmaf(cf, zb.x, G.z);
+            G.w = fmaf(cf, zb.y, G.w);
           }
         }
         if (last) {
@@ -461,6 +540,7 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
       for (int tl = 0; tl < tiles; ++tl, ++j) {
         const int m0 = (g * kTcGroupTiles + tl) * 128;
         const int nvalid = min(128, M_I - m0);
+        TRACE(3, tl & 1, j, 0);
         if (active) {
 #pragma unroll
           for (int i = 0; i < ITEMS; ++i) {
@@ -469,7 +549,17 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
             if (DET) {
               if (rr < nvalid) zz = load_row4(A.zS + ((int64_t)p * M_I + m0 + rr) * d, 4 * q, d, vec_ok);
             } else {
+#ifdef DPI_DBG_NO_RNG
+              {
+                const uint32_t hsh = (uint32_t)(m0 + rr) * 2654435761u + (uint32_t)q * 40503u;
+                zz = make_float4(__uint_as_float(0x3f000000u | (hsh & 0x7fffffu)) - 0.75f,
+                                 __uint_as_float(0x3f000000u | ((hsh >> 3) & 0x7fffffu)) - 0.75f,
+                                 __uint_as_float(0x3f000000u | ((hsh >> 6) & 0x7fffffu)) - 0.75f,
+                                 __uint_as_float(0x3f000000u | ((hsh >> 9) & 0x7fffffu)) - 0.75f);
+              }
+#else
               zz = normal4(A.seed, gp, kStreamIntegral, (uint32_t)(m0 + rr), (uint32_t)q);
+#endif
               if (!vec_ok) {
                 if (4 * q + 1 >= d) zz.y = 0.f;
                 if (4 * q + 2 >= d) zz.z = 0.f;
@@ -477,17 +567,19 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
               }
             }
             const bool ok = rr < nvalid;
-            zc[i][0] = ok ? pack_bf16x2(zz.x, zz.y) : 0u;
-            zc[i][1] = ok ? pack_bf16x2(zz.z, zz.w) : 0u;
+            zc[i][0] = ok ? pack_f16x2(zz.x, zz.y) : 0u;
+            zc[i][1] = ok ? pack_f16x2(zz.z, zz.w) : 0u;
           }
         }
         const int s = tl & 1;
         const uint32_t bit = 1u << s;
+        TRACE(3, s, j, 1);
         if (used & bit) {
           mbar_wait(bar(kBarSlotFree + s), (ph_free >> s) & 1u, 41);  // the slot's previous tile has left hV / hT
           ph_free ^= bit;
         }
         used |= bit;
+        TRACE(3, s, j, 2);
         if (active) {
           uint8_t* const zdst = smem + kOffSlot + (uint32_t)s * kSlotBytes;
 #pragma unroll
@@ -500,7 +592,9 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(kBarZFull + s));
+        TRACE(3, s, j, 3);
         if (pending == 2) bismut(z2, j2, u2, last2);
+        TRACE(3, s, j, 4);
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
           z2[i][0] = z1[i][0], z2[i][1] = z1[i][1];
@@ -551,14 +645,14 @@ cha_tc_finish_kernel(const float* __restrict__ partG, const float* __restrict__ 
   }
 }
 
-// dst = bf16 SWIZZLE_128B K-major image of W[n][col_off + k] (n < n_valid, k < k_valid; zero elsewhere)
+// dst = fp16 SWIZZLE_128B K-major image of W[n][col_off + k] (n < n_valid, k < k_valid; zero elsewhere)
 __global__ void pack_sw128_kernel(const float* __restrict__ W, int ld, int col_off, int n_valid, int k_valid,
                                   uint8_t* __restrict__ dst) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 128 * 128) return;
   const int n = i >> 7, k = i & 127;
   const float v = (n < n_valid && k < k_valid) ? W[(size_t)n * ld + col_off + k] : 0.f;
-  *reinterpret_cast<__nv_bfloat16*>(dst + sw128_offset((uint32_t)n, (uint32_t)k)) = __float2bfloat16_rn(v);
+  *reinterpret_cast<__half*>(dst + sw128_offset((uint32_t)n, (uint32_t)k)) = __float2half_rn(v);
 }
 
 // ---- UMMA self-test: D[128x128] = A[128x128] . B[128x128]^T through the same descriptors / layouts -------------
@@ -586,7 +680,7 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const uint8_t* __
     mbar_wait(barW, 0, 100);
     tc_fence_after();
     for (int ks = 0; ks < 8; ++ks)
-      umma_bf16(tmem, desc_kstep(sbase, ks), desc_kstep(sbase + kOperandBytes, ks), make_idesc_bf16(128, 128), ks > 0);
+      umma_bf16(tmem, desc_kstep(sbase, ks), desc_kstep(sbase + kOperandBytes, ks), make_idesc_f16(128, 128), ks > 0);
     tc_commit(barD);
   }
   __syncwarp();
@@ -637,18 +731,20 @@ int tc_pack_network(const dpi_network& net, const ProblemDev& P, const MlpDev& M
   // per-column fp32 constants travel as kernel parameters (constant bank): copy the packed vectors back once
   DPI_CUDA_CHECK(cudaStreamSynchronize(st));
   TcNetDev T{};
-  DPI_CUDA_CHECK(cudaMemcpy(T.consts.wt, M.wt, 128 * sizeof(float), cudaMemcpyDeviceToHost));
-  DPI_CUDA_CHECK(cudaMemcpy(T.consts.wsum, M.wsum, 128 * sizeof(float), cudaMemcpyDeviceToHost));
-  for (int l = 0; l < 3; ++l)
-    DPI_CUDA_CHECK(cudaMemcpy(T.consts.b[l], M.bh[l], 128 * sizeof(float), cudaMemcpyDeviceToHost));
-  DPI_CUDA_CHECK(cudaMemcpy(T.consts.wout, M.wout, 128 * sizeof(float), cudaMemcpyDeviceToHost));
+  // activations are carried scaled by log2(e) (see epi_pass): scale the vectors that add to / read from them
+  std::vector<float> wt(128), wsum(128), bh(128), wout(128);
+  DPI_CUDA_CHECK(cudaMemcpy(wt.data(), M.wt, 128 * sizeof(float), cudaMemcpyDeviceToHost));
+  DPI_CUDA_CHECK(cudaMemcpy(wsum.data(), M.wsum, 128 * sizeof(float), cudaMemcpyDeviceToHost));
+  DPI_CUDA_CHECK(cudaMemcpy(wout.data(), M.wout, 128 * sizeof(float), cudaMemcpyDeviceToHost));
   DPI_CUDA_CHECK(cudaMemcpy(&T.consts.bout, M.bout, sizeof(float), cudaMemcpyDeviceToHost));
-  // activations are carried scaled by log2(e) (see epi_hidden): scale the vectors that add to / read from them
-  for (int i = 0; i < 128; ++i) {
-    T.consts.wt[i] *= kLog2e;
-    T.consts.wsum[i] *= kLog2e;
-    for (int l = 0; l < 3; ++l) T.consts.b[l][i] *= kLog2e;
-    T.consts.wout[i] *= 0.6931471805599453f;
+  for (int i = 0; i < 128; ++i) T.consts.wt[i] = wt[i] * kLog2e;
+  for (int i = 0; i < 64; ++i) {
+    T.consts.wsum16[i] = h2_const(wsum[2 * i] * kLog2e, wsum[2 * i + 1] * kLog2e);
+    T.consts.wout16[i] = h2_const(wout[2 * i] * 0.6931471805599453f, wout[2 * i + 1] * 0.6931471805599453f);
+  }
+  for (int l = 0; l < 3; ++l) {
+    DPI_CUDA_CHECK(cudaMemcpy(bh.data(), M.bh[l], 128 * sizeof(float), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 64; ++i) T.consts.b16[l][i] = h2_const(bh[2 * i] * kLog2e, bh[2 * i + 1] * kLog2e);
   }
   T.W = img;
   T.nx = P.nx;
@@ -692,6 +788,15 @@ int launch_cha_tc_path(const ProblemDev& P, const TcNetDev& N, const float* tx, 
   A.nq = N.nq;
   const int grid = (int)(A.n_units < N.num_sms ? A.n_units : N.num_sms);
   int rc;
+#ifdef DPI_TC_TRACE
+  long long* trace_dev = nullptr;
+  const size_t trace_bytes = sizeof(long long) * (4 * 2 * 8192);
+  if (getenv("DPI_TC_TRACE_FILE")) {
+    cudaMalloc((void**)&trace_dev, trace_bytes);
+    cudaMemsetAsync(trace_dev, 0, trace_bytes, st);
+    A.trace = trace_dev;
+  }
+#endif
   const bool det = zS != nullptr;
   if (N.cls == 16)
     rc = det ? launch_tc_t<8, 16, true>(P, N, A, grid, st) : launch_tc_t<8, 16, false>(P, N, A, grid, st);
@@ -700,6 +805,22 @@ int launch_cha_tc_path(const ProblemDev& P, const TcNetDev& N, const float* tx, 
   else
     rc = det ? launch_tc_t<16, 8, true>(P, N, A, grid, st) : launch_tc_t<16, 8, false>(P, N, A, grid, st);
   if (rc) return rc;
+#ifdef DPI_TC_TRACE
+  if (trace_dev) {
+    std::vector<long long> hbuf(4 * 2 * 8192);
+    cudaStreamSynchronize(st);
+    cudaMemcpy(hbuf.data(), trace_dev, trace_bytes, cudaMemcpyDeviceToHost);
+    cudaFree(trace_dev);
+    if (FILE* f = fopen(getenv("DPI_TC_TRACE_FILE"), "w")) {
+      for (int r = 0; r < 4; ++r)
+        for (int i = 0; i < 8192; ++i) {
+          const long long code = hbuf[(size_t)r * 2 * 8192 + 2 * i], clk = hbuf[(size_t)r * 2 * 8192 + 2 * i + 1];
+          if (clk) fprintf(f, "%lld %lld\n", (long long)(r == 0 ? 1 : (r == 3 ? 3 : 2)) * 1000000 + code, clk);
+        }
+      fclose(f);
+    }
+  }
+#endif
   cha_tc_finish_kernel<<<(unsigned)n, 128, 0, st>>>(partG, partF, A.units_per_point, N.cls, P.nx, M_I, bound, y);
   DPI_CUDA_CHECK(cudaGetLastError());
   return DPI_OK;

@@ -2,6 +2,7 @@
 // UMMA shared-memory descriptors and the SWIZZLE_128B K-major operand layout.  Inline PTX only (no CUTLASS).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -23,6 +24,11 @@ __host__ __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t
 // N>>3 at bits [17,23), M>>4 at bits [24,29)
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// same with fp16 operands (format code 0 for A and B)
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -116,6 +122,44 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Warp-convergent issue: every lane executes the surrounding (uniform) address arithmetic, so the descriptors live in
+// uniform registers, and only the elected lane issues.  (Issuing from inside an `if (lane == 0)` region makes the
+// compiler wrap every tcgen05.mma in a waterfall loop of R2UR broadcasts, ~150 cycles per instruction.)
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t p;
+  asm volatile("{\n.reg .pred q;\nelect.sync _|q, 0xffffffff;\nselp.u32 %0, 1, 0, q;\n}" : "=r"(p));
+  return p;
+}
+__device__ __forceinline__ void umma_bf16_p(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate, uint32_t leader) {
+  asm volatile(
+      "{\n.reg .pred p, q;\nsetp.ne.b32 p, %4, 0;\nsetp.ne.b32 q, %5, 0;\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_p(uint32_t bar, uint32_t leader) {
+  asm volatile(
+      "{\n.reg .pred q;\nsetp.ne.b32 q, %1, 0;\n"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}" ::"r"(bar),
+      "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_p(uint32_t bar, uint32_t bytes, uint32_t leader) {
+  asm volatile(
+      "{\n.reg .pred q;\nsetp.ne.b32 q, %2, 0;\n"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n}" ::"r"(bar),
+      "r"(bytes), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_p(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar,
+                                           uint32_t leader) {
+  asm volatile(
+      "{\n.reg .pred q;\nsetp.ne.b32 q, %4, 0;\n"
+      "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n}" ::"r"(dst_smem),
+      "l"(src), "r"(bytes), "r"(bar), "r"(leader)
+      : "memory");
+}
 // 32 lanes x 32 columns of 32-bit: thread i of warp w reads TMEM lane 32*(w%4)+i, columns [c, c+32)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -149,6 +193,50 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<const uint32_t*>(&v);
 }
+// ---- packed fp16x2 arithmetic (two columns per instruction) ---------------------------------------
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t h2_add(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("add.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t h2_mul(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t h2_fma(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+__device__ __forceinline__ uint32_t h2_min(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("min.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t h2_max(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("max.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t h2_ex2(uint32_t a) {
+  uint32_t r;
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(r) : "r"(a));
+  return r;
+}
+__device__ __forceinline__ float2 h2_unpack(uint32_t v) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&v));
+}
+__host__ __device__ __forceinline__ uint32_t h2_const(float lo, float hi) {
+  const __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }

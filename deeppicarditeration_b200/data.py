@@ -7,7 +7,8 @@ without a CUDA device, or with a combination the library has not built, raises.
 Differences that are deliberate and visible:
   * labels are float32 tensors (the reference's configs run in float64); pass `out_dtype=torch.float64` to get
     them cast for a float64 trainer.  Arithmetic: fp32 CUDA-core path (`precision="fp32"`, within 1e-4 rel of the
-    fp64 reference on replayed draws) or bf16 tcgen05 tensor cores with fp32 accumulation (`precision="bf16"`, 1e-2).
+    fp64 reference on replayed draws) or the 16-bit tcgen05 tensor-core path with fp32 accumulation (`precision="f16"`:
+    fp16 operands, within 1e-2; `"bf16"` is accepted as an alias of the same path).
   * randomness is a counter-based Philox stream keyed by (`seed`, global point index) instead of torch's global
     generator, so the labels of a point do not depend on the batch size, the call pattern or the GPU count.
     Successive `sample*` calls advance the point index; `rank`/`world_size` give each GPU a disjoint index range.

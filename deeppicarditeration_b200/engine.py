@@ -129,7 +129,8 @@ class LabelEngine:
     def _cfg(M_T, M_I, precision, bound, seed, base):
         cfg = nat.dpi_label_config()
         cfg.M_T, cfg.M_I = int(M_T), int(M_I)
-        cfg.precision = {"fp32": nat.DPI_PREC_FP32, "bf16": nat.DPI_PREC_BF16}[precision]
+        cfg.precision = {"fp32": nat.DPI_PREC_FP32, "f16": nat.DPI_PREC_F16, "fp16": nat.DPI_PREC_F16,
+                         "bf16": nat.DPI_PREC_F16}[precision]  # "bf16": alias of the 16-bit tensor-core path
         cfg.sample_bound = float(bound) if bound is not None and math.isfinite(bound) else 0.0
         cfg.seed = seed & (2**64 - 1)
         cfg.point_index_base = int(base)
@@ -190,7 +191,7 @@ class LabelEngine:
         return int(self.lib.dpi_launch_count(self.h))
 
     def selftest_umma(self, A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
-        """D = bf16(A) @ bf16(B).T on the tensor cores (128x128x128), for the hardware self-test."""
+        """D = fp16(A) @ fp16(B).T on the tensor cores (128x128x128), for the hardware self-test."""
         A, B = _f32c(A, self.device), _f32c(B, self.device)
         assert A.shape == (128, 128) and B.shape == (128, 128)
         D = torch.empty(128, 128, device=self.device, dtype=torch.float32)
@@ -215,15 +216,15 @@ class LabelEngine:
 # torch custom op: thin shim so the label generator composes with torch code (streams, graphs capture-free).
 # ------------------------------------------------------------------------------------------------
 @torch.library.custom_op("picard_b200::label_gen", mutates_args=(), device_types="cuda")
-def label_gen_op(tx: torch.Tensor, engine_id: int, M_T: int, M_I: int, bf16: bool, sample_bound: float, seed: int,
+def label_gen_op(tx: torch.Tensor, engine_id: int, M_T: int, M_I: int, f16: bool, sample_bound: float, seed: int,
                  point_index_base: int, zT: Optional[torch.Tensor] = None, u_s: Optional[torch.Tensor] = None,
                  zS: Optional[torch.Tensor] = None, idx: Optional[torch.Tensor] = None) -> torch.Tensor:
     eng = _ENGINES[engine_id]
     draws = None if zT is None else {"zT": zT, "u_s": u_s, "zS": zS, "idx": idx}
-    return eng.label_gen(tx, M_T, M_I, precision="bf16" if bf16 else "fp32", sample_bound=sample_bound, seed=seed,
+    return eng.label_gen(tx, M_T, M_I, precision="f16" if f16 else "fp32", sample_bound=sample_bound, seed=seed,
                          point_index_base=point_index_base, draws=draws)
 
 
 @label_gen_op.register_fake
-def _(tx, engine_id, M_T, M_I, bf16, sample_bound, seed, point_index_base, zT=None, u_s=None, zS=None, idx=None):
+def _(tx, engine_id, M_T, M_I, f16, sample_bound, seed, point_index_base, zT=None, u_s=None, zS=None, idx=None):
     return torch.empty_like(tx, dtype=torch.float32)

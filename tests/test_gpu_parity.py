@@ -10,7 +10,7 @@ from tests.golden_util import Golden, golden_names
 pytestmark = pytest.mark.gpu
 
 TOL_FP32 = 1e-4
-TOL_BF16 = 1e-2
+TOL_BF16 = 1e-2  # north-star tolerance of the 16-bit tensor-core path (fp16 operands; "bf16" is an alias)
 
 BUILT = golden_names()  # every fixture generated from the reference: Burgers / GBM+SDGD / HJB, MLP / PISGradNet / Zero
 
@@ -145,13 +145,13 @@ def test_umma_selftest_matches_bf16_matmul():
     A = torch.randn(128, 128, generator=g)
     B = torch.randn(128, 128, generator=g)
     D = e.selftest_umma(A, B).cpu().double()
-    ref = A.bfloat16().double() @ B.bfloat16().double().t()
+    ref = A.half().double() @ B.half().double().t()
     assert orc.rel_l2(D, ref) < 1e-5
     # structured operands catch transposition / swizzle mix-ups that random data could hide statistically
     A2 = torch.arange(128.).view(-1, 1).repeat(1, 128) / 128 + torch.eye(128)
     B2 = torch.arange(128.).view(1, -1).repeat(128, 1) / 64 - torch.eye(128)
     D2 = e.selftest_umma(A2, B2).cpu().double()
-    ref2 = A2.bfloat16().double() @ B2.bfloat16().double().t()
+    ref2 = A2.half().double() @ B2.half().double().t()
     assert orc.rel_l2(D2, ref2) < 1e-5
     e.close()
 
@@ -164,7 +164,7 @@ def test_labels_match_reference_bf16(name):
     from tests.gpu_util import draws_dict
     g = Golden(name)
     e = _engine(g)
-    y = e.label_gen(g.tx, g.M_T, g.M_I, precision="bf16", draws=draws_dict(g.draws)).double().cpu()
+    y = e.label_gen(g.tx, g.M_T, g.M_I, precision="f16", draws=draws_dict(g.draws)).double().cpu()
     assert torch.isfinite(y).all()
     assert orc.rel_l2(y, g.y) < TOL_BF16
     assert orc.rel_l2(y[:, 1:], g.y[:, 1:]) < TOL_BF16
@@ -187,7 +187,7 @@ def test_bf16_path_agrees_with_fp32_path_on_the_same_philox_draws(nx, M_T, M_I, 
     e = engine_for(eq, net)
     tx = e.sample_tx(n, seed=3)
     y32 = e.label_gen(tx, M_T, M_I, precision="fp32", seed=5).double().cpu()
-    y16 = e.label_gen(tx, M_T, M_I, precision="bf16", seed=5).double().cpu()
+    y16 = e.label_gen(tx, M_T, M_I, precision="f16", seed=5).double().cpu()
     assert torch.isfinite(y16).all()
     assert orc.rel_l2(y16, y32) < TOL_BF16
     assert orc.rel_l2(y16[:, :1], y32[:, :1]) < TOL_BF16
@@ -200,11 +200,20 @@ def test_bf16_shard_invariance_and_determinism():
     net = orc.make_mlp(101, [128] * 4, seed=5)
     e = engine_for(eq, net)
     tx = e.sample_tx(300, seed=7)
-    y = e.label_gen(tx, 64, 1500, precision="bf16", seed=7)
-    assert torch.equal(y, e.label_gen(tx, 64, 1500, precision="bf16", seed=7))
-    y_b = torch.cat([e.label_gen(tx[:11], 64, 1500, precision="bf16", seed=7),
-                     e.label_gen(tx[11:], 64, 1500, precision="bf16", seed=7, point_index_base=11)])
+    y = e.label_gen(tx, 64, 1500, precision="f16", seed=7)
+    assert torch.equal(y, e.label_gen(tx, 64, 1500, precision="f16", seed=7))
+    y_b = torch.cat([e.label_gen(tx[:11], 64, 1500, precision="f16", seed=7),
+                     e.label_gen(tx[11:], 64, 1500, precision="f16", seed=7, point_index_base=11)])
     assert torch.equal(y, y_b)
+    e.close()
+
+
+def test_bf16_alias_selects_the_same_path():
+    from tests.gpu_util import engine_for
+    eq = orc.Cha(100, 1.0, 5.0, 1.0)
+    e = engine_for(eq, orc.make_mlp(101, [128] * 4, seed=5))
+    tx = e.sample_tx(8, seed=1)
+    assert torch.equal(e.label_gen(tx, 32, 256, precision="f16", seed=2), e.label_gen(tx, 32, 256, precision="bf16", seed=2))
     e.close()
 
 
@@ -214,5 +223,5 @@ def test_bf16_rejects_unsupported_network_loudly():
     e = engine_for(eq, orc.make_mlp(101, [64, 64], seed=1))
     tx = e.sample_tx(4, seed=0)
     with pytest.raises(NotImplementedError):
-        e.label_gen(tx, 16, 16, precision="bf16")
+        e.label_gen(tx, 16, 16, precision="f16")
     e.close()
