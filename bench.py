@@ -270,7 +270,10 @@ def run_b200(args, wl):
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         with open(tp) as f:
-            traffic = json.load(f).get(f"{args.workload}:{prec}")
+            rec = json.load(f).get(f"{args.workload}:{'f16' if prec in ('f16', 'bf16') else prec}")
+            # ncu dram__bytes_read.sum + dram__bytes_write.sum of the integral kernel, valid for the same launch size only
+            if isinstance(rec, dict) and rec.get("launch_points") == n:
+                traffic = rec.get("dram_bytes_per_launch")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -31,6 +31,8 @@ struct dpi_handle {
   TcNetDev tc{};
   bool tc_ready = false;
   PisDev pis{};
+  dpi_linear mlp_raw[DPI_MAX_LINEAR] = {};  // the caller's MLP tensors (torch layout), for dpi_net_eval
+  int n_mlp_raw = 0;
   // activations of one chunk of rows of the batched-GEMM (PISGradNet) path
   float* hjb_scratch = nullptr;
   int64_t hjb_scratch_floats = 0;
@@ -361,6 +363,8 @@ int dpi_set_network(dpi_handle* h, const dpi_network* net, void* stream) {
       M.bh[l] = bh[l];
     }
     h->mlp = M;
+    for (int l = 0; l < L; ++l) h->mlp_raw[l] = net->main[l];
+    h->n_mlp_raw = L;
     // bf16 tensor-core packing (tcgen05 path) when the shape qualifies
     rc = tc_pack_network(*net, h->P, M, h->net_bufs, &h->tc, &h->tc_ready, &h->launches, st);
     if (rc) return rc;
@@ -584,6 +588,19 @@ int dpi_net_eval(dpi_handle* h, const float* tx, int64_t n, float* u, float* du,
     rc = launch_cha_simt_base(h->P, h->mlp, tx, n, h->fb, h->c0, u, nullptr, false, st);
     if (!rc) h->launches += 1;
     return rc;
+  }
+  if (h->net_kind == DPI_NET_MLP) {
+    // value and full input gradient through the batched-GEMM pipeline (any equation, any hidden widths)
+    const int64_t per_row = mlp_eval_scratch_floats(h->mlp_raw, h->n_mlp_raw, 1) * (int64_t)sizeof(float);
+    const int64_t rpc = std::max<int64_t>(1, std::min<int64_t>(n, kHjbScratchBudget / per_row));
+    int rc = ensure_hjb_scratch(h, mlp_eval_scratch_floats(h->mlp_raw, h->n_mlp_raw, rpc));
+    if (rc) return rc;
+    return launch_mlp_eval(h->mlp_raw, h->n_mlp_raw, h->P.nx, tx, n, h->hjb_scratch, rpc, u, du, st, &h->launches);
+  }
+  if (h->net_kind == DPI_NET_ZERO) {
+    if (u) DPI_CUDA_CHECK(cudaMemsetAsync(u, 0, sizeof(float) * n, st));
+    if (du) DPI_CUDA_CHECK(cudaMemsetAsync(du, 0, sizeof(float) * n * h->P.nx, st));
+    return DPI_OK;
   }
   if (h->net_kind == DPI_NET_PISGRAD && h->P.eq == DPI_EQ_OU) {
     const int64_t per_row = hjb_scratch_floats(h->pis, h->P.nx, 1) * (int64_t)sizeof(float);

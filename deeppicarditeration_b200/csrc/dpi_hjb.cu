@@ -544,6 +544,78 @@ int launch_hjb_paths(const ProblemDev& P, const PisDev& N, const float* tx, int6
   return DPI_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Plain MLP u_k: value and full input gradient at the rows of tx (picard/data.py:1230,1245-1251 as used by the
+// evaluation callback, picard/utils.py:362-458): forward chain keeping ELU', then one VJP with cotangent 1.
+// scratch: ones [R] | act A [R][hmax] | act B [R][hmax] | E_l [R][hmax] per hidden layer.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void fill_ones_kernel(float* __restrict__ p, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 1.f;
+}
+
+int64_t mlp_eval_scratch_floats(const dpi_linear* L, int n_lin, int64_t rows) {
+  int hmax = 1;
+  for (int l = 0; l < n_lin - 1; ++l) hmax = std::max(hmax, L[l].n_out);
+  return rows * (int64_t)(1 + (2 + (n_lin - 1)) * hmax) + 64;
+}
+
+int launch_mlp_eval(const dpi_linear* L, int n_lin, int d, const float* tx, int64_t n, float* scratch,
+                    int64_t rows_per_chunk, float* u, float* du, cudaStream_t st, int64_t* launches) {
+  int hmax = 1;
+  for (int l = 0; l < n_lin - 1; ++l) hmax = std::max(hmax, L[l].n_out);
+  for (int64_t p0 = 0; p0 < n; p0 += rows_per_chunk) {
+    const int64_t R = std::min<int64_t>(rows_per_chunk, n - p0);
+    float* ones = scratch;
+    float* bufs[2] = {scratch + ((R + 3) / 4) * 4, scratch + ((R + 3) / 4) * 4 + R * (int64_t)hmax};
+    float* E0 = bufs[1] + R * (int64_t)hmax;
+    auto Eof = [&](int l) { return E0 + (int64_t)l * R * hmax; };
+    int rc;
+    // forward
+    const float* cur = tx + p0 * (1 + d);
+    int ld = 1 + d;
+    for (int l = 0; l < n_lin - 1; ++l) {
+      GemmArgs g{};
+      g.A = cur, g.lda = ld, g.B = L[l].W, g.ldb = L[l].n_in, g.b_kn = 0, g.bias = L[l].b;
+      g.C = bufs[l & 1], g.ldc = L[l].n_out, g.D = Eof(l), g.ldd = L[l].n_out;
+      g.R = R, g.N = L[l].n_out, g.K = L[l].n_in, g.epi = kEpiBiasEluD;
+      if ((rc = gemm(g, st, launches))) return rc;
+      cur = bufs[l & 1], ld = L[l].n_out;
+    }
+    if (u) {
+      GemmArgs g{};
+      g.A = cur, g.lda = ld, g.B = L[n_lin - 1].W, g.ldb = L[n_lin - 1].n_in, g.b_kn = 0, g.bias = L[n_lin - 1].b;
+      g.C = u + p0, g.ldc = 1, g.R = R, g.N = 1, g.K = L[n_lin - 1].n_in, g.epi = kEpiBias;
+      if ((rc = gemm(g, st, launches))) return rc;
+    }
+    if (du) {
+      fill_ones_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(ones, R);
+      DPI_CUDA_CHECK(cudaGetLastError());
+      *launches += 1;
+      // c = 1 . W_last (K = 1), masked by ELU' of the last hidden layer; then back through the hidden layers
+      const int wl = L[n_lin - 1].n_in;
+      GemmArgs g{};
+      g.A = ones, g.lda = 1, g.B = L[n_lin - 1].W, g.ldb = wl, g.b_kn = 1, g.E = Eof(n_lin - 2), g.lde = wl;
+      g.C = bufs[0], g.ldc = wl, g.R = R, g.N = wl, g.K = 1, g.epi = kEpiMulE;
+      if ((rc = gemm(g, st, launches))) return rc;
+      const float* c = bufs[0];
+      int cld = wl, b = 1;
+      for (int l = n_lin - 2; l >= 1; --l) {
+        GemmArgs h{};
+        h.A = c, h.lda = cld, h.B = L[l].W, h.ldb = L[l].n_in, h.b_kn = 1, h.E = Eof(l - 1), h.lde = L[l].n_in;
+        h.C = bufs[b], h.ldc = L[l].n_in, h.R = R, h.N = L[l].n_in, h.K = L[l].n_out, h.epi = kEpiMulE;
+        if ((rc = gemm(h, st, launches))) return rc;
+        c = bufs[b], cld = L[l].n_in, b ^= 1;
+      }
+      GemmArgs h{};
+      h.A = c, h.lda = cld, h.B = L[0].W + 1, h.ldb = 1 + d, h.b_kn = 1;
+      h.C = du + p0 * d, h.ldc = d, h.R = R, h.N = d, h.K = L[0].n_out, h.epi = kEpiNone;
+      if ((rc = gemm(h, st, launches))) return rc;
+    }
+  }
+  return DPI_OK;
+}
+
 int launch_hjb_eval(const ProblemDev& P, const PisDev& N, const float* tx, int64_t n, float* scratch,
                     int64_t rows_per_chunk, float* u, float* du, cudaStream_t st, int64_t* launches) {
   const int d = P.nx;

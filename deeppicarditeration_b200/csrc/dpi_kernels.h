@@ -94,6 +94,11 @@ int launch_hjb_paths(const ProblemDev& P, const PisDev& net, const float* tx, in
 int launch_hjb_eval(const ProblemDev& P, const PisDev& net, const float* tx, int64_t n, float* scratch,
                     int64_t rows_per_chunk, float* u, float* du, cudaStream_t st, int64_t* launches);
 
+// plain MLP: u [n] and grad_x u [n, d] (either may be null); weights in torch layout, used in place
+int64_t mlp_eval_scratch_floats(const dpi_linear* L, int n_lin, int64_t rows);
+int launch_mlp_eval(const dpi_linear* L, int n_lin, int d, const float* tx, int64_t n, float* scratch,
+                    int64_t rows_per_chunk, float* u, float* du, cudaStream_t st, int64_t* launches);
+
 // y = clip(y + add, +-bound) elementwise helpers used by the Zero-network shortcuts
 int launch_finish_zero(const ProblemDev& P, const float* tx, int64_t n, float bound, float* y, cudaStream_t st);
 

@@ -99,6 +99,25 @@ def test_philox_labels_agree_with_oracle_statistically():
     e.close()
 
 
+@pytest.mark.parametrize("nx,hidden", [(100, [128] * 4), (10, [64, 64]), (37, [96, 40, 72])])
+def test_mlp_value_and_full_gradient_match_autograd(nx, hidden):
+    """dpi_net_eval on a plain MLP: u and the full input gradient (one VJP through the batched-GEMM pipeline) vs
+    fp64 autograd of the oracle network (picard/data.py:1245-1251 computes exactly this with torch.autograd.grad)."""
+    from tests.gpu_util import engine_for
+    eq = orc.Cha(nx, 1.0, 5.0, 1.0)
+    net = orc.make_mlp(1 + nx, hidden, seed=11, gain=1.4)
+    e = engine_for(eq, net)
+    gen = torch.Generator().manual_seed(5)
+    tx = torch.randn(53, 1 + nx, generator=gen, dtype=torch.float64)
+    txg = tx.clone().requires_grad_()
+    u_ref = net.forward(txg)
+    (g_ref,) = torch.autograd.grad(u_ref.sum(), txg)
+    u, du = e.net_eval(tx, want_grad=True)
+    assert orc.rel_l2(u.double().cpu().view(-1, 1), u_ref.detach()) < 1e-5
+    assert orc.rel_l2(du.double().cpu(), g_ref[:, 1:]) < 1e-5
+    e.close()
+
+
 def test_pisgradnet_value_and_gradient_match_oracle():
     """dpi_net_eval on PISGradNet: u and the closed-form grad_x u (one VJP through nn_module) vs the fp64 oracle,
     whose closed form is itself checked against autograd of the reference network in tests/test_oracle_golden.py."""
