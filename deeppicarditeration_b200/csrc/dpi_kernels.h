@@ -61,14 +61,15 @@ struct alignas(16) TcConsts {
 struct TcNetDev {
   const void* W;  // 4 x [128 x 128] fp16 operand images (K-major, SWIZZLE_128B): W1 x-columns, W2, W3, W4
   TcConsts consts;
-  int nx, ksteps1, nq, cls, num_sms;
+  int nx, ksteps1, no, cls, num_sms;
 };
 int tc_pack_network(const dpi_network& net, const ProblemDev& P, const MlpDev& M, std::vector<void*>& owner,
                     TcNetDev* out, bool* ready, int64_t* launches, cudaStream_t st);
 int64_t tc_units_per_point(int M_I);
-constexpr int64_t kTcPartGFloatsPerUnit = 16 * 128;
+constexpr int kTcMaxClasses = 32;  // row classes of the producer mapping (partial sums per unit)
+constexpr int64_t kTcPartGFloatsPerUnit = kTcMaxClasses * 128;
 constexpr int64_t kTcPartFFloatsPerUnit = 8;  // [slot][lane quarter]
-// partG [n*units][16][128], partF [n*units][8]: scratch for the unit partial sums
+// partG [n*units][32][128], partF [n*units][8]: scratch for the unit partial sums
 int launch_cha_tc_path(const ProblemDev& P, const TcNetDev& net, const float* tx, int64_t n, int M_I, uint64_t seed,
                        int64_t base, const float* u_s, const float* zS, const float* fb, const float* c0, float bound,
                        float* partG, float* partF, float* y, cudaStream_t st);

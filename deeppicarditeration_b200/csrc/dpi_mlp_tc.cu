@@ -46,7 +46,10 @@ using namespace tc;
 // MMA/TMA warpgroup 96 -> 32, epilogue 96 -> 88, producers 96 -> 136 (2 x 88 + 2 x 136 + 32 = 480 = 5 x 96).
 constexpr int kTcThreads = 640;
 constexpr int kProdWarp0 = 8, kMmaWarp = 16, kTmaWarp = 17;
-constexpr int kEpiRegs = 88, kProdRegs = 136, kMmaRegs = 32;
+#ifndef DPI_EPI_REGS
+#define DPI_EPI_REGS 88
+#endif
+constexpr int kEpiRegs = DPI_EPI_REGS, kProdRegs = 224 - DPI_EPI_REGS, kMmaRegs = 32;
 constexpr float kLog2e = 1.4426950408889634f;
 
 // shared memory map (dynamic, 1024-byte aligned)
@@ -85,7 +88,8 @@ struct TcArgs {
   int units_per_point;
   int tiles_per_point;
   int ksteps1;  // ceil(d/16)
-  int nq;       // ceil(d/4) quads of dims
+  int no;       // ceil(d/8) octets of dims (one Philox block, one 16-byte operand chunk each)
+  int cls;      // row classes of the producer mapping: cls * no <= 256, cls <= kTcMaxClasses
   long long* trace;  // developer timeline (DPI_TC_TRACE builds only), else null
 };
 
@@ -222,7 +226,7 @@ struct TileCursor {
   }
 };
 
-template <int ITEMS, int CLS, bool DET>
+template <int ITEMS, bool DET>
 __global__ void __launch_bounds__(kTcThreads, 1)
 cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcConsts C,
               const __grid_constant__ TcArgs A) {
@@ -480,55 +484,63 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
   } else {
     // =================================== increment producers ===================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kProdRegs));
-    // All 8 warps draw every tile: thread (q, c) owns the 4 dims [4q, 4q+4) of the rows r = c + CLS i.  A tile's
-    // increments are generated into registers (no dependence on shared memory), stored into the slot's hV buffer once
-    // the slot's previous tile has left it, and kept until the tile's Bismut coefficients arrive two tiles later.
+    // All 8 warps draw every tile: thread (o, c) owns the 8 dims [8o, 8o+8) -- one Philox block, one 16-byte operand
+    // chunk -- of the rows r = c + cls i.  A tile's increments are generated into registers (no dependence on shared
+    // memory), stored into the slot's hV buffer once the slot's previous tile has left it, and kept until the tile's
+    // Bismut coefficients arrive two tiles later.
     const int tl_id = threadIdx.x - 32 * kProdWarp0;
-    const int nq = A.nq;
-    const int q = tl_id % nq, c = tl_id / nq;
-    const bool active = c < CLS;
-    const bool vec_ok = (d & 3) == 0;
-    constexpr int PERIOD = (CLS % 8 == 0) ? 1 : ((CLS % 4 == 0) ? 2 : ((CLS % 2 == 0) ? 4 : 8));
-    uint32_t zoff[PERIOD];  // byte offset of item i in a slot's hV image: zoff[i % PERIOD] + (i / PERIOD) PERIOD CLS 128
+    const int no = A.no, cls = A.cls;
+    const int o = tl_id % no, c = tl_id / no;
+    const bool active = c < cls;
+    const bool vec_ok = (d & 3) == 0, oct_ok = (d & 7) == 0;
+    uint32_t zoff[ITEMS];  // byte offset of item i in a slot's hV image (K panel, row, swizzled 16-byte chunk)
 #pragma unroll
-    for (int k = 0; k < PERIOD; ++k) {
-      const uint32_t rr = (uint32_t)(c + CLS * k);
-      zoff[k] = (uint32_t)(q >> 4) * kPanelBytes + rr * 128u + (((uint32_t)((q & 15) >> 1) ^ (rr & 7u)) << 4) +
-                (uint32_t)(q & 1) * 8u;
+    for (int i = 0; i < ITEMS; ++i) {
+      const uint32_t rr = (uint32_t)(c + cls * i);
+      zoff[i] = (uint32_t)(o >> 3) * kPanelBytes + rr * 128u + (((uint32_t)(o & 7) ^ (rr & 7u)) << 4);
     }
     const float* coef_s = reinterpret_cast<const float*>(smem + kOffCoef);
-    uint32_t zc[ITEMS][2], z1[ITEMS][2], z2[ITEMS][2];
-    float4 G = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint4 zc[ITEMS], z1[ITEMS], z2[ITEMS];  // fp16x8 per item: current tile and the two tiles in flight
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) z1[i] = z2[i] = make_uint4(0u, 0u, 0u, 0u);
+    float4 Ga = make_float4(0.f, 0.f, 0.f, 0.f), Gb = make_float4(0.f, 0.f, 0.f, 0.f);
     uint32_t ph_free = 0, used = 0, ph_coef = 0, j = 0;
     int pending = 0;
+    int64_t u1 = 0, u2 = 0;      // units of the pending tiles (1 = newer, 2 = older)
+    bool last1 = false, last2 = false;
+    uint32_t j1 = 0, j2 = 0;
     TRACE_DECL(3);
 #ifdef DPI_TC_TRACE
     if (tl_id != 0) trace_p = nullptr;
 #endif
-    int64_t u1 = 0, u2 = 0;      // units of the pending tiles (1 = newer, 2 = older)
-    bool last1 = false, last2 = false;
-    uint32_t j1 = 0, j2 = 0;
     // Bismut accumulation of a finished tile: G_j += coef_m Z_mj (fp16 Z, exactly what the MLP saw)
-    auto bismut = [&](const uint32_t (&z)[ITEMS][2], uint32_t jt, int64_t ut, bool last) {
-      const uint32_t cb = jt % 3u;
-      mbar_wait(bar(kBarCoef + (int)cb), (ph_coef >> cb) & 1u, 40);
-      ph_coef ^= 1u << cb;
+    auto bismut = [&](const uint4 (&z)[ITEMS], uint32_t jt, int64_t ut, bool last) {
+      const uint32_t cbuf = jt % 3u;
+      mbar_wait(bar(kBarCoef + (int)cbuf), (ph_coef >> cbuf) & 1u, 40);
+      ph_coef ^= 1u << cbuf;
       if (active) {
-        const float* cf_s = coef_s + cb * 128u + c;
+        const float* cf_s = coef_s + cbuf * 128u;
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
-          if (CLS * i + (CLS - 1) < 128 || c + CLS * i < 128) {
-            const float cf = cf_s[CLS * i];
-            const float2 za = h2_unpack(z[i][0]), zb = h2_unpack(z[i][1]);
-            G.x = fmaf(cf, za.x, G.x);
-            G.y = fmaf(cf, za.y, G.y);
-            G.z = fmaf(cf, zb.x, G.z);
-            G.w = fmaf(cf, zb.y, G.w);
+          const int rr = c + cls * i;
+          if (rr < 128) {
+            const float cf = cf_s[rr];
+            const float2 p0 = h2_unpack(z[i].x), p1 = h2_unpack(z[i].y), p2 = h2_unpack(z[i].z), p3 = h2_unpack(z[i].w);
+            Ga.x = fmaf(cf, p0.x, Ga.x);
+            Ga.y = fmaf(cf, p0.y, Ga.y);
+            Ga.z = fmaf(cf, p1.x, Ga.z);
+            Ga.w = fmaf(cf, p1.y, Ga.w);
+            Gb.x = fmaf(cf, p2.x, Gb.x);
+            Gb.y = fmaf(cf, p2.y, Gb.y);
+            Gb.z = fmaf(cf, p3.x, Gb.z);
+            Gb.w = fmaf(cf, p3.y, Gb.w);
           }
         }
         if (last) {
-          *reinterpret_cast<float4*>(A.partG + (ut * 16 + c) * 128 + 4 * q) = G;
-          G = make_float4(0.f, 0.f, 0.f, 0.f);
+          float* gp_ = A.partG + (ut * kTcMaxClasses + c) * 128 + 8 * o;
+          *reinterpret_cast<float4*>(gp_) = Ga;
+          *reinterpret_cast<float4*>(gp_ + 4) = Gb;
+          Ga = Gb = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
     };
@@ -544,31 +556,43 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
         if (active) {
 #pragma unroll
           for (int i = 0; i < ITEMS; ++i) {
-            const int rr = c + CLS * i;
-            float4 zz = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int rr = c + cls * i;
+            float4 za = make_float4(0.f, 0.f, 0.f, 0.f), zb = za;
             if (DET) {
-              if (rr < nvalid) zz = load_row4(A.zS + ((int64_t)p * M_I + m0 + rr) * d, 4 * q, d, vec_ok);
+              if (rr < nvalid) {
+                const float* row = A.zS + ((int64_t)p * M_I + m0 + rr) * d;
+                za = load_row4(row, 8 * o, d, vec_ok);
+                zb = load_row4(row, 8 * o + 4, d, vec_ok);
+              }
             } else {
 #ifdef DPI_DBG_NO_RNG
               {
-                const uint32_t hsh = (uint32_t)(m0 + rr) * 2654435761u + (uint32_t)q * 40503u;
-                zz = make_float4(__uint_as_float(0x3f000000u | (hsh & 0x7fffffu)) - 0.75f,
+                const uint32_t hsh = (uint32_t)(m0 + rr) * 2654435761u + (uint32_t)o * 40503u;
+                za = make_float4(__uint_as_float(0x3f000000u | (hsh & 0x7fffffu)) - 0.75f,
                                  __uint_as_float(0x3f000000u | ((hsh >> 3) & 0x7fffffu)) - 0.75f,
                                  __uint_as_float(0x3f000000u | ((hsh >> 6) & 0x7fffffu)) - 0.75f,
                                  __uint_as_float(0x3f000000u | ((hsh >> 9) & 0x7fffffu)) - 0.75f);
+                zb = za;
               }
 #else
-              zz = normal4(A.seed, gp, kStreamIntegral, (uint32_t)(m0 + rr), (uint32_t)q);
+              normal8(A.seed, gp, kStreamIntegral, (uint32_t)(m0 + rr), (uint32_t)o, za, zb);
 #endif
-              if (!vec_ok) {
-                if (4 * q + 1 >= d) zz.y = 0.f;
-                if (4 * q + 2 >= d) zz.z = 0.f;
-                if (4 * q + 3 >= d) zz.w = 0.f;
+              if (!oct_ok) {
+                float* zf = reinterpret_cast<float*>(&za);  // za, zb are adjacent locals only by luck: mask separately
+                if (8 * o + 1 >= d) za.y = 0.f;
+                if (8 * o + 2 >= d) za.z = 0.f;
+                if (8 * o + 3 >= d) za.w = 0.f;
+                if (8 * o + 4 >= d) zb.x = 0.f;
+                if (8 * o + 5 >= d) zb.y = 0.f;
+                if (8 * o + 6 >= d) zb.z = 0.f;
+                if (8 * o + 7 >= d) zb.w = 0.f;
+                (void)zf;
               }
             }
             const bool ok = rr < nvalid;
-            zc[i][0] = ok ? pack_f16x2(zz.x, zz.y) : 0u;
-            zc[i][1] = ok ? pack_f16x2(zz.z, zz.w) : 0u;
+            zc[i] = ok ? make_uint4(pack_f16x2(za.x, za.y), pack_f16x2(za.z, za.w), pack_f16x2(zb.x, zb.y),
+                                    pack_f16x2(zb.z, zb.w))
+                       : make_uint4(0u, 0u, 0u, 0u);
           }
         }
         const int s = tl & 1;
@@ -584,9 +608,7 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
           uint8_t* const zdst = smem + kOffSlot + (uint32_t)s * kSlotBytes;
 #pragma unroll
           for (int i = 0; i < ITEMS; ++i) {
-            if (CLS * i + (CLS - 1) < 128 || c + CLS * i < 128)
-              *reinterpret_cast<uint2*>(zdst + zoff[i % PERIOD] + (uint32_t)((i / PERIOD) * PERIOD * CLS * 128)) =
-                  make_uint2(zc[i][0], zc[i][1]);
+            if (c + cls * i < 128) *reinterpret_cast<uint4*>(zdst + zoff[i]) = zc[i];
           }
         }
         fence_proxy_async();
@@ -597,8 +619,8 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
         TRACE(3, s, j, 4);
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
-          z2[i][0] = z1[i][0], z2[i][1] = z1[i][1];
-          z1[i][0] = zc[i][0], z1[i][1] = zc[i][1];
+          z2[i] = z1[i];
+          z1[i] = zc[i];
         }
         j2 = j1, u2 = u1, last2 = last1;
         j1 = j, u1 = u, last1 = (tl == tiles - 1);
@@ -629,7 +651,7 @@ cha_tc_finish_kernel(const float* __restrict__ partG, const float* __restrict__ 
   if (j < d) {
     float s = 0.f;
     for (int g = 0; g < units_per_point; ++g)
-      for (int c = 0; c < cls; ++c) s += partG[((p * units_per_point + g) * 16 + c) * 128 + j];
+      for (int c = 0; c < cls; ++c) s += partG[((p * units_per_point + g) * kTcMaxClasses + c) * 128 + j];
     float v = yp[1 + j] + s * invM;
     if (clip) v = fminf(fmaxf(v, -bound), bound);
     yp[1 + j] = v;
@@ -701,9 +723,9 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const uint8_t* __
   }
 }
 
-template <int ITEMS, int CLS, bool DET>
+template <int ITEMS, bool DET>
 int launch_tc_t(const ProblemDev& P, const TcNetDev& N, const TcArgs& A, int grid, cudaStream_t st) {
-  auto k = cha_tc_kernel<ITEMS, CLS, DET>;
+  auto k = cha_tc_kernel<ITEMS, DET>;
   DPI_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
   k<<<grid, kTcThreads, kTcSmemBytes, st>>>(P, N.consts, A);
   DPI_CUDA_CHECK(cudaGetLastError());
@@ -749,8 +771,8 @@ int tc_pack_network(const dpi_network& net, const ProblemDev& P, const MlpDev& M
   T.W = img;
   T.nx = P.nx;
   T.ksteps1 = (P.nx + 15) / 16;
-  T.nq = (P.nx + 3) / 4;
-  T.cls = T.nq <= 16 ? 16 : (T.nq <= 25 ? 10 : 8);  // row classes of the 256 producer threads: cls * nq <= 256
+  T.no = (P.nx + 7) / 8;
+  T.cls = 256 / T.no < kTcMaxClasses ? 256 / T.no : kTcMaxClasses;  // row classes of the 256 producer threads
   int dev = 0, sms = 0;
   DPI_CUDA_CHECK(cudaGetDevice(&dev));
   DPI_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -785,7 +807,8 @@ int launch_cha_tc_path(const ProblemDev& P, const TcNetDev& N, const float* tx, 
   A.partF = partF;
   A.M_I = M_I;
   A.ksteps1 = N.ksteps1;
-  A.nq = N.nq;
+  A.no = N.no;
+  A.cls = N.cls;
   const int grid = (int)(A.n_units < N.num_sms ? A.n_units : N.num_sms);
   int rc;
 #ifdef DPI_TC_TRACE
@@ -798,12 +821,14 @@ int launch_cha_tc_path(const ProblemDev& P, const TcNetDev& N, const float* tx, 
   }
 #endif
   const bool det = zS != nullptr;
-  if (N.cls == 16)
-    rc = det ? launch_tc_t<8, 16, true>(P, N, A, grid, st) : launch_tc_t<8, 16, false>(P, N, A, grid, st);
-  else if (N.cls == 10)
-    rc = det ? launch_tc_t<13, 10, true>(P, N, A, grid, st) : launch_tc_t<13, 10, false>(P, N, A, grid, st);
-  else
-    rc = det ? launch_tc_t<16, 8, true>(P, N, A, grid, st) : launch_tc_t<16, 8, false>(P, N, A, grid, st);
+  const int items = (128 + N.cls - 1) / N.cls;  // rows per producer thread: 4 (d <= 64) .. 8 (d > 104)
+  switch (items) {
+    case 4: rc = det ? launch_tc_t<4, true>(P, N, A, grid, st) : launch_tc_t<4, false>(P, N, A, grid, st); break;
+    case 5: rc = det ? launch_tc_t<5, true>(P, N, A, grid, st) : launch_tc_t<5, false>(P, N, A, grid, st); break;
+    case 6: rc = det ? launch_tc_t<6, true>(P, N, A, grid, st) : launch_tc_t<6, false>(P, N, A, grid, st); break;
+    case 7: rc = det ? launch_tc_t<7, true>(P, N, A, grid, st) : launch_tc_t<7, false>(P, N, A, grid, st); break;
+    default: rc = det ? launch_tc_t<8, true>(P, N, A, grid, st) : launch_tc_t<8, false>(P, N, A, grid, st); break;
+  }
   if (rc) return rc;
 #ifdef DPI_TC_TRACE
   if (trace_dev) {

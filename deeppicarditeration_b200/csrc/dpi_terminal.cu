@@ -2,8 +2,8 @@
 //
 // Restates (not ports) picard/data.py:161-167 (t), picard/equations.py:118-119,217-230 (x) and
 // picard/data.py:899-926 (terminal estimator with Bismut weights).  The reference materialises five
-// [n*M_T, nx] fp64 tensors in HBM; here a warp owns one MC sample at a time, each lane generates its 4 Brownian
-// increments per 128-dim slot from Philox in registers (or streams them with one coalesced 16-byte load in
+// [n*M_T, nx] fp64 tensors in HBM; here a half-warp owns one MC sample at a time, each lane generates its 8 Brownian
+// increments per 128-dim slot (one Philox block) in registers (or streams them with one coalesced 16-byte load in
 // deterministic mode), the payoff statistics are warp-shuffle reduced, and the Bismut-weighted sums stay in
 // registers until one label row per point is written.  HBM traffic: (1+nx) floats in, (1+nx) floats out per point.
 #include "dpi_common.cuh"
@@ -92,9 +92,9 @@ terminal_kernel(const ProblemDev P, const float* __restrict__ tx, int M_T, uint6
   constexpr int LDC = NSLOT * 128;  // padded dim count
   extern __shared__ __align__(16) float smem[];
   float* cst = smem;                          // [NCH][LDC]
-  float* red = smem + PO::NCH * LDC;          // [kTermWarps][LDC + 8]
+  float* red = smem + PO::NCH * LDC;          // [2 kTermWarps][LDC + 8]: one row per half-warp
   __shared__ float base[NS > 1 ? NS : 1];     // x-dependent scalars of g
-  __shared__ float red_v[kTermWarps];
+  __shared__ float red_v[2 * kTermWarps];
 
   const int d = P.nx;
   const int64_t p = blockIdx.x;
@@ -150,67 +150,87 @@ terminal_kernel(const ProblemDev P, const float* __restrict__ tx, int M_T, uint6
     g0 = PO::eval(P, st, base, 0.f);
   }
 
-  // ---- MC loop: warp <-> sample, lane <-> 4 dims per 128-dim slot ------------------------------
-  float4 acc[NSLOT];
+  // ---- MC loop: half-warp <-> sample, lane <-> 8 dims per 128-dim slot (one Philox block = 8 normals) ----------
+  const int hl = lane & 15, half = lane >> 4;
+  float4 acc[NSLOT][2];
 #pragma unroll
-  for (int q = 0; q < NSLOT; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int q = 0; q < NSLOT; ++q) acc[q][0] = acc[q][1] = make_float4(0.f, 0.f, 0.f, 0.f);
   float acc_v = 0.f;
   const uint64_t gp = (uint64_t)(point_base + p);
+  const bool oct_ok = (d & 7) == 0;
 
-  for (int m = warp; m < M_T; m += kTermWarps) {
-    float4 z[NSLOT];
+  for (int mb = 2 * warp; mb < M_T; mb += 2 * kTermWarps) {
+    const int m = mb + half;
+    const bool live = m < M_T;
+    float4 z[NSLOT][2];
     float st[NS];
 #pragma unroll
     for (int k = 0; k < NS; ++k) st[k] = 0.f;
 #pragma unroll
     for (int q = 0; q < NSLOT; ++q) {
-      const int j0 = 4 * lane + 128 * q;
-      if (j0 < d) {
+      const int j0 = 8 * hl + 128 * q;
+      z[q][0] = z[q][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j0 < d && live) {
         if (DET) {
-          z[q] = load_row4(zT + ((int64_t)p * M_T + m) * d, j0, d, vec_ok);
+          z[q][0] = load_row4(zT + ((int64_t)p * M_T + m) * d, j0, d, vec_ok);
+          z[q][1] = load_row4(zT + ((int64_t)p * M_T + m) * d, j0 + 4, d, vec_ok);
         } else {
-          z[q] = normal4(seed, gp, kStreamTerminal, (uint32_t)m, (uint32_t)(j0 >> 2));
-          if (j0 + 1 >= d) z[q].y = 0.f;
-          if (j0 + 2 >= d) z[q].z = 0.f;
-          if (j0 + 3 >= d) z[q].w = 0.f;
+          normal8(seed, gp, kStreamTerminal, (uint32_t)m, (uint32_t)(j0 >> 3), z[q][0], z[q][1]);
+          if (!oct_ok) {
+            float* zf = reinterpret_cast<float*>(&z[q][0]);
+#pragma unroll
+            for (int i = 1; i < 8; ++i)
+              if (j0 + i >= d) zf[i] = 0.f;
+          }
         }
-        PO::accumulate(st, z[q], cst, LDC, j0, a);
-      } else {
-        z[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (EQ == DPI_EQ_OU) PO::accumulate(st, z[q], cst, LDC, j0, a);  // padded dims contribute 0 (ivar=0)
+        PO::accumulate(st, z[q][0], cst, LDC, j0, a);
+        PO::accumulate(st, z[q][1], cst, LDC, j0 + 4, a);
+      } else if (EQ == DPI_EQ_OU) {
+        // padded dims contribute 0 (ivar = 0); dims of a dead sample are discarded below
+        PO::accumulate(st, z[q][0], cst, LDC, j0, a);
+        PO::accumulate(st, z[q][1], cst, LDC, j0 + 4, a);
       }
     }
 #pragma unroll
-    for (int k = 0; k < NS; ++k) st[k] = warp_sum(st[k]);
-    const float dg = PO::eval(P, st, base, a) - g0;
-    acc_v += dg;
+    for (int k = 0; k < NS; ++k) {
 #pragma unroll
-    for (int q = 0; q < NSLOT; ++q) {
-      acc[q].x = fmaf(dg, z[q].x, acc[q].x);
-      acc[q].y = fmaf(dg, z[q].y, acc[q].y);
-      acc[q].z = fmaf(dg, z[q].z, acc[q].z);
-      acc[q].w = fmaf(dg, z[q].w, acc[q].w);
+      for (int o = 8; o > 0; o >>= 1) st[k] += __shfl_xor_sync(0xffffffffu, st[k], o);  // over the 16 lanes of a sample
     }
+    const float dg = live ? PO::eval(P, st, base, a) - g0 : 0.f;
+    if (hl == 0) acc_v += dg;
+#pragma unroll
+    for (int q = 0; q < NSLOT; ++q)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        acc[q][h].x = fmaf(dg, z[q][h].x, acc[q][h].x);
+        acc[q][h].y = fmaf(dg, z[q][h].y, acc[q][h].y);
+        acc[q][h].z = fmaf(dg, z[q][h].z, acc[q][h].z);
+        acc[q][h].w = fmaf(dg, z[q][h].w, acc[q][h].w);
+      }
   }
 
   // ---- cross-warp reduction, one label row per point -------------------------------------------
   constexpr int LDR = LDC + 8;
+  const int rrow = 2 * warp + half;
 #pragma unroll
-  for (int q = 0; q < NSLOT; ++q) *reinterpret_cast<float4*>(red + warp * LDR + 4 * lane + 128 * q) = acc[q];
-  if (lane == 0) red_v[warp] = acc_v;
+  for (int q = 0; q < NSLOT; ++q) {
+    *reinterpret_cast<float4*>(red + rrow * LDR + 8 * hl + 128 * q) = acc[q][0];
+    *reinterpret_cast<float4*>(red + rrow * LDR + 8 * hl + 128 * q + 4) = acc[q][1];
+  }
+  if (hl == 0) red_v[rrow] = acc_v;
   __syncthreads();
   float* yp = y + p * (int64_t)(1 + d);
   const float inv = 1.f / ((float)M_T * a);
   for (int j = threadIdx.x; j < d; j += kTermThreads) {
     float s = 0.f;
 #pragma unroll
-    for (int w = 0; w < kTermWarps; ++w) s += red[w * LDR + j];
+    for (int w = 0; w < 2 * kTermWarps; ++w) s += red[w * LDR + j];
     yp[1 + j] = s * inv;
   }
   if (threadIdx.x == 0) {
     float s = 0.f;
 #pragma unroll
-    for (int w = 0; w < kTermWarps; ++w) s += red_v[w];
+    for (int w = 0; w < 2 * kTermWarps; ++w) s += red_v[w];
     yp[0] = s / (float)M_T + g0;
   }
 }
@@ -247,7 +267,7 @@ int launch_terminal_t(const ProblemDev& P, const float* tx, int64_t n, int M_T, 
                       const float* zT, float* y, cudaStream_t st) {
   using PO = Payoff<EQ>;
   constexpr int LDC = NSLOT * 128;
-  const size_t smem = sizeof(float) * (PO::NCH * LDC + kTermWarps * (LDC + 8));
+  const size_t smem = sizeof(float) * (PO::NCH * LDC + 2 * kTermWarps * (LDC + 8));
   auto kd = terminal_kernel<EQ, NSLOT, true>;
   auto kp = terminal_kernel<EQ, NSLOT, false>;
   if (smem > 48 * 1024) {
