@@ -492,7 +492,7 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
     const int no = A.no, cls = A.cls;
     const int o = tl_id % no, c = tl_id / no;
     const bool active = c < cls;
-    const bool vec_ok = (d & 3) == 0, oct_ok = (d & 7) == 0;
+    const bool vec_ok = (d & 3) == 0;
     uint32_t zoff[ITEMS];  // byte offset of item i in a slot's hV image (K panel, row, swizzled 16-byte chunk)
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
@@ -577,17 +577,8 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
 #else
               normal8(A.seed, gp, kStreamIntegral, (uint32_t)(m0 + rr), (uint32_t)o, za, zb);
 #endif
-              if (!oct_ok) {
-                float* zf = reinterpret_cast<float*>(&za);  // za, zb are adjacent locals only by luck: mask separately
-                if (8 * o + 1 >= d) za.y = 0.f;
-                if (8 * o + 2 >= d) za.z = 0.f;
-                if (8 * o + 3 >= d) za.w = 0.f;
-                if (8 * o + 4 >= d) zb.x = 0.f;
-                if (8 * o + 5 >= d) zb.y = 0.f;
-                if (8 * o + 6 >= d) zb.z = 0.f;
-                if (8 * o + 7 >= d) zb.w = 0.f;
-                (void)zf;
-              }
+              // dims >= d of the last octet stay as drawn: their W1 columns are zero and their Bismut sums are never
+              // read, so masking them would only cost instructions
             }
             const bool ok = rr < nvalid;
             zc[i] = ok ? make_uint4(pack_f16x2(za.x, za.y), pack_f16x2(za.z, za.w), pack_f16x2(zb.x, zb.y),

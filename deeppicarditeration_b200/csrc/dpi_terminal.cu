@@ -26,9 +26,10 @@ struct Payoff;
 template <>
 struct Payoff<DPI_EQ_CHA> {
   static constexpr int NS = 1;
-  static constexpr int NCH = 0;  // per-dim constant channels in shared memory
+  static constexpr int NCH = 1;  // per-dim constant channels in shared memory: 1 for j < d, 0 for the padded dims
   __device__ static void accumulate(float (&st)[NS], const float4 z, const float* cst, int ldc, int j0, float a) {
-    st[0] += (z.x + z.y) + (z.z + z.w);
+    const float4 w = *reinterpret_cast<const float4*>(cst + j0);
+    st[0] += (w.x * z.x + w.y * z.y) + (w.z * z.z + w.w * z.w);
   }
   __device__ static float eval(const ProblemDev& P, const float (&st)[NS], const float* base, float a) {
     return sigmoidf_(P.T + P.cha_k * (base[0] + a * st[0]));
@@ -109,7 +110,9 @@ terminal_kernel(const ProblemDev P, const float* __restrict__ tx, int M_T, uint6
     const int ch = i / LDC, j = i - ch * LDC;
     float v = 0.f;
     if (j < d) {
-      if (EQ == DPI_EQ_GBM) {
+      if (EQ == DPI_EQ_CHA) {
+        v = 1.f;
+      } else if (EQ == DPI_EQ_GBM) {
         if (ch < P.gbm_nodes) v = P.gbm_w[ch * (1 + d) + 1 + j];
       } else if (EQ == DPI_EQ_OU) {
         const int k = ch >> 1;
@@ -157,7 +160,6 @@ terminal_kernel(const ProblemDev P, const float* __restrict__ tx, int M_T, uint6
   for (int q = 0; q < NSLOT; ++q) acc[q][0] = acc[q][1] = make_float4(0.f, 0.f, 0.f, 0.f);
   float acc_v = 0.f;
   const uint64_t gp = (uint64_t)(point_base + p);
-  const bool oct_ok = (d & 7) == 0;
 
   for (int mb = 2 * warp; mb < M_T; mb += 2 * kTermWarps) {
     const int m = mb + half;
@@ -176,12 +178,8 @@ terminal_kernel(const ProblemDev P, const float* __restrict__ tx, int M_T, uint6
           z[q][1] = load_row4(zT + ((int64_t)p * M_T + m) * d, j0 + 4, d, vec_ok);
         } else {
           normal8(seed, gp, kStreamTerminal, (uint32_t)m, (uint32_t)(j0 >> 3), z[q][0], z[q][1]);
-          if (!oct_ok) {
-            float* zf = reinterpret_cast<float*>(&z[q][0]);
-#pragma unroll
-            for (int i = 1; i < 8; ++i)
-              if (j0 + i >= d) zf[i] = 0.f;
-          }
+          // dims >= d of the last octet stay as drawn: every payoff statistic weights them with a zero constant and
+          // their Bismut sums are never written out
         }
         PO::accumulate(st, z[q][0], cst, LDC, j0, a);
         PO::accumulate(st, z[q][1], cst, LDC, j0 + 4, a);
