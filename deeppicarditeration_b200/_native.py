@@ -22,6 +22,7 @@ EXPORTED_SYMBOLS = (
     "dpi_version", "dpi_last_error", "dpi_create", "dpi_destroy", "dpi_set_problem", "dpi_set_network",
     "dpi_sample_tx", "dpi_label_gen", "dpi_label_gen_host", "dpi_net_eval", "dpi_launch_count",
     "dpi_set_stage_timing", "dpi_stage_ms", "dpi_selftest_umma",
+    "dpi_train_init", "dpi_train_param_count", "dpi_train_grad", "dpi_train_adam",
 )
 
 
@@ -59,6 +60,11 @@ class dpi_label_config(C.Structure):
     ]
 
 
+class dpi_train_config(C.Structure):
+    _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+                ("loss_beta", C.c_float), ("fixed_weight", C.c_float)]
+
+
 _lib = None
 
 
@@ -90,6 +96,12 @@ def load() -> C.CDLL:
     lib.dpi_set_stage_timing.argtypes = [H, C.c_int]
     lib.dpi_stage_ms.argtypes = [H, C.c_int, C.POINTER(C.c_float)]
     lib.dpi_selftest_umma.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.dpi_train_init.argtypes = [H, C.POINTER(dpi_network), C.c_int64, C.c_void_p]
+    lib.dpi_train_param_count.argtypes = [H]
+    lib.dpi_train_param_count.restype = C.c_int64
+    lib.dpi_train_grad.argtypes = [H, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(dpi_train_config), C.c_void_p,
+                                   C.c_void_p, C.c_void_p]
+    lib.dpi_train_adam.argtypes = [H, C.c_void_p, C.POINTER(dpi_train_config), C.c_int64, C.c_void_p]
     for name in EXPORTED_SYMBOLS:
         getattr(lib, name)  # AttributeError if a declared symbol is not exported
     _lib = lib

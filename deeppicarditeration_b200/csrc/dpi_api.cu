@@ -31,6 +31,11 @@ struct dpi_handle {
   TcNetDev tc{};
   bool tc_ready = false;
   PisDev pis{};
+  // regression step: trainable MLP (caller's tensors), Adam moments, activation scratch
+  dpi_linear train_lin[DPI_MAX_LINEAR] = {};
+  int n_train_lin = 0;
+  int64_t train_params = 0, train_max_batch = 0;
+  float *train_m = nullptr, *train_v = nullptr, *train_scratch = nullptr;
   dpi_linear mlp_raw[DPI_MAX_LINEAR] = {};  // the caller's MLP tensors (torch layout), for dpi_net_eval
   int n_mlp_raw = 0;
   // activations of one chunk of rows of the batched-GEMM (PISGradNet) path
@@ -199,6 +204,9 @@ int dpi_destroy(dpi_handle* h) {
   if (h->partG) cudaFree(h->partG);
   if (h->partF) cudaFree(h->partF);
   if (h->hjb_scratch) cudaFree(h->hjb_scratch);
+  if (h->train_m) cudaFree(h->train_m);
+  if (h->train_v) cudaFree(h->train_v);
+  if (h->train_scratch) cudaFree(h->train_scratch);
   for (int s = 0; s < DPI_STAGE_COUNT; ++s)
     for (int e = 0; e < 2; ++e)
       if (h->ev[s][e]) cudaEventDestroy(h->ev[s][e]);
@@ -611,6 +619,77 @@ int dpi_net_eval(dpi_handle* h, const float* tx, int64_t n, float* u, float* du,
   }
   set_error("dpi_net_eval: full input gradient not built yet");
   return DPI_ERR_UNSUPPORTED;
+}
+
+int dpi_train_init(dpi_handle* h, const dpi_network* net, int64_t max_batch, void* stream) {
+  if (!h || !net || max_batch < 1) {
+    set_error("dpi_train_init: bad arguments");
+    return DPI_ERR_INVALID;
+  }
+  if (net->kind != DPI_NET_MLP) {
+    set_error("dpi_train_init: the regression step is built for plain MLPs (NETWORK.PISGRADNET false)");
+    return DPI_ERR_UNSUPPORTED;
+  }
+  const int L = net->n_main;
+  if (L < 2 || L > DPI_MAX_LINEAR || net->main[L - 1].n_out != 1) {
+    set_error("dpi_train_init: need 2..%d Linear layers ending in a scalar output (NETWORK.TYPE = Value)", DPI_MAX_LINEAR);
+    return DPI_ERR_INVALID;
+  }
+  for (int l = 0; l < L; ++l) {
+    const dpi_linear& ll = net->main[l];
+    if (!ll.W || !ll.b || ll.n_out < 1 || (l > 0 && ll.n_in != net->main[l - 1].n_out)) {
+      set_error("dpi_train_init: layer %d has an inconsistent shape [%d,%d]", l, ll.n_out, ll.n_in);
+      return DPI_ERR_INVALID;
+    }
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  DPI_CUDA_CHECK(cudaSetDevice(h->device));
+  DPI_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (h->train_m) cudaFree(h->train_m);
+  if (h->train_v) cudaFree(h->train_v);
+  if (h->train_scratch) cudaFree(h->train_scratch);
+  h->train_m = h->train_v = h->train_scratch = nullptr;
+  for (int l = 0; l < L; ++l) h->train_lin[l] = net->main[l];
+  h->n_train_lin = L;
+  h->train_params = train_param_count(h->train_lin, L);
+  h->train_max_batch = max_batch;
+  DPI_CUDA_CHECK(cudaMalloc((void**)&h->train_m, sizeof(float) * h->train_params));
+  DPI_CUDA_CHECK(cudaMalloc((void**)&h->train_v, sizeof(float) * h->train_params));
+  DPI_CUDA_CHECK(cudaMalloc((void**)&h->train_scratch, sizeof(float) * train_scratch_floats(h->train_lin, L, max_batch)));
+  DPI_CUDA_CHECK(cudaMemsetAsync(h->train_m, 0, sizeof(float) * h->train_params, st));
+  DPI_CUDA_CHECK(cudaMemsetAsync(h->train_v, 0, sizeof(float) * h->train_params, st));
+  return DPI_OK;
+}
+
+int64_t dpi_train_param_count(const dpi_handle* h) { return h ? h->train_params : 0; }
+
+int dpi_train_grad(dpi_handle* h, const float* tx, const float* y, int64_t batch, const dpi_train_config* cfg,
+                   float* grad_flat, float* losses, void* stream) {
+  if (!h || !h->n_train_lin) {
+    set_error("dpi_train_grad: call dpi_train_init first");
+    return DPI_ERR_STATE;
+  }
+  if (!tx || !y || !cfg || !grad_flat || !losses || batch < 1 || batch > h->train_max_batch) {
+    set_error("dpi_train_grad: bad arguments (batch=%lld, max_batch=%lld)", (long long)batch, (long long)h->train_max_batch);
+    return DPI_ERR_INVALID;
+  }
+  DPI_CUDA_CHECK(cudaSetDevice(h->device));
+  return launch_train_grad(h->train_lin, h->n_train_lin, tx, y, batch, cfg->loss_beta, cfg->fixed_weight, h->train_scratch,
+                           grad_flat, losses, reinterpret_cast<cudaStream_t>(stream), &h->launches);
+}
+
+int dpi_train_adam(dpi_handle* h, const float* grad_flat, const dpi_train_config* cfg, int64_t step, void* stream) {
+  if (!h || !h->n_train_lin) {
+    set_error("dpi_train_adam: call dpi_train_init first");
+    return DPI_ERR_STATE;
+  }
+  if (!grad_flat || !cfg || step < 1) {
+    set_error("dpi_train_adam: bad arguments");
+    return DPI_ERR_INVALID;
+  }
+  DPI_CUDA_CHECK(cudaSetDevice(h->device));
+  return launch_train_adam(h->train_lin, h->n_train_lin, grad_flat, h->train_m, h->train_v, cfg->lr, cfg->beta1, cfg->beta2,
+                           cfg->eps, step, reinterpret_cast<cudaStream_t>(stream), &h->launches);
 }
 
 int64_t dpi_launch_count(const dpi_handle* h) { return h ? h->launches : 0; }

@@ -28,31 +28,6 @@ namespace {
 constexpr int BM = 128, BN = 128, BK = 16, kGemmThreads = 256;
 constexpr int kLds = BM + 4;  // 528-byte rows: 16-byte aligned, the +4 skews the k rows across banks
 
-enum GemmEpi : int {
-  kEpiNone = 0,      // C = acc
-  kEpiBias = 1,      // C = acc + bias
-  kEpiBiasElu = 2,   // C = ELU(acc + bias)
-  kEpiBiasEluD = 3,  // C = ELU(acc + bias), D = ELU'(acc + bias)
-  kEpiMulE = 4       // C = acc * E        (VJP through an ELU: cotangent times the stored ELU')
-};
-
-struct GemmArgs {
-  const float* A;
-  int lda;
-  const float* B;
-  int ldb;
-  int b_kn;
-  const float* bias;
-  const float* E;
-  int lde;
-  float* C;
-  int ldc;
-  float* D;
-  int ldd;
-  int64_t R;
-  int N, K, epi;
-};
-
 __device__ __forceinline__ void load8(const float* __restrict__ p, int i0, int limit, bool vec, float (&v)[8]) {
   // elements [i0, i0+8) of a contiguous run of `limit` floats starting at p; zero beyond
   if (vec && i0 + 7 < limit) {
@@ -69,6 +44,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2) sgemm_kernel(const GemmArgs g
   __shared__ __align__(16) float As[2][BK][kLds];
   __shared__ __align__(16) float Bs[2][BK][kLds];
   const int t = threadIdx.x;
+  const int M_ = (int)g.R;  // output rows (when a_km: columns of the stored A)
   const int64_t r0 = (int64_t)blockIdx.x * BM;
   const int n0 = blockIdx.y * BN;
   const int K = g.K, N = g.N;
@@ -79,13 +55,20 @@ __global__ void __launch_bounds__(kGemmThreads, 2) sgemm_kernel(const GemmArgs g
   const int lrow = t & 127, lkq = (t >> 7) * 8;
   // B when b_kn == 1: thread owns 8 consecutive n of one k row
   const int bk_k = t >> 4, bk_n = (t & 15) * 8;
-  const float* arow = (r0 + lrow < g.R) ? g.A + (r0 + lrow) * (int64_t)g.lda : nullptr;
+  const float* arow = (!g.a_km && r0 + lrow < g.R) ? g.A + (r0 + lrow) * (int64_t)g.lda : nullptr;
   const float* brow = nullptr;
   if (!g.b_kn && n0 + lrow < N) brow = g.B + (int64_t)(n0 + lrow) * g.ldb;
 
   float ra[8], rb[8];
   auto fetch = [&](int k0) {
-    if (arow) {
+    if (g.a_km) {  // A stored [K][M]: thread owns 8 consecutive m of one k row (weight-gradient GEMMs)
+      if (k0 + bk_k < K) {
+        load8(g.A + (int64_t)(k0 + bk_k) * g.lda, (int)r0 + bk_n, M_, a_vec, ra);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ra[i] = 0.f;
+      }
+    } else if (arow) {
       load8(arow, k0 + lkq, K, a_vec, ra);
     } else {
 #pragma unroll
@@ -108,8 +91,13 @@ __global__ void __launch_bounds__(kGemmThreads, 2) sgemm_kernel(const GemmArgs g
     }
   };
   auto stash = [&](int buf) {
+    if (g.a_km) {
+      *reinterpret_cast<float4*>(&As[buf][bk_k][bk_n]) = make_float4(ra[0], ra[1], ra[2], ra[3]);
+      *reinterpret_cast<float4*>(&As[buf][bk_k][bk_n + 4]) = make_float4(ra[4], ra[5], ra[6], ra[7]);
+    } else {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) As[buf][lkq + i][lrow] = ra[i];
+      for (int i = 0; i < 8; ++i) As[buf][lkq + i][lrow] = ra[i];
+    }
     if (!g.b_kn) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) Bs[buf][lkq + i][lrow] = rb[i];
@@ -187,6 +175,12 @@ __global__ void __launch_bounds__(kGemmThreads, 2) sgemm_kernel(const GemmArgs g
             if (col + j < N) v[j] *= __ldg(ep + j);
         }
       }
+      if (g.epi == kEpiKeepMulE) {  // C = acc (pre-activation tangent), D = acc * E (tangent through the ELU)
+        const float* ep = g.E + row * (int64_t)g.lde + col;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (col + j < N) dv[j] = v[j] * __ldg(ep + j);
+      }
       float* cp = g.C + row * (int64_t)g.ldc + col;
       if (full && c_vec) {
         *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
@@ -195,7 +189,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2) sgemm_kernel(const GemmArgs g
         for (int j = 0; j < 4; ++j)
           if (col + j < N) cp[j] = v[j];
       }
-      if (g.epi == kEpiBiasEluD) {
+      if (g.epi == kEpiBiasEluD || g.epi == kEpiKeepMulE) {
         float* dp = g.D + row * (int64_t)g.ldd + col;
         if (full && d_vec) {
           *reinterpret_cast<float4*>(dp) = make_float4(dv[0], dv[1], dv[2], dv[3]);
@@ -209,7 +203,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2) sgemm_kernel(const GemmArgs g
   }
 }
 
-int gemm(const GemmArgs& g, cudaStream_t st, int64_t* launches) {
+int gemm_impl(const GemmArgs& g, cudaStream_t st, int64_t* launches) {
   if (g.R <= 0 || g.N <= 0) return DPI_OK;
   dim3 grid((unsigned)((g.R + BM - 1) / BM), (unsigned)((g.N + BN - 1) / BN));
   sgemm_kernel<<<grid, kGemmThreads, 0, st>>>(g);
@@ -451,7 +445,7 @@ int eval_rows(const PisDev& N, int d, const Scratch& S, int64_t R, cudaStream_t 
     GemmArgs g{};
     g.A = A, g.lda = lda, g.B = L.W, g.ldb = L.n_in, g.b_kn = 0, g.bias = L.b, g.C = C, g.ldc = ldc, g.D = D, g.ldd = ldd;
     g.R = R1, g.N = N_, g.K = L.n_in, g.epi = epi;
-    return gemm(g, st, launches);
+    return gemm_impl(g, st, launches);
   };
   // t_encoder (solution.py:170-174): Linear(128,64) ELU Linear(64,64) -> columns [0,64) of the nn_module input
   if ((rc = G(S.rows.emb, 128, N.t_encoder[0], 64, S.t1, 64, kEpiBiasElu))) return rc;
@@ -508,6 +502,8 @@ int eval_rows(const PisDev& N, int d, const Scratch& S, int64_t R, cudaStream_t 
 }
 
 }  // namespace
+
+int gemm(const GemmArgs& g, cudaStream_t st, int64_t* launches) { return gemm_impl(g, st, launches); }
 
 int64_t hjb_scratch_floats(const PisDev& N, int d, int64_t rows) { return (rows + 1) * floats_per_row(N, d) + 64; }
 

@@ -76,6 +76,35 @@ int launch_cha_tc_path(const ProblemDev& P, const TcNetDev& net, const float* tx
 // D[128x128] = A[128x128] . B[128x128]^T (fp32 row-major device buffers, rounded to bf16) through tcgen05
 int tc_umma_selftest(const float* A, const float* B, float* D, cudaStream_t st);
 
+// ---- generic fp32 GEMM with fused epilogues (dpi_hjb.cu): C[R,N] = epilogue(A . B) ---------------------------
+// A [R][K] row-major (or [K][R] when a_km), B = W [N][K] (b_kn = 0: y = x W^T) or W [K][N] (b_kn = 1: c W)
+enum GemmEpi : int {
+  kEpiNone = 0,      // C = acc
+  kEpiBias = 1,      // C = acc + bias
+  kEpiBiasElu = 2,   // C = ELU(acc + bias)
+  kEpiBiasEluD = 3,  // C = ELU(acc + bias), D = ELU'(acc + bias)
+  kEpiMulE = 4,      // C = acc * E        (VJP through an ELU: cotangent times the stored ELU')
+  kEpiKeepMulE = 5   // C = acc, D = acc * E   (JVP through an ELU, keeping the pre-activation tangent)
+};
+struct GemmArgs {
+  const float* A;
+  int lda;
+  const float* B;
+  int ldb;
+  int b_kn;
+  const float* bias;
+  const float* E;
+  int lde;
+  float* C;
+  int ldc;
+  float* D;
+  int ldd;
+  int64_t R;
+  int N, K, epi;
+  int a_km;
+};
+int gemm(const GemmArgs& g, cudaStream_t st, int64_t* launches);
+
 // ---- HJB / PISGradNet, fp32 batched-GEMM pipeline (dpi_hjb.cu) -------------------------------------------
 // Weight pointers are the caller's torch-layout tensors (W [n_out, n_in] row-major), used in place.
 struct PisDev {
@@ -99,6 +128,14 @@ int launch_hjb_eval(const ProblemDev& P, const PisDev& net, const float* tx, int
 int64_t mlp_eval_scratch_floats(const dpi_linear* L, int n_lin, int64_t rows);
 int launch_mlp_eval(const dpi_linear* L, int n_lin, int d, const float* tx, int64_t n, float* scratch,
                     int64_t rows_per_chunk, float* u, float* du, cudaStream_t st, int64_t* launches);
+
+// ---- regression step for a scalar-output MLP (dpi_train.cu) ---------------------------------------------------
+int64_t train_param_count(const dpi_linear* L, int n_lin);
+int64_t train_scratch_floats(const dpi_linear* L, int n_lin, int64_t B);
+int launch_train_grad(const dpi_linear* L, int n_lin, const float* tx, const float* y, int64_t B, float beta, float fw,
+                      float* scratch, float* grad_flat, float* losses, cudaStream_t st, int64_t* launches);
+int launch_train_adam(const dpi_linear* L, int n_lin, const float* grad_flat, float* m, float* v, float lr, float b1,
+                      float b2, float eps, int64_t step, cudaStream_t st, int64_t* launches);
 
 // y = clip(y + add, +-bound) elementwise helpers used by the Zero-network shortcuts
 int launch_finish_zero(const ProblemDev& P, const float* tx, int64_t n, float bound, float* y, cudaStream_t st);

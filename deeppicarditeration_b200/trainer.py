@@ -1,0 +1,90 @@
+"""Host-side mirror of the reference's regression step for one Picard iteration.
+
+`RegressionTrainer` plays the role of `PicardSolutionGradientWrapper.training_step` + `loss.backward()` +
+`torch.optim.Adam.step()` (picard/solution_jac.py:172-216, picard/solution.py:93-97) for a scalar-output MLP with
+`FixedLossScaler`: same loss, same optimiser, fp32 master weights held in the solution's own `nn.Linear` tensors and
+updated in place by the library (no torch autograd on this path).  Data-parallel runs all-reduce the flat gradient
+between `dpi_train_grad` and `dpi_train_adam` (NCCL through torch.distributed), which keeps every rank's replica of
+`u_k` identical without a separate broadcast.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _native as nat
+from .engine import LabelEngine
+from .solution import _linears
+
+
+class RegressionTrainer:
+    def __init__(self, solution, *, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, loss_beta: float = 0.0,
+                 fixed_weight: float = 1.0, max_batch: int = 4096, device="cuda", process_group=None):
+        model = getattr(solution, "model", solution)
+        if not isinstance(model, torch.nn.Sequential):
+            raise NotImplementedError("the B200 regression step is built for plain MLPs (Linear + ELU)")
+        self.linears = [m for m in model if isinstance(m, torch.nn.Linear)]
+        _linears(model, type(solution).__name__)  # raises for anything but Linear / ELU(alpha=1)
+        for m in self.linears:
+            if m.weight.dtype != torch.float32 or not m.weight.is_cuda or not m.weight.is_contiguous():
+                raise ValueError("RegressionTrainer updates the solution's tensors in place: they must be contiguous "
+                                 "float32 CUDA tensors (solution.float().cuda())")
+        if self.linears[-1].out_features != 1:
+            raise NotImplementedError("only NETWORK.TYPE=Value (scalar output) is built")
+        self.engine = LabelEngine(device)
+        self.device = self.engine.device
+        self.cfg = nat.dpi_train_config(lr, betas[0], betas[1], eps, loss_beta, fixed_weight)
+        net = nat.dpi_network()
+        net.kind = nat.DPI_NET_MLP
+        net.n_main = len(self.linears)
+        for i, m in enumerate(self.linears):
+            net.main[i].W, net.main[i].b = m.weight.data_ptr(), m.bias.data_ptr()
+            net.main[i].n_out, net.main[i].n_in = m.out_features, m.in_features
+        with torch.cuda.device(self.device):
+            nat.check(self.engine.lib.dpi_train_init(self.engine.h, C.byref(net), max_batch, self.engine._stream()),
+                      "dpi_train_init")
+        self.n_params = int(self.engine.lib.dpi_train_param_count(self.engine.h))
+        self.grad = torch.empty(self.n_params, device=self.device, dtype=torch.float32)
+        self.losses = torch.zeros(3, device=self.device, dtype=torch.float32)
+        self.step_count = 0
+        self.pg = process_group
+
+    def close(self):
+        self.engine.close()
+
+    def backward(self, tx: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        """Loss terms and the flat parameter gradient of one mini-batch; returns losses [total, value, gradient]."""
+        tx = tx.detach().to(self.device, torch.float32).contiguous()
+        y = y.detach().to(self.device, torch.float32).contiguous()
+        assert tx.shape == y.shape and tx.shape[1] == self.linears[0].in_features
+        e = self.engine
+        with torch.cuda.device(self.device):
+            nat.check(e.lib.dpi_train_grad(e.h, C.c_void_p(tx.data_ptr()), C.c_void_p(y.data_ptr()), tx.shape[0],
+                                           C.byref(self.cfg), C.c_void_p(self.grad.data_ptr()),
+                                           C.c_void_p(self.losses.data_ptr()), e._stream()), "dpi_train_grad")
+        self._keep = (tx, y)
+        return self.losses
+
+    def step(self, tx: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        """One optimiser step on a mini-batch (solution_jac.py:172-216 + Adam)."""
+        losses = self.backward(tx, y)
+        if self.pg is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
+                                   and torch.distributed.get_world_size() > 1):
+            torch.distributed.all_reduce(self.grad, op=torch.distributed.ReduceOp.AVG, group=self.pg)
+        self.step_count += 1
+        e = self.engine
+        with torch.cuda.device(self.device):
+            nat.check(e.lib.dpi_train_adam(e.h, C.c_void_p(self.grad.data_ptr()), C.byref(self.cfg), self.step_count,
+                                           e._stream()), "dpi_train_adam")
+        return losses
+
+    def fit(self, tx: torch.Tensor, y: torch.Tensor, batch_size: int, n_epochs: int) -> Optional[torch.Tensor]:
+        """The reference's inner loop over one iteration's label set: unshuffled mini-batches (config.py:90), n_epochs passes."""
+        last = None
+        n = tx.shape[0]
+        for _ in range(n_epochs):
+            for i in range(0, n, batch_size):
+                last = self.step(tx[i:i + batch_size], y[i:i + batch_size])
+        return last

@@ -153,6 +153,28 @@ int dpi_label_gen_host(dpi_handle* h, const float* tx_in_host, int64_t n, const 
 /* u_k and its input gradient on rows of tx: u [n], du [n, nx] (either may be NULL). fp32 path. */
 int dpi_net_eval(dpi_handle* h, const float* tx, int64_t n, float* u, float* du, void* stream);
 
+/* ---- regression step (the trainer's inner loop) -------------------------------------------
+ *   dpi_train_init  <- PicardSolutionGradientWrapper.__init__ + configure_optimizers   picard/solution_jac.py:125-146,
+ *                                                                                       picard/solution.py:93-97
+ *   dpi_train_grad  <- PicardSolutionGradientWrapper.training_step + loss.backward()   picard/solution_jac.py:172-216
+ *   dpi_train_adam  <- torch.optim.Adam.step()                                          picard/solution.py:95-97
+ * The network is a scalar-output MLP (NETWORK.TYPE = Value) whose Linear tensors are DEVICE fp32 pointers in torch
+ * layout; they are the master weights and are updated in place.  dpi_train_grad writes the gradient of
+ *   loss = mean_b w_b (u - y_0)^2 + fixed_weight * sum_j mean_b w_b (d_j u - y_j)^2 ,   w_b = exp(loss_beta * t_b)
+ * flat in torch parameters() order (W_0, b_0, W_1, b_1, ...) and losses[3] = {total, value, gradient} (device).  Between
+ * dpi_train_grad and dpi_train_adam a data-parallel caller all-reduces (averages) the flat gradient over its ranks. */
+typedef struct {
+  float lr, beta1, beta2, eps; /* torch.optim.Adam defaults: 1e-3, 0.9, 0.999, 1e-8 */
+  float loss_beta;             /* TRAIN.LOSS.beta */
+  float fixed_weight;          /* TRAIN.LOSS.SCALER.kwargs.fixed_weight (FixedLossScaler) */
+} dpi_train_config;
+int dpi_train_init(dpi_handle* h, const dpi_network* mlp, int64_t max_batch, void* stream);
+int64_t dpi_train_param_count(const dpi_handle* h);
+int dpi_train_grad(dpi_handle* h, const float* tx, const float* y, int64_t batch, const dpi_train_config* cfg,
+                   float* grad_flat, float* losses, void* stream);
+int dpi_train_adam(dpi_handle* h, const float* grad_flat, const dpi_train_config* cfg, int64_t step /* 1-based */,
+                   void* stream);
+
 /* Kernels launched by this handle since creation (for bench.py's gpu_launches). */
 int64_t dpi_launch_count(const dpi_handle* h);
 
