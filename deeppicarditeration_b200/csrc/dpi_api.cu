@@ -35,7 +35,7 @@ struct dpi_handle {
   dpi_linear train_lin[DPI_MAX_LINEAR] = {};
   int n_train_lin = 0;
   int64_t train_params = 0, train_max_batch = 0;
-  float *train_m = nullptr, *train_v = nullptr, *train_scratch = nullptr;
+  float *train_m = nullptr, *train_v = nullptr, *train_scratch = nullptr, *train_grad = nullptr;
   dpi_linear mlp_raw[DPI_MAX_LINEAR] = {};  // the caller's MLP tensors (torch layout), for dpi_net_eval
   int n_mlp_raw = 0;
   // activations of one chunk of rows of the batched-GEMM (PISGradNet) path
@@ -207,6 +207,7 @@ int dpi_destroy(dpi_handle* h) {
   if (h->train_m) cudaFree(h->train_m);
   if (h->train_v) cudaFree(h->train_v);
   if (h->train_scratch) cudaFree(h->train_scratch);
+  if (h->train_grad) cudaFree(h->train_grad);
   for (int s = 0; s < DPI_STAGE_COUNT; ++s)
     for (int e = 0; e < 2; ++e)
       if (h->ev[s][e]) cudaEventDestroy(h->ev[s][e]);
@@ -648,7 +649,8 @@ int dpi_train_init(dpi_handle* h, const dpi_network* net, int64_t max_batch, voi
   if (h->train_m) cudaFree(h->train_m);
   if (h->train_v) cudaFree(h->train_v);
   if (h->train_scratch) cudaFree(h->train_scratch);
-  h->train_m = h->train_v = h->train_scratch = nullptr;
+  if (h->train_grad) cudaFree(h->train_grad);
+  h->train_m = h->train_v = h->train_scratch = h->train_grad = nullptr;
   for (int l = 0; l < L; ++l) h->train_lin[l] = net->main[l];
   h->n_train_lin = L;
   h->train_params = train_param_count(h->train_lin, L);
@@ -656,6 +658,7 @@ int dpi_train_init(dpi_handle* h, const dpi_network* net, int64_t max_batch, voi
   DPI_CUDA_CHECK(cudaMalloc((void**)&h->train_m, sizeof(float) * h->train_params));
   DPI_CUDA_CHECK(cudaMalloc((void**)&h->train_v, sizeof(float) * h->train_params));
   DPI_CUDA_CHECK(cudaMalloc((void**)&h->train_scratch, sizeof(float) * train_scratch_floats(h->train_lin, L, max_batch)));
+  DPI_CUDA_CHECK(cudaMalloc((void**)&h->train_grad, sizeof(float) * (h->train_params + 4)));
   DPI_CUDA_CHECK(cudaMemsetAsync(h->train_m, 0, sizeof(float) * h->train_params, st));
   DPI_CUDA_CHECK(cudaMemsetAsync(h->train_v, 0, sizeof(float) * h->train_params, st));
   return DPI_OK;
@@ -690,6 +693,37 @@ int dpi_train_adam(dpi_handle* h, const float* grad_flat, const dpi_train_config
   DPI_CUDA_CHECK(cudaSetDevice(h->device));
   return launch_train_adam(h->train_lin, h->n_train_lin, grad_flat, h->train_m, h->train_v, cfg->lr, cfg->beta1, cfg->beta2,
                            cfg->eps, step, reinterpret_cast<cudaStream_t>(stream), &h->launches);
+}
+
+int dpi_train_fit(dpi_handle* h, const float* tx, const float* y, int64_t n, int64_t batch, int64_t n_epochs,
+                  const dpi_train_config* cfg, int64_t first_step, float* losses_last, void* stream) {
+  if (!h || !h->n_train_lin) {
+    set_error("dpi_train_fit: call dpi_train_init first");
+    return DPI_ERR_STATE;
+  }
+  if (!tx || !y || !cfg || n < 1 || batch < 1 || batch > h->train_max_batch || n_epochs < 0 || first_step < 1) {
+    set_error("dpi_train_fit: bad arguments (n=%lld batch=%lld max_batch=%lld)", (long long)n, (long long)batch,
+              (long long)h->train_max_batch);
+    return DPI_ERR_INVALID;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  DPI_CUDA_CHECK(cudaSetDevice(h->device));
+  const int ld = h->train_lin[0].n_in;
+  float* losses = h->train_grad + h->train_params;
+  int64_t step = first_step;
+  for (int64_t e = 0; e < n_epochs; ++e)
+    for (int64_t i = 0; i < n; i += batch, ++step) {
+      const int64_t b = std::min<int64_t>(batch, n - i);
+      int rc = launch_train_grad(h->train_lin, h->n_train_lin, tx + i * ld, y + i * ld, b, cfg->loss_beta,
+                                 cfg->fixed_weight, h->train_scratch, h->train_grad, losses, st, &h->launches);
+      if (rc) return rc;
+      rc = launch_train_adam(h->train_lin, h->n_train_lin, h->train_grad, h->train_m, h->train_v, cfg->lr, cfg->beta1,
+                             cfg->beta2, cfg->eps, step, st, &h->launches);
+      if (rc) return rc;
+    }
+  if (losses_last)
+    DPI_CUDA_CHECK(cudaMemcpyAsync(losses_last, losses, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return DPI_OK;
 }
 
 int64_t dpi_launch_count(const dpi_handle* h) { return h ? h->launches : 0; }

@@ -40,6 +40,58 @@ __device__ __forceinline__ void load8(const float* __restrict__ p, int i0, int l
   }
 }
 
+// epilogue of 4 consecutive columns [col, col+4) of one output row
+__device__ __forceinline__ void gemm_epilogue4(const GemmArgs& g, int64_t row, int col, float (&v)[4], bool c_vec,
+                                               bool d_vec, bool e_vec) {
+  const int N = g.N;
+  float dv[4] = {0.f, 0.f, 0.f, 0.f};
+  const bool full = col + 3 < N;
+  if (g.epi == kEpiBias || g.epi == kEpiBiasElu || g.epi == kEpiBiasEluD) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (col + j < N) v[j] += __ldg(g.bias + col + j);
+  }
+  if (g.epi == kEpiBiasElu || g.epi == kEpiBiasEluD) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) elu_d1(v[j], v[j], dv[j]);
+  }
+  if (g.epi == kEpiMulE) {
+    const float* ep = g.E + row * (int64_t)g.lde + col;
+    if (full && e_vec) {
+      const float4 e = __ldg(reinterpret_cast<const float4*>(ep));
+      v[0] *= e.x, v[1] *= e.y, v[2] *= e.z, v[3] *= e.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (col + j < N) v[j] *= __ldg(ep + j);
+    }
+  }
+  if (g.epi == kEpiKeepMulE) {  // C = acc (pre-activation tangent), D = acc * E (tangent through the ELU)
+    const float* ep = g.E + row * (int64_t)g.lde + col;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (col + j < N) dv[j] = v[j] * __ldg(ep + j);
+  }
+  float* cp = g.C + row * (int64_t)g.ldc + col;
+  if (full && c_vec) {
+    *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (col + j < N) cp[j] = v[j];
+  }
+  if (g.epi == kEpiBiasEluD || g.epi == kEpiKeepMulE) {
+    float* dp = g.D + row * (int64_t)g.ldd + col;
+    if (full && d_vec) {
+      *reinterpret_cast<float4*>(dp) = make_float4(dv[0], dv[1], dv[2], dv[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (col + j < N) dp[j] = dv[j];
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kGemmThreads, 2) sgemm_kernel(const GemmArgs g) {
   __shared__ __align__(16) float As[2][BK][kLds];
   __shared__ __align__(16) float Bs[2][BK][kLds];
@@ -153,58 +205,155 @@ __global__ void __launch_bounds__(kGemmThreads, 2) sgemm_kernel(const GemmArgs g
       const int col = n0 + jg * 64 + tx * 4;
       if (col >= N) continue;
       float v[4] = {acc[i][jg * 4 + 0], acc[i][jg * 4 + 1], acc[i][jg * 4 + 2], acc[i][jg * 4 + 3]};
-      float dv[4] = {0.f, 0.f, 0.f, 0.f};
-      const bool full = col + 3 < N;
-      if (g.epi == kEpiBias || g.epi == kEpiBiasElu || g.epi == kEpiBiasEluD) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (col + j < N) v[j] += __ldg(g.bias + col + j);
-      }
-      if (g.epi == kEpiBiasElu || g.epi == kEpiBiasEluD) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) elu_d1(v[j], v[j], dv[j]);
-      }
-      if (g.epi == kEpiMulE) {
-        const float* ep = g.E + row * (int64_t)g.lde + col;
-        if (full && e_vec) {
-          const float4 e = __ldg(reinterpret_cast<const float4*>(ep));
-          v[0] *= e.x, v[1] *= e.y, v[2] *= e.z, v[3] *= e.w;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (col + j < N) v[j] *= __ldg(ep + j);
-        }
-      }
-      if (g.epi == kEpiKeepMulE) {  // C = acc (pre-activation tangent), D = acc * E (tangent through the ELU)
-        const float* ep = g.E + row * (int64_t)g.lde + col;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (col + j < N) dv[j] = v[j] * __ldg(ep + j);
-      }
-      float* cp = g.C + row * (int64_t)g.ldc + col;
-      if (full && c_vec) {
-        *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (col + j < N) cp[j] = v[j];
-      }
-      if (g.epi == kEpiBiasEluD || g.epi == kEpiKeepMulE) {
-        float* dp = g.D + row * (int64_t)g.ldd + col;
-        if (full && d_vec) {
-          *reinterpret_cast<float4*>(dp) = make_float4(dv[0], dv[1], dv[2], dv[3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (col + j < N) dp[j] = dv[j];
-        }
-      }
+      gemm_epilogue4(g, row, col, v, c_vec, d_vec, e_vec);
     }
   }
 }
 
+// Small problems (the regression step: a few hundred rows, 128-wide layers): 64x64x16 tiles, 4x4 per thread, optional
+// split-K over gridDim.z with partials [z][R][N] in g.ws (epilogue kEpiNone only; summed by splitk_reduce_kernel in a
+// fixed order, so the result does not depend on scheduling).
+constexpr int SM_T = 64, SM_K = 16, kLdsS = SM_T + 4;
+__global__ void __launch_bounds__(256) sgemm_small_kernel(const GemmArgs g, int k_per_split) {
+  __shared__ __align__(16) float As[2][SM_K][kLdsS];
+  __shared__ __align__(16) float Bs[2][SM_K][kLdsS];
+  const int t = threadIdx.x;
+  const int64_t r0 = (int64_t)blockIdx.x * SM_T;
+  const int n0 = blockIdx.y * SM_T;
+  const int N = g.N, M_ = (int)g.R;
+  const int kbeg = blockIdx.z * k_per_split, kend = min(g.K, kbeg + k_per_split);
+  const bool a_vec = ((g.lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0);
+  const bool b_vec = ((g.ldb & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.B) & 15) == 0);
+  // row-major operand ([rows][K]): thread owns 4 consecutive k of one row; transposed operand ([K][cols]): 4 consecutive cols
+  const int lrow = t >> 2, lk4 = (t & 3) * 4;
+  const int tk = t >> 4, tn4 = (t & 15) * 4;
+  auto ld4 = [&](const float* p, int i0, int limit, bool vec, float (&v)[4]) {
+    if (vec && i0 + 3 < limit) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(p + i0));
+      v[0] = q.x, v[1] = q.y, v[2] = q.z, v[3] = q.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = (i0 + i < limit) ? __ldg(p + i0 + i) : 0.f;
+    }
+  };
+  float ra[4], rb[4];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ra[i] = rb[i] = 0.f;
+    if (g.a_km) {
+      if (k0 + tk < kend) ld4(g.A + (int64_t)(k0 + tk) * g.lda, (int)r0 + tn4, M_, a_vec, ra);
+    } else if (r0 + lrow < g.R) {
+      ld4(g.A + (r0 + lrow) * (int64_t)g.lda, k0 + lk4, kend, a_vec, ra);
+    }
+    if (g.b_kn) {
+      if (k0 + tk < kend) ld4(g.B + (int64_t)(k0 + tk) * g.ldb, n0 + tn4, N, b_vec, rb);
+    } else if (n0 + lrow < N) {
+      ld4(g.B + (int64_t)(n0 + lrow) * g.ldb, k0 + lk4, kend, b_vec, rb);
+    }
+  };
+  auto stash = [&](int buf) {
+    if (g.a_km) {
+      *reinterpret_cast<float4*>(&As[buf][tk][tn4]) = make_float4(ra[0], ra[1], ra[2], ra[3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) As[buf][lk4 + i][lrow] = ra[i];
+    }
+    if (g.b_kn) {
+      *reinterpret_cast<float4*>(&Bs[buf][tk][tn4]) = make_float4(rb[0], rb[1], rb[2], rb[3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) Bs[buf][lk4 + i][lrow] = rb[i];
+    }
+  };
+  const int ty = t >> 4, tx = t & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int nk = (kend - kbeg + SM_K - 1) / SM_K;
+  if (nk > 0) {
+    fetch(kbeg);
+    stash(0);
+  }
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) fetch(kbeg + (kt + 1) * SM_K);
+#pragma unroll
+    for (int kk = 0; kk < SM_K; ++kk) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+      const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) {
+      stash(buf ^ 1);
+      __syncthreads();
+    }
+  }
+  const int col = n0 + tx * 4;
+  if (col >= N) return;
+  if (gridDim.z > 1) {  // split-K partial
+    float* wsz = g.ws + (int64_t)blockIdx.z * g.R * N;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t row = r0 + ty * 4 + i;
+      if (row >= g.R) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (col + j < N) wsz[row * N + col + j] = acc[i][j];
+    }
+    return;
+  }
+  const bool c_vec = ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
+  const bool d_vec = g.D && ((g.ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.D) & 15) == 0);
+  const bool e_vec = g.E && ((g.lde & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.E) & 15) == 0);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t row = r0 + ty * 4 + i;
+    if (row >= g.R) continue;
+    float v[4] = {acc[i][0], acc[i][1], acc[i][2], acc[i][3]};
+    gemm_epilogue4(g, row, col, v, c_vec, d_vec, e_vec);
+  }
+}
+
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, int64_t R, int N, float* __restrict__ C,
+                                     int ldc) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * N) return;
+  float s = 0.f;
+  for (int z = 0; z < splits; ++z) s += ws[(int64_t)z * R * N + i];
+  C[(i / N) * ldc + (i % N)] = s;
+}
+
 int gemm_impl(const GemmArgs& g, cudaStream_t st, int64_t* launches) {
   if (g.R <= 0 || g.N <= 0) return DPI_OK;
+  const int64_t big_tiles = ((g.R + BM - 1) / BM) * ((g.N + BN - 1) / BN);
+  if (big_tiles < 96) {
+    // too few 128x128 tiles to fill the 148 SMs: small tiles, and split K when even those are few
+    const int64_t tiles = ((g.R + SM_T - 1) / SM_T) * ((g.N + SM_T - 1) / SM_T);
+    int splits = 1;
+    if (g.ws && g.epi == kEpiNone && tiles < 64 && g.K >= 256) {
+      splits = (int)std::min<int64_t>({(int64_t)16, (int64_t)g.K / 64, (int64_t)g.ws_splits});
+      if (splits < 1) splits = 1;
+    }
+    const int kps = ((g.K + splits - 1) / splits + SM_K - 1) / SM_K * SM_K;
+    splits = (g.K + kps - 1) / kps;
+    dim3 grid((unsigned)((g.R + SM_T - 1) / SM_T), (unsigned)((g.N + SM_T - 1) / SM_T), (unsigned)splits);
+    sgemm_small_kernel<<<grid, 256, 0, st>>>(g, kps);
+    DPI_CUDA_CHECK(cudaGetLastError());
+    if (launches) *launches += 1;
+    if (splits > 1) {
+      splitk_reduce_kernel<<<(unsigned)((g.R * g.N + 255) / 256), 256, 0, st>>>(g.ws, splits, g.R, g.N, g.C, g.ldc);
+      DPI_CUDA_CHECK(cudaGetLastError());
+      if (launches) *launches += 1;
+    }
+    return DPI_OK;
+  }
   dim3 grid((unsigned)((g.R + BM - 1) / BM), (unsigned)((g.N + BN - 1) / BN));
   sgemm_kernel<<<grid, kGemmThreads, 0, st>>>(g);
   DPI_CUDA_CHECK(cudaGetLastError());

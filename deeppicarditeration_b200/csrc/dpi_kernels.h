@@ -102,6 +102,8 @@ struct GemmArgs {
   int64_t R;
   int N, K, epi;
   int a_km;
+  float* ws;      // optional split-K workspace [ws_splits][R][N] (epi == kEpiNone only)
+  int ws_splits;
 };
 int gemm(const GemmArgs& g, cudaStream_t st, int64_t* launches);
 

@@ -143,7 +143,8 @@ int64_t train_scratch_floats(const dpi_linear* L, int n_lin, int64_t B) {
   for (int l = 0; l < n_lin - 1; ++l) hmax = std::max(hmax, L[l].n_out);
   // per layer: stacked activations [2B][H], ELU' [B][H], tangent pre-activations [B][H]; two stacked adjoint
   // buffers; stacked input [2B][1+d]; g [B][1+d]; u, a [B]
-  return (int64_t)n_lin * 4 * B * hmax + 2 * 2 * B * hmax + 3 * B * (int64_t)(L[0].n_in) + 2 * B + 64 * n_lin + 256;
+  return (int64_t)n_lin * 4 * B * hmax + 2 * 2 * B * hmax + 3 * B * (int64_t)(L[0].n_in) + 2 * B + 16 * (int64_t)hmax * hmax +
+         64 * n_lin + 256;
 }
 
 // grad_flat [n_params] in torch parameters() order (W_0, b_0, W_1, b_1, ...); losses [3] = total, value, gradient
@@ -173,6 +174,7 @@ int launch_train_grad(const dpi_linear* L, int n_lin, const float* tx, const flo
   float* g = take((int64_t)B * d1);
   float* u = take(B);
   float* a = take(B);
+  float* ws = take(16 * (int64_t)hmax * hmax);  // split-K partials of the weight-gradient GEMMs
   int rc;
   auto wd = [&](int l) { return l == 0 ? d1 : L[l - 1].n_out; };  // width of HB[l]
   auto ew = [&](int threads_total) { return (unsigned)((threads_total + 255) / 256); };
@@ -255,6 +257,7 @@ int launch_train_grad(const dpi_linear* L, int n_lin, const float* tx, const flo
       GemmArgs G{};
       G.A = zb, G.lda = Ho, G.a_km = 1, G.B = HB[l], G.ldb = Hi, G.b_kn = 1;
       G.C = grad_flat + offW[l], G.ldc = Hi, G.R = Ho, G.N = Hi, G.K = 2 * B, G.epi = kEpiNone;
+      G.ws = ws, G.ws_splits = 16;
       if ((rc = gemm(G, st, launches))) return rc;
       train_colsum_kernel<<<(Ho + 7) / 8, 256, 0, st>>>(zb, Ho, nullptr, B, Ho, nullptr, grad_flat + offb[l]);
       DPI_CUDA_CHECK(cudaGetLastError());

@@ -82,8 +82,22 @@ class RegressionTrainer:
 
     def fit(self, tx: torch.Tensor, y: torch.Tensor, batch_size: int, n_epochs: int) -> Optional[torch.Tensor]:
         """The reference's inner loop over one iteration's label set: unshuffled mini-batches (config.py:90), n_epochs passes."""
-        last = None
         n = tx.shape[0]
+        distributed = self.pg is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
+                                              and torch.distributed.get_world_size() > 1)
+        if not distributed:
+            # single device: the whole inner loop runs natively (no host round trip between the steps)
+            tx = tx.detach().to(self.device, torch.float32).contiguous()
+            y = y.detach().to(self.device, torch.float32).contiguous()
+            e = self.engine
+            with torch.cuda.device(self.device):
+                nat.check(e.lib.dpi_train_fit(e.h, C.c_void_p(tx.data_ptr()), C.c_void_p(y.data_ptr()), n, batch_size,
+                                              n_epochs, C.byref(self.cfg), self.step_count + 1,
+                                              C.c_void_p(self.losses.data_ptr()), e._stream()), "dpi_train_fit")
+            self.step_count += n_epochs * ((n + batch_size - 1) // batch_size)
+            self._keep = (tx, y)
+            return self.losses
+        last = None
         for _ in range(n_epochs):
             for i in range(0, n, batch_size):
                 last = self.step(tx[i:i + batch_size], y[i:i + batch_size])

@@ -174,6 +174,12 @@ int dpi_train_grad(dpi_handle* h, const float* tx, const float* y, int64_t batch
                    float* grad_flat, float* losses, void* stream);
 int dpi_train_adam(dpi_handle* h, const float* grad_flat, const dpi_train_config* cfg, int64_t step /* 1-based */,
                    void* stream);
+/* The trainer's inner loop over one iteration's label set on ONE device, without returning to the host between steps
+ * (picard_iteration.py: Trainer.fit over dataset_with_gradients): n_epochs passes over the n rows of (tx, y) in
+ * unshuffled mini-batches of `batch` (config.py:90), Adam step counter continuing from first_step (1-based).
+ * losses_last [3] (device, nullable) receives the loss terms of the last step.  Asynchronous on `stream`. */
+int dpi_train_fit(dpi_handle* h, const float* tx, const float* y, int64_t n, int64_t batch, int64_t n_epochs,
+                  const dpi_train_config* cfg, int64_t first_step, float* losses_last, void* stream);
 
 /* Kernels launched by this handle since creation (for bench.py's gpu_launches). */
 int64_t dpi_launch_count(const dpi_handle* h);
