@@ -175,12 +175,39 @@ __device__ __forceinline__ void epi_pass(const TcConsts& C, uint32_t tacc, uint8
                    MODE == kPassHidden ? bias[col / 2] : C.b16[2][col / 2]);
         tg = pack_f16x2(__uint_as_float(tt[k2]), __uint_as_float(tt[k2 + 1]));
       }
+#if defined(DPI_DBG_ELU_FP32)
+      uint32_t e, h, dh;
+      {
+        float2 zf, tf;
+        if (MODE == kPassFirst) {
+          zf = h2_unpack(z), tf = h2_unpack(tg);
+        } else {
+          const uint32_t* bb = (MODE == kPassHidden) ? bias : C.b16[2];
+          const float2 bf = h2_unpack(bb[col / 2]);
+          zf = make_float2(__uint_as_float(vv[k2]) + bf.x, __uint_as_float(vv[k2 + 1]) + bf.y);
+          tf = make_float2(__uint_as_float(tt[k2]), __uint_as_float(tt[k2 + 1]));
+        }
+        const float e0 = exp2f(fminf(zf.x, 0.f)), e1 = exp2f(fminf(zf.y, 0.f));
+        e = pack_f16x2(e0, e1);
+        h = pack_f16x2(fmaxf(zf.x, fmaf(e0, kLog2e, -kLog2e)), fmaxf(zf.y, fmaf(e1, kLog2e, -kLog2e)));
+        dh = pack_f16x2(e0 * tf.x, e1 * tf.y);
+      }
+#else
       const uint32_t e = h2_ex2(h2_min(z, kZero));           // ELU'(z) = 2^min(z',0)
       const uint32_t h = h2_max(z, h2_fma(e, kL, kNegL));    // log2e ELU(z)
       const uint32_t dh = h2_mul(e, tg);
+#endif
       if (MODE == kPassOut) {
+#if defined(DPI_DBG_OUT_FP32)
+        {
+          const float2 wf = h2_unpack(C.wout16[col / 2]), hf = h2_unpack(h), df = h2_unpack(dh);
+          pu = fmaf(wf.x, hf.x, fmaf(wf.y, hf.y, pu));
+          pD = fmaf(wf.x, df.x, fmaf(wf.y, df.y, pD));
+        }
+#else
         accU = h2_fma(C.wout16[col / 2], h, accU);
         accD = h2_fma(C.wout16[col / 2], dh, accD);
+#endif
       } else {
         hv[k2 / 2] = h;
         ht[k2 / 2] = dh;
@@ -431,7 +458,8 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
           uu = DET ? __ldg(A.u_s + p * M_I + m)
                    : u01(philox_at(A.seed, (uint64_t)(A.point_base + p), kStreamS, (uint32_t)m, 0u).x);
         const float a = sqrtf(uu * dT) * P.sigma;
-        const float s2 = (uu * dT + t) * kLog2e, a2 = a * kLog2e;
+        // z1' = log2e z1: the time column w_t' and c0' carry the factor already, the accumulator (W_x Z) does not
+        const float s2 = uu * dT + t, a2 = a * kLog2e;
         float pu = 0.f, pD = 0.f;
 
         int pass_no = 0;
@@ -467,6 +495,9 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
         // output layer, f (equations.py:297-302) and the Bismut coefficient of this row
         const float uval = pu + C.bout;
         const float f = P.sigma * (P.cha_k * uval - P.cha_c) * (P.sigma * pD);
+#ifdef DPI_TC_DEBUG_UD
+        if (A.trace && valid) reinterpret_cast<float2*>(A.trace)[p * M_I + m] = make_float2(uval, pD);
+#endif
         if (valid) fsum += dT * f;
         const uint32_t cb = j % 3u;
         coef_s[cb * 128u + r] = valid ? dT * (f - fbp) / a : 0.f;
@@ -802,6 +833,14 @@ int launch_cha_tc_path(const ProblemDev& P, const TcNetDev& N, const float* tx, 
   A.cls = N.cls;
   const int grid = (int)(A.n_units < N.num_sms ? A.n_units : N.num_sms);
   int rc;
+#ifdef DPI_TC_DEBUG_UD
+  float2* ud_dev = nullptr;
+  if (getenv("DPI_TC_UD_FILE")) {
+    cudaMalloc((void**)&ud_dev, sizeof(float2) * (size_t)n * M_I);
+    cudaMemsetAsync(ud_dev, 0, sizeof(float2) * (size_t)n * M_I, st);
+    A.trace = reinterpret_cast<long long*>(ud_dev);
+  }
+#endif
 #ifdef DPI_TC_TRACE
   long long* trace_dev = nullptr;
   const size_t trace_bytes = sizeof(long long) * (4 * 2 * 8192);
@@ -833,6 +872,18 @@ int launch_cha_tc_path(const ProblemDev& P, const TcNetDev& N, const float* tx, 
           const long long code = hbuf[(size_t)r * 2 * 8192 + 2 * i], clk = hbuf[(size_t)r * 2 * 8192 + 2 * i + 1];
           if (clk) fprintf(f, "%lld %lld\n", (long long)(r == 0 ? 1 : (r == 3 ? 3 : 2)) * 1000000 + code, clk);
         }
+      fclose(f);
+    }
+  }
+#endif
+#ifdef DPI_TC_DEBUG_UD
+  if (ud_dev) {
+    std::vector<float2> hb((size_t)n * M_I);
+    cudaStreamSynchronize(st);
+    cudaMemcpy(hb.data(), ud_dev, sizeof(float2) * hb.size(), cudaMemcpyDeviceToHost);
+    cudaFree(ud_dev);
+    if (FILE* f = fopen(getenv("DPI_TC_UD_FILE"), "wb")) {
+      fwrite(hb.data(), sizeof(float2), hb.size(), f);
       fclose(f);
     }
   }

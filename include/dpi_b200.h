@@ -56,7 +56,7 @@ typedef enum {
 typedef enum { DPI_EQ_CHA = 0, DPI_EQ_GBM = 1, DPI_EQ_OU = 2 } dpi_equation_kind;
 typedef enum { DPI_NET_ZERO = 0, DPI_NET_MLP = 1, DPI_NET_PISGRAD = 2 } dpi_network_kind;
 /* arithmetic of the u_k GEMM chain: fp32 FMA (labels within 1e-4 rel of the fp64 reference) or the 16-bit tcgen05
- * tensor-core path with fp32 accumulation (within 1e-2 rel; measured 4e-4).  The tensor-core operands are IEEE fp16,
+ * tensor-core path with fp32 accumulation (within 1e-2 rel; measured 6e-5).  The tensor-core operands are IEEE fp16,
  * not bf16: three more mantissa bits at the same operand width, and the bias/ELU/ELU' epilogue runs in packed
  * fp16x2.  Its range limit is |log2(e) x pre-activation| < 6.5e4, far above anything a trained u_k produces.
  * DPI_PREC_BF16 is kept as an alias of the same path for callers written against the first revision. */

@@ -188,10 +188,10 @@ def test_labels_match_reference_bf16(name):
     assert orc.rel_l2(y, g.y) < TOL_BF16
     assert orc.rel_l2(y[:, 1:], g.y[:, 1:]) < TOL_BF16
     assert orc.rel_l2(y[:, :1], g.y[:, :1]) < TOL_BF16
-    # the integral estimator on its own (terminal part subtracted).  For this random-init net it is ~1 % of the label
-    # norm and its gradient columns are a low signal-to-noise MC sum, so bf16 rounding of the increments (2^-9
-    # relative per term) shows up amplified; 1e-1 of the integral part is 1e-3 of the label.
-    assert orc.rel_l2(y - g.y_terminal, g.y_integral) < 10 * TOL_BF16
+    assert orc.rel_l2(y, g.y) < 1e-3  # measured 6.2e-5: far inside the north-star tolerance
+    # the integral estimator on its own (terminal part subtracted): for this random-init net it is ~1 % of the label
+    # norm and its gradient columns are a low signal-to-noise MC sum, so it is the sharpest view on the tensor-core path
+    assert orc.rel_l2(y - g.y_terminal, g.y_integral) < TOL_BF16
     e.close()
 
 
@@ -211,6 +211,25 @@ def test_bf16_path_agrees_with_fp32_path_on_the_same_philox_draws(nx, M_T, M_I, 
     assert orc.rel_l2(y16, y32) < TOL_BF16
     assert orc.rel_l2(y16[:, :1], y32[:, :1]) < TOL_BF16
     e.close()
+
+
+@pytest.mark.parametrize("gain", [1.0, 2.0, 3.0])
+def test_tensor_core_integral_part_tracks_fp32_for_large_weights(gain):
+    """Networks with large weights (what training produces) make the integral estimator a large part of the label; the
+    16-bit path must follow the fp32 path on the same Philox draws there too.  (This is the case that exposed a
+    doubly-scaled time column: invisible on default-init weights, 4-7 % off at gain >= 2.)"""
+    from tests.gpu_util import engine_for
+    eq = orc.Cha(100, 1.0, 5.0, 1.0)
+    net = orc.make_mlp(101, [128] * 4, seed=2, gain=gain)
+    e, ez = engine_for(eq, net), engine_for(eq, orc.ZeroNet())
+    tx = e.sample_tx(128, seed=3)
+    yz = ez.label_gen(tx, 512, 1024, seed=5).double()  # terminal part only (u_k == 0)
+    i32 = e.label_gen(tx, 512, 1024, precision="fp32", seed=5).double() - yz
+    i16 = e.label_gen(tx, 512, 1024, precision="f16", seed=5).double() - yz
+    assert orc.rel_l2(i16[:, :1], i32[:, :1]) < 3e-3
+    assert orc.rel_l2(i16[:, 1:], i32[:, 1:]) < TOL_BF16
+    e.close()
+    ez.close()
 
 
 def test_bf16_shard_invariance_and_determinism():
