@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = (
     "dpi_version", "dpi_last_error", "dpi_create", "dpi_destroy", "dpi_set_problem", "dpi_set_network",
     "dpi_sample_tx", "dpi_label_gen", "dpi_label_gen_host", "dpi_net_eval", "dpi_launch_count",
     "dpi_set_stage_timing", "dpi_stage_ms", "dpi_selftest_umma",
-    "dpi_train_init", "dpi_train_param_count", "dpi_train_grad", "dpi_train_adam", "dpi_train_fit",
+    "dpi_train_init", "dpi_train_param_count", "dpi_train_grad", "dpi_train_adam", "dpi_train_fit", "dpi_train_reset",
 )
 
 
@@ -102,6 +102,7 @@ def load() -> C.CDLL:
     lib.dpi_train_grad.argtypes = [H, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(dpi_train_config), C.c_void_p,
                                    C.c_void_p, C.c_void_p]
     lib.dpi_train_adam.argtypes = [H, C.c_void_p, C.POINTER(dpi_train_config), C.c_int64, C.c_void_p]
+    lib.dpi_train_reset.argtypes = [H, C.c_void_p]
     lib.dpi_train_fit.argtypes = [H, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.POINTER(dpi_train_config),
                                   C.c_int64, C.c_void_p, C.c_void_p]
     for name in EXPORTED_SYMBOLS:

@@ -36,6 +36,14 @@ struct dpi_handle {
   int n_train_lin = 0;
   int64_t train_params = 0, train_max_batch = 0;
   float *train_m = nullptr, *train_v = nullptr, *train_scratch = nullptr, *train_grad = nullptr;
+  // dpi_train_fit replays one optimiser step as a CUDA graph on an internal stream
+  cudaStream_t train_stream = nullptr;
+  cudaEvent_t train_ev_in = nullptr, train_ev_out = nullptr;
+  float *train_stage_tx = nullptr, *train_stage_y = nullptr;
+  long long* train_step_dev = nullptr;
+  cudaGraphExec_t train_graph = nullptr;
+  int64_t train_graph_batch = 0, train_graph_nodes = 0;
+  dpi_train_config train_graph_cfg{};
   dpi_linear mlp_raw[DPI_MAX_LINEAR] = {};  // the caller's MLP tensors (torch layout), for dpi_net_eval
   int n_mlp_raw = 0;
   // activations of one chunk of rows of the batched-GEMM (PISGradNet) path
@@ -208,6 +216,13 @@ int dpi_destroy(dpi_handle* h) {
   if (h->train_v) cudaFree(h->train_v);
   if (h->train_scratch) cudaFree(h->train_scratch);
   if (h->train_grad) cudaFree(h->train_grad);
+  if (h->train_graph) cudaGraphExecDestroy(h->train_graph);
+  if (h->train_stage_tx) cudaFree(h->train_stage_tx);
+  if (h->train_stage_y) cudaFree(h->train_stage_y);
+  if (h->train_step_dev) cudaFree(h->train_step_dev);
+  if (h->train_ev_in) cudaEventDestroy(h->train_ev_in);
+  if (h->train_ev_out) cudaEventDestroy(h->train_ev_out);
+  if (h->train_stream) cudaStreamDestroy(h->train_stream);
   for (int s = 0; s < DPI_STAGE_COUNT; ++s)
     for (int e = 0; e < 2; ++e)
       if (h->ev[s][e]) cudaEventDestroy(h->ev[s][e]);
@@ -650,6 +665,12 @@ int dpi_train_init(dpi_handle* h, const dpi_network* net, int64_t max_batch, voi
   if (h->train_v) cudaFree(h->train_v);
   if (h->train_scratch) cudaFree(h->train_scratch);
   if (h->train_grad) cudaFree(h->train_grad);
+  if (h->train_graph) cudaGraphExecDestroy(h->train_graph);
+  if (h->train_stage_tx) cudaFree(h->train_stage_tx);
+  if (h->train_stage_y) cudaFree(h->train_stage_y);
+  h->train_graph = nullptr;
+  h->train_graph_batch = 0;
+  h->train_stage_tx = h->train_stage_y = nullptr;
   h->train_m = h->train_v = h->train_scratch = h->train_grad = nullptr;
   for (int l = 0; l < L; ++l) h->train_lin[l] = net->main[l];
   h->n_train_lin = L;
@@ -659,12 +680,32 @@ int dpi_train_init(dpi_handle* h, const dpi_network* net, int64_t max_batch, voi
   DPI_CUDA_CHECK(cudaMalloc((void**)&h->train_v, sizeof(float) * h->train_params));
   DPI_CUDA_CHECK(cudaMalloc((void**)&h->train_scratch, sizeof(float) * train_scratch_floats(h->train_lin, L, max_batch)));
   DPI_CUDA_CHECK(cudaMalloc((void**)&h->train_grad, sizeof(float) * (h->train_params + 4)));
+  DPI_CUDA_CHECK(cudaMalloc((void**)&h->train_stage_tx, sizeof(float) * max_batch * net->main[0].n_in));
+  DPI_CUDA_CHECK(cudaMalloc((void**)&h->train_stage_y, sizeof(float) * max_batch * net->main[0].n_in));
+  if (!h->train_step_dev) DPI_CUDA_CHECK(cudaMalloc((void**)&h->train_step_dev, sizeof(long long)));
+  if (!h->train_stream) {
+    DPI_CUDA_CHECK(cudaStreamCreateWithFlags(&h->train_stream, cudaStreamNonBlocking));
+    DPI_CUDA_CHECK(cudaEventCreateWithFlags(&h->train_ev_in, cudaEventDisableTiming));
+    DPI_CUDA_CHECK(cudaEventCreateWithFlags(&h->train_ev_out, cudaEventDisableTiming));
+  }
   DPI_CUDA_CHECK(cudaMemsetAsync(h->train_m, 0, sizeof(float) * h->train_params, st));
   DPI_CUDA_CHECK(cudaMemsetAsync(h->train_v, 0, sizeof(float) * h->train_params, st));
   return DPI_OK;
 }
 
 int64_t dpi_train_param_count(const dpi_handle* h) { return h ? h->train_params : 0; }
+
+int dpi_train_reset(dpi_handle* h, void* stream) {
+  if (!h || !h->n_train_lin) {
+    set_error("dpi_train_reset: call dpi_train_init first");
+    return DPI_ERR_STATE;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  DPI_CUDA_CHECK(cudaSetDevice(h->device));
+  DPI_CUDA_CHECK(cudaMemsetAsync(h->train_m, 0, sizeof(float) * h->train_params, st));
+  DPI_CUDA_CHECK(cudaMemsetAsync(h->train_v, 0, sizeof(float) * h->train_params, st));
+  return DPI_OK;
+}
 
 int dpi_train_grad(dpi_handle* h, const float* tx, const float* y, int64_t batch, const dpi_train_config* cfg,
                    float* grad_flat, float* losses, void* stream) {
@@ -710,19 +751,59 @@ int dpi_train_fit(dpi_handle* h, const float* tx, const float* y, int64_t n, int
   DPI_CUDA_CHECK(cudaSetDevice(h->device));
   const int ld = h->train_lin[0].n_in;
   float* losses = h->train_grad + h->train_params;
-  int64_t step = first_step;
+  cudaStream_t ts = h->train_stream;
+  // the internal stream picks up after everything queued on the caller's stream (labels, previous fit)
+  DPI_CUDA_CHECK(cudaEventRecord(h->train_ev_in, st));
+  DPI_CUDA_CHECK(cudaStreamWaitEvent(ts, h->train_ev_in, 0));
+  const long long step0 = (long long)first_step;
+  DPI_CUDA_CHECK(cudaMemcpyAsync(h->train_step_dev, &step0, sizeof(long long), cudaMemcpyHostToDevice, ts));
+  DPI_CUDA_CHECK(cudaStreamSynchronize(ts));  // step0 lives on this call's stack
+  auto same_cfg = [&](const dpi_train_config& c) { return std::memcmp(&c, cfg, sizeof(dpi_train_config)) == 0; };
   for (int64_t e = 0; e < n_epochs; ++e)
-    for (int64_t i = 0; i < n; i += batch, ++step) {
+    for (int64_t i = 0; i < n; i += batch) {
       const int64_t b = std::min<int64_t>(batch, n - i);
-      int rc = launch_train_grad(h->train_lin, h->n_train_lin, tx + i * ld, y + i * ld, b, cfg->loss_beta,
-                                 cfg->fixed_weight, h->train_scratch, h->train_grad, losses, st, &h->launches);
-      if (rc) return rc;
-      rc = launch_train_adam(h->train_lin, h->n_train_lin, h->train_grad, h->train_m, h->train_v, cfg->lr, cfg->beta1,
-                             cfg->beta2, cfg->eps, step, st, &h->launches);
-      if (rc) return rc;
+      DPI_CUDA_CHECK(cudaMemcpyAsync(h->train_stage_tx, tx + i * ld, sizeof(float) * b * ld, cudaMemcpyDeviceToDevice, ts));
+      DPI_CUDA_CHECK(cudaMemcpyAsync(h->train_stage_y, y + i * ld, sizeof(float) * b * ld, cudaMemcpyDeviceToDevice, ts));
+      if (b == batch) {
+        if (!h->train_graph || h->train_graph_batch != b || !same_cfg(h->train_graph_cfg)) {
+          // (re)capture one optimiser step: ~45 small kernels whose launch cost would otherwise dominate
+          if (h->train_graph) cudaGraphExecDestroy(h->train_graph);
+          h->train_graph = nullptr;
+          cudaGraph_t graph = nullptr;
+          int64_t nodes = 0;
+          DPI_CUDA_CHECK(cudaStreamBeginCapture(ts, cudaStreamCaptureModeRelaxed));
+          int rc = launch_train_grad(h->train_lin, h->n_train_lin, h->train_stage_tx, h->train_stage_y, b, cfg->loss_beta,
+                                     cfg->fixed_weight, h->train_scratch, h->train_grad, losses, ts, &nodes);
+          if (!rc)
+            rc = launch_train_adam_dev(h->train_lin, h->n_train_lin, h->train_grad, h->train_m, h->train_v, cfg->lr,
+                                       cfg->beta1, cfg->beta2, cfg->eps, h->train_step_dev, ts, &nodes);
+          cudaError_t ce = cudaStreamEndCapture(ts, &graph);
+          if (rc) {
+            if (graph) cudaGraphDestroy(graph);
+            return rc;
+          }
+          DPI_CUDA_CHECK(ce);
+          DPI_CUDA_CHECK(cudaGraphInstantiate(&h->train_graph, graph, 0));
+          cudaGraphDestroy(graph);
+          h->train_graph_batch = b;
+          h->train_graph_nodes = nodes;
+          h->train_graph_cfg = *cfg;
+        }
+        DPI_CUDA_CHECK(cudaGraphLaunch(h->train_graph, ts));
+        h->launches += h->train_graph_nodes;
+      } else {  // ragged last mini-batch: plain launches
+        int rc = launch_train_grad(h->train_lin, h->n_train_lin, h->train_stage_tx, h->train_stage_y, b, cfg->loss_beta,
+                                   cfg->fixed_weight, h->train_scratch, h->train_grad, losses, ts, &h->launches);
+        if (rc) return rc;
+        rc = launch_train_adam_dev(h->train_lin, h->n_train_lin, h->train_grad, h->train_m, h->train_v, cfg->lr, cfg->beta1,
+                                   cfg->beta2, cfg->eps, h->train_step_dev, ts, &h->launches);
+        if (rc) return rc;
+      }
     }
   if (losses_last)
-    DPI_CUDA_CHECK(cudaMemcpyAsync(losses_last, losses, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    DPI_CUDA_CHECK(cudaMemcpyAsync(losses_last, losses, 3 * sizeof(float), cudaMemcpyDeviceToDevice, ts));
+  DPI_CUDA_CHECK(cudaEventRecord(h->train_ev_out, ts));
+  DPI_CUDA_CHECK(cudaStreamWaitEvent(st, h->train_ev_out, 0));
   return DPI_OK;
 }
 

@@ -139,6 +139,9 @@ int launch_train_grad(const dpi_linear* L, int n_lin, const float* tx, const flo
 int launch_train_adam(const dpi_linear* L, int n_lin, const float* grad_flat, float* m, float* v, float lr, float b1,
                       float b2, float eps, int64_t step, cudaStream_t st, int64_t* launches);
 
+int launch_train_adam_dev(const dpi_linear* L, int n_lin, const float* grad_flat, float* m, float* v, float lr, float b1,
+                          float b2, float eps, long long* step_dev, cudaStream_t st, int64_t* launches);
+
 // y = clip(y + add, +-bound) elementwise helpers used by the Zero-network shortcuts
 int launch_finish_zero(const ProblemDev& P, const float* tx, int64_t n, float bound, float* y, cudaStream_t st);
 

@@ -130,6 +130,26 @@ __global__ void train_bcast_mul_kernel(const float* __restrict__ e, const float*
   c[i] = __ldg(e + i) * __ldg(w + (i % H));
 }
 
+// Adam with the (1-based) step read from device memory, for replay from a CUDA graph; train_step_inc_kernel advances it
+__global__ void train_adam_dev_kernel(const AdamTable T, const float* __restrict__ grad, float* __restrict__ m,
+                                      float* __restrict__ v, float lr, float b1, float b2, float eps,
+                                      const long long* __restrict__ step, int64_t total) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const float st = (float)(*step);
+  const float bc1 = 1.f - powf(b1, st), bc2 = 1.f - powf(b2, st);
+  int s = 0;
+  while (s + 1 < T.n_seg && i >= T.seg[s + 1].off) ++s;
+  float* p = T.seg[s].p + (i - T.seg[s].off);
+  const float gi = grad[i];
+  const float mi = fmaf(b1, m[i], (1.f - b1) * gi);
+  const float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);
+  m[i] = mi;
+  v[i] = vi;
+  *p -= (lr / bc1) * mi / (sqrtf(vi / bc2) + eps);
+}
+__global__ void train_step_inc_kernel(long long* step) { *step += 1; }
+
 }  // namespace
 
 int64_t train_param_count(const dpi_linear* L, int n_lin) {
@@ -289,6 +309,24 @@ int launch_train_adam(const dpi_linear* L, int n_lin, const float* grad_flat, fl
   train_adam_kernel<<<(unsigned)((off + 255) / 256), 256, 0, st>>>(T, grad_flat, m, v, lr, b1, b2, eps, bc1, bc2, off);
   DPI_CUDA_CHECK(cudaGetLastError());
   *launches += 1;
+  return DPI_OK;
+}
+
+int launch_train_adam_dev(const dpi_linear* L, int n_lin, const float* grad_flat, float* m, float* v, float lr, float b1,
+                          float b2, float eps, long long* step_dev, cudaStream_t st, int64_t* launches) {
+  AdamTable T{};
+  int64_t off = 0;
+  T.n_seg = 0;
+  for (int l = 0; l < n_lin; ++l) {
+    T.seg[T.n_seg++] = AdamSeg{const_cast<float*>(L[l].W), off, (int64_t)L[l].n_out * L[l].n_in};
+    off += (int64_t)L[l].n_out * L[l].n_in;
+    T.seg[T.n_seg++] = AdamSeg{const_cast<float*>(L[l].b), off, (int64_t)L[l].n_out};
+    off += L[l].n_out;
+  }
+  train_adam_dev_kernel<<<(unsigned)((off + 255) / 256), 256, 0, st>>>(T, grad_flat, m, v, lr, b1, b2, eps, step_dev, off);
+  train_step_inc_kernel<<<1, 1, 0, st>>>(step_dev);
+  DPI_CUDA_CHECK(cudaGetLastError());
+  *launches += 2;
   return DPI_OK;
 }
 

@@ -52,6 +52,8 @@ def run_picard(equation, neurons: Sequence[int], n_iterations: int, *, data_size
     frozen = ZeroSolution(1)
     history: List[Dict[str, float]] = []
     gen = None
+    trainer = RegressionTrainer(model, lr=lr, loss_beta=loss_beta, fixed_weight=fixed_weight, max_batch=batch_size,
+                                device=dev)
     t_label = t_train = 0.0
     for i in range(1, n_iterations + 1):
         if gen is None:
@@ -66,12 +68,10 @@ def run_picard(equation, neurons: Sequence[int], n_iterations: int, *, data_size
         tx, y = gen.sample_with_gradients(data_size)
         torch.cuda.synchronize(dev)
         t1 = time.perf_counter()
-        trainer = RegressionTrainer(model, lr=lr, loss_beta=loss_beta, fixed_weight=fixed_weight, max_batch=batch_size,
-                                    device=dev)  # fresh Adam state per iteration, weights carried over
+        trainer.reset_optimizer()  # fresh Adam state per iteration, weights carried over
         losses = trainer.fit(tx, y, batch_size, n_epochs)
         torch.cuda.synchronize(dev)
         t2 = time.perf_counter()
-        trainer.close()
         t_label += t1 - t0
         t_train += t2 - t1
         frozen = model
@@ -83,6 +83,7 @@ def run_picard(equation, neurons: Sequence[int], n_iterations: int, *, data_size
             if log:
                 log(f"picard iter {i:3d}: loss {m['loss']:.3e}  rRMSE {m['rRMSE']:.3e}  rRMSEg {m['rRMSEg']:.3e}  "
                     f"labels {m['label_ms']:.1f} ms  regression {m['train_ms']:.1f} ms")
+    trainer.close()
     if gen is not None:
         gen.engine.close()
     return {"model": model, "history": history, "label_s": t_label, "train_s": t_train}

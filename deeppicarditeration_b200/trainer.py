@@ -54,6 +54,13 @@ class RegressionTrainer:
     def close(self):
         self.engine.close()
 
+    def reset_optimizer(self):
+        """Fresh Adam state, weights kept: what the reference gets from a new Trainer per Picard iteration."""
+        e = self.engine
+        with torch.cuda.device(self.device):
+            nat.check(e.lib.dpi_train_reset(e.h, e._stream()), "dpi_train_reset")
+        self.step_count = 0
+
     def backward(self, tx: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
         """Loss terms and the flat parameter gradient of one mini-batch; returns losses [total, value, gradient]."""
         tx = tx.detach().to(self.device, torch.float32).contiguous()

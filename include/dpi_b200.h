@@ -170,6 +170,9 @@ typedef struct {
 } dpi_train_config;
 int dpi_train_init(dpi_handle* h, const dpi_network* mlp, int64_t max_batch, void* stream);
 int64_t dpi_train_param_count(const dpi_handle* h);
+/* Fresh optimiser state (Adam moments zeroed): the reference builds a new Trainer/optimiser for every Picard iteration
+ * (picard_iteration.py:279-289) while the network weights carry over (NETWORK.RELOAD). */
+int dpi_train_reset(dpi_handle* h, void* stream);
 int dpi_train_grad(dpi_handle* h, const float* tx, const float* y, int64_t batch, const dpi_train_config* cfg,
                    float* grad_flat, float* losses, void* stream);
 int dpi_train_adam(dpi_handle* h, const float* grad_flat, const dpi_train_config* cfg, int64_t step /* 1-based */,
