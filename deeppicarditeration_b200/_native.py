@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-# DPI_B200_LIB: developer override used by tools_variants.py to time experimental builds of the same library
+# DPI_B200_LIB: developer override used by tools/variants.py to time experimental builds of the same library
 LIB_PATH = os.environ.get("DPI_B200_LIB") or os.path.join(_PKG, "libdpi_b200.so")
 
 DPI_MAX_LINEAR = 8

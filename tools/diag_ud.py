@@ -1,6 +1,6 @@
 """Developer helper: per-sample (u, D) of the tensor-core path (debug build) vs the fp64 oracle on replayed draws."""
 import os, sys, subprocess, numpy as np, torch
-ROOT = os.path.dirname(os.path.abspath(__file__)); sys.path.insert(0, ROOT)
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 if len(sys.argv) > 1 and sys.argv[1] == "child":
     from oracle import dpi_oracle as orc
     from tests.gpu_util import engine_for

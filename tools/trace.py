@@ -1,6 +1,6 @@
 """Developer helper: run the DPI_TC_TRACE variant once and print the CTA-0 timeline summary."""
 import os, sys, subprocess, collections
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 out = os.path.join(ROOT, "gpurun_out", "tc_trace.txt")
 os.makedirs(os.path.dirname(out), exist_ok=True)
 env = dict(os.environ, DPI_B200_LIB=os.path.join(ROOT, "deeppicarditeration_b200", "variants", "lib_trace.so"),

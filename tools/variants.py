@@ -1,8 +1,8 @@
 """Developer helper (not product, not bench): build experimental variants of libdpi_b200.so with extra nvcc defines
-and time the bf16 integral kernel with each.  Usage on the build box:  python tools_variants.py build NAME=-DFLAG ...
-On the GPU box:  python tools_variants.py run [points] [M]"""
+and time the bf16 integral kernel with each.  Usage on the build box:  python tools/variants.py build NAME=-DFLAG ...
+On the GPU box:  python tools/variants.py run [points] [M]"""
 import os, subprocess, sys
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "deeppicarditeration_b200")
 VDIR = os.path.join(PKG, "variants")
 sys.path.insert(0, ROOT)
@@ -28,6 +28,6 @@ else:
     libs = sorted(f for f in os.listdir(VDIR) if f.endswith(".so"))
     for lib in libs:
         env = dict(os.environ, DPI_B200_LIB=os.path.join(VDIR, lib))
-        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools_quick_bench.py"), "bf16", n, M], env=env,
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "quick_bench.py"), "bf16", n, M], env=env,
                            capture_output=True, text=True, timeout=300)
         print(lib, (r.stdout.strip().splitlines() or [r.stderr[-300:]])[-1])
