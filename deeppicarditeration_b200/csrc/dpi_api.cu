@@ -498,11 +498,16 @@ int dpi_label_gen(dpi_handle* h, const float* tx, int64_t n, const dpi_label_con
       set_error("dpi_label_gen: GBMEquationComplexExact needs HESSIAN_APPROXIMATION.method=SDGD (sdgd_v >= 1)");
       return DPI_ERR_UNSUPPORTED;
     }
-    if (cfg->precision != DPI_PREC_FP32) {
-      set_error("dpi_label_gen: the SDGD (2-jet) path is fp32 only");
-      return DPI_ERR_UNSUPPORTED;
-    }
     StageTimer tm(h, DPI_STAGE_INTEGRAL, st);
+    if (cfg->precision != DPI_PREC_FP32) {
+      // 16-bit tensor-core path: hidden layers of the 2-jets as tcgen05 GEMMs (u_k == 0 has no network to evaluate)
+      if (h->net_kind == DPI_NET_MLP) {
+        rc = launch_gbm_tc(P, h->mlp, tx, n, cfg->M_I, cfg->seed, cfg->point_index_base, draws ? draws->u_s : nullptr,
+                           draws ? draws->zS : nullptr, draws ? draws->idx : nullptr, bound, y, st);
+        if (!rc) h->launches += 1;
+        return rc;
+      }
+    }
     rc = launch_gbm_simt(P, h->mlp, h->net_kind == DPI_NET_ZERO, tx, n, cfg->M_I, cfg->seed, cfg->point_index_base,
                          draws ? draws->u_s : nullptr, draws ? draws->zS : nullptr, draws ? draws->idx : nullptr,
                          bound, y, st);

@@ -47,6 +47,10 @@ int launch_gbm_simt(const ProblemDev& P, const MlpDev& net, bool zero_net, const
                     uint64_t seed, int64_t base, const float* u_s, const float* zS, const int32_t* idx, float bound,
                     float* y, cudaStream_t st);
 
+// same on the tensor cores (dpi_gbm_tc.cu): fp16 jets through the hidden layers, nx <= 127, v <= 127
+int launch_gbm_tc(const ProblemDev& P, const MlpDev& net, const float* tx, int64_t n, int M_I, uint64_t seed, int64_t base,
+                  const float* u_s, const float* zS, const int32_t* idx, float bound, float* y, cudaStream_t st);
+
 // ---- 16-bit tcgen05 path (dpi_mlp_tc.cu): fp16 operands, fp32 accumulation ---------------------------------------------------------------
 constexpr int kTcGroupTiles = 8;  // 128-sample tiles per work unit (fixed: the summation order must not depend on n)
 // per-column fp32 constants of the network, passed to the kernel by value (constant bank)

@@ -175,7 +175,7 @@ def test_umma_selftest_matches_bf16_matmul():
     e.close()
 
 
-TC_GOLDEN = ["burgers_100d_mlp128"]
+TC_GOLDEN = ["burgers_100d_mlp128", "gbm_100d_mlp64_sdgd"]
 
 
 @pytest.mark.parametrize("name", TC_GOLDEN)
@@ -230,6 +230,25 @@ def test_tensor_core_integral_part_tracks_fp32_for_large_weights(gain):
     assert orc.rel_l2(i16[:, 1:], i32[:, 1:]) < TOL_BF16
     e.close()
     ez.close()
+
+
+def test_gbm_tensor_core_path_tracks_fp32_on_the_same_philox_draws():
+    """SDGD 2-jets through tcgen05 (fp16 operands) vs the fp32 kernel: identical Philox counters for increments and
+    sampled coordinates, so the two differ only by operand rounding; also shard invariance of the tensor-core kernel."""
+    g = Golden("gbm_100d_mlp64_sdgd")
+    net = orc.make_mlp(101, [64, 64, 64], seed=4, gain=1.5)
+    from tests.gpu_util import engine_for
+    e = engine_for(g.eq, net, 100)
+    tx = e.sample_tx(24, seed=2)
+    y32 = e.label_gen(tx, 128, 160, precision="fp32", seed=6).double().cpu()
+    y16 = e.label_gen(tx, 128, 160, precision="f16", seed=6).double().cpu()
+    assert torch.isfinite(y16).all()
+    assert orc.rel_l2(y16, y32) < TOL_BF16
+    assert orc.rel_l2(y16[:, :1], y32[:, :1]) < TOL_BF16
+    y_b = torch.cat([e.label_gen(tx[:9], 128, 160, precision="f16", seed=6),
+                     e.label_gen(tx[9:], 128, 160, precision="f16", seed=6, point_index_base=9)]).double().cpu()
+    assert torch.equal(y16, y_b)
+    e.close()
 
 
 def test_bf16_shard_invariance_and_determinism():
