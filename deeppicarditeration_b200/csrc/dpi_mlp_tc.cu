@@ -15,7 +15,7 @@
 //   * 8 producer warps draw the Brownian increments with Philox4x32-10 + Box-Muller in registers, round them to fp16,
 //     store the [128 x d] A-operand tile when the slot frees up, and KEEP them in registers: once the tile's Bismut
 //     coefficients are known they accumulate G_j += coef_m Z_mj there, so increments never leave the SM;
-//   * one thread issues tcgen05.mma for both slots in a fixed round-robin order, one thread issues the TMA copies;
+//   * one issuing thread per slot feeds tcgen05.mma (each blocks only on its own slot), one thread issues the TMA copies;
 //   * 4 epilogue warps per slot (thread = sample row) read the accumulators with tcgen05.ld, apply bias/ELU/ELU' in
 //     packed fp16x2 arithmetic (two columns per instruction; its absolute error stays below the rounding of the
 //     16-bit operands it produces) and write the next layer's A operands straight into the swizzled shared-memory
@@ -27,6 +27,7 @@
 // launch geometry and of how points are sharded.
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 #include "dpi_common.cuh"
@@ -39,13 +40,17 @@ using namespace tc;
 
 // ---- roles ---------------------------------------------------------------------------------------------------
 // warps 0-3: epilogue of tile slot 0, warps 4-7: epilogue of tile slot 1 (warp & 3 = TMEM lane quarter),
-// warps 8-15: increment producers, warp 16: MMA issuer (one thread), warp 17: TMA issuer (one thread).
+// warps 8-15: increment producers, warps 16 / 18: MMA issuers of slot 0 / 1 (one thread each), warp 17: TMA issuer
+// (one thread), warp 19: idle.
 // The register file is per SM sub-partition (512 registers per lane, warp w lives on sub-partition w % 4), so each
 // sub-partition holds one warp of every warpgroup.  setmaxnreg only moves registers inside the CTA's own pool (what
 // its warps have released), so the re-split must balance against the launch allocation of 96 per thread:
 // MMA/TMA warpgroup 96 -> 32, epilogue 96 -> 88, producers 96 -> 136 (2 x 88 + 2 x 136 + 32 = 480 = 5 x 96).
 constexpr int kTcThreads = 640;
-constexpr int kProdWarp0 = 8, kMmaWarp = 16, kTmaWarp = 17;
+#ifndef DPI_TC_ISSUERS
+#define DPI_TC_ISSUERS 1
+#endif
+constexpr int kProdWarp0 = 8, kMmaWarp = 16, kTmaWarp = 17, kMmaWarp1 = 18;
 #ifndef DPI_EPI_REGS
 #define DPI_EPI_REGS 88
 #endif
@@ -129,102 +134,95 @@ enum : int { kPassFirst = 0, kPassHidden = 1, kPassOut = 2 };
 #endif
 constexpr int kEpiUnroll = DPI_EPI_UNROLL;  // chunks per loop iteration of an epilogue pass (even)
 
+#ifndef DPI_EPI_CW
+#define DPI_EPI_CW 16
+#endif
+#ifndef DPI_EPI_DB
+#define DPI_EPI_DB 0
+#endif
+constexpr int kEpiCW = DPI_EPI_CW;       // accumulator columns per tcgen05.ld (8 or 16)
+constexpr bool kEpiDB = DPI_EPI_DB != 0; // prefetch the next chunk under the arithmetic of the current one
+static_assert(kEpiCW == 8 || kEpiCW == 16 || kEpiCW == 32, "chunk width");
+
+template <int N>
+__device__ __forceinline__ void tmem_ldN(uint32_t taddr, uint32_t (&r)[N]) {
+  if constexpr (N == 8) tmem_ld8(taddr, r);
+  else if constexpr (N == 16) tmem_ld16(taddr, r);
+  else tmem_ld32(taddr, r);
+}
+
 template <int MODE>
 __device__ __forceinline__ void epi_pass(const TcConsts& C, uint32_t tacc, uint8_t* hv_row, uint8_t* ht_row,
                                          uint32_t rx, const float* c0_s, int layer, float s2, float a2, float& pu,
                                          float& pD) {
-  uint32_t v[2][8], tv[2][8];
-  float4 cc[2][2];  // first pass: c0 of the current / next chunk (prefetched like the accumulators)
-  tmem_ld8(tacc, v[0]);
-  if (MODE != kPassFirst) tmem_ld8(tacc + 128u, tv[0]);
-  if (MODE == kPassFirst) {
-    cc[0][0] = *reinterpret_cast<const float4*>(&c0_s[0]);
-    cc[0][1] = *reinterpret_cast<const float4*>(&c0_s[4]);
-  }
+  constexpr int NB = kEpiDB ? 2 : 1, NCH = 128 / kEpiCW, G = kEpiCW / 8;
+  uint32_t v[NB][kEpiCW], tv[NB][kEpiCW];
+  float4 cc[NB][2 * G];  // first pass: c0 of the current / next chunk (prefetched like the accumulators)
+  auto fetch = [&](int ch, int b) {
+    tmem_ldN<kEpiCW>(tacc + (uint32_t)(ch * kEpiCW), v[b]);
+    if (MODE != kPassFirst) tmem_ldN<kEpiCW>(tacc + 128u + (uint32_t)(ch * kEpiCW), tv[b]);
+    if (MODE == kPassFirst) {
+#pragma unroll
+      for (int i = 0; i < 2 * G; ++i) cc[b][i] = *reinterpret_cast<const float4*>(&c0_s[ch * kEpiCW + 4 * i]);
+    }
+  };
+  if (kEpiDB) fetch(0, 0);
   const uint32_t* bias = C.b16[layer];
   const uint32_t kL = h2_const(kLog2e, kLog2e), kNegL = h2_const(-kLog2e, -kLog2e), kZero = 0u;
   uint32_t accU = 0u, accD = 0u;  // output pass: fp16x2 partial dot products, flushed to fp32 every 16 columns
-  // rolled two chunks at a time (static double-buffer indices): the pass is a short loop that stays in the
-  // instruction cache; per-column constants are then fetched with indexed constant loads
+  // rolled a few chunks at a time: the pass is a short loop that stays in the instruction cache; per-column
+  // constants are then fetched with indexed constant loads
 #pragma unroll kEpiUnroll
-  for (int ch = 0; ch < 16; ++ch) {
+  for (int ch = 0; ch < NCH; ++ch) {
+    const int b = kEpiDB ? (ch & 1) : 0;
+    if (!kEpiDB) fetch(ch, 0);
     tmem_ld_wait();
-    if (ch + 1 < 16) {
-      tmem_ld8(tacc + (uint32_t)((ch + 1) * 8), v[(ch + 1) & 1]);
-      if (MODE != kPassFirst) tmem_ld8(tacc + 128u + (uint32_t)((ch + 1) * 8), tv[(ch + 1) & 1]);
-      if (MODE == kPassFirst) {
-        cc[(ch + 1) & 1][0] = *reinterpret_cast<const float4*>(&c0_s[(ch + 1) * 8]);
-        cc[(ch + 1) & 1][1] = *reinterpret_cast<const float4*>(&c0_s[(ch + 1) * 8 + 4]);
-      }
-    }
-    const uint32_t* vv = v[ch & 1];
-    const uint32_t* tt = tv[ch & 1];
-    uint32_t hv[4], ht[4];
+    if (kEpiDB && ch + 1 < NCH) fetch(ch + 1, (ch + 1) & 1);
 #pragma unroll
-    for (int k2 = 0; k2 < 8; k2 += 2) {  // two columns per packed instruction
-      const int col = ch * 8 + k2;
-      uint32_t z, tg;
-      if (MODE == kPassFirst) {
-        const float4 c0 = cc[ch & 1][k2 / 4];
-        const float c0a = (k2 & 2) ? c0.z : c0.x, c0b = (k2 & 2) ? c0.w : c0.y;
-        z = pack_f16x2(fmaf(a2, __uint_as_float(vv[k2]), fmaf(s2, C.wt[col], c0a)),
-                       fmaf(a2, __uint_as_float(vv[k2 + 1]), fmaf(s2, C.wt[col + 1], c0b)));
-        tg = C.wsum16[col / 2];
-      } else {
-        z = h2_add(pack_f16x2(__uint_as_float(vv[k2]), __uint_as_float(vv[k2 + 1])),
-                   MODE == kPassHidden ? bias[col / 2] : C.b16[2][col / 2]);
-        tg = pack_f16x2(__uint_as_float(tt[k2]), __uint_as_float(tt[k2 + 1]));
-      }
-#if defined(DPI_DBG_ELU_FP32)
-      uint32_t e, h, dh;
-      {
-        float2 zf, tf;
+    for (int g = 0; g < G; ++g) {  // groups of 8 columns = one 16-byte operand chunk of the value and tangent rows
+      const uint32_t* vv = &v[b][8 * g];
+      const uint32_t* tt = &tv[b][8 * g];
+      const int c8 = ch * G + g;   // 16-byte chunk index 0..15
+      uint32_t hv[4], ht[4];
+#pragma unroll
+      for (int k2 = 0; k2 < 8; k2 += 2) {  // two columns per packed instruction
+        const int col = c8 * 8 + k2;
+        uint32_t z, tg;
         if (MODE == kPassFirst) {
-          zf = h2_unpack(z), tf = h2_unpack(tg);
+          const float4 c0 = cc[b][2 * g + k2 / 4];
+          const float c0a = (k2 & 2) ? c0.z : c0.x, c0b = (k2 & 2) ? c0.w : c0.y;
+          z = pack_f16x2(fmaf(a2, __uint_as_float(vv[k2]), fmaf(s2, C.wt[col], c0a)),
+                         fmaf(a2, __uint_as_float(vv[k2 + 1]), fmaf(s2, C.wt[col + 1], c0b)));
+          tg = C.wsum16[col / 2];
         } else {
-          const uint32_t* bb = (MODE == kPassHidden) ? bias : C.b16[2];
-          const float2 bf = h2_unpack(bb[col / 2]);
-          zf = make_float2(__uint_as_float(vv[k2]) + bf.x, __uint_as_float(vv[k2 + 1]) + bf.y);
-          tf = make_float2(__uint_as_float(tt[k2]), __uint_as_float(tt[k2 + 1]));
+          z = h2_add(pack_f16x2(__uint_as_float(vv[k2]), __uint_as_float(vv[k2 + 1])),
+                     MODE == kPassHidden ? bias[col / 2] : C.b16[2][col / 2]);
+          tg = pack_f16x2(__uint_as_float(tt[k2]), __uint_as_float(tt[k2 + 1]));
         }
-        const float e0 = exp2f(fminf(zf.x, 0.f)), e1 = exp2f(fminf(zf.y, 0.f));
-        e = pack_f16x2(e0, e1);
-        h = pack_f16x2(fmaxf(zf.x, fmaf(e0, kLog2e, -kLog2e)), fmaxf(zf.y, fmaf(e1, kLog2e, -kLog2e)));
-        dh = pack_f16x2(e0 * tf.x, e1 * tf.y);
+        const uint32_t e = h2_ex2(h2_min(z, kZero));           // ELU'(z) = 2^min(z',0)
+        const uint32_t h = h2_max(z, h2_fma(e, kL, kNegL));    // log2e ELU(z)
+        const uint32_t dh = h2_mul(e, tg);
+        if (MODE == kPassOut) {
+          accU = h2_fma(C.wout16[col / 2], h, accU);
+          accD = h2_fma(C.wout16[col / 2], dh, accD);
+        } else {
+          hv[k2 / 2] = h;
+          ht[k2 / 2] = dh;
+        }
       }
-#else
-      const uint32_t e = h2_ex2(h2_min(z, kZero));           // ELU'(z) = 2^min(z',0)
-      const uint32_t h = h2_max(z, h2_fma(e, kL, kNegL));    // log2e ELU(z)
-      const uint32_t dh = h2_mul(e, tg);
-#endif
       if (MODE == kPassOut) {
-#if defined(DPI_DBG_OUT_FP32)
-        {
-          const float2 wf = h2_unpack(C.wout16[col / 2]), hf = h2_unpack(h), df = h2_unpack(dh);
-          pu = fmaf(wf.x, hf.x, fmaf(wf.y, hf.y, pu));
-          pD = fmaf(wf.x, df.x, fmaf(wf.y, df.y, pD));
+        if (c8 & 1) {
+          const float2 fu = h2_unpack(accU), fd = h2_unpack(accD);
+          pu += fu.x + fu.y;
+          pD += fd.x + fd.y;
+          accU = accD = 0u;
         }
-#else
-        accU = h2_fma(C.wout16[col / 2], h, accU);
-        accD = h2_fma(C.wout16[col / 2], dh, accD);
-#endif
       } else {
-        hv[k2 / 2] = h;
-        ht[k2 / 2] = dh;
+        // 16-byte chunk c8 of this row: K panel (c8 >> 3), chunk index XOR-swizzled with (row & 7)
+        const uint32_t off = (uint32_t)(c8 >> 3) * kPanelBytes + (((uint32_t)(c8 & 7) << 4) ^ rx);
+        *reinterpret_cast<uint4*>(hv_row + off) = make_uint4(hv[0], hv[1], hv[2], hv[3]);
+        *reinterpret_cast<uint4*>(ht_row + off) = make_uint4(ht[0], ht[1], ht[2], ht[3]);
       }
-    }
-    if (MODE == kPassOut) {
-      if (ch & 1) {
-        const float2 fu = h2_unpack(accU), fd = h2_unpack(accD);
-        pu += fu.x + fu.y;
-        pD += fd.x + fd.y;
-        accU = accD = 0u;
-      }
-    } else {
-      // 16-byte chunk ch of this row: K panel (ch >> 3), chunk index XOR-swizzled with (row & 7)
-      const uint32_t off = (uint32_t)(ch >> 3) * kPanelBytes + (((uint32_t)(ch & 7) << 4) ^ rx);
-      *reinterpret_cast<uint4*>(hv_row + off) = make_uint4(hv[0], hv[1], hv[2], hv[3]);
-      *reinterpret_cast<uint4*>(ht_row + off) = make_uint4(ht[0], ht[1], ht[2], ht[3]);
     }
   }
 }
@@ -290,6 +288,10 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + kOffTmemPtr);
+#ifdef DPI_TC_TRACE
+  unsigned long long cta_t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(cta_t0));
+#endif
   if (tmem != 0u) {  // all 512 columns of the SM belong to this CTA: the MMA issuer relies on base column 0
     if (threadIdx.x == 0) printf("dpi tc: unexpected TMEM base 0x%x\n", tmem);
     __trap();
@@ -297,6 +299,84 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
 
   if (warp >= kMmaWarp) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kMmaRegs));
+#if DPI_TC_ISSUERS == 2
+    if (warp == kMmaWarp || warp == kMmaWarp1) {
+      // =================================== MMA issuers ===================================
+      // One issuing warp per tile slot: each walks its slot's tiles layer by layer and blocks only on its own
+      // slot's barriers, so a slot whose operands are late (increments, W1) never holds up the other slot's
+      // layers.  (A single issuer serving both slots in a fixed order did exactly that: 2-3 k cycles per tile.)
+      // The whole warp runs this (uniform) control flow; the elected lane issues tcgen05.mma / commit.
+      const uint32_t leader = elect_one();
+      // lane-0 broadcast marks the slot as warp-uniform for the compiler (uniform registers / datapath)
+      const int s = __shfl_sync(0xffffffffu, warp == kMmaWarp ? 0 : 1, 0);
+      TRACE_DECL(s == 0 ? 0 : 4);
+#ifdef DPI_TC_TRACE
+      if (lane != 0) trace_p = nullptr;
+#endif
+      mbar_wait(bar(kBarW), 0, 0);
+      constexpr uint32_t idesc = make_idesc_f16(128, 128);
+      const uint32_t b_ar = bar(kBarAReady + s), b_acc = bar(kBarAccFull + s);
+      // The operand descriptors are rebuilt per layer from a freshly broadcast slot index: this code runs in the 32
+      // registers left after setmaxnreg, and hoisting the 32 descriptor sums out of the loops would spill.
+#define DPI_MMA_OPERANDS()                                                              \
+  const uint32_t sl = (uint32_t)__shfl_sync(0xffffffffu, s, 0);                         \
+  const uint32_t acc = sl * 256u; /* TMEM base is column 0 (checked at allocation) */   \
+  const uint32_t slot = sbase + kOffSlot + sl * kSlotBytes;                             \
+  const uint64_t dV = make_desc_sw128(slot), dT = make_desc_sw128(slot + kOperandBytes)
+      uint32_t ph_z = 0, ph_w1 = 0, ph_ar = 0;
+      bool used = false;
+      TileCursor cur;
+      for (cur.init(A); cur.valid(A); cur.next(A)) {
+        if ((cur.tl & 1) != s) continue;
+        // ---- layer 1: accumulators free (output pass of the slot's previous tile done), increments stored,
+        //      W1 landed in hT
+        TRACE(1, s, 0, 10);
+        if (used) {
+          mbar_wait(b_ar, ph_ar, 10);
+          ph_ar ^= 1u;
+        }
+        used = true;
+        mbar_wait(bar(kBarZFull + s), ph_z, 11);
+        ph_z ^= 1u;
+        mbar_wait(bar(kBarW1Full + s), ph_w1, 12);
+        ph_w1 ^= 1u;
+        tc_fence_after();
+        TRACE(1, s, 0, 11);
+        {
+          DPI_MMA_OPERANDS();
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            if (ks < A.ksteps1) {
+              const uint64_t o = (uint64_t)((ks >> 2) * 1024 + (ks & 3) * 2);
+              umma_bf16_p(acc, dV + o, dT + o, idesc, ks > 0, leader);
+            }
+          }
+        }
+        tc_commit_p(b_acc, leader);
+        TRACE(1, s, 0, 12);
+        // ---- layers 2..4: value rows and tangent rows against the resident weights
+#pragma unroll 1
+        for (int l = 2; l <= 4; ++l) {
+          TRACE(1, s, 0, l * 10 + 0);
+          mbar_wait(b_ar, ph_ar, 13);
+          ph_ar ^= 1u;
+          tc_fence_after();
+          TRACE(1, s, 0, l * 10 + 1);
+          DPI_MMA_OPERANDS();
+          const uint32_t lu = (uint32_t)__shfl_sync(0xffffffffu, l, 0);
+          const uint64_t dW = make_desc_sw128(sbase + kOffW + (lu - 2u) * kOperandBytes);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t o = (uint64_t)((ks >> 2) * 1024 + (ks & 3) * 2);
+            umma_bf16_p(acc, dV + o, dW + o, idesc, ks > 0, leader);
+            umma_bf16_p(acc + 128u, dT + o, dW + o, idesc, ks > 0, leader);
+          }
+          tc_commit_p(b_acc, leader);
+          if (l == 4) tc_commit_p(bar(kBarSlotFree + s), leader);
+          TRACE(1, s, 0, l * 10 + 2);
+        }
+      }
+#else
     if (warp == kMmaWarp) {
       // =================================== MMA issuer ===================================
       // The whole warp runs this (uniform) control flow; the elected lane issues tcgen05.mma / commit.
@@ -378,6 +458,7 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
           lay1 = (lay1 == 4) ? 0 : lay1 + 1;
         }
       }
+#endif
     } else if (warp == kTmaWarp) {
       // =================================== TMA issuer ===================================
       const uint32_t leader = elect_one();
@@ -655,6 +736,16 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
 
   tc_fence_before();
   __syncthreads();
+#ifdef DPI_TC_TRACE
+  if (A.trace && threadIdx.x == 0) {  // per-CTA wall time (globaltimer, ns) and SM id
+    unsigned long long t1;
+    uint32_t smid;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    long long* q = A.trace + 5 * 2 * kTraceCap + 4 * blockIdx.x;
+    q[0] = (long long)cta_t0, q[1] = (long long)t1, q[2] = smid, q[3] = 1;
+  }
+#endif
   if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
@@ -843,7 +934,7 @@ int launch_cha_tc_path(const ProblemDev& P, const TcNetDev& N, const float* tx, 
 #endif
 #ifdef DPI_TC_TRACE
   long long* trace_dev = nullptr;
-  const size_t trace_bytes = sizeof(long long) * (4 * 2 * 8192);
+  const size_t trace_bytes = sizeof(long long) * (6 * 2 * 8192);
   if (getenv("DPI_TC_TRACE_FILE")) {
     cudaMalloc((void**)&trace_dev, trace_bytes);
     cudaMemsetAsync(trace_dev, 0, trace_bytes, st);
@@ -862,17 +953,22 @@ int launch_cha_tc_path(const ProblemDev& P, const TcNetDev& N, const float* tx, 
   if (rc) return rc;
 #ifdef DPI_TC_TRACE
   if (trace_dev) {
-    std::vector<long long> hbuf(4 * 2 * 8192);
+    std::vector<long long> hbuf(6 * 2 * 8192);
     cudaStreamSynchronize(st);
     cudaMemcpy(hbuf.data(), trace_dev, trace_bytes, cudaMemcpyDeviceToHost);
     cudaFree(trace_dev);
     if (FILE* f = fopen(getenv("DPI_TC_TRACE_FILE"), "w")) {
-      for (int r = 0; r < 4; ++r)
+      for (int r = 0; r < 5; ++r)
         for (int i = 0; i < 8192; ++i) {
           const long long code = hbuf[(size_t)r * 2 * 8192 + 2 * i], clk = hbuf[(size_t)r * 2 * 8192 + 2 * i + 1];
-          if (clk) fprintf(f, "%lld %lld\n", (long long)(r == 0 ? 1 : (r == 3 ? 3 : 2)) * 1000000 + code, clk);
+          if (clk) fprintf(f, "%lld %lld\n", (long long)((r == 0 || r == 4) ? 1 : (r == 3 ? 3 : 2)) * 1000000 + code, clk);
         }
       fclose(f);
+      if (FILE* g = fopen((std::string(getenv("DPI_TC_TRACE_FILE")) + ".cta").c_str(), "w")) {
+        const long long* q = hbuf.data() + (size_t)5 * 2 * 8192;
+        for (int b = 0; b < 2048 && q[4 * b + 3]; ++b) fprintf(g, "%d %lld %lld %lld\n", b, q[4 * b], q[4 * b + 1], q[4 * b + 2]);
+        fclose(g);
+      }
     }
   }
 #endif

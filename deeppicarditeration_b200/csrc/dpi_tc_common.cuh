@@ -67,13 +67,28 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Spin with a watchdog: a protocol bug must trap (and fail the launch) instead of hanging the GPU box.
+// try_wait with a suspend-time hint (ns): the warp sleeps in hardware until the phase completes or the hint
+// expires, instead of burning issue slots that the epilogue and producer warps of the same SMSP need.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
+// Wait with a watchdog: a protocol bug must trap (and fail the launch) instead of hanging the GPU box.  The
+// watchdog counts spins (two instructions per retry); the first version read clock64 on every retry and the
+// waiting warps issued a third of all instructions of the kernel.
+#ifndef DPI_TC_WAIT_HINT_NS
+#define DPI_TC_WAIT_HINT_NS 20000u
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
   uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3FFu) == 0 && clock64() - t0 > 4000000000LL) {
+  while (!mbar_try_wait_hint(bar, parity, DPI_TC_WAIT_HINT_NS)) {
+    if (++spins > (1u << 26)) {
 #ifdef DPI_TC_WATCHDOG_PRINTF
       printf("dpi tc watchdog: block %d thread %d stuck on barrier tag %d parity %u\n", (int)blockIdx.x,
              (int)threadIdx.x, tag, parity);

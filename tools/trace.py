@@ -58,3 +58,11 @@ print("producer intervals:")
 for k in sorted(dp): print("  ", k, sum(dp[k]) / len(dp[k]), len(dp[k]))
 mm = len(M) // 2
 print("MMA events (mid-run):"); show(M, mm, mm + 30)
+
+try:
+    rows = [tuple(map(int, l.split())) for l in open(out + ".cta")]
+    t00 = min(r[1] for r in rows); dur = sorted((r[2] - r[1], r[0], r[3], r[1] - t00) for r in rows)
+    print("per-CTA wall ns: min %d median %d max %d; kernel span %d" % (dur[0][0], dur[len(dur)//2][0], dur[-1][0], max(r[2] for r in rows) - t00))
+    print("slowest:", dur[-8:]); print("fastest:", dur[:8])
+except OSError:
+    pass
