@@ -117,7 +117,8 @@ int ensure_parts(dpi_handle* h, int64_t units) {
   h->partG = h->partF = nullptr;
   h->part_units = 0;
   DPI_CUDA_CHECK(cudaMalloc((void**)&h->partG, sizeof(float) * units * kTcPartGFloatsPerUnit));
-  DPI_CUDA_CHECK(cudaMalloc((void**)&h->partF, sizeof(float) * units * kTcPartFFloatsPerUnit));
+  // + the unit hand-out counter of the tensor-core kernel (one int behind the partials)
+  DPI_CUDA_CHECK(cudaMalloc((void**)&h->partF, sizeof(float) * (units * kTcPartFFloatsPerUnit + 4)));
   h->part_units = units;
   return DPI_OK;
 }
@@ -546,7 +547,9 @@ int dpi_label_gen(dpi_handle* h, const float* tx, int64_t n, const dpi_label_con
         rc = launch_cha_tc_path(P, h->tc, tx + p0 * (1 + d), np, cfg->M_I, cfg->seed, cfg->point_index_base + p0,
                                 draws ? draws->u_s + p0 * cfg->M_I : nullptr,
                                 draws ? draws->zS + p0 * (int64_t)cfg->M_I * d : nullptr, h->fb + p0,
-                                h->c0 + p0 * h->mlp.HP, bound, h->partG, h->partF, y + p0 * (1 + d), st);
+                                h->c0 + p0 * h->mlp.HP, bound, h->partG, h->partF,
+                                reinterpret_cast<int*>(h->partF + h->part_units * kTcPartFFloatsPerUnit),
+                                y + p0 * (1 + d), st);
         if (rc) return rc;
         h->launches += 2;
       }

@@ -76,7 +76,7 @@ constexpr int64_t kTcPartFFloatsPerUnit = 8;  // [slot][lane quarter]
 // partG [n*units][32][128], partF [n*units][8]: scratch for the unit partial sums
 int launch_cha_tc_path(const ProblemDev& P, const TcNetDev& net, const float* tx, int64_t n, int M_I, uint64_t seed,
                        int64_t base, const float* u_s, const float* zS, const float* fb, const float* c0, float bound,
-                       float* partG, float* partF, float* y, cudaStream_t st);
+                       float* partG, float* partF, int* unit_counter, float* y, cudaStream_t st);
 // D[128x128] = A[128x128] . B[128x128]^T (fp32 row-major device buffers, rounded to bf16) through tcgen05
 int tc_umma_selftest(const float* A, const float* B, float* D, cudaStream_t st);
 

@@ -15,7 +15,8 @@
 //   * 8 producer warps draw the Brownian increments with Philox4x32-10 + Box-Muller in registers, round them to fp16,
 //     store the [128 x d] A-operand tile when the slot frees up, and KEEP them in registers: once the tile's Bismut
 //     coefficients are known they accumulate G_j += coef_m Z_mj there, so increments never leave the SM;
-//   * one issuing thread per slot feeds tcgen05.mma (each blocks only on its own slot), one thread issues the TMA copies;
+//   * one thread issues tcgen05.mma for both slots in a fixed round-robin order (one issuing warp per slot was
+//     measured 5 % slower), one thread issues the TMA copies and pulls the CTA's next work unit from a global counter;
 //   * 4 epilogue warps per slot (thread = sample row) read the accumulators with tcgen05.ld, apply bias/ELU/ELU' in
 //     packed fp16x2 arithmetic (two columns per instruction; its absolute error stays below the rounding of the
 //     16-bit operands it produces) and write the next layer's A operands straight into the swizzled shared-memory
@@ -40,17 +41,14 @@ using namespace tc;
 
 // ---- roles ---------------------------------------------------------------------------------------------------
 // warps 0-3: epilogue of tile slot 0, warps 4-7: epilogue of tile slot 1 (warp & 3 = TMEM lane quarter),
-// warps 8-15: increment producers, warps 16 / 18: MMA issuers of slot 0 / 1 (one thread each), warp 17: TMA issuer
-// (one thread), warp 19: idle.
+// warps 8-15: increment producers, warp 16: MMA issuer (one thread), warp 17: TMA issuer (one thread) and unit
+// hand-out, warps 18-19: idle.
 // The register file is per SM sub-partition (512 registers per lane, warp w lives on sub-partition w % 4), so each
 // sub-partition holds one warp of every warpgroup.  setmaxnreg only moves registers inside the CTA's own pool (what
 // its warps have released), so the re-split must balance against the launch allocation of 96 per thread:
 // MMA/TMA warpgroup 96 -> 32, epilogue 96 -> 88, producers 96 -> 136 (2 x 88 + 2 x 136 + 32 = 480 = 5 x 96).
 constexpr int kTcThreads = 640;
-#ifndef DPI_TC_ISSUERS
-#define DPI_TC_ISSUERS 1
-#endif
-constexpr int kProdWarp0 = 8, kMmaWarp = 16, kTmaWarp = 17, kMmaWarp1 = 18;
+constexpr int kProdWarp0 = 8, kMmaWarp = 16, kTmaWarp = 17;
 #ifndef DPI_EPI_REGS
 #define DPI_EPI_REGS 88
 #endif
@@ -63,9 +61,10 @@ constexpr uint32_t kOffSlot = 3 * kOperandBytes;           // tile slot s at + s
 constexpr uint32_t kSlotBytes = 2 * kOperandBytes;
 constexpr uint32_t kOffC0 = kOffSlot + 2 * kSlotBytes;     // [2 slots][128] first-layer constant of the slot's point
 constexpr uint32_t kOffCoef = kOffC0 + 1024;               // [3][128] Bismut coefficients (ring over tiles)
-constexpr uint32_t kOffBars = kOffCoef + 1536;             // 16 mbarriers
-constexpr uint32_t kOffTmemPtr = kOffBars + 128;
-constexpr uint32_t kTcSmemBytes = kOffTmemPtr + 16;        // 232,080 B <= 232,448 B
+constexpr uint32_t kOffBars = kOffCoef + 1536;             // 20 mbarriers
+constexpr uint32_t kOffTmemPtr = kOffBars + 160;
+constexpr uint32_t kOffUnits = kOffTmemPtr + 16;           // [4] ring of unit ids handed out by the global counter
+constexpr uint32_t kTcSmemBytes = kOffUnits + 16;          // 232,128 B <= 232,448 B
 
 enum Bar : int {
   kBarW = 0,         // W2..W4 landed (TMA)
@@ -74,7 +73,8 @@ enum Bar : int {
   kBarSlotFree = 5,  // [2] layer-4 MMAs of the slot's tile have completed: hV / hT may be overwritten (tcgen05.commit)
   kBarAccFull = 7,   // [2] a layer's accumulators are complete (tcgen05.commit, 4 per tile)
   kBarAReady = 9,    // [2] an epilogue pass is done: next A operand written, accumulators read (4 epilogue warps)
-  kBarCoef = 11      // [3] Bismut coefficients of a tile written (4 epilogue warps)
+  kBarCoef = 11,     // [3] Bismut coefficients of a tile written (4 epilogue warps)
+  kBarUnit = 14      // [4] the CTA's k-th unit id is in ring entry k % 4 (TMA warp)
 };
 
 struct TcArgs {
@@ -95,6 +95,7 @@ struct TcArgs {
   int ksteps1;  // ceil(d/16)
   int no;       // ceil(d/8) octets of dims (one Philox block, one 16-byte operand chunk each)
   int cls;      // row classes of the producer mapping: cls * no <= 256, cls <= kTcMaxClasses
+  int* unit_counter;  // next unit to hand out (zeroed before the launch)
   long long* trace;  // developer timeline (DPI_TC_TRACE builds only), else null
 };
 
@@ -227,13 +228,31 @@ __device__ __forceinline__ void epi_pass(const TcConsts& C, uint32_t tacc, uint8
   }
 }
 
-// flat cursor over this CTA's tiles: unit u = blockIdx.x + k gridDim.x, tile tl inside the unit; slot = tl & 1, so
-// the slot of a tile (and with it the order of every floating-point sum) does not depend on the launch geometry
+// Units are handed out dynamically: SMs do not run at exactly the same speed (3-8 % spread between the fastest and
+// the slowest CTA of a statically partitioned launch), so each CTA pulls its next unit from a global counter.  The
+// TMA warp -- the role that runs ahead of all others -- fetches one unit ahead and publishes the CTA's k-th unit id
+// in a 4-entry shared-memory ring; every role walks the same sequence k = 0, 1, ... and stops at the first id
+// >= n_units.  All roles are within one unit of each other, so an entry is never overwritten while it is still
+// read, and a waiter can never be two phases behind.  Partial sums are indexed by the unit id: which CTA computes
+// a unit changes nothing in the result.
+struct UnitFeed {
+  const volatile int* ring;
+  uint32_t bar0;
+  __device__ __forceinline__ int64_t get(uint32_t k) const {
+    mbar_wait(bar0 + 8u * (k & 3u), (k >> 2) & 1u, 50);
+    return (int64_t)ring[k & 3u];
+  }
+};
+
+// flat cursor over this CTA's tiles: unit u = the CTA's k-th unit, tile tl inside the unit; slot = tl & 1, so the
+// slot of a tile (and with it the order of every floating-point sum) does not depend on the launch geometry
 struct TileCursor {
   int64_t u;
   int tl, tiles;
-  __device__ __forceinline__ void init(const TcArgs& A) {
-    u = blockIdx.x;
+  uint32_t k;
+  __device__ __forceinline__ void init(const TcArgs& A, const UnitFeed& F) {
+    k = 0;
+    u = F.get(0);
     tl = 0;
     tiles = (u < A.n_units) ? tiles_of(A, u) : 0;
   }
@@ -242,9 +261,9 @@ struct TileCursor {
     return min(kTcGroupTiles, A.tiles_per_point - g * kTcGroupTiles);
   }
   __device__ __forceinline__ bool valid(const TcArgs& A) const { return u < A.n_units; }
-  __device__ __forceinline__ void next(const TcArgs& A) {
+  __device__ __forceinline__ void next(const TcArgs& A, const UnitFeed& F) {
     if (++tl == tiles) {
-      u += gridDim.x;
+      u = F.get(++k);
       tl = 0;
       tiles = (u < A.n_units) ? tiles_of(A, u) : 0;
     }
@@ -261,6 +280,7 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
   const int d = P.nx;
   const int UP = A.units_per_point, M_I = A.M_I;
   auto bar = [&](int i) -> uint32_t { return sbase + kOffBars + 8u * (uint32_t)i; };
+  const UnitFeed feed{reinterpret_cast<const volatile int*>(smem + kOffUnits), sbase + kOffBars + 8u * (uint32_t)kBarUnit};
 
   if (threadIdx.x == 0) {
     if (sbase & 1023u) {
@@ -276,6 +296,7 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
       mbar_init(bar(kBarAReady + s), 4);
     }
     for (int b = 0; b < 3; ++b) mbar_init(bar(kBarCoef + b), 4);
+    for (int b = 0; b < 4; ++b) mbar_init(bar(kBarUnit + b), 1);
     fence_barrier_init();
   }
   // The layer-1 MMA reads K = 16 ceil(d/16) columns of the slot's hV buffer; the producers write the first d of them
@@ -299,84 +320,6 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
 
   if (warp >= kMmaWarp) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kMmaRegs));
-#if DPI_TC_ISSUERS == 2
-    if (warp == kMmaWarp || warp == kMmaWarp1) {
-      // =================================== MMA issuers ===================================
-      // One issuing warp per tile slot: each walks its slot's tiles layer by layer and blocks only on its own
-      // slot's barriers, so a slot whose operands are late (increments, W1) never holds up the other slot's
-      // layers.  (A single issuer serving both slots in a fixed order did exactly that: 2-3 k cycles per tile.)
-      // The whole warp runs this (uniform) control flow; the elected lane issues tcgen05.mma / commit.
-      const uint32_t leader = elect_one();
-      // lane-0 broadcast marks the slot as warp-uniform for the compiler (uniform registers / datapath)
-      const int s = __shfl_sync(0xffffffffu, warp == kMmaWarp ? 0 : 1, 0);
-      TRACE_DECL(s == 0 ? 0 : 4);
-#ifdef DPI_TC_TRACE
-      if (lane != 0) trace_p = nullptr;
-#endif
-      mbar_wait(bar(kBarW), 0, 0);
-      constexpr uint32_t idesc = make_idesc_f16(128, 128);
-      const uint32_t b_ar = bar(kBarAReady + s), b_acc = bar(kBarAccFull + s);
-      // The operand descriptors are rebuilt per layer from a freshly broadcast slot index: this code runs in the 32
-      // registers left after setmaxnreg, and hoisting the 32 descriptor sums out of the loops would spill.
-#define DPI_MMA_OPERANDS()                                                              \
-  const uint32_t sl = (uint32_t)__shfl_sync(0xffffffffu, s, 0);                         \
-  const uint32_t acc = sl * 256u; /* TMEM base is column 0 (checked at allocation) */   \
-  const uint32_t slot = sbase + kOffSlot + sl * kSlotBytes;                             \
-  const uint64_t dV = make_desc_sw128(slot), dT = make_desc_sw128(slot + kOperandBytes)
-      uint32_t ph_z = 0, ph_w1 = 0, ph_ar = 0;
-      bool used = false;
-      TileCursor cur;
-      for (cur.init(A); cur.valid(A); cur.next(A)) {
-        if ((cur.tl & 1) != s) continue;
-        // ---- layer 1: accumulators free (output pass of the slot's previous tile done), increments stored,
-        //      W1 landed in hT
-        TRACE(1, s, 0, 10);
-        if (used) {
-          mbar_wait(b_ar, ph_ar, 10);
-          ph_ar ^= 1u;
-        }
-        used = true;
-        mbar_wait(bar(kBarZFull + s), ph_z, 11);
-        ph_z ^= 1u;
-        mbar_wait(bar(kBarW1Full + s), ph_w1, 12);
-        ph_w1 ^= 1u;
-        tc_fence_after();
-        TRACE(1, s, 0, 11);
-        {
-          DPI_MMA_OPERANDS();
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            if (ks < A.ksteps1) {
-              const uint64_t o = (uint64_t)((ks >> 2) * 1024 + (ks & 3) * 2);
-              umma_bf16_p(acc, dV + o, dT + o, idesc, ks > 0, leader);
-            }
-          }
-        }
-        tc_commit_p(b_acc, leader);
-        TRACE(1, s, 0, 12);
-        // ---- layers 2..4: value rows and tangent rows against the resident weights
-#pragma unroll 1
-        for (int l = 2; l <= 4; ++l) {
-          TRACE(1, s, 0, l * 10 + 0);
-          mbar_wait(b_ar, ph_ar, 13);
-          ph_ar ^= 1u;
-          tc_fence_after();
-          TRACE(1, s, 0, l * 10 + 1);
-          DPI_MMA_OPERANDS();
-          const uint32_t lu = (uint32_t)__shfl_sync(0xffffffffu, l, 0);
-          const uint64_t dW = make_desc_sw128(sbase + kOffW + (lu - 2u) * kOperandBytes);
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            const uint64_t o = (uint64_t)((ks >> 2) * 1024 + (ks & 3) * 2);
-            umma_bf16_p(acc, dV + o, dW + o, idesc, ks > 0, leader);
-            umma_bf16_p(acc + 128u, dT + o, dW + o, idesc, ks > 0, leader);
-          }
-          tc_commit_p(b_acc, leader);
-          if (l == 4) tc_commit_p(bar(kBarSlotFree + s), leader);
-          TRACE(1, s, 0, l * 10 + 2);
-        }
-      }
-#else
     if (warp == kMmaWarp) {
       // =================================== MMA issuer ===================================
       // The whole warp runs this (uniform) control flow; the elected lane issues tcgen05.mma / commit.
@@ -384,11 +327,10 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
       TRACE_DECL(0);
 #ifdef DPI_TC_TRACE
       if (lane != 0) trace_p = nullptr;
-#endif
       mbar_wait(bar(kBarW), 0, 0);
       constexpr uint32_t idesc = make_idesc_f16(128, 128);
       TileCursor cur;
-      cur.init(A);
+      cur.init(A, feed);
       int lay0 = 0, lay1 = 0, slt0 = 0, slt1 = 0;  // two in-flight tiles: next layer to issue (0 = none) and slot
       uint32_t ph_z = 0, ph_w1 = 0, ph_ar = 0, used = 0;  // bit s = slot s
       auto issue = [&](int s, int l) {
@@ -442,11 +384,11 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
       for (;;) {
         if (lay0 == 0 && cur.valid(A) && (lay1 == 0 || slt1 != (cur.tl & 1))) {
           slt0 = cur.tl & 1, lay0 = 1;
-          cur.next(A);
+          cur.next(A, feed);
         }
         if (lay1 == 0 && cur.valid(A) && (lay0 == 0 || slt0 != (cur.tl & 1))) {
           slt1 = cur.tl & 1, lay1 = 1;
-          cur.next(A);
+          cur.next(A, feed);
         }
         if (lay0 == 0 && lay1 == 0) break;
         if (lay0) {
@@ -469,8 +411,20 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
         bulk_g2s_p(sbase + kOffW + (uint32_t)i * 8192u, Wg + kOperandBytes + (size_t)i * 8192, 8192u, bar(kBarW), leader);
       const int n_chunks = (d > 64) ? 4 : 2;  // K panels of the W1 image that layer 1 reads (16 KB each)
       uint32_t ph_free = 0, used = 0;
+      // unit hand-out: the CTA's k-th unit comes from the global counter; it is fetched one unit ahead (the atomic's
+      // round trip stays off every critical path) and published through the ring (see UnitFeed)
+      volatile int* ring = reinterpret_cast<volatile int*>(smem + kOffUnits);
+      auto publish = [&](uint32_t k) {
+        if (leader) {
+          ring[k & 3u] = atomicAdd(A.unit_counter, 1);
+          mbar_arrive(bar(kBarUnit + (int)(k & 3u)));  // release: the ring store is visible to whoever sees the phase
+        }
+        __syncwarp();
+      };
+      publish(0);
       TileCursor cur;
-      for (cur.init(A); cur.valid(A); cur.next(A)) {
+      for (cur.init(A, feed); cur.valid(A); cur.next(A, feed)) {
+        if (cur.tl == 0) publish(cur.k + 1u);  // a valid unit always announces its successor (possibly the terminator)
         const int s = cur.tl & 1;
         const uint32_t bit = 1u << s;
         if (used & bit) {
@@ -505,20 +459,24 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
 #endif
     // per-point scalars are fetched one unit ahead so that their latency is off the slot's critical path
     float t_n = 0.f, fb_n = 0.f, c0_n = 0.f;
-    if ((int64_t)blockIdx.x < A.n_units) {
-      const int64_t pn = (int64_t)blockIdx.x / UP;
+    int64_t u_n = feed.get(0);
+    if (u_n < A.n_units) {
+      const int64_t pn = u_n / UP;
       t_n = __ldg(A.tx + pn * (int64_t)(1 + d));
       fb_n = __ldg(A.fb + pn);
       c0_n = __ldg(A.c0 + pn * 128 + r);
     }
-    for (int64_t u = blockIdx.x; u < A.n_units; u += gridDim.x) {
+    for (uint32_t k = 0;; ++k) {
+      const int64_t u = u_n;
+      if (u >= A.n_units) break;
       const int64_t p = u / UP;
       const int g = (int)(u % UP);
       const int tiles = min(kTcGroupTiles, A.tiles_per_point - g * kTcGroupTiles);
       const float t = t_n, fbp = fb_n, c0v = kLog2e * c0_n;
       const float dT = P.T - t;
-      if (u + gridDim.x < A.n_units) {
-        const int64_t pn = (u + gridDim.x) / UP;
+      u_n = feed.get(k + 1u);  // published when the TMA warp started on unit k
+      if (u_n < A.n_units) {
+        const int64_t pn = u_n / UP;
         t_n = __ldg(A.tx + pn * (int64_t)(1 + d));
         fb_n = __ldg(A.fb + pn);
         c0_n = __ldg(A.c0 + pn * 128 + r);
@@ -656,7 +614,9 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
         }
       }
     };
-    for (int64_t u = blockIdx.x; u < A.n_units; u += gridDim.x) {
+    for (uint32_t k = 0;; ++k) {
+      const int64_t u = feed.get(k);
+      if (u >= A.n_units) break;
       const int64_t p = u / UP;
       const int g = (int)(u % UP);
       const int tiles = min(kTcGroupTiles, A.tiles_per_point - g * kTcGroupTiles);
@@ -902,9 +862,15 @@ int64_t tc_units_per_point(int M_I) {
 
 int launch_cha_tc_path(const ProblemDev& P, const TcNetDev& N, const float* tx, int64_t n, int M_I, uint64_t seed,
                        int64_t base, const float* u_s, const float* zS, const float* fb, const float* c0, float bound,
-                       float* partG, float* partF, float* y, cudaStream_t st) {
+                       float* partG, float* partF, int* unit_counter, float* y, cudaStream_t st) {
   if (n <= 0) return DPI_OK;
+  if (n * tc_units_per_point(M_I) > 0x7fffff00LL) {
+    fprintf(stderr, "dpi tc: too many units in one launch\n");
+    return DPI_ERR_INVALID;
+  }
   TcArgs A{};
+  A.unit_counter = unit_counter;
+  DPI_CUDA_CHECK(cudaMemsetAsync(unit_counter, 0, sizeof(int), st));
   A.W = N.W;
   A.tx = tx;
   A.tiles_per_point = (M_I + 127) / 128;
