@@ -46,24 +46,54 @@ struct ProblemDev {
 // Philox4x32-10 (Salmon et al. 2011), counter-based: every (point, stream, sample, dim-block) has its own
 // counter, so labels are independent of launch geometry, shard size and GPU count.
 // ---------------------------------------------------------------------------------------------
+// One round: two 32x32 -> 64-bit products (one IMAD.WIDE each) and two three-input XORs.
+__device__ __forceinline__ uint4 philox_round(uint4 c, uint32_t kx, uint32_t ky) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+  const uint64_t p0 = (uint64_t)M0 * c.x, p1 = (uint64_t)M1 * c.z;
+  return make_uint4((uint32_t)(p1 >> 32) ^ c.y ^ kx, (uint32_t)p1, (uint32_t)(p0 >> 32) ^ c.w ^ ky, (uint32_t)p0);
+}
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
-  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+  constexpr uint32_t W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
-    const uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
-    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    c = philox_round(c, k.x, k.y);
     k.x += W0;
     k.y += W1;
   }
   return c;
 }
 
+// The ten round keys of a seed, computed once on the host.  Passed as a kernel parameter they sit in the constant
+// bank and feed the XORs as instruction operands: the generator-bound kernels save the 20 key additions per block.
+struct PhiloxKeys {
+  uint32_t kx[10], ky[10];
+};
+inline PhiloxKeys make_philox_keys(uint64_t seed) {
+  PhiloxKeys K;
+  uint32_t kx = (uint32_t)seed, ky = (uint32_t)(seed >> 32);
+  for (int r = 0; r < 10; ++r) {
+    K.kx[r] = kx, K.ky[r] = ky;
+    kx += 0x9E3779B9u, ky += 0xBB67AE85u;
+  }
+  return K;
+}
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, const PhiloxKeys& K) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) c = philox_round(c, K.kx[r], K.ky[r]);
+  return c;
+}
+
+__device__ __forceinline__ uint4 philox_counter(uint64_t point, uint32_t stream, uint32_t sample, uint32_t block) {
+  // counter = {dim block, sample, point[31:0], point[47:32] | stream<<16}
+  return make_uint4(block, sample, (uint32_t)point, ((uint32_t)(point >> 32) & 0xFFFFu) | (stream << 16));
+}
 __device__ __forceinline__ uint4 philox_at(uint64_t seed, uint64_t point, uint32_t stream, uint32_t sample,
                                            uint32_t block) {
-  // counter = {dim block, sample, point[31:0], point[47:32] | stream<<16}
-  const uint4 c = make_uint4(block, sample, (uint32_t)point, ((uint32_t)(point >> 32) & 0xFFFFu) | (stream << 16));
-  return philox4x32_10(c, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  return philox4x32_10(philox_counter(point, stream, sample, block), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+}
+__device__ __forceinline__ uint4 philox_at(const PhiloxKeys& K, uint64_t point, uint32_t stream, uint32_t sample,
+                                           uint32_t block) {
+  return philox4x32_10(philox_counter(point, stream, sample, block), K);
 }
 
 // uniform in the OPEN interval (0,1): (x>>8 + 0.5) * 2^-24
@@ -91,6 +121,15 @@ __device__ __forceinline__ void box_muller16(uint32_t w, float& z0, float& z1) {
 __device__ __forceinline__ void normal8(uint64_t seed, uint64_t point, uint32_t stream, uint32_t sample, uint32_t block8,
                                         float4& za, float4& zb) {
   const uint4 r = philox_at(seed, point, stream, sample, block8);
+  box_muller16(r.x, za.x, za.y);
+  box_muller16(r.y, za.z, za.w);
+  box_muller16(r.z, zb.x, zb.y);
+  box_muller16(r.w, zb.z, zb.w);
+}
+
+__device__ __forceinline__ void normal8(const PhiloxKeys& K, uint64_t point, uint32_t stream, uint32_t sample,
+                                        uint32_t block8, float4& za, float4& zb) {
+  const uint4 r = philox_at(K, point, stream, sample, block8);
   box_muller16(r.x, za.x, za.y);
   box_muller16(r.y, za.z, za.w);
   box_muller16(r.z, zb.x, zb.y);

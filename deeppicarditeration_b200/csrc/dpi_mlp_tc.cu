@@ -83,6 +83,7 @@ struct TcArgs {
   int64_t n_units;
   int64_t point_base;
   uint64_t seed;
+  PhiloxKeys keys;  // round keys of `seed`
   const float* u_s;
   const float* zS;
   const float* fb;  // [n] control variate f(t,x)
@@ -327,6 +328,7 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
       TRACE_DECL(0);
 #ifdef DPI_TC_TRACE
       if (lane != 0) trace_p = nullptr;
+#endif
       mbar_wait(bar(kBarW), 0, 0);
       constexpr uint32_t idesc = make_idesc_f16(128, 128);
       TileCursor cur;
@@ -400,7 +402,6 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
           lay1 = (lay1 == 4) ? 0 : lay1 + 1;
         }
       }
-#endif
     } else if (warp == kTmaWarp) {
       // =================================== TMA issuer ===================================
       const uint32_t leader = elect_one();
@@ -647,7 +648,7 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
                 zb = za;
               }
 #else
-              normal8(A.seed, gp, kStreamIntegral, (uint32_t)(m0 + rr), (uint32_t)o, za, zb);
+              normal8(A.keys, gp, kStreamIntegral, (uint32_t)(m0 + rr), (uint32_t)o, za, zb);
 #endif
               // dims >= d of the last octet stay as drawn: their W1 columns are zero and their Bismut sums are never
               // read, so masking them would only cost instructions
@@ -878,6 +879,7 @@ int launch_cha_tc_path(const ProblemDev& P, const TcNetDev& N, const float* tx, 
   A.n_units = n * A.units_per_point;
   A.point_base = base;
   A.seed = seed;
+  A.keys = make_philox_keys(seed);
   A.u_s = u_s;
   A.zS = zS;
   A.fb = fb;

@@ -78,17 +78,23 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity
       : "memory");
   return ok != 0;
 }
-// Wait with a watchdog: a protocol bug must trap (and fail the launch) instead of hanging the GPU box.  The
-// watchdog counts spins (two instructions per retry); the first version read clock64 on every retry and the
-// waiting warps issued a third of all instructions of the kernel.
+// Wait with a watchdog: a protocol bug must trap (and fail the launch) instead of hanging the GPU box.  The slow
+// path reads the nanosecond timer once on entry and then only every 64th retry (the first version read clock64 on
+// every retry and the waiting warps issued a third of all instructions of the kernel).
 #ifndef DPI_TC_WAIT_HINT_NS
 #define DPI_TC_WAIT_HINT_NS 20000u
 #endif
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
   if (mbar_try_wait(bar, parity)) return;
+  const unsigned long long t0 = global_ns();
   uint32_t spins = 0;
   while (!mbar_try_wait_hint(bar, parity, DPI_TC_WAIT_HINT_NS)) {
-    if (++spins > (1u << 26)) {
+    if ((++spins & 63u) == 0 && global_ns() - t0 > 2000000000ull) {  // 2 s: three orders above any legitimate wait
 #ifdef DPI_TC_WATCHDOG_PRINTF
       printf("dpi tc watchdog: block %d thread %d stuck on barrier tag %d parity %u\n", (int)blockIdx.x,
              (int)threadIdx.x, tag, parity);

@@ -86,7 +86,7 @@ struct Payoff<DPI_EQ_OU> {
 // ---------------------------------------------------------------------------------------------
 template <int EQ, int NSLOT, bool DET>
 __global__ void __launch_bounds__(kTermThreads)
-terminal_kernel(const ProblemDev P, const float* __restrict__ tx, int M_T, uint64_t seed, int64_t point_base,
+terminal_kernel(const ProblemDev P, const float* __restrict__ tx, int M_T, const PhiloxKeys keys, int64_t point_base,
                 const float* __restrict__ zT, float* __restrict__ y) {
   using PO = Payoff<EQ>;
   constexpr int NS = PO::NS;
@@ -177,7 +177,7 @@ terminal_kernel(const ProblemDev P, const float* __restrict__ tx, int M_T, uint6
           z[q][0] = load_row4(zT + ((int64_t)p * M_T + m) * d, j0, d, vec_ok);
           z[q][1] = load_row4(zT + ((int64_t)p * M_T + m) * d, j0 + 4, d, vec_ok);
         } else {
-          normal8(seed, gp, kStreamTerminal, (uint32_t)m, (uint32_t)(j0 >> 3), z[q][0], z[q][1]);
+          normal8(keys, gp, kStreamTerminal, (uint32_t)m, (uint32_t)(j0 >> 3), z[q][0], z[q][1]);
           // dims >= d of the last octet stay as drawn: every payoff statistic weights them with a zero constant and
           // their Bismut sums are never written out
         }
@@ -273,9 +273,9 @@ int launch_terminal_t(const ProblemDev& P, const float* tx, int64_t n, int M_T, 
     DPI_CUDA_CHECK(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   if (zT)
-    kd<<<(unsigned)n, kTermThreads, smem, st>>>(P, tx, M_T, seed, base, zT, y);
+    kd<<<(unsigned)n, kTermThreads, smem, st>>>(P, tx, M_T, make_philox_keys(seed), base, zT, y);
   else
-    kp<<<(unsigned)n, kTermThreads, smem, st>>>(P, tx, M_T, seed, base, nullptr, y);
+    kp<<<(unsigned)n, kTermThreads, smem, st>>>(P, tx, M_T, make_philox_keys(seed), base, nullptr, y);
   DPI_CUDA_CHECK(cudaGetLastError());
   return DPI_OK;
 }
