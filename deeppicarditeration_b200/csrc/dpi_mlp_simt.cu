@@ -189,7 +189,8 @@ cha_simt_kernel(const ProblemDev P, const MlpDev N, const float* __restrict__ tx
         const float lin = c0_s[col] + a_s[r] * acc1[i][c];
         if (mode == kModeBase && c0_out != nullptr) {
           const int64_t pt = p * G::RT + r;
-          if (pt < n) c0_out[pt * HP + col] = lin;
+          // the tensor-core kernel carries its activations scaled by log2(e): hand it the constant pre-scaled
+          if (pt < n) c0_out[pt * HP + col] = emu ? lin * 1.4426950408889634f : lin;
         }
         float h, e1;
         elu_d1(lin + s_s[r] * wt_s[col], h, e1);

@@ -59,8 +59,8 @@ constexpr float kLog2e = 1.4426950408889634f;
 constexpr uint32_t kOffW = 0;                              // W2, W3, W4 operand images (3 x 32 KB), resident
 constexpr uint32_t kOffSlot = 3 * kOperandBytes;           // tile slot s at + s * 64 KB: hV (32 KB) | hT (32 KB)
 constexpr uint32_t kSlotBytes = 2 * kOperandBytes;
-constexpr uint32_t kOffC0 = kOffSlot + 2 * kSlotBytes;     // [2 slots][128] first-layer constant of the slot's point
-constexpr uint32_t kOffCoef = kOffC0 + 1024;               // [3][128] Bismut coefficients (ring over tiles)
+constexpr uint32_t kOffExch = kOffSlot + 2 * kSlotBytes;   // [128] float2: output-layer partials handed between the halves
+constexpr uint32_t kOffCoef = kOffExch + 1024;              // [3][128] Bismut coefficients (ring over tiles)
 constexpr uint32_t kOffBars = kOffCoef + 1536;             // 20 mbarriers
 constexpr uint32_t kOffTmemPtr = kOffBars + 160;
 constexpr uint32_t kOffUnits = kOffTmemPtr + 16;           // [4] ring of unit ids handed out by the global counter
@@ -72,7 +72,7 @@ enum Bar : int {
   kBarZFull = 3,     // [2] increments stored in the slot's hV buffer (8 producer warps)
   kBarSlotFree = 5,  // [2] layer-4 MMAs of the slot's tile have completed: hV / hT may be overwritten (tcgen05.commit)
   kBarAccFull = 7,   // [2] a layer's accumulators are complete (tcgen05.commit, 4 per tile)
-  kBarAReady = 9,    // [2] an epilogue pass is done: next A operand written, accumulators read (4 epilogue warps)
+  kBarAReady = 9,    // [2] an epilogue pass is done: next A operand written, accumulators read (8 epilogue warps)
   kBarCoef = 11,     // [3] Bismut coefficients of a tile written (4 epilogue warps)
   kBarUnit = 14      // [4] the CTA's k-th unit id is in ring entry k % 4 (TMA warp)
 };
@@ -155,9 +155,12 @@ __device__ __forceinline__ void tmem_ldN(uint32_t taddr, uint32_t (&r)[N]) {
 
 template <int MODE>
 __device__ __forceinline__ void epi_pass(const TcConsts& C, uint32_t tacc, uint8_t* hv_row, uint8_t* ht_row,
-                                         uint32_t rx, const float* c0_s, int layer, float s2, float a2, float& pu,
-                                         float& pD) {
-  constexpr int NB = kEpiDB ? 2 : 1, NCH = 128 / kEpiCW, G = kEpiCW / 8;
+                                         uint32_t rx, int half, const float* __restrict__ c0_s, int layer, float s2,
+                                         float a2, float& pu, float& pD) {
+  // this warp's half of the row: columns [64 half, 64 half + 64); c0_s = the point's (log2e-scaled) first-layer
+  // constants in global memory (512 B per point, read by every tile of the point: L1 hits)
+  constexpr int NB = kEpiDB ? 2 : 1, NCH = 64 / kEpiCW, G = kEpiCW / 8;
+  const int ch0 = half * NCH;
   uint32_t v[NB][kEpiCW], tv[NB][kEpiCW];
   float4 cc[NB][2 * G];  // first pass: c0 of the current / next chunk (prefetched like the accumulators)
   auto fetch = [&](int ch, int b) {
@@ -165,21 +168,22 @@ __device__ __forceinline__ void epi_pass(const TcConsts& C, uint32_t tacc, uint8
     if (MODE != kPassFirst) tmem_ldN<kEpiCW>(tacc + 128u + (uint32_t)(ch * kEpiCW), tv[b]);
     if (MODE == kPassFirst) {
 #pragma unroll
-      for (int i = 0; i < 2 * G; ++i) cc[b][i] = *reinterpret_cast<const float4*>(&c0_s[ch * kEpiCW + 4 * i]);
+      for (int i = 0; i < 2 * G; ++i) cc[b][i] = __ldg(reinterpret_cast<const float4*>(&c0_s[ch * kEpiCW + 4 * i]));
     }
   };
-  if (kEpiDB) fetch(0, 0);
+  if (kEpiDB) fetch(ch0, 0);
   const uint32_t* bias = C.b16[layer];
   const uint32_t kL = h2_const(kLog2e, kLog2e), kNegL = h2_const(-kLog2e, -kLog2e), kZero = 0u;
   uint32_t accU = 0u, accD = 0u;  // output pass: fp16x2 partial dot products, flushed to fp32 every 16 columns
   // rolled a few chunks at a time: the pass is a short loop that stays in the instruction cache; per-column
   // constants are then fetched with indexed constant loads
 #pragma unroll kEpiUnroll
-  for (int ch = 0; ch < NCH; ++ch) {
-    const int b = kEpiDB ? (ch & 1) : 0;
+  for (int ci = 0; ci < NCH; ++ci) {
+    const int ch = ch0 + ci;
+    const int b = kEpiDB ? (ci & 1) : 0;
     if (!kEpiDB) fetch(ch, 0);
     tmem_ld_wait();
-    if (kEpiDB && ch + 1 < NCH) fetch(ch + 1, (ch + 1) & 1);
+    if (kEpiDB && ci + 1 < NCH) fetch(ch + 1, (ci + 1) & 1);
 #pragma unroll
     for (int g = 0; g < G; ++g) {  // groups of 8 columns = one 16-byte operand chunk of the value and tangent rows
       const uint32_t* vv = &v[b][8 * g];
@@ -213,7 +217,7 @@ __device__ __forceinline__ void epi_pass(const TcConsts& C, uint32_t tacc, uint8
         }
       }
       if (MODE == kPassOut) {
-        if (c8 & 1) {
+        if ((G == 1 ? ci : g) & 1) {
           const float2 fu = h2_unpack(accU), fd = h2_unpack(accD);
           pu += fu.x + fu.y;
           pD += fd.x + fd.y;
@@ -294,7 +298,7 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
       mbar_init(bar(kBarZFull + s), 8);
       mbar_init(bar(kBarSlotFree + s), 1);
       mbar_init(bar(kBarAccFull + s), 1);
-      mbar_init(bar(kBarAReady + s), 4);
+      mbar_init(bar(kBarAReady + s), 8);
     }
     for (int b = 0; b < 3; ++b) mbar_init(bar(kBarCoef + b), 4);
     for (int b = 0; b < 4; ++b) mbar_init(bar(kBarUnit + b), 1);
@@ -442,30 +446,43 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
     __syncwarp();
   } else if (warp < kProdWarp0) {
     // =================================== epilogue warps ===================================
+    // All eight warps work on ONE tile at a time: warp (q, h) owns TMEM lane quarter q (rows 32q..32q+31) and the
+    // column half h of every pass, and the passes of the two slots are interleaved in the order in which the MMA
+    // issuer produces their accumulators: P1(A) P1(B) P2(A) P2(B) ... P4(A) P4(B) for the tile pair (A, B) =
+    // (slot 0, slot 1).  While the warps are busy with one slot the tensor pipe runs the other slot's layer, so
+    // in steady state nobody waits; with four warps per slot (each slot on its own) the epilogue warps sat idle
+    // 40 % of the time and a pass took twice as long.
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
-    const int slot = warp >> 2, q = warp & 3;
+    const int q = warp & 3, h = warp >> 2;
     const int r = q * 32 + lane;
-    const uint32_t tacc = tmem + (uint32_t)slot * 256u + ((uint32_t)(q * 32) << 16);
-    uint8_t* const hv_row = smem + kOffSlot + (uint32_t)slot * kSlotBytes + (uint32_t)r * 128u;
-    uint8_t* const ht_row = hv_row + kOperandBytes;
+    const uint32_t tacc0 = tmem + ((uint32_t)(q * 32) << 16);
+    uint8_t* const hv_row0 = smem + kOffSlot + (uint32_t)r * 128u;
     const uint32_t rx = (uint32_t)(r & 7) << 4;
-    float* c0_s = reinterpret_cast<float*>(smem + kOffC0) + slot * 128;
+    float2* exch = reinterpret_cast<float2*>(smem + kOffExch);  // [128] output-layer partial sums of the other half
     float* coef_s = reinterpret_cast<float*>(smem + kOffCoef);
-    const uint32_t b_acc = bar(kBarAccFull + slot), b_ar = bar(kBarAReady + slot);
-    uint32_t ph_acc = 0, j = 0;
-    int64_t c0_point = -1;
-    TRACE_DECL(1 + slot);
+    uint32_t ph_acc = 0, j = 0;  // ph_acc bit s = slot s
+    TRACE_DECL(1 + h);
 #ifdef DPI_TC_TRACE
     if (q != 0 || lane != 0) trace_p = nullptr;
 #endif
-    // per-point scalars are fetched one unit ahead so that their latency is off the slot's critical path
-    float t_n = 0.f, fb_n = 0.f, c0_n = 0.f;
+    auto wait_acc = [&](int s) {
+      mbar_wait(bar(kBarAccFull + s), (ph_acc >> s) & 1u, 30 + s);
+      ph_acc ^= 1u << s;
+      tc_fence_after();
+    };
+    auto pass_done = [&](int s) {  // next A operand written (generic -> async proxy), accumulators read
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(kBarAReady + s));
+    };
+    // per-point scalars are fetched one unit ahead so that their latency is off the critical path
+    float t_n = 0.f, fb_n = 0.f;
     int64_t u_n = feed.get(0);
     if (u_n < A.n_units) {
       const int64_t pn = u_n / UP;
       t_n = __ldg(A.tx + pn * (int64_t)(1 + d));
       fb_n = __ldg(A.fb + pn);
-      c0_n = __ldg(A.c0 + pn * 128 + r);
     }
     for (uint32_t k = 0;; ++k) {
       const int64_t u = u_n;
@@ -473,84 +490,102 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
       const int64_t p = u / UP;
       const int g = (int)(u % UP);
       const int tiles = min(kTcGroupTiles, A.tiles_per_point - g * kTcGroupTiles);
-      const float t = t_n, fbp = fb_n, c0v = kLog2e * c0_n;
+      const float t = t_n, fbp = fb_n;
       const float dT = P.T - t;
+      const float* c0g = A.c0 + p * 128;  // already scaled by log2e (baseline pass)
       u_n = feed.get(k + 1u);  // published when the TMA warp started on unit k
       if (u_n < A.n_units) {
         const int64_t pn = u_n / UP;
         t_n = __ldg(A.tx + pn * (int64_t)(1 + d));
         fb_n = __ldg(A.fb + pn);
-        c0_n = __ldg(A.c0 + pn * 128 + r);
       }
-      float fsum = 0.f;
-      for (int tl = 0; tl < tiles; ++tl, ++j) {
-        if ((tl & 1) != slot) continue;
-        if (p != c0_point) {
-          named_bar_sync(1 + slot, 128);  // every warp of the slot is past the first pass of the previous point
-          c0_s[r] = c0v;
-          named_bar_sync(1 + slot, 128);
-          c0_point = p;
+      float fsum = 0.f;  // value-label partial of the tiles this warp finalises (slot h)
+      for (int tl = 0; tl < tiles; tl += 2) {
+        const bool hasB = tl + 1 < tiles;
+        // per-row scalars of the two tiles: time sample, diffusion scale
+        float a_[2], s2_[2];
+        bool valid_[2];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const int m = (g * kTcGroupTiles + tl + s) * 128 + r;
+          valid_[s] = m < M_I && (s == 0 || hasB);
+          float uu = 0.5f;
+          if (valid_[s])
+            uu = DET ? __ldg(A.u_s + p * M_I + m)
+                     : u01(philox_at(A.keys, (uint64_t)(A.point_base + p), kStreamS, (uint32_t)m, 0u).x);
+          a_[s] = sqrtf(uu * dT) * P.sigma;
+          s2_[s] = uu * dT + t;
         }
-        const int m = (g * kTcGroupTiles + tl) * 128 + r;
-        const bool valid = m < M_I;
-        float uu = 0.5f;
-        if (valid)
-          uu = DET ? __ldg(A.u_s + p * M_I + m)
-                   : u01(philox_at(A.seed, (uint64_t)(A.point_base + p), kStreamS, (uint32_t)m, 0u).x);
-        const float a = sqrtf(uu * dT) * P.sigma;
-        // z1' = log2e z1: the time column w_t' and c0' carry the factor already, the accumulator (W_x Z) does not
-        const float s2 = uu * dT + t, a2 = a * kLog2e;
         float pu = 0.f, pD = 0.f;
-
-        int pass_no = 0;
-        auto pass_done = [&]() {
-          tc_fence_before();
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(b_ar);
-          TRACE(2, slot, j, pass_no * 10 + 2);
-          ++pass_no;
-        };
-        TRACE(2, slot, j, 0);
-        mbar_wait(b_acc, ph_acc, 30);
-        ph_acc ^= 1u;
-        tc_fence_after();
-        TRACE(2, slot, j, 1);
-        epi_pass<kPassFirst>(C, tacc, hv_row, ht_row, rx, c0_s, 0, s2, a2, pu, pD);
-        pass_done();
+        // ---- first pass: z1' = log2e z1: the time column w_t' and c0' carry the factor already, the accumulator
+        //      (W_x Z) does not
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          if (s == 0 || hasB) {
+            TRACE(2, s, j + s, 0);
+            wait_acc(s);
+            TRACE(2, s, j + s, 1);
+            uint8_t* const hv = hv_row0 + (uint32_t)s * kSlotBytes;
+            epi_pass<kPassFirst>(C, tacc0 + (uint32_t)s * 256u, hv, hv + kOperandBytes, rx, h, c0g, 0, s2_[s],
+                                 a_[s] * kLog2e, pu, pD);
+            pass_done(s);
+            TRACE(2, s, j + s, 2);
+          }
+        }
+        // ---- hidden passes
 #pragma unroll 1
         for (int l = 0; l < 2; ++l) {
-          mbar_wait(b_acc, ph_acc, 31);
-          ph_acc ^= 1u;
-          tc_fence_after();
-          TRACE(2, slot, j, pass_no * 10 + 1);
-          epi_pass<kPassHidden>(C, tacc, hv_row, ht_row, rx, c0_s, l, 0.f, 0.f, pu, pD);
-          pass_done();
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            if (s == 0 || hasB) {
+              wait_acc(s);
+              TRACE(2, s, j + s, (l + 1) * 10 + 1);
+              uint8_t* const hv = hv_row0 + (uint32_t)s * kSlotBytes;
+              epi_pass<kPassHidden>(C, tacc0 + (uint32_t)s * 256u, hv, hv + kOperandBytes, rx, h, c0g, l, 0.f, 0.f, pu,
+                                    pD);
+              pass_done(s);
+              TRACE(2, s, j + s, (l + 1) * 10 + 2);
+            }
+          }
         }
-        mbar_wait(b_acc, ph_acc, 32);
-        ph_acc ^= 1u;
-        tc_fence_after();
-        TRACE(2, slot, j, 31);
-        epi_pass<kPassOut>(C, tacc, hv_row, ht_row, rx, c0_s, 2, 0.f, 0.f, pu, pD);
-        // output layer, f (equations.py:297-302) and the Bismut coefficient of this row
-        const float uval = pu + C.bout;
-        const float f = P.sigma * (P.cha_k * uval - P.cha_c) * (P.sigma * pD);
+        // ---- output pass: each half takes the dot products over its 64 columns; the warp with h == slot adds the
+        //      other half's partials (one exchange buffer, the direction alternates with the slot) and finishes
+        //      the row: output layer, f (equations.py:297-302), Bismut coefficient
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          if (s == 0 || hasB) {
+            wait_acc(s);
+            TRACE(2, s, j + s, 31);
+            pu = pD = 0.f;
+            uint8_t* const hv = hv_row0 + (uint32_t)s * kSlotBytes;
+            epi_pass<kPassOut>(C, tacc0 + (uint32_t)s * 256u, hv, hv + kOperandBytes, rx, h, c0g, 2, 0.f, 0.f, pu, pD);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(kBarAReady + s));  // accumulators of the slot are free for the next tile
+            if (h != s) exch[r] = make_float2(pu, pD);
+            named_bar_sync(1 + q, 64);  // the two warps of lane quarter q
+            if (h == s) {
+              const float2 o = exch[r];
+              const float uval = (pu + o.x) + C.bout, Dv = pD + o.y;
+              const float f = P.sigma * (P.cha_k * uval - P.cha_c) * (P.sigma * Dv);
 #ifdef DPI_TC_DEBUG_UD
-        if (A.trace && valid) reinterpret_cast<float2*>(A.trace)[p * M_I + m] = make_float2(uval, pD);
+              if (A.trace && valid_[s])
+                reinterpret_cast<float2*>(A.trace)[p * M_I + (g * kTcGroupTiles + tl + s) * 128 + r] =
+                    make_float2(uval, Dv);
 #endif
-        if (valid) fsum += dT * f;
-        const uint32_t cb = j % 3u;
-        coef_s[cb * 128u + r] = valid ? dT * (f - fbp) / a : 0.f;
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          TRACE(2, slot, j, 32);
-          mbar_arrive(b_ar);                // accumulators of this slot are free for the next tile's layer 1
-          mbar_arrive(bar(kBarCoef + cb));  // (release: orders the coefficient stores of the whole warp)
+              if (valid_[s]) fsum += dT * f;
+              const uint32_t cb = (j + (uint32_t)s) % 3u;
+              coef_s[cb * 128u + r] = valid_[s] ? dT * (f - fbp) / a_[s] : 0.f;
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar(kBarCoef + cb));  // (release: orders the warp's coefficient stores)
+            }
+            TRACE(2, s, j + s, 32);
+          }
         }
+        j += hasB ? 2u : 1u;
       }
       const float ws = warp_sum(fsum);
-      if (lane == 0) A.partF[u * kTcPartFFloatsPerUnit + slot * 4 + q] = ws;
+      if (lane == 0) A.partF[u * kTcPartFFloatsPerUnit + h * 4 + q] = ws;
     }
   } else {
     // =================================== increment producers ===================================
