@@ -46,11 +46,12 @@ using namespace tc;
 // The register file is per SM sub-partition (512 registers per lane, warp w lives on sub-partition w % 4), so each
 // sub-partition holds one warp of every warpgroup.  setmaxnreg only moves registers inside the CTA's own pool (what
 // its warps have released), so the re-split must balance against the launch allocation of 96 per thread:
-// MMA/TMA warpgroup 96 -> 32, epilogue 96 -> 88, producers 96 -> 136 (2 x 88 + 2 x 136 + 32 = 480 = 5 x 96).
+// MMA/TMA warpgroup 96 -> 32, epilogue stays at 96, producers 96 -> 128 (2 x 96 + 2 x 128 + 32 = 480 = 5 x 96;
+// measured best of 80/144, 88/136, 96/128).
 constexpr int kTcThreads = 640;
 constexpr int kProdWarp0 = 8, kMmaWarp = 16, kTmaWarp = 17;
 #ifndef DPI_EPI_REGS
-#define DPI_EPI_REGS 88
+#define DPI_EPI_REGS 96
 #endif
 constexpr int kEpiRegs = DPI_EPI_REGS, kProdRegs = 224 - DPI_EPI_REGS, kMmaRegs = 32;
 constexpr float kLog2e = 1.4426950408889634f;
