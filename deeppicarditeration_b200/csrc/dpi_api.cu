@@ -38,6 +38,7 @@ struct dpi_handle {
   float *train_m = nullptr, *train_v = nullptr, *train_scratch = nullptr, *train_grad = nullptr;
   // dpi_train_fit replays one optimiser step as a CUDA graph on an internal stream
   cudaStream_t train_stream = nullptr;
+  TrainAux train_aux;  // side stream + fork/join events of the weight-gradient branch
   cudaEvent_t train_ev_in = nullptr, train_ev_out = nullptr;
   float *train_stage_tx = nullptr, *train_stage_y = nullptr;
   long long* train_step_dev = nullptr;
@@ -224,6 +225,12 @@ int dpi_destroy(dpi_handle* h) {
   if (h->train_ev_in) cudaEventDestroy(h->train_ev_in);
   if (h->train_ev_out) cudaEventDestroy(h->train_ev_out);
   if (h->train_stream) cudaStreamDestroy(h->train_stream);
+  if (h->train_aux.side) cudaStreamDestroy(h->train_aux.side);
+  for (int l = 0; l < DPI_MAX_LINEAR; ++l)
+    if (h->train_aux.fork[l]) cudaEventDestroy(h->train_aux.fork[l]);
+  if (h->train_aux.join) cudaEventDestroy(h->train_aux.join);
+  for (int i = 0; i < 3; ++i)
+    if (h->train_aux.pre[i]) cudaEventDestroy(h->train_aux.pre[i]);
   for (int s = 0; s < DPI_STAGE_COUNT; ++s)
     for (int e = 0; e < 2; ++e)
       if (h->ev[s][e]) cudaEventDestroy(h->ev[s][e]);
@@ -695,6 +702,11 @@ int dpi_train_init(dpi_handle* h, const dpi_network* net, int64_t max_batch, voi
     DPI_CUDA_CHECK(cudaStreamCreateWithFlags(&h->train_stream, cudaStreamNonBlocking));
     DPI_CUDA_CHECK(cudaEventCreateWithFlags(&h->train_ev_in, cudaEventDisableTiming));
     DPI_CUDA_CHECK(cudaEventCreateWithFlags(&h->train_ev_out, cudaEventDisableTiming));
+    DPI_CUDA_CHECK(cudaStreamCreateWithFlags(&h->train_aux.side, cudaStreamNonBlocking));
+    for (int l = 0; l < DPI_MAX_LINEAR; ++l)
+      DPI_CUDA_CHECK(cudaEventCreateWithFlags(&h->train_aux.fork[l], cudaEventDisableTiming));
+    DPI_CUDA_CHECK(cudaEventCreateWithFlags(&h->train_aux.join, cudaEventDisableTiming));
+    for (int i = 0; i < 3; ++i) DPI_CUDA_CHECK(cudaEventCreateWithFlags(&h->train_aux.pre[i], cudaEventDisableTiming));
   }
   DPI_CUDA_CHECK(cudaMemsetAsync(h->train_m, 0, sizeof(float) * h->train_params, st));
   DPI_CUDA_CHECK(cudaMemsetAsync(h->train_v, 0, sizeof(float) * h->train_params, st));
@@ -727,7 +739,7 @@ int dpi_train_grad(dpi_handle* h, const float* tx, const float* y, int64_t batch
   }
   DPI_CUDA_CHECK(cudaSetDevice(h->device));
   return launch_train_grad(h->train_lin, h->n_train_lin, tx, y, batch, cfg->loss_beta, cfg->fixed_weight, h->train_scratch,
-                           grad_flat, losses, reinterpret_cast<cudaStream_t>(stream), &h->launches);
+                           grad_flat, losses, reinterpret_cast<cudaStream_t>(stream), &h->launches, &h->train_aux);
 }
 
 int dpi_train_adam(dpi_handle* h, const float* grad_flat, const dpi_train_config* cfg, int64_t step, void* stream) {
@@ -781,7 +793,7 @@ int dpi_train_fit(dpi_handle* h, const float* tx, const float* y, int64_t n, int
           int64_t nodes = 0;
           DPI_CUDA_CHECK(cudaStreamBeginCapture(ts, cudaStreamCaptureModeRelaxed));
           int rc = launch_train_grad(h->train_lin, h->n_train_lin, h->train_stage_tx, h->train_stage_y, b, cfg->loss_beta,
-                                     cfg->fixed_weight, h->train_scratch, h->train_grad, losses, ts, &nodes);
+                                     cfg->fixed_weight, h->train_scratch, h->train_grad, losses, ts, &nodes, &h->train_aux);
           if (!rc)
             rc = launch_train_adam_dev(h->train_lin, h->n_train_lin, h->train_grad, h->train_m, h->train_v, cfg->lr,
                                        cfg->beta1, cfg->beta2, cfg->eps, h->train_step_dev, ts, &nodes);
@@ -801,7 +813,7 @@ int dpi_train_fit(dpi_handle* h, const float* tx, const float* y, int64_t n, int
         h->launches += h->train_graph_nodes;
       } else {  // ragged last mini-batch: plain launches
         int rc = launch_train_grad(h->train_lin, h->n_train_lin, h->train_stage_tx, h->train_stage_y, b, cfg->loss_beta,
-                                   cfg->fixed_weight, h->train_scratch, h->train_grad, losses, ts, &h->launches);
+                                   cfg->fixed_weight, h->train_scratch, h->train_grad, losses, ts, &h->launches, &h->train_aux);
         if (rc) return rc;
         rc = launch_train_adam_dev(h->train_lin, h->n_train_lin, h->train_grad, h->train_m, h->train_v, cfg->lr, cfg->beta1,
                                    cfg->beta2, cfg->eps, h->train_step_dev, ts, &h->launches);

@@ -213,7 +213,8 @@ __global__ void __launch_bounds__(kGemmThreads, 2) sgemm_kernel(const GemmArgs g
 // Small problems (the regression step: a few hundred rows, 128-wide layers): 64x64x16 tiles, 4x4 per thread, optional
 // split-K over gridDim.z with partials [z][R][N] in g.ws (epilogue kEpiNone only; summed by splitk_reduce_kernel in a
 // fixed order, so the result does not depend on scheduling).
-constexpr int SM_T = 64, SM_K = 16, kLdsS = SM_T + 4;
+constexpr int SM_T = 64, SM_K = 32, kLdsS = SM_T + 4;  // K step 32: these launches are latency bound, fewer round trips
+constexpr int SM_KH = SM_K / 16;
 __global__ void __launch_bounds__(256) sgemm_small_kernel(const GemmArgs g, int k_per_split) {
   __shared__ __align__(16) float As[2][SM_K][kLdsS];
   __shared__ __align__(16) float Bs[2][SM_K][kLdsS];
@@ -236,33 +237,40 @@ __global__ void __launch_bounds__(256) sgemm_small_kernel(const GemmArgs g, int 
       for (int i = 0; i < 4; ++i) v[i] = (i0 + i < limit) ? __ldg(p + i0 + i) : 0.f;
     }
   };
-  float ra[4], rb[4];
+  float ra[SM_KH][4], rb[SM_KH][4];
   auto fetch = [&](int k0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) ra[i] = rb[i] = 0.f;
-    if (g.a_km) {
-      if (k0 + tk < kend) ld4(g.A + (int64_t)(k0 + tk) * g.lda, (int)r0 + tn4, M_, a_vec, ra);
-    } else if (r0 + lrow < g.R) {
-      ld4(g.A + (r0 + lrow) * (int64_t)g.lda, k0 + lk4, kend, a_vec, ra);
-    }
-    if (g.b_kn) {
-      if (k0 + tk < kend) ld4(g.B + (int64_t)(k0 + tk) * g.ldb, n0 + tn4, N, b_vec, rb);
-    } else if (n0 + lrow < N) {
-      ld4(g.B + (int64_t)(n0 + lrow) * g.ldb, k0 + lk4, kend, b_vec, rb);
+    for (int q = 0; q < SM_KH; ++q) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) ra[q][i] = rb[q][i] = 0.f;
+      const int kq = k0 + 16 * q;
+      if (g.a_km) {
+        if (kq + tk < kend) ld4(g.A + (int64_t)(kq + tk) * g.lda, (int)r0 + tn4, M_, a_vec, ra[q]);
+      } else if (r0 + lrow < g.R) {
+        ld4(g.A + (r0 + lrow) * (int64_t)g.lda, kq + lk4, kend, a_vec, ra[q]);
+      }
+      if (g.b_kn) {
+        if (kq + tk < kend) ld4(g.B + (int64_t)(kq + tk) * g.ldb, n0 + tn4, N, b_vec, rb[q]);
+      } else if (n0 + lrow < N) {
+        ld4(g.B + (int64_t)(n0 + lrow) * g.ldb, kq + lk4, kend, b_vec, rb[q]);
+      }
     }
   };
   auto stash = [&](int buf) {
-    if (g.a_km) {
-      *reinterpret_cast<float4*>(&As[buf][tk][tn4]) = make_float4(ra[0], ra[1], ra[2], ra[3]);
-    } else {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) As[buf][lk4 + i][lrow] = ra[i];
-    }
-    if (g.b_kn) {
-      *reinterpret_cast<float4*>(&Bs[buf][tk][tn4]) = make_float4(rb[0], rb[1], rb[2], rb[3]);
-    } else {
+    for (int q = 0; q < SM_KH; ++q) {
+      if (g.a_km) {
+        *reinterpret_cast<float4*>(&As[buf][16 * q + tk][tn4]) = make_float4(ra[q][0], ra[q][1], ra[q][2], ra[q][3]);
+      } else {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) Bs[buf][lk4 + i][lrow] = rb[i];
+        for (int i = 0; i < 4; ++i) As[buf][16 * q + lk4 + i][lrow] = ra[q][i];
+      }
+      if (g.b_kn) {
+        *reinterpret_cast<float4*>(&Bs[buf][16 * q + tk][tn4]) = make_float4(rb[q][0], rb[q][1], rb[q][2], rb[q][3]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) Bs[buf][16 * q + lk4 + i][lrow] = rb[q][i];
+      }
     }
   };
   const int ty = t >> 4, tx = t & 15;

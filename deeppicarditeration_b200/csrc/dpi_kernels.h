@@ -138,8 +138,17 @@ int launch_mlp_eval(const dpi_linear* L, int n_lin, int d, const float* tx, int6
 // ---- regression step for a scalar-output MLP (dpi_train.cu) ---------------------------------------------------
 int64_t train_param_count(const dpi_linear* L, int n_lin);
 int64_t train_scratch_floats(const dpi_linear* L, int n_lin, int64_t B);
+// Side stream and events for the weight-gradient branch of the reverse sweep (fork after each adjoint kernel, one
+// join at the end); null side stream = everything on `st`.
+struct TrainAux {
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork[DPI_MAX_LINEAR] = {};
+  cudaEvent_t pre[3] = {};  // start of the step, loss terms written, tangent forward done
+  cudaEvent_t join = nullptr;
+};
 int launch_train_grad(const dpi_linear* L, int n_lin, const float* tx, const float* y, int64_t B, float beta, float fw,
-                      float* scratch, float* grad_flat, float* losses, cudaStream_t st, int64_t* launches);
+                      float* scratch, float* grad_flat, float* losses, cudaStream_t st, int64_t* launches,
+                      const TrainAux* aux = nullptr);
 int launch_train_adam(const dpi_linear* L, int n_lin, const float* grad_flat, float* m, float* v, float lr, float b1,
                       float b2, float eps, int64_t step, cudaStream_t st, int64_t* launches);
 

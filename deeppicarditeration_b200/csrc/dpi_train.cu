@@ -20,53 +20,72 @@
 namespace dpi {
 namespace {
 
-// loss terms, dL/du and dL/d(grad_x u).  One CTA (deterministic sums); B is a mini-batch (hundreds of rows).
-__global__ void __launch_bounds__(1024)
-train_loss_kernel(const float* __restrict__ tx, const float* __restrict__ y, const float* __restrict__ u,
+// loss terms, dL/du and dL/d(grad_x u).  One warp per row writes the row's two loss terms; a second, single-CTA
+// kernel adds the B row terms in a fixed order (deterministic; a single 1024-thread CTA over all B (1+d) elements
+// took 52 us, a fifth of the whole regression step).
+__global__ void __launch_bounds__(256)
+train_loss_kernel(const float* __restrict__ tx, const float* __restrict__ y, const float* __restrict__ hlast /* [B][H] */,
+                  const float* __restrict__ wout, const float* __restrict__ bout, int H,
                   const float* __restrict__ g /* [B][1+d] */, int B, int d, float beta, float fw,
-                  float* __restrict__ a /* [B] */, float* __restrict__ r /* [B][1+d] */, float* __restrict__ losses) {
-  __shared__ float red[2][32];
+                  float* __restrict__ a /* [B] */, float* __restrict__ r /* [B][1+d] */,
+                  float* __restrict__ rowl /* [B][2] */) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (b >= B) return;
+  // output layer u_b = w_out . h_b + b_out (a GEMV: not worth a launch of its own on the step's critical chain)
+  float ub = 0.f;
+  for (int k = lane; k < H; k += 32) ub = fmaf(__ldg(hlast + (int64_t)b * H + k), __ldg(wout + k), ub);
+  ub = warp_sum(ub) + __ldg(bout);
   const int ld = 1 + d;
   const float invB = 1.f / (float)B;
-  float lv = 0.f, lg = 0.f;
-  for (int i = threadIdx.x; i < B * ld; i += blockDim.x) {
-    const int b = i / ld, j = i - b * ld;
-    const float w = expf(beta * __ldg(tx + (int64_t)b * ld));
-    if (j == 0) {
-      const float dv = __ldg(u + b) - __ldg(y + (int64_t)b * ld);
-      lv += w * dv * dv;
-      a[b] = 2.f * w * dv * invB;
-      r[i] = 0.f;
-    } else {
-      const float dg = __ldg(g + i) - __ldg(y + i);
-      lg += w * dg * dg;
-      r[i] = 2.f * fw * w * dg * invB;
-    }
+  const float w = expf(beta * __ldg(tx + (int64_t)b * ld));
+  const int64_t row = (int64_t)b * ld;
+  float lg = 0.f;
+  for (int j = 1 + lane; j < ld; j += 32) {
+    const float dg = __ldg(g + row + j) - __ldg(y + row + j);
+    lg += w * dg * dg;
+    r[row + j] = 2.f * fw * w * dg * invB;
   }
+  lg = warp_sum(lg);
+  if (lane == 0) {
+    const float dv = ub - __ldg(y + row);
+    a[b] = 2.f * w * dv * invB;
+    r[row] = 0.f;
+    rowl[2 * b] = w * dv * dv;
+    rowl[2 * b + 1] = lg;
+  }
+}
+__global__ void __launch_bounds__(256)
+train_loss_finish_kernel(const float* __restrict__ rowl, int B, float fw, float* __restrict__ losses) {
+  __shared__ float red[2][8];
+  float lv = 0.f, lg = 0.f;
+  for (int b = threadIdx.x; b < B; b += 256) lv += rowl[2 * b], lg += rowl[2 * b + 1];
   lv = warp_sum(lv), lg = warp_sum(lg);
   if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = lv, red[1][threadIdx.x >> 5] = lg;
   __syncthreads();
-  if (threadIdx.x < 32) {
-    lv = (threadIdx.x < (blockDim.x >> 5)) ? red[0][threadIdx.x] : 0.f;
-    lg = (threadIdx.x < (blockDim.x >> 5)) ? red[1][threadIdx.x] : 0.f;
-    lv = warp_sum(lv), lg = warp_sum(lg);
-    if (threadIdx.x == 0) {
-      losses[1] = lv * invB;
-      losses[2] = lg * invB;
-      losses[0] = lv * invB + fw * lg * invB;
-    }
+  if (threadIdx.x == 0) {
+    lv = lg = 0.f;
+    for (int i = 0; i < 8; ++i) lv += red[0][i], lg += red[1][i];
+    const float invB = 1.f / (float)B;
+    losses[1] = lv * invB;
+    losses[2] = lg * invB;
+    losses[0] = lv * invB + fw * lg * invB;
   }
 }
 
-// top of the reverse sweep: hbar[b][k] = a_b w_out[k] (value rows), hdbar[b][k] = w_out[k] (tangent rows)
-__global__ void train_top_kernel(const float* __restrict__ a, const float* __restrict__ wout, int B, int H,
-                                 float* __restrict__ hb /* [2B][H] */) {
+// the same for the last hidden layer, whose incoming adjoints are hbar = a_b w_out (value rows), hdbar = w_out
+// (tangent rows): no buffer, no separate kernel
+__global__ void train_adjoint_top_kernel(const float* __restrict__ a, const float* __restrict__ wout,
+                                         const float* __restrict__ e, const float* __restrict__ zd, int B, int H,
+                                         float* __restrict__ zb /* [2B][H] */) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * H) return;
   const int b = i / H, k = i - b * H;
   const float w = __ldg(wout + k);
-  hb[i] = __ldg(a + b) * w;
-  hb[(int64_t)B * H + i] = w;
+  const float ee = __ldg(e + i), hbar = __ldg(a + b) * w, hdbar = w;
+  const float e2 = ee < 1.f ? ee : 0.f;
+  zb[i] = fmaf(hdbar * e2, __ldg(zd + i), hbar * ee);
+  zb[(int64_t)B * H + i] = hdbar * ee;
 }
 
 // adjoints through one ELU pair: zb = [hbar . e + hdbar . e2 . zd ; hdbar . e], e2 = ELU'' = (e < 1 ? e : 0)
@@ -163,13 +182,14 @@ int64_t train_scratch_floats(const dpi_linear* L, int n_lin, int64_t B) {
   for (int l = 0; l < n_lin - 1; ++l) hmax = std::max(hmax, L[l].n_out);
   // per layer: stacked activations [2B][H], ELU' [B][H], tangent pre-activations [B][H]; two stacked adjoint
   // buffers; stacked input [2B][1+d]; g [B][1+d]; u, a [B]
-  return (int64_t)n_lin * 4 * B * hmax + 2 * 2 * B * hmax + 3 * B * (int64_t)(L[0].n_in) + 2 * B + 16 * (int64_t)hmax * hmax +
-         64 * n_lin + 256;
+  return (int64_t)n_lin * 4 * B * hmax + (1 + (int64_t)n_lin) * 2 * B * hmax + 3 * B * (int64_t)(L[0].n_in) + 4 * B +
+         16 * (int64_t)hmax * hmax + 64 * n_lin + 256;
 }
 
 // grad_flat [n_params] in torch parameters() order (W_0, b_0, W_1, b_1, ...); losses [3] = total, value, gradient
 int launch_train_grad(const dpi_linear* L, int n_lin, const float* tx, const float* y, int64_t B64, float beta, float fw,
-                      float* scratch, float* grad_flat, float* losses, cudaStream_t st, int64_t* launches) {
+                      float* scratch, float* grad_flat, float* losses, cudaStream_t st, int64_t* launches,
+                      const TrainAux* aux) {
   const int B = (int)B64;
   const int d1 = L[0].n_in;  // 1 + d
   const int nh = n_lin - 1;  // hidden (ELU) layers; layer nh is the scalar output layer
@@ -190,10 +210,12 @@ int launch_train_grad(const dpi_linear* L, int n_lin, const float* tx, const flo
     ZD[l] = take((int64_t)B * hmax);
   }
   float* adjA = take(2 * (int64_t)B * hmax);
-  float* adjB = take(2 * (int64_t)B * hmax);
+  float* adjZ[DPI_MAX_LINEAR];  // one (zbar, zdbar) buffer per layer: the weight-gradient branch reads it concurrently
+  for (int l = 0; l < nh; ++l) adjZ[l] = take(2 * (int64_t)B * hmax);
+  float* adjB = adjZ[0];
   float* g = take((int64_t)B * d1);
-  float* u = take(B);
   float* a = take(B);
+  float* rowl = take(2 * (int64_t)B);  // per-row loss terms
   float* ws = take(16 * (int64_t)hmax * hmax);  // split-K partials of the weight-gradient GEMMs
   int rc;
   auto wd = [&](int l) { return l == 0 ? d1 : L[l - 1].n_out; };  // width of HB[l]
@@ -205,19 +227,25 @@ int launch_train_grad(const dpi_linear* L, int n_lin, const float* tx, const flo
     offb[l] = off, off += L[l].n_out;
   }
 
-  // ---- value forward (keeps ELU'), u ----
-  DPI_CUDA_CHECK(cudaMemcpyAsync(HB[0], tx, sizeof(float) * (size_t)B * d1, cudaMemcpyDeviceToDevice, st));
+  // Everything that only feeds the gradient buffers or the reported losses runs on a side stream (a parallel branch
+  // of the captured graph): the step is bound by its dependent chain of small kernels, not by their work.
+  cudaStream_t sw = (aux && aux->side) ? aux->side : st;
+  const bool forked = sw != st;
+  auto fork_at = [&](cudaEvent_t ev) -> int {
+    if (!forked) return DPI_OK;
+    DPI_CUDA_CHECK(cudaEventRecord(ev, st));
+    DPI_CUDA_CHECK(cudaStreamWaitEvent(sw, ev, 0));
+    return DPI_OK;
+  };
+  // ---- value forward (keeps ELU'); the scalar output layer is evaluated inside the loss kernel ----
+  // HB[0]'s value rows (a copy of tx) are only read by the first layer's weight gradient at the very end
+  if ((rc = fork_at(forked ? aux->pre[0] : nullptr))) return rc;
+  DPI_CUDA_CHECK(cudaMemcpyAsync(HB[0], tx, sizeof(float) * (size_t)B * d1, cudaMemcpyDeviceToDevice, sw));
   for (int l = 0; l < nh; ++l) {
     GemmArgs G{};
-    G.A = HB[l], G.lda = wd(l), G.B = L[l].W, G.ldb = L[l].n_in, G.bias = L[l].b;
+    G.A = (l == 0) ? tx : HB[l], G.lda = wd(l), G.B = L[l].W, G.ldb = L[l].n_in, G.bias = L[l].b;
     G.C = HB[l + 1], G.ldc = L[l].n_out, G.D = E[l + 1], G.ldd = L[l].n_out;
     G.R = B, G.N = L[l].n_out, G.K = L[l].n_in, G.epi = kEpiBiasEluD;
-    if ((rc = gemm(G, st, launches))) return rc;
-  }
-  {
-    GemmArgs G{};
-    G.A = HB[nh], G.lda = wd(nh), G.B = L[nh].W, G.ldb = L[nh].n_in, G.bias = L[nh].b;
-    G.C = u, G.ldc = 1, G.R = B, G.N = 1, G.K = L[nh].n_in, G.epi = kEpiBias;
     if ((rc = gemm(G, st, launches))) return rc;
   }
   // ---- input gradient by one reverse sweep: c = E_nh . w_out ; c = (c W_l) . E_l ; g = c W_0 ----
@@ -242,9 +270,12 @@ int launch_train_grad(const dpi_linear* L, int n_lin, const float* tx, const flo
     if ((rc = gemm(G, st, launches))) return rc;
   }
   // ---- loss, a = dL/du, r = dL/d(grad_x u) (tangent rows of HB[0]) ----
-  train_loss_kernel<<<1, 1024, 0, st>>>(tx, y, u, g, B, d1 - 1, beta, fw, a, HB[0] + (int64_t)B * d1, losses);
+  train_loss_kernel<<<(B + 7) / 8, 256, 0, st>>>(tx, y, HB[nh], L[nh].W, L[nh].b, L[nh].n_in, g, B, d1 - 1, beta, fw, a,
+                                                 HB[0] + (int64_t)B * d1, rowl);
+  if ((rc = fork_at(forked ? aux->pre[1] : nullptr))) return rc;
+  train_loss_finish_kernel<<<1, 256, 0, sw>>>(rowl, B, fw, losses);
   DPI_CUDA_CHECK(cudaGetLastError());
-  *launches += 1;
+  *launches += 2;
   // ---- tangent forward along r: zd_l = hd_{l-1} W_l^T (kept), hd_l = ELU'(z_l) . zd_l ----
   for (int l = 0; l < nh; ++l) {
     GemmArgs G{};
@@ -257,29 +288,38 @@ int launch_train_grad(const dpi_linear* L, int n_lin, const float* tx, const flo
   // ---- output layer gradients: dW_out = sum_b a_b h_nh + sum_b hd_nh ; db_out = sum_b a_b ----
   {
     const int H = L[nh].n_in;
-    train_colsum_kernel<<<(H + 7) / 8, 256, 0, st>>>(HB[nh], H, a, B, H, HB[nh] + (int64_t)B * H, grad_flat + offW[nh]);
-    train_colsum_kernel<<<1, 256, 0, st>>>(a, 1, nullptr, B, 1, nullptr, grad_flat + offb[nh]);
-    // top adjoints: hbar = a w_out (value rows), hdbar = w_out (tangent rows)
-    train_top_kernel<<<ew(B * H), 256, 0, st>>>(a, L[nh].W, B, H, adjA);
+    if ((rc = fork_at(forked ? aux->pre[2] : nullptr))) return rc;
+    train_colsum_kernel<<<(H + 7) / 8, 256, 0, sw>>>(HB[nh], H, a, B, H, HB[nh] + (int64_t)B * H, grad_flat + offW[nh]);
+    train_colsum_kernel<<<1, 256, 0, sw>>>(a, 1, nullptr, B, 1, nullptr, grad_flat + offb[nh]);
     DPI_CUDA_CHECK(cudaGetLastError());
-    *launches += 3;
+    *launches += 2;
   }
   // ---- reverse sweep through the (value, tangent) hidden layers ----
+  // The main chain is adjoint kernel -> (hbar, hdbar) GEMM per layer; the weight gradients (split-K GEMM, its
+  // reduction, the bias column sums) only read what the chain has already produced, so they run on a side stream
+  // (a parallel branch of the captured graph): the step is bound by the dependent chain of small kernels.
   {
     float* hb = adjA;   // [2B][wd(l+1)] adjoints of (h_{l+1}, hd_{l+1})
-    float* zb = adjB;   // [2B][wd(l+1)] adjoints of (z_{l+1}, zd_{l+1})
     for (int l = nh - 1; l >= 0; --l) {
       const int Ho = L[l].n_out, Hi = L[l].n_in;
-      train_adjoint_kernel<<<ew(B * Ho), 256, 0, st>>>(hb, E[l + 1], ZD[l + 1], B, Ho, zb);
+      float* zb = adjZ[l];  // [2B][wd(l+1)] adjoints of (z_{l+1}, zd_{l+1})
+      if (l == nh - 1)  // top adjoints hbar = a w_out (value rows), hdbar = w_out (tangent rows) formed on the fly
+        train_adjoint_top_kernel<<<ew(B * Ho), 256, 0, st>>>(a, L[nh].W, E[l + 1], ZD[l + 1], B, Ho, zb);
+      else
+        train_adjoint_kernel<<<ew(B * Ho), 256, 0, st>>>(hb, E[l + 1], ZD[l + 1], B, Ho, zb);
       DPI_CUDA_CHECK(cudaGetLastError());
       *launches += 1;
+      if (forked) {
+        DPI_CUDA_CHECK(cudaEventRecord(aux->fork[l], st));
+        DPI_CUDA_CHECK(cudaStreamWaitEvent(sw, aux->fork[l], 0));
+      }
       // dW_l [Ho][Hi] = [zbar; zdbar]^T [h_l; hd_l]   (A stored [K = 2B][M = Ho])
       GemmArgs G{};
       G.A = zb, G.lda = Ho, G.a_km = 1, G.B = HB[l], G.ldb = Hi, G.b_kn = 1;
       G.C = grad_flat + offW[l], G.ldc = Hi, G.R = Ho, G.N = Hi, G.K = 2 * B, G.epi = kEpiNone;
       G.ws = ws, G.ws_splits = 16;
-      if ((rc = gemm(G, st, launches))) return rc;
-      train_colsum_kernel<<<(Ho + 7) / 8, 256, 0, st>>>(zb, Ho, nullptr, B, Ho, nullptr, grad_flat + offb[l]);
+      if ((rc = gemm(G, sw, launches))) return rc;
+      train_colsum_kernel<<<(Ho + 7) / 8, 256, 0, sw>>>(zb, Ho, nullptr, B, Ho, nullptr, grad_flat + offb[l]);
       DPI_CUDA_CHECK(cudaGetLastError());
       *launches += 1;
       if (l > 0) {
@@ -289,6 +329,10 @@ int launch_train_grad(const dpi_linear* L, int n_lin, const float* tx, const flo
         H.C = hb, H.ldc = Hi, H.R = 2 * (int64_t)B, H.N = Hi, H.K = Ho, H.epi = kEpiNone;
         if ((rc = gemm(H, st, launches))) return rc;
       }
+    }
+    if (forked) {
+      DPI_CUDA_CHECK(cudaEventRecord(aux->join, sw));
+      DPI_CUDA_CHECK(cudaStreamWaitEvent(st, aux->join, 0));
     }
   }
   return DPI_OK;
