@@ -530,7 +530,7 @@ int dpi_label_gen(dpi_handle* h, const float* tx, int64_t n, const dpi_label_con
   if (h->net_kind == DPI_NET_MLP && P.eq == DPI_EQ_CHA) {
     const bool bf16 = cfg->precision == DPI_PREC_F16;  // 16-bit tensor-core path
     if (bf16 && !h->tc_ready) {
-      set_error("dpi_label_gen: the 16-bit tensor-core path needs the MLP [1+d,128,128,128,128,1] with d <= 128");
+      set_error("dpi_label_gen: the 16-bit tensor-core path needs the MLP [1+d,128,128,128,128,1] with d <= 1024");
       return DPI_ERR_UNSUPPORTED;
     }
     if ((rc = ensure_scratch(h, n, h->mlp.HP))) return rc;

@@ -63,6 +63,7 @@ struct alignas(16) TcConsts {
   float pad[3];
 };
 struct TcNetDev {
+  int nchunks = 1;  // first-layer K chunks of 128 input dims (d <= 1024)
   const void* W;  // 4 x [128 x 128] fp16 operand images (K-major, SWIZZLE_128B): W1 x-columns, W2, W3, W4
   TcConsts consts;
   int nx, ksteps1, no, cls, num_sms;

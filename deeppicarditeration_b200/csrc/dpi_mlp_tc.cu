@@ -97,6 +97,7 @@ struct TcArgs {
   int ksteps1;  // ceil(d/16)
   int no;       // ceil(d/8) octets of dims (one Philox block, one 16-byte operand chunk each)
   int cls;      // row classes of the producer mapping: cls * no <= 256, cls <= kTcMaxClasses
+  int nchunks;  // ceil(d / 128) first-layer K chunks (1 unless MULTI)
   int* unit_counter;  // next unit to hand out (zeroed before the launch)
   long long* trace;  // developer timeline (DPI_TC_TRACE builds only), else null
 };
@@ -276,7 +277,13 @@ struct TileCursor {
   }
 };
 
-template <int ITEMS, bool DET>
+// MULTI: 128 < d <= 1024.  The first layer is accumulated over ceil(d/128) chunks of 128 input dims: per chunk the
+// producers store the increments of those dims into the slot's hV, the TMA warp streams the matching W1 image into
+// hT, the MMA issuer adds the chunk's eight k-steps to the value accumulators and commits kBarSlotFree so that the
+// next chunk may overwrite the buffers.  The increments of a tile no longer fit in registers (8 x as many), so for
+// the Bismut sums they are drawn a second time from the same Philox counters once the coefficients are known (the
+// generator is counter based: no state to replay), warp w taking chunk w.
+template <int ITEMS, bool DET, bool MULTI>
 __global__ void __launch_bounds__(kTcThreads, 1)
 cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcConsts C,
               const __grid_constant__ TcArgs A) {
@@ -356,17 +363,34 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
             ph_ar ^= bit;
           }
           used |= bit;
-          mbar_wait(bar(kBarZFull + s), (ph_z >> s) & 1u, 11);
-          ph_z ^= bit;
-          mbar_wait(bar(kBarW1Full + s), (ph_w1 >> s) & 1u, 12);
-          ph_w1 ^= bit;
-          tc_fence_after();
-          TRACE(1, s, 0, l * 10 + 1);
+          if constexpr (MULTI) {
+            const int nch = A.nchunks;
+            for (int cch = 0; cch < nch; ++cch) {
+              mbar_wait(bar(kBarZFull + s), (ph_z >> s) & 1u, 11);
+              ph_z ^= bit;
+              mbar_wait(bar(kBarW1Full + s), (ph_w1 >> s) & 1u, 12);
+              ph_w1 ^= bit;
+              tc_fence_after();
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            if (ks < A.ksteps1) {
-              const uint64_t o = (uint64_t)((ks >> 2) * 1024 + (ks & 3) * 2);
-              umma_bf16_p(acc, dV + o, dT + o, idesc, ks > 0, leader);
+              for (int ks = 0; ks < 8; ++ks) {
+                const uint64_t o = (uint64_t)((ks >> 2) * 1024 + (ks & 3) * 2);
+                umma_bf16_p(acc, dV + o, dT + o, idesc, (uint32_t)((cch | ks) != 0), leader);
+              }
+              if (cch + 1 < nch) tc_commit_p(bar(kBarSlotFree + s), leader);  // hV / hT may take the next chunk
+            }
+          } else {
+            mbar_wait(bar(kBarZFull + s), (ph_z >> s) & 1u, 11);
+            ph_z ^= bit;
+            mbar_wait(bar(kBarW1Full + s), (ph_w1 >> s) & 1u, 12);
+            ph_w1 ^= bit;
+            tc_fence_after();
+            TRACE(1, s, 0, l * 10 + 1);
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+              if (ks < A.ksteps1) {
+                const uint64_t o = (uint64_t)((ks >> 2) * 1024 + (ks & 3) * 2);
+                umma_bf16_p(acc, dV + o, dT + o, idesc, ks > 0, leader);
+              }
             }
           }
           tc_commit_p(bar(kBarAccFull + s), leader);
@@ -414,7 +438,8 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
       mbar_arrive_expect_tx_p(bar(kBarW), 3u * kOperandBytes, leader);
 #pragma unroll 1
       for (int i = 0; i < 12; ++i)
-        bulk_g2s_p(sbase + kOffW + (uint32_t)i * 8192u, Wg + kOperandBytes + (size_t)i * 8192, 8192u, bar(kBarW), leader);
+        bulk_g2s_p(sbase + kOffW + (uint32_t)i * 8192u, Wg + (size_t)A.nchunks * kOperandBytes + (size_t)i * 8192, 8192u,
+                   bar(kBarW), leader);
       const int n_chunks = (d > 64) ? 4 : 2;  // K panels of the W1 image that layer 1 reads (16 KB each)
       uint32_t ph_free = 0, used = 0;
       // unit hand-out: the CTA's k-th unit comes from the global counter; it is fetched one unit ahead (the atomic's
@@ -433,15 +458,20 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
         if (cur.tl == 0) publish(cur.k + 1u);  // a valid unit always announces its successor (possibly the terminator)
         const int s = cur.tl & 1;
         const uint32_t bit = 1u << s;
-        if (used & bit) {
-          mbar_wait(bar(kBarSlotFree + s), (ph_free >> s) & 1u, 20);
-          ph_free ^= bit;
-        }
-        used |= bit;
         const uint32_t dst = sbase + kOffSlot + (uint32_t)s * kSlotBytes + kOperandBytes;
-        mbar_arrive_expect_tx_p(bar(kBarW1Full + s), (uint32_t)n_chunks * 8192u, leader);
-        for (int i = 0; i < n_chunks; ++i)
-          bulk_g2s_p(dst + (uint32_t)i * 8192u, Wg + (size_t)i * 8192, 8192u, bar(kBarW1Full + s), leader);
+        const int nch = MULTI ? A.nchunks : 1;
+        for (int cch = 0; cch < nch; ++cch) {
+          if (used & bit) {
+            mbar_wait(bar(kBarSlotFree + s), (ph_free >> s) & 1u, 20);
+            ph_free ^= bit;
+          }
+          used |= bit;
+          const int np = MULTI ? 4 : n_chunks;
+          mbar_arrive_expect_tx_p(bar(kBarW1Full + s), (uint32_t)np * 8192u, leader);
+          for (int i = 0; i < np; ++i)
+            bulk_g2s_p(dst + (uint32_t)i * 8192u, Wg + (size_t)cch * kOperandBytes + (size_t)i * 8192, 8192u,
+                       bar(kBarW1Full + s), leader);
+        }
       }
     }
     __syncwarp();
@@ -591,6 +621,119 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
   } else {
     // =================================== increment producers ===================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kProdRegs));
+    if constexpr (MULTI) {
+      // ---- 128 < d <= 1024: chunked first layer, increments drawn twice (see the kernel comment) ----
+      const int tl_id = threadIdx.x - 32 * kProdWarp0;
+      const int o = tl_id & 15, c = tl_id >> 4;  // octet inside the 128-dim chunk, row class: rows c + 16 i
+      const int pw = tl_id >> 5;                 // producer warp 0..7 = the chunk whose Bismut sums it owns
+      const int nch = A.nchunks;
+      const bool vec_ok = (d & 3) == 0;
+      uint32_t zoff[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t rr = (uint32_t)(c + 16 * i);
+        zoff[i] = (uint32_t)(o >> 3) * kPanelBytes + rr * 128u + (((uint32_t)(o & 7) ^ (rr & 7u)) << 4);
+      }
+      const float* coef_s = reinterpret_cast<const float*>(smem + kOffCoef);
+      float4 Ga = make_float4(0.f, 0.f, 0.f, 0.f), Gb = make_float4(0.f, 0.f, 0.f, 0.f);
+      uint32_t ph_free = 0, used = 0, ph_coef = 0, j = 0;
+      int pending = 0;
+      int64_t u1 = 0, u2 = 0;  // units of the pending tiles (1 = newer, 2 = older)
+      int m1 = 0, m2 = 0;      // their first samples
+      bool last1 = false, last2 = false;
+      uint32_t j1 = 0, j2 = 0;
+      // fp16-rounded increments of dims [8 oct, 8 oct + 8) of sample m of point pp: what the MLP saw
+      auto draw8 = [&](int64_t pp, int m, int oct, bool ok) -> uint4 {
+        float4 za = make_float4(0.f, 0.f, 0.f, 0.f), zb = za;
+        if (ok) {
+          if (DET) {
+            const float* row = A.zS + (pp * M_I + m) * d;
+            za = load_row4(row, 8 * oct, d, vec_ok);
+            zb = load_row4(row, 8 * oct + 4, d, vec_ok);
+          } else {
+            normal8(A.keys, (uint64_t)(A.point_base + pp), kStreamIntegral, (uint32_t)m, (uint32_t)oct, za, zb);
+          }
+        }
+        return ok ? make_uint4(pack_f16x2(za.x, za.y), pack_f16x2(za.z, za.w), pack_f16x2(zb.x, zb.y), pack_f16x2(zb.z, zb.w))
+                  : make_uint4(0u, 0u, 0u, 0u);
+      };
+      // Bismut accumulation of a finished tile: warp pw re-draws chunk pw (lane = octet x row parity, 64 rows each)
+      auto bismut = [&](uint32_t jt, int64_t ut, int mt0, bool last) {
+        const uint32_t cbuf = jt % 3u;
+        mbar_wait(bar(kBarCoef + (int)cbuf), (ph_coef >> cbuf) & 1u, 40);
+        ph_coef ^= 1u << cbuf;
+        const int bo = lane & 15, rh = lane >> 4, oct = 16 * pw + bo;
+        if (pw < nch && 8 * oct < d) {
+          const float* cf_s = coef_s + cbuf * 128u;
+          const int64_t pp = ut / UP;
+#pragma unroll 2
+          for (int i = 0; i < 64; ++i) {
+            const int rr = rh + 2 * i;
+            const float cf = cf_s[rr];
+            if (cf != 0.f) {  // rows past M_I (and exact zeros) contribute nothing
+              const uint4 z = draw8(pp, mt0 + rr, oct, true);
+              const float2 p0 = h2_unpack(z.x), p1 = h2_unpack(z.y), p2 = h2_unpack(z.z), p3 = h2_unpack(z.w);
+              Ga.x = fmaf(cf, p0.x, Ga.x);
+              Ga.y = fmaf(cf, p0.y, Ga.y);
+              Ga.z = fmaf(cf, p1.x, Ga.z);
+              Ga.w = fmaf(cf, p1.y, Ga.w);
+              Gb.x = fmaf(cf, p2.x, Gb.x);
+              Gb.y = fmaf(cf, p2.y, Gb.y);
+              Gb.z = fmaf(cf, p3.x, Gb.z);
+              Gb.w = fmaf(cf, p3.y, Gb.w);
+            }
+          }
+        }
+        if (last) {  // unit partial: [chunk][row parity][128]
+          if (pw < nch) {
+            float* gp_ = A.partG + ut * kTcPartGFloatsPerUnit + (int64_t)(pw * 2 + rh) * 128 + 8 * bo;
+            *reinterpret_cast<float4*>(gp_) = Ga;
+            *reinterpret_cast<float4*>(gp_ + 4) = Gb;
+          }
+          Ga = Gb = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      for (uint32_t k = 0;; ++k) {
+        const int64_t u = feed.get(k);
+        if (u >= A.n_units) break;
+        const int64_t p = u / UP;
+        const int g = (int)(u % UP);
+        const int tiles = min(kTcGroupTiles, A.tiles_per_point - g * kTcGroupTiles);
+        for (int tl = 0; tl < tiles; ++tl, ++j) {
+          const int m0 = (g * kTcGroupTiles + tl) * 128;
+          const int nvalid = min(128, M_I - m0);
+          const int s = tl & 1;
+          const uint32_t bit = 1u << s;
+          uint8_t* const zdst = smem + kOffSlot + (uint32_t)s * kSlotBytes;
+          for (int cch = 0; cch < nch; ++cch) {
+            const int oct = 16 * cch + o;
+            const bool col_ok = 8 * oct < d;
+            uint4 zc[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = c + 16 * i;
+              zc[i] = draw8(p, m0 + rr, oct, col_ok && rr < nvalid);
+            }
+            if (used & bit) {
+              mbar_wait(bar(kBarSlotFree + s), (ph_free >> s) & 1u, 41);  // previous chunk / tile has left hV / hT
+              ph_free ^= bit;
+            }
+            used |= bit;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(zdst + zoff[i]) = zc[i];
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(kBarZFull + s));
+          }
+          if (pending == 2) bismut(j2, u2, m2, last2);
+          j2 = j1, u2 = u1, m2 = m1, last2 = last1;
+          j1 = j, u1 = u, m1 = m0, last1 = (tl == tiles - 1);
+          if (pending < 2) ++pending;
+        }
+      }
+      if (pending == 2) bismut(j2, u2, m2, last2);
+      if (pending >= 1) bismut(j1, u1, m1, last1);
+    } else {
     // All 8 warps draw every tile: thread (o, c) owns the 8 dims [8o, 8o+8) -- one Philox block, one 16-byte operand
     // chunk -- of the rows r = c + cls i.  A tile's increments are generated into registers (no dependence on shared
     // memory), stored into the slot's hV buffer once the slot's previous tile has left it, and kept until the tile's
@@ -729,6 +872,7 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
     }
     if (pending == 2) bismut(z2, j2, u2, last2);
     if (pending >= 1) bismut(z1, j1, u1, last1);
+    }
   }
 
   tc_fence_before();
@@ -767,6 +911,35 @@ cha_tc_finish_kernel(const float* __restrict__ partG, const float* __restrict__ 
     yp[1 + j] = v;
   }
   if (j == 0) {
+    float s = 0.f;
+    for (int g = 0; g < units_per_point; ++g)
+      for (int qq = 0; qq < (int)kTcPartFFloatsPerUnit; ++qq)
+        s += partF[(p * units_per_point + g) * kTcPartFFloatsPerUnit + qq];
+    float v = yp[0] + s * invM;
+    if (clip) v = fminf(fmaxf(v, -bound), bound);
+    yp[0] = v;
+  }
+}
+
+// the same for the chunked layout (d > 128): unit partials are [chunk][row parity][128]
+__global__ void __launch_bounds__(128)
+cha_tc_finish_multi_kernel(const float* __restrict__ partG, const float* __restrict__ partF, int units_per_point, int d,
+                           int M_I, float bound, float* __restrict__ y) {
+  const int64_t p = blockIdx.x;
+  const float invM = 1.f / (float)M_I;
+  const bool clip = bound > 0.f && isfinite(bound);
+  float* yp = y + p * (int64_t)(1 + d);
+  for (int j = threadIdx.x; j < d; j += 128) {
+    const int cch = j >> 7, jj = j & 127;
+    float s = 0.f;
+    for (int g = 0; g < units_per_point; ++g)
+      for (int rh = 0; rh < 2; ++rh)
+        s += partG[(p * units_per_point + g) * kTcPartGFloatsPerUnit + (int64_t)(cch * 2 + rh) * 128 + jj];
+    float v = yp[1 + j] + s * invM;
+    if (clip) v = fminf(fmaxf(v, -bound), bound);
+    yp[1 + j] = v;
+  }
+  if (threadIdx.x == 0) {
     float s = 0.f;
     for (int g = 0; g < units_per_point; ++g)
       for (int qq = 0; qq < (int)kTcPartFFloatsPerUnit; ++qq)
@@ -833,9 +1006,9 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const uint8_t* __
   }
 }
 
-template <int ITEMS, bool DET>
+template <int ITEMS, bool DET, bool MULTI = false>
 int launch_tc_t(const ProblemDev& P, const TcNetDev& N, const TcArgs& A, int grid, cudaStream_t st) {
-  auto k = cha_tc_kernel<ITEMS, DET>;
+  auto k = cha_tc_kernel<ITEMS, DET, MULTI>;
   DPI_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
   k<<<grid, kTcThreads, kTcSmemBytes, st>>>(P, N.consts, A);
   DPI_CUDA_CHECK(cudaGetLastError());
@@ -848,18 +1021,21 @@ int tc_pack_network(const dpi_network& net, const ProblemDev& P, const MlpDev& M
                     TcNetDev* out, bool* ready, int64_t* launches, cudaStream_t st) {
   *ready = false;
   const int L = net.n_main;
-  if (L != 5 || P.nx > 128) return DPI_OK;  // this kernel: Linear(1+d,128), 3 x Linear(128,128), Linear(128,1)
+  if (L != 5 || P.nx > 1024) return DPI_OK;  // this kernel: Linear(1+d,128), 3 x Linear(128,128), Linear(128,1)
+  const int nch = (P.nx + 127) / 128;        // first-layer K chunks of 128 input dims
   for (int l = 0; l < L - 1; ++l)
     if (net.main[l].n_out != 128) return DPI_OK;
   void* img = nullptr;
-  DPI_CUDA_CHECK(cudaMalloc(&img, 4 * (size_t)tc::kOperandBytes));
+  DPI_CUDA_CHECK(cudaMalloc(&img, (size_t)(nch + 3) * tc::kOperandBytes));
   owner.push_back(img);
   uint8_t* base = reinterpret_cast<uint8_t*>(img);
-  pack_sw128_kernel<<<64, 256, 0, st>>>(net.main[0].W, 1 + P.nx, 1, 128, P.nx, base);
+  for (int cch = 0; cch < nch; ++cch)  // W1 x-columns [128 cch, 128 cch + 128)
+    pack_sw128_kernel<<<64, 256, 0, st>>>(net.main[0].W, 1 + P.nx, 1 + 128 * cch, 128, std::min(128, P.nx - 128 * cch),
+                                          base + (size_t)cch * tc::kOperandBytes);
   for (int l = 1; l <= 3; ++l)
-    pack_sw128_kernel<<<64, 256, 0, st>>>(net.main[l].W, 128, 0, 128, 128, base + (size_t)l * tc::kOperandBytes);
+    pack_sw128_kernel<<<64, 256, 0, st>>>(net.main[l].W, 128, 0, 128, 128, base + (size_t)(nch - 1 + l) * tc::kOperandBytes);
   DPI_CUDA_CHECK(cudaGetLastError());
-  *launches += 4;
+  *launches += nch + 3;
   // per-column fp32 constants travel as kernel parameters (constant bank): copy the packed vectors back once
   DPI_CUDA_CHECK(cudaStreamSynchronize(st));
   TcNetDev T{};
@@ -880,8 +1056,9 @@ int tc_pack_network(const dpi_network& net, const ProblemDev& P, const MlpDev& M
   }
   T.W = img;
   T.nx = P.nx;
-  T.ksteps1 = (P.nx + 15) / 16;
-  T.no = (P.nx + 7) / 8;
+  T.nchunks = nch;
+  T.ksteps1 = nch > 1 ? 8 : (P.nx + 15) / 16;
+  T.no = nch > 1 ? 16 : (P.nx + 7) / 8;
   T.cls = 256 / T.no < kTcMaxClasses ? 256 / T.no : kTcMaxClasses;  // row classes of the 256 producer threads
   int dev = 0, sms = 0;
   DPI_CUDA_CHECK(cudaGetDevice(&dev));
@@ -926,6 +1103,7 @@ int launch_cha_tc_path(const ProblemDev& P, const TcNetDev& N, const float* tx, 
   A.ksteps1 = N.ksteps1;
   A.no = N.no;
   A.cls = N.cls;
+  A.nchunks = N.nchunks;
   const int grid = (int)(A.n_units < N.num_sms ? A.n_units : N.num_sms);
   int rc;
 #ifdef DPI_TC_DEBUG_UD
@@ -947,6 +1125,9 @@ int launch_cha_tc_path(const ProblemDev& P, const TcNetDev& N, const float* tx, 
 #endif
   const bool det = zS != nullptr;
   const int items = (128 + N.cls - 1) / N.cls;  // rows per producer thread: 4 (d <= 64) .. 8 (d > 104)
+  if (N.nchunks > 1) {
+    rc = det ? launch_tc_t<8, true, true>(P, N, A, grid, st) : launch_tc_t<8, false, true>(P, N, A, grid, st);
+  } else
   switch (items) {
     case 4: rc = det ? launch_tc_t<4, true>(P, N, A, grid, st) : launch_tc_t<4, false>(P, N, A, grid, st); break;
     case 5: rc = det ? launch_tc_t<5, true>(P, N, A, grid, st) : launch_tc_t<5, false>(P, N, A, grid, st); break;
@@ -988,7 +1169,10 @@ int launch_cha_tc_path(const ProblemDev& P, const TcNetDev& N, const float* tx, 
     }
   }
 #endif
-  cha_tc_finish_kernel<<<(unsigned)n, 128, 0, st>>>(partG, partF, A.units_per_point, N.cls, P.nx, M_I, bound, y);
+  if (N.nchunks > 1)
+    cha_tc_finish_multi_kernel<<<(unsigned)n, 128, 0, st>>>(partG, partF, A.units_per_point, P.nx, M_I, bound, y);
+  else
+    cha_tc_finish_kernel<<<(unsigned)n, 128, 0, st>>>(partG, partF, A.units_per_point, N.cls, P.nx, M_I, bound, y);
   DPI_CUDA_CHECK(cudaGetLastError());
   return DPI_OK;
 }

@@ -55,13 +55,39 @@ def test_burgers_1000d_sweep_shape_matches_oracle_on_replayed_draws():
     y = e.label_gen(tx, M, M, precision="fp32", draws=draws_dict(d)).double().cpu()
     assert orc.rel_l2(y, y_ref) < 1e-4
     assert orc.rel_l2(y[:, 1:], y_ref[:, 1:]) < 1e-4
-    with pytest.raises(NotImplementedError):
-        e.label_gen(tx, M, M, precision="f16")  # the tensor-core kernel is d <= 128
+    # the tensor-core kernel at this width: first layer accumulated over 8 chunks of 128 input dims
+    y16 = e.label_gen(tx, M, M, precision="f16", draws=draws_dict(d)).double().cpu()
+    assert orc.rel_l2(y16, y_ref) < 1e-2
+    assert orc.rel_l2(y16[:, 1:], y_ref[:, 1:]) < 1e-2
     # Philox mode at this width: shard-invariant
     txp = e.sample_tx(6, seed=3)
     yp = e.label_gen(txp, 32, 32, seed=5)
     yq = torch.cat([e.label_gen(txp[:2], 32, 32, seed=5), e.label_gen(txp[2:], 32, 32, seed=5, point_index_base=2)])
     assert torch.equal(yp, yq) and torch.isfinite(yp).all()
+    e.close()
+
+
+@pytest.mark.parametrize("nx", [200, 1000, 1024])
+def test_chunked_tensor_core_path_tracks_fp32_on_the_same_philox_draws(nx):
+    """128 < d <= 1024 on tcgen05: the first layer is accumulated over ceil(d/128) chunks and the increments are drawn
+    twice from the same Philox counters (operand tile, Bismut sums).  Same counters as the fp32 kernel, so the two
+    differ only by operand rounding; bitwise shard invariance; ragged sample counts."""
+    eq = orc.Cha(nx, 1.0, 5.0, 1.0)
+    net = orc.make_mlp(1 + nx, [128] * 4, seed=11, gain=1.3)
+    e = _eng(eq, net)
+    tx = e.sample_tx(10, seed=4)
+    for M_I in (300, 1100):  # 3 tiles (one ragged) / 9 tiles = two units, the second with a single tile
+        y32 = e.label_gen(tx, 64, M_I, precision="fp32", seed=8).double().cpu()
+        y16 = e.label_gen(tx, 64, M_I, precision="f16", seed=8).double().cpu()
+        assert torch.isfinite(y16).all()
+        assert orc.rel_l2(y16, y32) < 1e-2
+        assert orc.rel_l2(y16[:, 1:], y32[:, 1:]) < 1e-2
+        yb = torch.cat([e.label_gen(tx[:3], 64, M_I, precision="f16", seed=8),
+                        e.label_gen(tx[3:], 64, M_I, precision="f16", seed=8, point_index_base=3)]).double().cpu()
+        assert torch.equal(y16, yb)
+    with pytest.raises(NotImplementedError):
+        e2 = _eng(orc.Cha(1100, 1.0, 5.0, 1.0), orc.make_mlp(1101, [128] * 4, seed=1))
+        e2.label_gen(e2.sample_tx(2, seed=1), 8, 8, precision="f16")  # d > 1024: fp32 path only
     e.close()
 
 
