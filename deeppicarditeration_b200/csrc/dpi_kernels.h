@@ -52,7 +52,12 @@ int launch_gbm_tc(const ProblemDev& P, const MlpDev& net, const float* tx, int64
                   const float* u_s, const float* zS, const int32_t* idx, float bound, float* y, cudaStream_t st);
 
 // ---- 16-bit tcgen05 path (dpi_mlp_tc.cu): fp16 operands, fp32 accumulation ---------------------------------------------------------------
-constexpr int kTcGroupTiles = 8;  // 128-sample tiles per work unit (fixed: the summation order must not depend on n)
+#ifndef DPI_TC_GROUP_TILES
+#define DPI_TC_GROUP_TILES 16
+#endif
+// 128-sample tiles per work unit (fixed: the summation order must not depend on n).  8, 16 and 32 run equally fast at
+// the bench size; 16 halves the unit-partial traffic of 8 and still gives 512 points (one of eight GPUs) 7 units per SM.
+constexpr int kTcGroupTiles = DPI_TC_GROUP_TILES;
 // per-column fp32 constants of the network, passed to the kernel by value (constant bank)
 struct alignas(16) TcConsts {
   float wt[128];            // log2e W1[:,0]                time column (fp32: multiplies the per-row time)

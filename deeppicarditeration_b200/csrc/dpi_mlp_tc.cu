@@ -4,7 +4,7 @@
 // solution.py:123-135) with the first-layer GEMM and the three hidden 128x128 GEMMs (value and tangent) on the
 // 5th-generation tensor cores:
 //
-//   * one persistent CTA per SM.  A work unit is (collocation point, group of 8 tiles); a tile is 128 MC samples =
+//   * one persistent CTA per SM.  A work unit is (collocation point, group of 16 tiles); a tile is 128 MC samples =
 //     128 TMEM lanes.  TWO tiles are in flight per CTA, one per "slot": while the epilogue warps of one slot turn a
 //     layer's accumulators into the next layer's operands, the tensor pipe runs the other slot's layer;
 //   * shared memory: the hidden weights W2..W4 stay resident as fp16 K-major SWIZZLE_128B operand images (3 x 32 KB);

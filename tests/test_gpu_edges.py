@@ -76,7 +76,7 @@ def test_chunked_tensor_core_path_tracks_fp32_on_the_same_philox_draws(nx):
     net = orc.make_mlp(1 + nx, [128] * 4, seed=11, gain=1.3)
     e = _eng(eq, net)
     tx = e.sample_tx(10, seed=4)
-    for M_I in (300, 1100):  # 3 tiles (one ragged) / 9 tiles = two units, the second with a single tile
+    for M_I in (300, 2100):  # 3 tiles (one ragged) / 17 tiles = two units, the second with a single ragged tile
         y32 = e.label_gen(tx, 64, M_I, precision="fp32", seed=8).double().cpu()
         y16 = e.label_gen(tx, 64, M_I, precision="f16", seed=8).double().cpu()
         assert torch.isfinite(y16).all()
