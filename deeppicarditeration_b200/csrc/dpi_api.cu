@@ -568,14 +568,13 @@ int dpi_label_gen(dpi_handle* h, const float* tx, int64_t n, const dpi_label_con
     return rc;
   }
   if (h->net_kind == DPI_NET_PISGRAD && P.eq == DPI_EQ_OU) {
-    if (cfg->precision != DPI_PREC_FP32) {
-      set_error("dpi_label_gen: the PISGradNet path is fp32 only");
-      return DPI_ERR_UNSUPPORTED;
-    }
+    // reduced precision here = the wide GEMMs of nn_module on the tensor cores with TF32 operands (fp32 in memory)
+    PisDev pis = h->pis;
+    pis.tf32 = cfg->precision != DPI_PREC_FP32;
     const int64_t ppc = std::min<int64_t>(n, hjb_points_per_chunk(h->pis, P.nx, cfg->M_I, kHjbScratchBudget));
     if ((rc = ensure_hjb_scratch(h, hjb_scratch_floats(h->pis, P.nx, ppc * (cfg->M_I + 1))))) return rc;
     StageTimer tm(h, DPI_STAGE_INTEGRAL, st);
-    return launch_hjb_paths(P, h->pis, tx, n, cfg->M_I, cfg->seed, cfg->point_index_base, draws ? draws->u_s : nullptr,
+    return launch_hjb_paths(P, pis, tx, n, cfg->M_I, cfg->seed, cfg->point_index_base, draws ? draws->u_s : nullptr,
                             draws ? draws->zS : nullptr, bound, h->hjb_scratch, ppc, y, st, &h->launches);
   }
   set_error("dpi_label_gen: equation %d with network kind %d is not built yet", P.eq, h->net_kind);

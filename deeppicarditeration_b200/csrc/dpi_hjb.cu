@@ -18,6 +18,7 @@
 
 #include "dpi_common.cuh"
 #include "dpi_kernels.h"
+#include "dpi_gemm_epi.cuh"
 
 namespace dpi {
 namespace {
@@ -37,58 +38,6 @@ __device__ __forceinline__ void load8(const float* __restrict__ p, int i0, int l
   } else {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = (i0 + i < limit) ? __ldg(p + i0 + i) : 0.f;
-  }
-}
-
-// epilogue of 4 consecutive columns [col, col+4) of one output row
-__device__ __forceinline__ void gemm_epilogue4(const GemmArgs& g, int64_t row, int col, float (&v)[4], bool c_vec,
-                                               bool d_vec, bool e_vec) {
-  const int N = g.N;
-  float dv[4] = {0.f, 0.f, 0.f, 0.f};
-  const bool full = col + 3 < N;
-  if (g.epi == kEpiBias || g.epi == kEpiBiasElu || g.epi == kEpiBiasEluD) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (col + j < N) v[j] += __ldg(g.bias + col + j);
-  }
-  if (g.epi == kEpiBiasElu || g.epi == kEpiBiasEluD) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) elu_d1(v[j], v[j], dv[j]);
-  }
-  if (g.epi == kEpiMulE) {
-    const float* ep = g.E + row * (int64_t)g.lde + col;
-    if (full && e_vec) {
-      const float4 e = __ldg(reinterpret_cast<const float4*>(ep));
-      v[0] *= e.x, v[1] *= e.y, v[2] *= e.z, v[3] *= e.w;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (col + j < N) v[j] *= __ldg(ep + j);
-    }
-  }
-  if (g.epi == kEpiKeepMulE) {  // C = acc (pre-activation tangent), D = acc * E (tangent through the ELU)
-    const float* ep = g.E + row * (int64_t)g.lde + col;
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (col + j < N) dv[j] = v[j] * __ldg(ep + j);
-  }
-  float* cp = g.C + row * (int64_t)g.ldc + col;
-  if (full && c_vec) {
-    *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
-  } else {
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (col + j < N) cp[j] = v[j];
-  }
-  if (g.epi == kEpiBiasEluD || g.epi == kEpiKeepMulE) {
-    float* dp = g.D + row * (int64_t)g.ldd + col;
-    if (full && d_vec) {
-      *reinterpret_cast<float4*>(dp) = make_float4(dv[0], dv[1], dv[2], dv[3]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (col + j < N) dp[j] = dv[j];
-    }
   }
 }
 
@@ -340,6 +289,7 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, i
 
 int gemm_impl(const GemmArgs& g, cudaStream_t st, int64_t* launches) {
   if (g.R <= 0 || g.N <= 0) return DPI_OK;
+  if (g.tf32 && gemm_tf32_eligible(g)) return gemm_tf32(g, st, launches);
   const int64_t big_tiles = ((g.R + BM - 1) / BM) * ((g.N + BN - 1) / BN);
   if (big_tiles < 96) {
     // too few 128x128 tiles to fill the 148 SMs: small tiles, and split K when even those are few
@@ -601,7 +551,7 @@ int eval_rows(const PisDev& N, int d, const Scratch& S, int64_t R, cudaStream_t 
                int ldd = 0) {
     GemmArgs g{};
     g.A = A, g.lda = lda, g.B = L.W, g.ldb = L.n_in, g.b_kn = 0, g.bias = L.b, g.C = C, g.ldc = ldc, g.D = D, g.ldd = ldd;
-    g.R = R1, g.N = N_, g.K = L.n_in, g.epi = epi;
+    g.R = R1, g.N = N_, g.K = L.n_in, g.epi = epi, g.tf32 = N.tf32;
     return gemm_impl(g, st, launches);
   };
   // t_encoder (solution.py:170-174): Linear(128,64) ELU Linear(64,64) -> columns [0,64) of the nn_module input
@@ -639,7 +589,7 @@ int eval_rows(const PisDev& N, int d, const Scratch& S, int64_t R, cudaStream_t 
                   int ldc) {
       GemmArgs g{};
       g.A = A, g.lda = lda, g.B = Bp, g.ldb = ldb, g.b_kn = 1, g.E = E, g.lde = lde, g.C = C, g.ldc = ldc;
-      g.R = R, g.N = N_, g.K = K_, g.epi = E ? kEpiMulE : kEpiNone;
+      g.R = R, g.N = N_, g.K = K_, g.epi = E ? kEpiMulE : kEpiNone, g.tf32 = N.tf32;
       return gemm(g, st, launches);
     };
     float* bufs[2] = {S.hA, S.hB};

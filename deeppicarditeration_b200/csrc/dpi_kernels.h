@@ -114,8 +114,12 @@ struct GemmArgs {
   int a_km;
   float* ws;      // optional split-K workspace [ws_splits][R][N] (epi == kEpiNone only)
   int ws_splits;
+  int tf32;       // 1: use the TF32 tcgen05 GEMM when the shape is eligible
 };
 int gemm(const GemmArgs& g, cudaStream_t st, int64_t* launches);
+// TF32 tcgen05 GEMM (dpi_gemm_tc.cu): same arguments and epilogues; K % 32 == 0, no a_km, R >= 128, N >= 64
+bool gemm_tf32_eligible(const GemmArgs& g);
+int gemm_tf32(const GemmArgs& g, cudaStream_t st, int64_t* launches);
 
 // ---- HJB / PISGradNet, fp32 batched-GEMM pipeline (dpi_hjb.cu) -------------------------------------------
 // Weight pointers are the caller's torch-layout tensors (W [n_out, n_in] row-major), used in place.
@@ -125,6 +129,7 @@ struct PisDev {
   dpi_linear main[DPI_MAX_LINEAR], t_encoder[DPI_MAX_LINEAR], smooth_net[DPI_MAX_LINEAR];
   const float* phase;  // [64]
   const float* coeff;  // [64]
+  int tf32;            // 1: eligible GEMMs on the tensor cores (TF32 operands, fp32 accumulate; dpi_gemm_tc.cu)
 };
 int64_t hjb_scratch_floats(const PisDev& net, int d, int64_t rows);
 int64_t hjb_points_per_chunk(const PisDev& net, int d, int M_I, int64_t budget_bytes);

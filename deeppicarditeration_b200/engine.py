@@ -130,7 +130,7 @@ class LabelEngine:
         cfg = nat.dpi_label_config()
         cfg.M_T, cfg.M_I = int(M_T), int(M_I)
         cfg.precision = {"fp32": nat.DPI_PREC_FP32, "f16": nat.DPI_PREC_F16, "fp16": nat.DPI_PREC_F16,
-                         "bf16": nat.DPI_PREC_F16}[precision]  # "bf16": alias of the 16-bit tensor-core path
+                         "bf16": nat.DPI_PREC_F16, "tf32": nat.DPI_PREC_F16}[precision]  # aliases of the reduced-precision tensor-core paths
         cfg.sample_bound = float(bound) if bound is not None and math.isfinite(bound) else 0.0
         cfg.seed = seed & (2**64 - 1)
         cfg.point_index_base = int(base)
