@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(kThreads, 2) tf32_gemm_kernel(const GemmArgs g
   const int64_t r0 = rt * kTile;
   const int n0 = nt * kTile;
   const int K = g.K, N = g.N;
-  const int nk = K / kStageK;
+  const int nk = (K + kStageK - 1) / kStageK;  // the last chunk may be partial (K % 4 == 0): zero-filled
 
   if (t == 0) {
     for (int s = 0; s < kStages; ++s) mbar_init(bars + 8u * s, 1);
@@ -73,8 +73,8 @@ __global__ void __launch_bounds__(kThreads, 2) tf32_gemm_kernel(const GemmArgs g
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int row = (t >> 3) + 32 * i, c4 = t & 7;
-      const bool ok = r0 + row < g.R;
-      const float* src = g.A + (ok ? (r0 + row) : 0) * (int64_t)g.lda + k0 + 4 * c4;
+      const bool ok = r0 + row < g.R && k0 + 4 * c4 < K;
+      const float* src = g.A + (ok ? (r0 + row) * (int64_t)g.lda + k0 + 4 * c4 : 0);
       cp_async16(a_dst + (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((c4 ^ (row & 7)) << 4), src,
                  ok ? 16u : 0u);
     }
@@ -82,8 +82,8 @@ __global__ void __launch_bounds__(kThreads, 2) tf32_gemm_kernel(const GemmArgs g
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int row = (t >> 3) + 32 * i, c4 = t & 7;
-        const bool ok = n0 + row < N;
-        const float* src = g.B + (int64_t)(ok ? (n0 + row) : 0) * g.ldb + k0 + 4 * c4;
+        const bool ok = n0 + row < N && k0 + 4 * c4 < K;
+        const float* src = g.B + (ok ? (int64_t)(n0 + row) * g.ldb + k0 + 4 * c4 : 0);
         cp_async16(b_dst + (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((c4 ^ (row & 7)) << 4), src,
                    ok ? 16u : 0u);
       }
@@ -93,8 +93,8 @@ __global__ void __launch_bounds__(kThreads, 2) tf32_gemm_kernel(const GemmArgs g
       for (int i = 0; i < 16; ++i) {
         const int e = t + kThreads * i;  // 0 .. 4095
         const int k = e >> 7, n = e & 127;
-        const bool ok = n0 + n < N;
-        const float* src = g.B + (int64_t)(k0 + k) * g.ldb + (ok ? (n0 + n) : 0);
+        const bool ok = n0 + n < N && k0 + k < K;
+        const float* src = g.B + (ok ? (int64_t)(k0 + k) * g.ldb + n0 + n : 0);
         cp_async4(b_dst + (uint32_t)(n >> 3) * 1024u + (uint32_t)(n & 7) * 128u + (uint32_t)(((k >> 2) ^ (n & 7)) << 4) +
                       (uint32_t)(k & 3) * 4u,
                   src, ok ? 4u : 0u);
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(kThreads, 2) tf32_gemm_kernel(const GemmArgs g
 }  // namespace
 
 bool gemm_tf32_eligible(const GemmArgs& g) {
-  return !g.a_km && g.K % kStageK == 0 && g.K >= kStageK && (g.lda & 3) == 0 && (g.b_kn || (g.ldb & 3) == 0) &&
+  return !g.a_km && g.K % 4 == 0 && g.K >= kStageK && (g.lda & 3) == 0 && (g.b_kn || (g.ldb & 3) == 0) &&
          (reinterpret_cast<uintptr_t>(g.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.B) & 15) == 0 && g.R >= kTile &&
          g.N >= 64;
 }

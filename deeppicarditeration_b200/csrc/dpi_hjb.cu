@@ -472,36 +472,70 @@ __global__ void __launch_bounds__(256) hjb_final_kernel(const ProblemDev P, cons
 // MC reduction (data.py:514-527): y[p] += mean_m dT (f_m - f_b) (1, Z_m / (a_m)) + (dT f_b, 0); clip (data.py:222).
 // One CTA per point, thread j owns gradient component j; fixed summation order.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+// Four groups of 128 threads take the samples in tiles of 128: a group first writes the tile's 128 coefficients to
+// shared memory (one division per sample instead of one per (sample, component)), then thread j of the group adds
+// coef_m Z_mj over the tile; the four group sums are added in a fixed order.
+constexpr int kRedGroups = 4;
+__global__ void __launch_bounds__(128 * kRedGroups)
 hjb_reduce_kernel(const ProblemDev P, const float* __restrict__ tx, int M_I, const float* __restrict__ f,
                   const float* __restrict__ z, const float* __restrict__ sa, float bound, float* __restrict__ y) {
+  __shared__ float coef_s[kRedGroups][128];
+  __shared__ float part[kRedGroups][1024 + 1];
   const int64_t p = blockIdx.x;
   const int d = P.nx, rpp = M_I + 1;
+  const int gq = threadIdx.x >> 7, tj = threadIdx.x & 127;
   const float dT = P.T - __ldg(tx + p * (int64_t)(1 + d));
   const int64_t rb = p * rpp;
   const float fb = __ldg(f + rb + M_I);
   const float invM = 1.f / (float)M_I;
   const bool clip = bound > 0.f && isfinite(bound);
   float* yp = y + p * (int64_t)(1 + d);
-  for (int j = threadIdx.x; j < d; j += blockDim.x) {
-    float G = 0.f;
-    for (int m = 0; m < M_I; ++m) {
-      const float coef = dT * (__ldg(f + rb + m) - fb) / __ldg(sa + 2 * (rb + m) + 1);
-      G = fmaf(coef, __ldg(z + (rb + m) * d + j), G);
+  float G[8], fs = 0.f;  // components tj + 128 k (d <= 1024)
+#pragma unroll
+  for (int k = 0; k < 8; ++k) G[k] = 0.f;
+  const int n_tiles = (M_I + 127) / 128;
+  for (int tile = gq; tile - gq < n_tiles; tile += kRedGroups) {  // same trip count for every group (barriers inside)
+    const int m0 = tile * 128;
+    const int m = m0 + tj;
+    float cf = 0.f;
+    if (m < M_I) {
+      const float fm = __ldg(f + rb + m);
+      cf = dT * (fm - fb) / __ldg(sa + 2 * (rb + m) + 1);
+      fs += fm;
     }
-    float v = yp[1 + j] + G * invM;
+    __syncthreads();  // the previous tile's coefficients have been consumed
+    coef_s[gq][tj] = cf;
+    __syncthreads();
+    const int cnt = min(128, M_I - m0);
+    for (int i = 0; i < cnt; ++i) {
+      const float c = coef_s[gq][i];
+      const float* zr = z + (rb + m0 + i) * d;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int j = tj + 128 * k;
+        if (j < d) G[k] = fmaf(c, __ldg(zr + j), G[k]);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) part[gq][tj + 128 * k] = G[k];
+  fs = warp_sum(fs);
+  __shared__ float fpart[kRedGroups * 4];
+  if ((threadIdx.x & 31) == 0) fpart[threadIdx.x >> 5] = fs;
+  __syncthreads();
+  for (int j = threadIdx.x; j < d; j += blockDim.x) {
+    float Gs = 0.f;
+    for (int q = 0; q < kRedGroups; ++q) Gs += part[q][j];
+    float v = yp[1 + j] + Gs * invM;
     if (clip) v = fminf(fmaxf(v, -bound), bound);
     yp[1 + j] = v;
   }
-  if (threadIdx.x < 32) {
-    float fs = 0.f;
-    for (int m = threadIdx.x; m < M_I; m += 32) fs += __ldg(f + rb + m);
-    fs = warp_sum(fs);
-    if (threadIdx.x == 0) {
-      float v = yp[0] + dT * fs * invM;
-      if (clip) v = fminf(fmaxf(v, -bound), bound);
-      yp[0] = v;
-    }
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < kRedGroups * 4; ++i) s += fpart[i];
+    float v = yp[0] + dT * s * invM;
+    if (clip) v = fminf(fmaxf(v, -bound), bound);
+    yp[0] = v;
   }
 }
 
@@ -639,7 +673,7 @@ int launch_hjb_paths(const ProblemDev& P, const PisDev& N, const float* tx, int6
     F.in = S.rows.in, F.nout = S.nout, F.jtx = S.jtx, F.sraw = S.sraw, F.sa = S.rows.sa, F.f = S.f, F.R = R;
     hjb_final_kernel<<<(unsigned)((R + 7) / 8), 256, 0, st>>>(P, F);
     DPI_CUDA_CHECK(cudaGetLastError());
-    hjb_reduce_kernel<<<(unsigned)np, 128, 0, st>>>(P, tx + p0 * (1 + d), M_I, S.f, S.rows.z, S.rows.sa, bound,
+    hjb_reduce_kernel<<<(unsigned)np, 128 * kRedGroups, 0, st>>>(P, tx + p0 * (1 + d), M_I, S.f, S.rows.z, S.rows.sa, bound,
                                                     y + p0 * (1 + d));
     DPI_CUDA_CHECK(cudaGetLastError());
     *launches += 2;

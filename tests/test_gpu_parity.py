@@ -153,6 +153,33 @@ def test_hjb_full_width_network_runs_chunked_and_is_shard_invariant():
     e.close()
 
 
+def test_hjb_tensor_core_gemms_track_the_fp32_pipeline():
+    """PISGradNet with the wide nn_module GEMMs on tcgen05 (TF32 operands read from the fp32 buffers, fp32
+    accumulation): replayed reference draws against the fp64 oracle, the fp32 pipeline on the same Philox draws
+    (forward and [K][N] backward weights, partial K chunks 164 and 100, ragged row and column tiles), shard invariance."""
+    from tests.gpu_util import engine_for, draws_dict
+    g = Golden("hjb_100d_pisgrad")
+    net = orc.make_pisgrad(g.nx, [512] * 4, T=g.T, seed=4, phase_scale=0.3)
+    e = engine_for(g.eq, net)
+    n, M = 5, 40  # 205 rows: one full and one ragged 128-row tile
+    d = orc.draw(g.eq, n, M, M, None, torch.Generator().manual_seed(3), round_fp32=True)
+    tx = orc.sample_tx(g.eq, d)
+    y_ref = orc.generate_with_gradients(g.eq, net, tx, d, M, M)
+    y19 = e.label_gen(tx, M, M, precision="tf32", draws=draws_dict(d)).double().cpu()
+    assert orc.rel_l2(y19, y_ref) < TOL_BF16
+    assert orc.rel_l2(y19[:, 1:], y_ref[:, 1:]) < TOL_BF16
+    txp = e.sample_tx(20, seed=2)
+    y32 = e.label_gen(txp, 64, 300, precision="fp32", seed=9).double().cpu()
+    y19 = e.label_gen(txp, 64, 300, precision="tf32", seed=9).double().cpu()
+    assert torch.isfinite(y19).all()
+    assert orc.rel_l2(y19, y32) < 2e-3 and orc.rel_l2(y19[:, 1:], y32[:, 1:]) < 2e-3
+    assert not torch.equal(y19, y32)  # the tensor-core path really ran
+    y_b = torch.cat([e.label_gen(txp[:7], 64, 300, precision="tf32", seed=9),
+                     e.label_gen(txp[7:], 64, 300, precision="tf32", seed=9, point_index_base=7)]).double().cpu()
+    assert torch.equal(y19, y_b)
+    e.close()
+
+
 # ---------------------------------------------------------------------------------------------------------
 # bf16 tensor-core (tcgen05) path
 # ---------------------------------------------------------------------------------------------------------
