@@ -110,9 +110,15 @@ __device__ __forceinline__ void box_muller16(uint32_t w, float& z0, float& z1) {
   const float xr = __uint_as_float(((w << 7) & 0x007FFF80u) | 0x3F800000u);
   const float xa = __uint_as_float(((w >> 9) & 0x007FFF80u) | 0x3F800000u);
   const float u = xr - 0.99999237060546875f;                 // (k + 1/2) 2^-16
+#ifdef DPI_DBG_BM_NOXU  // sensitivity builds only: same instruction count without the four MUFU ops (wrong numbers)
+  const float r = fmaf(-1.3862943611198906f, fmaf(u, 0.5f, 0.25f), 2.f) * 0.7f;
+  const float ang = fmaf(xa, 6.283185307179586f, -6.283137370279964f) * 0.15915494f;
+  float s = fmaf(ang, 0.5f, -0.25f), c = fmaf(ang, -0.5f, 0.25f);
+#else
   const float r = sqrtf(-1.3862943611198906f * __log2f(u));  // sqrt(-2 ln u) = sqrt(-2 ln2 log2 u)
   float s, c;
   __sincosf(fmaf(xa, 6.283185307179586f, -6.283137370279964f), &s, &c);  // 2 pi (k' + 1/2) 2^-16
+#endif
   z0 = r * c;
   z1 = r * s;
 }
