@@ -51,6 +51,17 @@ __device__ __forceinline__ uint32_t a_off(int row, int k) {  // byte offset of e
   return (uint32_t)row * 128u + ((((uint32_t)k >> 3) ^ ((uint32_t)row & 7u)) << 4) + ((uint32_t)k & 7u) * 2u;
 }
 
+// four block sums behind one pair of barriers (the row pipeline is barrier bound)
+__device__ void block_sum4(GbmTcSmem& S, float& a, float& b, float& c, float& e) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  a = warp_sum(a), b = warp_sum(b), c = warp_sum(c), e = warp_sum(e);
+  __syncthreads();
+  if (lane == 0) S.part[0][warp] = a, S.part[1][warp] = b, S.part[2][warp] = c, S.part[3][warp] = e;
+  __syncthreads();
+  a = b = c = e = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) a += S.part[0][w], b += S.part[1][w], c += S.part[2][w], e += S.part[3][w];
+}
 __device__ void block_sum3(GbmTcSmem& S, float& a, float& b, float& c) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   a = warp_sum(a), b = warp_sum(b), c = warp_sum(c);
@@ -75,9 +86,7 @@ __device__ float gbm_source(GbmTcSmem& S, const ProblemDev& P, float s, float a,
       if (P.gbm_nodes > 2) p2 = S.gw[2][tid] * X;
       if (P.gbm_nodes > 3) p3 = S.gw[3][tid] * X;
     }
-    block_sum3(S, p0, p1, p2);
-    float z = 0.f;
-    block_sum3(S, p3, z, dummy);
+    block_sum4(S, p0, p1, p2, p3);
     arg[0] = p0, arg[1] = p1, arg[2] = p2, arg[3] = p3;
   }
   float ut = 0.f;
@@ -350,8 +359,7 @@ gbm_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ MlpD
       const float dj = S.diag[S.idx[tid]];
       a1 = ujj, a2 = fabsf(ujj), b1 = dj, b2 = fabsf(dj);
     }
-    block_sum3(S, a1, a2, b1);
-    block_sum3(S, b2, z0, z0);
+    block_sum4(S, a1, a2, b1, b2);
     const float f = alpha_term * (a1 * inv_v) + abs_term * (a2 * inv_v) + src;
     const float fb = alpha_term * (b1 * inv_v) + abs_term * (b2 * inv_v) + src_b;
     fsum += dT * f;
