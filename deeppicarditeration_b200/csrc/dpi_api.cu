@@ -434,6 +434,16 @@ int dpi_set_network(dpi_handle* h, const dpi_network* net, void* stream) {
     for (int l = 0; l < net->n_t_encoder; ++l) N.t_encoder[l] = net->t_encoder[l];
     for (int l = 0; l < net->n_smooth; ++l) N.smooth_net[l] = net->smooth_net[l];
     N.phase = net->timestep_phase, N.coeff = net->timestep_coeff;
+    // K-major ([n_in][n_out]) copies of the nn_module weights: the VJP GEMMs of the tensor-core path then load both
+    // operands with 16-byte copies instead of transposing a [K][N] weight element by element
+    for (int l = 0; l < net->n_main; ++l) {
+      float* wt = nullptr;
+      DPI_CUDA_CHECK(cudaMalloc((void**)&wt, sizeof(float) * (size_t)net->main[l].n_out * net->main[l].n_in));
+      h->net_bufs.push_back(wt);
+      if (int rc_t = gemm_transpose(net->main[l].W, net->main[l].n_out, net->main[l].n_in, wt, st)) return rc_t;
+      N.main_t[l] = wt;
+    }
+    h->launches += net->n_main;
     h->pis = N;
     h->has_net = true;
     (void)st;

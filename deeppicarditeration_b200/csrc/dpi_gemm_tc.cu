@@ -167,7 +167,27 @@ __global__ void __launch_bounds__(kThreads, 2) tf32_gemm_kernel(const GemmArgs g
   }
 }
 
+__global__ void transpose_kernel(const float* __restrict__ W, int rows, int cols, float* __restrict__ WT) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? W[(size_t)r * cols + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < cols && r < rows) WT[(size_t)c * rows + r] = tile[threadIdx.x][i];
+  }
+}
+
 }  // namespace
+
+int gemm_transpose(const float* W, int rows, int cols, float* WT, cudaStream_t st) {
+  transpose_kernel<<<dim3((cols + 31) / 32, (rows + 31) / 32), dim3(32, 8), 0, st>>>(W, rows, cols, WT);
+  DPI_CUDA_CHECK(cudaGetLastError());
+  return DPI_OK;
+}
 
 bool gemm_tf32_eligible(const GemmArgs& g) {
   return !g.a_km && g.K % 4 == 0 && g.K >= kStageK && (g.lda & 3) == 0 && (g.b_kn || (g.ldb & 3) == 0) &&

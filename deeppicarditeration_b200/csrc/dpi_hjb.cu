@@ -619,25 +619,31 @@ int eval_rows(const PisDev& N, int d, const Scratch& S, int64_t R, cudaStream_t 
   }
   // VJP with cotangent x: c = x W_last; c = (c . ELU'(z_l)) W_l for l = L-2 .. 0; keep the x columns of the result
   {
+    // Bt (optional): the same weight block transposed, [N_][ldbt] K-major -- used by the tensor-core path
     auto GB = [&](const float* A, int lda, int K_, const float* Bp, int ldb, int N_, const float* E, int lde, float* C,
-                  int ldc) {
+                  int ldc, const float* Bt = nullptr, int ldbt = 0) {
       GemmArgs g{};
       g.A = A, g.lda = lda, g.B = Bp, g.ldb = ldb, g.b_kn = 1, g.E = E, g.lde = lde, g.C = C, g.ldc = ldc;
       g.R = R, g.N = N_, g.K = K_, g.epi = E ? kEpiMulE : kEpiNone, g.tf32 = N.tf32;
+      if (N.tf32 && Bt) g.B = Bt, g.ldb = ldbt, g.b_kn = 0;
       return gemm(g, st, launches);
     };
     float* bufs[2] = {S.hA, S.hB};
     const int wl = N.main[L - 1].n_in;
-    if ((rc = GB(S.rows.in + 64, 64 + d, d, N.main[L - 1].W, wl, wl, S.E[L - 2], wl, bufs[0], wl))) return rc;
+    // main_t[l] = W_l^T is [n_in][n_out]: row n (an input of layer l) holds the K = n_out weights the VJP contracts
+    if ((rc = GB(S.rows.in + 64, 64 + d, d, N.main[L - 1].W, wl, wl, S.E[L - 2], wl, bufs[0], wl, N.main_t[L - 1], d)))
+      return rc;
     const float* cur = bufs[0];
     int ld = wl, b = 1;
     for (int l = L - 2; l >= 1; --l) {
       const int win = N.main[l].n_in, wout = N.main[l].n_out;
-      if ((rc = GB(cur, ld, wout, N.main[l].W, win, win, S.E[l - 1], win, bufs[b], win))) return rc;
+      if ((rc = GB(cur, ld, wout, N.main[l].W, win, win, S.E[l - 1], win, bufs[b], win, N.main_t[l], wout))) return rc;
       cur = bufs[b], ld = win, b ^= 1;
     }
     const int w0 = N.main[0].n_out;
-    if ((rc = GB(cur, ld, w0, N.main[0].W + 64, 64 + d, d, nullptr, 0, S.jtx, d))) return rc;
+    if ((rc = GB(cur, ld, w0, N.main[0].W + 64, 64 + d, d, nullptr, 0, S.jtx, d,
+                 N.main_t[0] ? N.main_t[0] + (size_t)64 * w0 : nullptr, w0)))
+      return rc;
   }
   return DPI_OK;
 }

@@ -120,6 +120,8 @@ int gemm(const GemmArgs& g, cudaStream_t st, int64_t* launches);
 // TF32 tcgen05 GEMM (dpi_gemm_tc.cu): same arguments and epilogues; K % 32 == 0, no a_km, R >= 128, N >= 64
 bool gemm_tf32_eligible(const GemmArgs& g);
 int gemm_tf32(const GemmArgs& g, cudaStream_t st, int64_t* launches);
+// WT [cols][rows] = W [rows][cols]^T
+int gemm_transpose(const float* W, int rows, int cols, float* WT, cudaStream_t st);
 
 // ---- HJB / PISGradNet, fp32 batched-GEMM pipeline (dpi_hjb.cu) -------------------------------------------
 // Weight pointers are the caller's torch-layout tensors (W [n_out, n_in] row-major), used in place.
@@ -130,6 +132,7 @@ struct PisDev {
   const float* phase;  // [64]
   const float* coeff;  // [64]
   int tf32;            // 1: eligible GEMMs on the tensor cores (TF32 operands, fp32 accumulate; dpi_gemm_tc.cu)
+  const float* main_t[DPI_MAX_LINEAR];  // main[l].W transposed ([n_in][n_out]): K-major operands for the VJP GEMMs
 };
 int64_t hjb_scratch_floats(const PisDev& net, int d, int64_t rows);
 int64_t hjb_points_per_chunk(const PisDev& net, int d, int M_I, int64_t budget_bytes);
