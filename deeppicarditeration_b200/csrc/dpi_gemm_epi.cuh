@@ -32,6 +32,20 @@ __device__ __forceinline__ void gemm_epilogue4(const GemmArgs& g, int64_t row, i
         if (col + j < N) v[j] *= __ldg(ep + j);
     }
   }
+  if (g.epi == kEpiMulDElu) {  // the forward pass kept h = ELU(z) only: e^z = h + 1 where h <= 0
+    const float* ep = g.E + row * (int64_t)g.lde + col;
+    float h[4] = {1.f, 1.f, 1.f, 1.f};
+    if (full && e_vec) {
+      const float4 e = __ldg(reinterpret_cast<const float4*>(ep));
+      h[0] = e.x, h[1] = e.y, h[2] = e.z, h[3] = e.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (col + j < N) h[j] = __ldg(ep + j);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] *= (h[j] > 0.f) ? 1.f : h[j] + 1.f;
+  }
   if (g.epi == kEpiKeepMulE) {  // C = acc (pre-activation tangent), D = acc * E (tangent through the ELU)
     const float* ep = g.E + row * (int64_t)g.lde + col;
 #pragma unroll

@@ -606,14 +606,14 @@ int eval_rows(const PisDev& N, int d, const Scratch& S, int64_t R, cudaStream_t 
   // nn_module forward (solution.py:195-203), keeping ELU' of every hidden layer for the VJP
   const int L = N.n_main;
   {
+    // every hidden activation h_l = ELU(z_l) is kept in S.E[l]: the VJP recovers ELU'(z_l) from it (h > 0 ? 1 : h + 1),
+    // so a layer writes one tensor, not two
     const float* cur = S.rows.in;
     int ld = 64 + d;
-    float* bufs[2] = {S.hA, S.hB};
     for (int l = 0; l < L - 1; ++l) {
-      float* out = bufs[l & 1];
       const int w = N.main[l].n_out;
-      if ((rc = G(cur, ld, N.main[l], w, out, w, kEpiBiasEluD, S.E[l], w))) return rc;
-      cur = out, ld = w;
+      if ((rc = G(cur, ld, N.main[l], w, S.E[l], w, kEpiBiasElu))) return rc;
+      cur = S.E[l], ld = w;
     }
     if ((rc = G(cur, ld, N.main[L - 1], d, S.nout, d, kEpiBias))) return rc;
   }
@@ -624,7 +624,7 @@ int eval_rows(const PisDev& N, int d, const Scratch& S, int64_t R, cudaStream_t 
                   int ldc, const float* Bt = nullptr, int ldbt = 0) {
       GemmArgs g{};
       g.A = A, g.lda = lda, g.B = Bp, g.ldb = ldb, g.b_kn = 1, g.E = E, g.lde = lde, g.C = C, g.ldc = ldc;
-      g.R = R, g.N = N_, g.K = K_, g.epi = E ? kEpiMulE : kEpiNone, g.tf32 = N.tf32;
+      g.R = R, g.N = N_, g.K = K_, g.epi = E ? kEpiMulDElu : kEpiNone, g.tf32 = N.tf32;
       if (N.tf32 && Bt) g.B = Bt, g.ldb = ldbt, g.b_kn = 0;
       return gemm(g, st, launches);
     };

@@ -94,7 +94,8 @@ enum GemmEpi : int {
   kEpiBiasElu = 2,   // C = ELU(acc + bias)
   kEpiBiasEluD = 3,  // C = ELU(acc + bias), D = ELU'(acc + bias)
   kEpiMulE = 4,      // C = acc * E        (VJP through an ELU: cotangent times the stored ELU')
-  kEpiKeepMulE = 5   // C = acc, D = acc * E   (JVP through an ELU, keeping the pre-activation tangent)
+  kEpiKeepMulE = 5,  // C = acc, D = acc * E   (JVP through an ELU, keeping the pre-activation tangent)
+  kEpiMulDElu = 6    // C = acc * ELU'(z) with E = the stored ACTIVATION h = ELU(z): ELU' = h > 0 ? 1 : h + 1
 };
 struct GemmArgs {
   const float* A;
