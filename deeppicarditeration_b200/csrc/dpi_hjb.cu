@@ -162,11 +162,15 @@ __global__ void __launch_bounds__(kGemmThreads, 2) sgemm_kernel(const GemmArgs g
 // Small problems (the regression step: a few hundred rows, 128-wide layers): 64x64x16 tiles, 4x4 per thread, optional
 // split-K over gridDim.z with partials [z][R][N] in g.ws (epilogue kEpiNone only; summed by splitk_reduce_kernel in a
 // fixed order, so the result does not depend on scheduling).
-constexpr int SM_T = 64, SM_K = 32, kLdsS = SM_T + 4;  // K step 32: these launches are latency bound, fewer round trips
+// K step 128: these launches are latency bound (a 512 x 128 x 128 problem is 16 CTAs), so a CTA fetches its whole K
+// panel in one round trip (32 independent 16-byte loads per thread) instead of one trip per 16 or 32 columns
+constexpr int SM_T = 64, SM_K = 128, kLdsS = SM_T + 4;
+constexpr size_t kSmallSmemBytes = 2 * 2 * (size_t)SM_K * kLdsS * sizeof(float);  // As[2], Bs[2]
 constexpr int SM_KH = SM_K / 16;
 __global__ void __launch_bounds__(256) sgemm_small_kernel(const GemmArgs g, int k_per_split) {
-  __shared__ __align__(16) float As[2][SM_K][kLdsS];
-  __shared__ __align__(16) float Bs[2][SM_K][kLdsS];
+  extern __shared__ __align__(16) float sm_small[];
+  float (*As)[SM_K][kLdsS] = reinterpret_cast<float (*)[SM_K][kLdsS]>(sm_small);
+  float (*Bs)[SM_K][kLdsS] = As + 2;
   const int t = threadIdx.x;
   const int64_t r0 = (int64_t)blockIdx.x * SM_T;
   const int n0 = blockIdx.y * SM_T;
@@ -237,7 +241,7 @@ __global__ void __launch_bounds__(256) sgemm_small_kernel(const GemmArgs g, int 
   for (int kt = 0; kt < nk; ++kt) {
     const int buf = kt & 1;
     if (kt + 1 < nk) fetch(kbeg + (kt + 1) * SM_K);
-#pragma unroll
+#pragma unroll 16
     for (int kk = 0; kk < SM_K; ++kk) {
       const float4 a4 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
       const float4 b4 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
@@ -302,7 +306,12 @@ int gemm_impl(const GemmArgs& g, cudaStream_t st, int64_t* launches) {
     const int kps = ((g.K + splits - 1) / splits + SM_K - 1) / SM_K * SM_K;
     splits = (g.K + kps - 1) / kps;
     dim3 grid((unsigned)((g.R + SM_T - 1) / SM_T), (unsigned)((g.N + SM_T - 1) / SM_T), (unsigned)splits);
-    sgemm_small_kernel<<<grid, 256, 0, st>>>(g, kps);
+    static bool attr_set = false;
+    if (!attr_set) {
+      DPI_CUDA_CHECK(cudaFuncSetAttribute(sgemm_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSmemBytes));
+      attr_set = true;
+    }
+    sgemm_small_kernel<<<grid, 256, kSmallSmemBytes, st>>>(g, kps);
     DPI_CUDA_CHECK(cudaGetLastError());
     if (launches) *launches += 1;
     if (splits > 1) {
