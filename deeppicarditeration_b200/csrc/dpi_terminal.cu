@@ -84,8 +84,11 @@ struct Payoff<DPI_EQ_OU> {
 };
 
 // ---------------------------------------------------------------------------------------------
+#ifndef DPI_TERM_MINBLOCKS
+#define DPI_TERM_MINBLOCKS 1
+#endif
 template <int EQ, int NSLOT, bool DET>
-__global__ void __launch_bounds__(kTermThreads)
+__global__ void __launch_bounds__(kTermThreads, DPI_TERM_MINBLOCKS)
 terminal_kernel(const ProblemDev P, const float* __restrict__ tx, int M_T, const PhiloxKeys keys, int64_t point_base,
                 const float* __restrict__ zT, float* __restrict__ y) {
   using PO = Payoff<EQ>;
