@@ -60,6 +60,8 @@ struct dpi_handle {
   // unit partial sums of the tensor-core path
   float* partG = nullptr;
   float* partF = nullptr;
+  void* tc_zring = nullptr;  // increment ring of the chunked tensor-core kernel (tc_zring_bytes)
+  size_t tc_zring_size = 0;
   int64_t part_units = 0;
   // staging for the *_host entry points
   float* stage_tx = nullptr;
@@ -212,6 +214,7 @@ int dpi_destroy(dpi_handle* h) {
   if (h->stage_tx) cudaFree(h->stage_tx);
   if (h->stage_y) cudaFree(h->stage_y);
   if (h->partG) cudaFree(h->partG);
+  if (h->tc_zring) cudaFree(h->tc_zring);
   if (h->partF) cudaFree(h->partF);
   if (h->hjb_scratch) cudaFree(h->hjb_scratch);
   if (h->train_m) cudaFree(h->train_m);
@@ -558,6 +561,12 @@ int dpi_label_gen(dpi_handle* h, const float* tx, int64_t n, const dpi_label_con
       if (chunk < 1) chunk = 1;
       if (chunk > n) chunk = n;
       if ((rc = ensure_parts(h, chunk * upp))) return rc;
+      if (tc_zring_bytes(h->tc) > h->tc_zring_size) {
+        if (h->tc_zring) cudaFree(h->tc_zring);
+        h->tc_zring = nullptr, h->tc_zring_size = 0;
+        DPI_CUDA_CHECK(cudaMalloc(&h->tc_zring, tc_zring_bytes(h->tc)));
+        h->tc_zring_size = tc_zring_bytes(h->tc);
+      }
       const int d = P.nx;
       for (int64_t p0 = 0; p0 < n; p0 += chunk) {
         const int64_t np = (n - p0 < chunk) ? n - p0 : chunk;
@@ -565,7 +574,7 @@ int dpi_label_gen(dpi_handle* h, const float* tx, int64_t n, const dpi_label_con
                                 draws ? draws->u_s + p0 * cfg->M_I : nullptr,
                                 draws ? draws->zS + p0 * (int64_t)cfg->M_I * d : nullptr, h->fb + p0,
                                 h->c0 + p0 * h->mlp.HP, bound, h->partG, h->partF,
-                                reinterpret_cast<int*>(h->partF + h->part_units * kTcPartFFloatsPerUnit),
+                                reinterpret_cast<int*>(h->partF + h->part_units * kTcPartFFloatsPerUnit), h->tc_zring,
                                 y + p0 * (1 + d), st);
         if (rc) return rc;
         h->launches += 2;

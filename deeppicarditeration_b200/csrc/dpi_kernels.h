@@ -82,7 +82,9 @@ constexpr int64_t kTcPartFFloatsPerUnit = 8;  // [slot][lane quarter]
 // partG [n*units][32][128], partF [n*units][8]: scratch for the unit partial sums
 int launch_cha_tc_path(const ProblemDev& P, const TcNetDev& net, const float* tx, int64_t n, int M_I, uint64_t seed,
                        int64_t base, const float* u_s, const float* zS, const float* fb, const float* c0, float bound,
-                       float* partG, float* partF, int* unit_counter, float* y, cudaStream_t st);
+                       float* partG, float* partF, int* unit_counter, void* zring, float* y, cudaStream_t st);
+// bytes of the increment ring of the chunked (d > 128) tensor-core kernel: 4 tiles x chunks x 32 KB per SM
+inline size_t tc_zring_bytes(const TcNetDev& net) { return net.nchunks > 1 ? (size_t)net.num_sms * 4 * net.nchunks * 32768 : 0; }
 // D[128x128] = A[128x128] . B[128x128]^T (fp32 row-major device buffers, rounded to bf16) through tcgen05
 int tc_umma_selftest(const float* A, const float* B, float* D, cudaStream_t st);
 

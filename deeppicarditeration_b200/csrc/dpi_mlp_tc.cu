@@ -91,6 +91,7 @@ struct TcArgs {
   const float* c0;  // [n][128]
   float* partG;     // [units][16][128]
   float* partF;     // [units][8]
+  uint4* zring;     // MULTI only: [grid][4 tiles][chunks][128 rows][16 octets] fp16x8 increments awaiting their coefficients
   int M_I;
   int units_per_point;
   int tiles_per_point;
@@ -280,9 +281,9 @@ struct TileCursor {
 // MULTI: 128 < d <= 1024.  The first layer is accumulated over ceil(d/128) chunks of 128 input dims: per chunk the
 // producers store the increments of those dims into the slot's hV, the TMA warp streams the matching W1 image into
 // hT, the MMA issuer adds the chunk's eight k-steps to the value accumulators and commits kBarSlotFree so that the
-// next chunk may overwrite the buffers.  The increments of a tile no longer fit in registers (8 x as many), so for
-// the Bismut sums they are drawn a second time from the same Philox counters once the coefficients are known (the
-// generator is counter based: no state to replay), warp w taking chunk w.
+// next chunk may overwrite the buffers.  The increments of a tile no longer fit in registers (8 x as many), so
+// they also go (fp16) to a per-CTA ring in global memory and are read back for the Bismut sums once the coefficients
+// are known, warp w taking chunk w.
 template <int ITEMS, bool DET, bool MULTI>
 __global__ void __launch_bounds__(kTcThreads, 1)
 cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcConsts C,
@@ -622,7 +623,7 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
     // =================================== increment producers ===================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kProdRegs));
     if constexpr (MULTI) {
-      // ---- 128 < d <= 1024: chunked first layer, increments drawn twice (see the kernel comment) ----
+      // ---- 128 < d <= 1024: chunked first layer, increments kept in a global ring (see the kernel comment) ----
       const int tl_id = threadIdx.x - 32 * kProdWarp0;
       const int o = tl_id & 15, c = tl_id >> 4;  // octet inside the 128-dim chunk, row class: rows c + 16 i
       const int pw = tl_id >> 5;                 // producer warp 0..7 = the chunk whose Bismut sums it owns
@@ -657,7 +658,14 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
         return ok ? make_uint4(pack_f16x2(za.x, za.y), pack_f16x2(za.z, za.w), pack_f16x2(zb.x, zb.y), pack_f16x2(zb.z, zb.w))
                   : make_uint4(0u, 0u, 0u, 0u);
       };
-      // Bismut accumulation of a finished tile: warp pw re-draws chunk pw (lane = octet x row parity, 64 rows each)
+      // The fp16 increments of the tiles whose coefficients are outstanding wait in a per-CTA ring in global memory
+      // (4 tiles x chunks x 32 KB, L2 resident for the most part): written once by the generating threads, read
+      // back by warp pw for chunk pw (lane = octet x row parity, 64 rows each).  Re-drawing them from the Philox
+      // counters instead cost as much as the first draw -- and the generator is what bounds this kernel.
+      // Four slots although only three tiles are ever live: a warp that is done with the sums of tile j-2 starts
+      // writing tile j+1 while a slower warp may still be reading tile j-2 (three slots would alias them); the
+      // per-chunk increments barrier keeps the warps within one tile of each other.
+      uint4* const zring = A.zring + (size_t)blockIdx.x * ((size_t)4 * nch * 2048);
       auto bismut = [&](uint32_t jt, int64_t ut, int mt0, bool last) {
         const uint32_t cbuf = jt % 3u;
         mbar_wait(bar(kBarCoef + (int)cbuf), (ph_coef >> cbuf) & 1u, 40);
@@ -665,25 +673,24 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
         const int bo = lane & 15, rh = lane >> 4, oct = 16 * pw + bo;
         if (pw < nch && 8 * oct < d) {
           const float* cf_s = coef_s + cbuf * 128u;
-          const int64_t pp = ut / UP;
-#pragma unroll 2
+          const uint4* zr = zring + ((size_t)(jt & 3u) * nch + pw) * 2048 + bo;
+#pragma unroll 4
           for (int i = 0; i < 64; ++i) {
             const int rr = rh + 2 * i;
             const float cf = cf_s[rr];
-            if (cf != 0.f) {  // rows past M_I (and exact zeros) contribute nothing
-              const uint4 z = draw8(pp, mt0 + rr, oct, true);
-              const float2 p0 = h2_unpack(z.x), p1 = h2_unpack(z.y), p2 = h2_unpack(z.z), p3 = h2_unpack(z.w);
-              Ga.x = fmaf(cf, p0.x, Ga.x);
-              Ga.y = fmaf(cf, p0.y, Ga.y);
-              Ga.z = fmaf(cf, p1.x, Ga.z);
-              Ga.w = fmaf(cf, p1.y, Ga.w);
-              Gb.x = fmaf(cf, p2.x, Gb.x);
-              Gb.y = fmaf(cf, p2.y, Gb.y);
-              Gb.z = fmaf(cf, p3.x, Gb.z);
-              Gb.w = fmaf(cf, p3.y, Gb.w);
-            }
+            const uint4 z = __ldcg(zr + rr * 16);
+            const float2 p0 = h2_unpack(z.x), p1 = h2_unpack(z.y), p2 = h2_unpack(z.z), p3 = h2_unpack(z.w);
+            Ga.x = fmaf(cf, p0.x, Ga.x);
+            Ga.y = fmaf(cf, p0.y, Ga.y);
+            Ga.z = fmaf(cf, p1.x, Ga.z);
+            Ga.w = fmaf(cf, p1.y, Ga.w);
+            Gb.x = fmaf(cf, p2.x, Gb.x);
+            Gb.y = fmaf(cf, p2.y, Gb.y);
+            Gb.z = fmaf(cf, p3.x, Gb.z);
+            Gb.w = fmaf(cf, p3.y, Gb.w);
           }
         }
+        (void)mt0;
         if (last) {  // unit partial: [chunk][row parity][128]
           if (pw < nch) {
             float* gp_ = A.partG + ut * kTcPartGFloatsPerUnit + (int64_t)(pw * 2 + rh) * 128 + 8 * bo;
@@ -724,7 +731,13 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(kBarZFull + s));
+            {  // keep the chunk for the Bismut sums (rows c + 16 i, octet o of ring slot j % 4)
+              uint4* zw = zring + ((size_t)(j & 3u) * nch + cch) * 2048 + o;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) __stcg(zw + (c + 16 * i) * 16, zc[i]);
+            }
           }
+          __threadfence_block();
           if (pending == 2) bismut(j2, u2, m2, last2);
           j2 = j1, u2 = u1, m2 = m1, last2 = last1;
           j1 = j, u1 = u, m1 = m0, last1 = (tl == tiles - 1);
@@ -1076,7 +1089,7 @@ int64_t tc_units_per_point(int M_I) {
 
 int launch_cha_tc_path(const ProblemDev& P, const TcNetDev& N, const float* tx, int64_t n, int M_I, uint64_t seed,
                        int64_t base, const float* u_s, const float* zS, const float* fb, const float* c0, float bound,
-                       float* partG, float* partF, int* unit_counter, float* y, cudaStream_t st) {
+                       float* partG, float* partF, int* unit_counter, void* zring, float* y, cudaStream_t st) {
   if (n <= 0) return DPI_OK;
   if (n * tc_units_per_point(M_I) > 0x7fffff00LL) {
     fprintf(stderr, "dpi tc: too many units in one launch\n");
@@ -1084,6 +1097,8 @@ int launch_cha_tc_path(const ProblemDev& P, const TcNetDev& N, const float* tx, 
   }
   TcArgs A{};
   A.unit_counter = unit_counter;
+  A.zring = reinterpret_cast<uint4*>(zring);
+  if (N.nchunks > 1 && !zring) return DPI_ERR_INVALID;
   DPI_CUDA_CHECK(cudaMemsetAsync(unit_counter, 0, sizeof(int), st));
   A.W = N.W;
   A.tx = tx;

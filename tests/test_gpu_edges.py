@@ -69,9 +69,10 @@ def test_burgers_1000d_sweep_shape_matches_oracle_on_replayed_draws():
 
 @pytest.mark.parametrize("nx", [200, 1000, 1024])
 def test_chunked_tensor_core_path_tracks_fp32_on_the_same_philox_draws(nx):
-    """128 < d <= 1024 on tcgen05: the first layer is accumulated over ceil(d/128) chunks and the increments are drawn
-    twice from the same Philox counters (operand tile, Bismut sums).  Same counters as the fp32 kernel, so the two
-    differ only by operand rounding; bitwise shard invariance; ragged sample counts."""
+    """128 < d <= 1024 on tcgen05: the first layer is accumulated over ceil(d/128) chunks and the increments wait for
+    their Bismut coefficients in a per-CTA ring in global memory.  Same Philox counters as the fp32 kernel, so the two
+    differ only by operand rounding; bitwise shard invariance (which is also what catches a race on the ring);
+    ragged sample counts."""
     eq = orc.Cha(nx, 1.0, 5.0, 1.0)
     net = orc.make_mlp(1 + nx, [128] * 4, seed=11, gain=1.3)
     e = _eng(eq, net)
