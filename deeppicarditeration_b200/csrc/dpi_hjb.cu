@@ -481,33 +481,36 @@ __global__ void __launch_bounds__(256) hjb_final_kernel(const ProblemDev P, cons
 // MC reduction (data.py:514-527): y[p] += mean_m dT (f_m - f_b) (1, Z_m / (a_m)) + (dT f_b, 0); clip (data.py:222).
 // One CTA per point, thread j owns gradient component j; fixed summation order.
 // ------------------------------------------------------------------------------------------------------------
-// Four groups of 128 threads take the samples in tiles of 128: a group first writes the tile's 128 coefficients to
-// shared memory (one division per sample instead of one per (sample, component)), then thread j of the group adds
-// coef_m Z_mj over the tile; the four group sums are added in a fixed order.
-constexpr int kRedGroups = 4;
+// blockIdx.y slices the samples (kRedSlices slices per point, so that a chunk of a few dozen points still fills the
+// GPU); inside a CTA four groups of 128 threads take the slice's samples in tiles of 128: a group first writes the
+// tile's 128 coefficients to shared memory (one division per sample instead of one per (sample, component)), then
+// thread j of the group adds coef_m Z_mj over the tile.  Slice partials [point][slice][1 + d] are added in a fixed
+// order by hjb_reduce_finish_kernel.
+constexpr int kRedGroups = 4, kRedSlices = 8;
 __global__ void __launch_bounds__(128 * kRedGroups)
 hjb_reduce_kernel(const ProblemDev P, const float* __restrict__ tx, int M_I, const float* __restrict__ f,
-                  const float* __restrict__ z, const float* __restrict__ sa, float bound, float* __restrict__ y) {
+                  const float* __restrict__ z, const float* __restrict__ sa, float* __restrict__ part) {
   __shared__ float coef_s[kRedGroups][128];
-  __shared__ float part[kRedGroups][1024 + 1];
+  __shared__ float gpart[kRedGroups][1024 + 1];
+  __shared__ float fpart[kRedGroups * 4];
   const int64_t p = blockIdx.x;
+  const int slice = blockIdx.y;
   const int d = P.nx, rpp = M_I + 1;
   const int gq = threadIdx.x >> 7, tj = threadIdx.x & 127;
   const float dT = P.T - __ldg(tx + p * (int64_t)(1 + d));
   const int64_t rb = p * rpp;
   const float fb = __ldg(f + rb + M_I);
-  const float invM = 1.f / (float)M_I;
-  const bool clip = bound > 0.f && isfinite(bound);
-  float* yp = y + p * (int64_t)(1 + d);
   float G[8], fs = 0.f;  // components tj + 128 k (d <= 1024)
 #pragma unroll
   for (int k = 0; k < 8; ++k) G[k] = 0.f;
   const int n_tiles = (M_I + 127) / 128;
-  for (int tile = gq; tile - gq < n_tiles; tile += kRedGroups) {  // same trip count for every group (barriers inside)
+  const int t_per = (n_tiles + kRedSlices - 1) / kRedSlices;
+  const int t_beg = slice * t_per, t_end = min(n_tiles, t_beg + t_per);
+  for (int tile = t_beg + gq; tile - gq < t_end; tile += kRedGroups) {  // same trip count for every group
     const int m0 = tile * 128;
     const int m = m0 + tj;
     float cf = 0.f;
-    if (m < M_I) {
+    if (tile < t_end && m < M_I) {
       const float fm = __ldg(f + rb + m);
       cf = dT * (fm - fb) / __ldg(sa + 2 * (rb + m) + 1);
       fs += fm;
@@ -515,7 +518,7 @@ hjb_reduce_kernel(const ProblemDev P, const float* __restrict__ tx, int M_I, con
     __syncthreads();  // the previous tile's coefficients have been consumed
     coef_s[gq][tj] = cf;
     __syncthreads();
-    const int cnt = min(128, M_I - m0);
+    const int cnt = (tile < t_end) ? min(128, M_I - m0) : 0;
     for (int i = 0; i < cnt; ++i) {
       const float c = coef_s[gq][i];
       const float* zr = z + (rb + m0 + i) * d;
@@ -527,24 +530,37 @@ hjb_reduce_kernel(const ProblemDev P, const float* __restrict__ tx, int M_I, con
     }
   }
 #pragma unroll
-  for (int k = 0; k < 8; ++k) part[gq][tj + 128 * k] = G[k];
+  for (int k = 0; k < 8; ++k) gpart[gq][tj + 128 * k] = G[k];
   fs = warp_sum(fs);
-  __shared__ float fpart[kRedGroups * 4];
   if ((threadIdx.x & 31) == 0) fpart[threadIdx.x >> 5] = fs;
   __syncthreads();
+  float* out = part + (p * kRedSlices + slice) * (int64_t)(1 + d);
   for (int j = threadIdx.x; j < d; j += blockDim.x) {
     float Gs = 0.f;
-    for (int q = 0; q < kRedGroups; ++q) Gs += part[q][j];
-    float v = yp[1 + j] + Gs * invM;
-    if (clip) v = fminf(fmaxf(v, -bound), bound);
-    yp[1 + j] = v;
+    for (int q = 0; q < kRedGroups; ++q) Gs += gpart[q][j];
+    out[1 + j] = Gs;
   }
   if (threadIdx.x == 0) {
     float s = 0.f;
     for (int i = 0; i < kRedGroups * 4; ++i) s += fpart[i];
-    float v = yp[0] + dT * s * invM;
+    out[0] = s;
+  }
+}
+__global__ void __launch_bounds__(128)
+hjb_reduce_finish_kernel(const ProblemDev P, const float* __restrict__ tx, int M_I, const float* __restrict__ part,
+                         float bound, float* __restrict__ y) {
+  const int64_t p = blockIdx.x;
+  const int d = P.nx;
+  const float dT = P.T - __ldg(tx + p * (int64_t)(1 + d));
+  const float invM = 1.f / (float)M_I;
+  const bool clip = bound > 0.f && isfinite(bound);
+  float* yp = y + p * (int64_t)(1 + d);
+  for (int j = threadIdx.x; j < 1 + d; j += blockDim.x) {
+    float s = 0.f;
+    for (int q = 0; q < kRedSlices; ++q) s += part[(p * kRedSlices + q) * (int64_t)(1 + d) + j];
+    float v = yp[j] + (j == 0 ? dT * s : s) * invM;
     if (clip) v = fminf(fmaxf(v, -bound), bound);
-    yp[0] = v;
+    yp[j] = v;
   }
 }
 
@@ -688,10 +704,12 @@ int launch_hjb_paths(const ProblemDev& P, const PisDev& N, const float* tx, int6
     F.in = S.rows.in, F.nout = S.nout, F.jtx = S.jtx, F.sraw = S.sraw, F.sa = S.rows.sa, F.f = S.f, F.R = R;
     hjb_final_kernel<<<(unsigned)((R + 7) / 8), 256, 0, st>>>(P, F);
     DPI_CUDA_CHECK(cudaGetLastError());
-    hjb_reduce_kernel<<<(unsigned)np, 128 * kRedGroups, 0, st>>>(P, tx + p0 * (1 + d), M_I, S.f, S.rows.z, S.rows.sa, bound,
-                                                    y + p0 * (1 + d));
+    // slice partials live in hA (free once the VJP is done): np x kRedSlices x (1 + d) floats
+    hjb_reduce_kernel<<<dim3((unsigned)np, kRedSlices), 128 * kRedGroups, 0, st>>>(P, tx + p0 * (1 + d), M_I, S.f, S.rows.z,
+                                                                                S.rows.sa, S.hA);
+    hjb_reduce_finish_kernel<<<(unsigned)np, 128, 0, st>>>(P, tx + p0 * (1 + d), M_I, S.hA, bound, y + p0 * (1 + d));
     DPI_CUDA_CHECK(cudaGetLastError());
-    *launches += 2;
+    *launches += 3;
   }
   return DPI_OK;
 }
