@@ -107,8 +107,20 @@ __device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5
 __device__ __forceinline__ void box_muller16(uint32_t w, float& z0, float& z1) {
   // 16-bit integer -> float through the mantissa (1 + k 2^-16 in [1, 2)): shift, mask|or, add -- no int-to-float
   // conversion instruction, which would share the quarter-rate XU pipe with the four MUFU ops below
+#ifdef DPI_BM_LOP3
+  // (x & mask) | one in ONE LOP3: both constants have to sit in registers for that (an instruction takes a single
+  // immediate), so they come through an opaque asm the compiler cannot fold back into immediates
+  uint32_t kmask, kone;
+  asm("mov.b32 %0, 0x007FFF80;" : "=r"(kmask));
+  asm("mov.b32 %0, 0x3F800000;" : "=r"(kone));
+  uint32_t br, ba;
+  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(br) : "r"(w << 7), "r"(kmask), "r"(kone));
+  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(ba) : "r"(w >> 9), "r"(kmask), "r"(kone));
+  const float xr = __uint_as_float(br), xa = __uint_as_float(ba);
+#else
   const float xr = __uint_as_float(((w << 7) & 0x007FFF80u) | 0x3F800000u);
   const float xa = __uint_as_float(((w >> 9) & 0x007FFF80u) | 0x3F800000u);
+#endif
   const float u = xr - 0.99999237060546875f;                 // (k + 1/2) 2^-16
 #ifdef DPI_DBG_BM_NOXU  // sensitivity builds only: same instruction count without the four MUFU ops (wrong numbers)
   const float r = fmaf(-1.3862943611198906f, fmaf(u, 0.5f, 0.25f), 2.f) * 0.7f;

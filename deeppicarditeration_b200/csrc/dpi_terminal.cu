@@ -6,6 +6,9 @@
 // increments per 128-dim slot (one Philox block) in registers (or streams them with one coalesced 16-byte load in
 // deterministic mode), the payoff statistics are warp-shuffle reduced, and the Bismut-weighted sums stay in
 // registers until one label row per point is written.  HBM traffic: (1+nx) floats in, (1+nx) floats out per point.
+// single-LOP3 mantissa assembly in Box-Muller: 2 % faster here; in the tensor-core kernel the two extra registers of
+// the constants push its producers into spills, so it is a per-translation-unit switch
+#define DPI_BM_LOP3
 #include "dpi_common.cuh"
 #include "dpi_kernels.h"
 
