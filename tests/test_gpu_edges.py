@@ -92,6 +92,20 @@ def test_chunked_tensor_core_path_tracks_fp32_on_the_same_philox_draws(nx):
     e.close()
 
 
+def test_chunked_tensor_core_path_is_reproducible_run_to_run():
+    """The increment ring of the d > 128 kernel is shared between warps (written by the generating threads, read by
+    the warp that owns the chunk's Bismut sums): a race on it would show up as run-to-run differences.  Many tiles
+    per CTA, several repetitions, bitwise equality."""
+    eq = orc.Cha(300, 1.0, 5.0, 1.0)
+    e = _eng(eq, orc.make_mlp(301, [128] * 4, seed=2, gain=1.2))
+    tx = e.sample_tx(600, seed=5)  # 2 units per point at M_I = 2500 -> ~8 units = 80 tiles per CTA
+    y0 = e.label_gen(tx, 16, 2500, precision="f16", seed=4)
+    assert torch.isfinite(y0).all()
+    for _ in range(4):
+        assert torch.equal(e.label_gen(tx, 16, 2500, precision="f16", seed=4), y0)
+    e.close()
+
+
 def test_large_call_is_chunked_transparently():
     """More points than the unit-partial scratch holds at once (256 MB): the call is split inside the library and the
     labels equal those of explicit shards."""
