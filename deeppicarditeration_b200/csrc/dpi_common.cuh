@@ -104,23 +104,31 @@ __device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5
 // The pair (z0, z1) takes 2^32 distinct values; the radius is a midpoint rule with 65536 equiprobable cells
 // (|z| <= 4.86: the missing tail has probability 1.2e-6, its contribution to E[z^2] is 3e-5), the angle an equispaced
 // rule with 65536 nodes, which is spectrally accurate for the smooth periodic integrands it feeds.
+#ifdef DPI_BM_LOP3
+constexpr bool kBmLop3Default = true;
+#else
+constexpr bool kBmLop3Default = false;
+#endif
+template <bool LOP3 = kBmLop3Default>
 __device__ __forceinline__ void box_muller16(uint32_t w, float& z0, float& z1) {
   // 16-bit integer -> float through the mantissa (1 + k 2^-16 in [1, 2)): shift, mask|or, add -- no int-to-float
   // conversion instruction, which would share the quarter-rate XU pipe with the four MUFU ops below
-#ifdef DPI_BM_LOP3
-  // (x & mask) | one in ONE LOP3: both constants have to sit in registers for that (an instruction takes a single
-  // immediate), so they come through an opaque asm the compiler cannot fold back into immediates
-  uint32_t kmask, kone;
-  asm("mov.b32 %0, 0x007FFF80;" : "=r"(kmask));
-  asm("mov.b32 %0, 0x3F800000;" : "=r"(kone));
-  uint32_t br, ba;
-  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(br) : "r"(w << 7), "r"(kmask), "r"(kone));
-  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(ba) : "r"(w >> 9), "r"(kmask), "r"(kone));
-  const float xr = __uint_as_float(br), xa = __uint_as_float(ba);
-#else
-  const float xr = __uint_as_float(((w << 7) & 0x007FFF80u) | 0x3F800000u);
-  const float xa = __uint_as_float(((w >> 9) & 0x007FFF80u) | 0x3F800000u);
-#endif
+  float xr, xa;
+  if constexpr (LOP3) {
+    // (x & mask) | one in ONE LOP3: both constants have to sit in registers for that (an instruction takes a single
+    // immediate), so they come through an opaque asm the compiler cannot fold back into immediates.  Same bits as
+    // the plain form; worth 2 % where the generator bounds the kernel and two registers are to spare.
+    uint32_t kmask, kone;
+    asm("mov.b32 %0, 0x007FFF80;" : "=r"(kmask));
+    asm("mov.b32 %0, 0x3F800000;" : "=r"(kone));
+    uint32_t br, ba;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(br) : "r"(w << 7), "r"(kmask), "r"(kone));
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(ba) : "r"(w >> 9), "r"(kmask), "r"(kone));
+    xr = __uint_as_float(br), xa = __uint_as_float(ba);
+  } else {
+    xr = __uint_as_float(((w << 7) & 0x007FFF80u) | 0x3F800000u);
+    xa = __uint_as_float(((w >> 9) & 0x007FFF80u) | 0x3F800000u);
+  }
   const float u = xr - 0.99999237060546875f;                 // (k + 1/2) 2^-16
 #ifdef DPI_DBG_BM_NOXU  // sensitivity builds only: same instruction count without the four MUFU ops (wrong numbers)
   const float r = fmaf(-1.3862943611198906f, fmaf(u, 0.5f, 0.25f), 2.f) * 0.7f;
@@ -145,13 +153,14 @@ __device__ __forceinline__ void normal8(uint64_t seed, uint64_t point, uint32_t 
   box_muller16(r.w, zb.z, zb.w);
 }
 
+template <bool LOP3 = kBmLop3Default>
 __device__ __forceinline__ void normal8(const PhiloxKeys& K, uint64_t point, uint32_t stream, uint32_t sample,
                                         uint32_t block8, float4& za, float4& zb) {
   const uint4 r = philox_at(K, point, stream, sample, block8);
-  box_muller16(r.x, za.x, za.y);
-  box_muller16(r.y, za.z, za.w);
-  box_muller16(r.z, zb.x, zb.y);
-  box_muller16(r.w, zb.z, zb.w);
+  box_muller16<LOP3>(r.x, za.x, za.y);
+  box_muller16<LOP3>(r.y, za.z, za.w);
+  box_muller16<LOP3>(r.z, zb.x, zb.y);
+  box_muller16<LOP3>(r.w, zb.z, zb.w);
 }
 
 // normals of dims [4 q, 4 q + 4): half of a normal8 block.  For the kernels that are not bound by the generator and

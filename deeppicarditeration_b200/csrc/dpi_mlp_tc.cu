@@ -652,7 +652,7 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
             za = load_row4(row, 8 * oct, d, vec_ok);
             zb = load_row4(row, 8 * oct + 4, d, vec_ok);
           } else {
-            normal8(A.keys, (uint64_t)(A.point_base + pp), kStreamIntegral, (uint32_t)m, (uint32_t)oct, za, zb);
+            normal8<true>(A.keys, (uint64_t)(A.point_base + pp), kStreamIntegral, (uint32_t)m, (uint32_t)oct, za, zb);
           }
         }
         return ok ? make_uint4(pack_f16x2(za.x, za.y), pack_f16x2(za.z, za.w), pack_f16x2(zb.x, zb.y), pack_f16x2(zb.z, zb.w))
