@@ -87,11 +87,14 @@ struct Payoff<DPI_EQ_OU> {
 };
 
 // ---------------------------------------------------------------------------------------------
+#ifndef DPI_TERM_WIDE_SLOTS
+#define DPI_TERM_WIDE_SLOTS 8  // NSLOT from which the kernel is held to 128 registers (2 CTAs per SM): 12 % faster at d = 1000 despite 96 B of spills
+#endif
 #ifndef DPI_TERM_MINBLOCKS
 #define DPI_TERM_MINBLOCKS 1
 #endif
 template <int EQ, int NSLOT, bool DET>
-__global__ void __launch_bounds__(kTermThreads, DPI_TERM_MINBLOCKS)
+__global__ void __launch_bounds__(kTermThreads, (NSLOT >= DPI_TERM_WIDE_SLOTS) ? 2 : DPI_TERM_MINBLOCKS)
 terminal_kernel(const ProblemDev P, const float* __restrict__ tx, int M_T, const PhiloxKeys keys, int64_t point_base,
                 const float* __restrict__ zT, float* __restrict__ y) {
   using PO = Payoff<EQ>;
