@@ -484,7 +484,8 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
     // (slot 0, slot 1).  While the warps are busy with one slot the tensor pipe runs the other slot's layer, so
     // in steady state nobody waits; with four warps per slot (each slot on its own) the epilogue warps sat idle
     // 40 % of the time and a pass took twice as long.
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
+    if constexpr (kEpiRegs > 96) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
     const int q = warp & 3, h = warp >> 2;
     const int r = q * 32 + lane;
     const uint32_t tacc0 = tmem + ((uint32_t)(q * 32) << 16);
