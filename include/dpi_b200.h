@@ -59,7 +59,10 @@ typedef enum { DPI_NET_ZERO = 0, DPI_NET_MLP = 1, DPI_NET_PISGRAD = 2 } dpi_netw
  * tensor-core path with fp32 accumulation (within 1e-2 rel; measured 6e-5).  The tensor-core operands are IEEE fp16,
  * not bf16: three more mantissa bits at the same operand width, and the bias/ELU/ELU' epilogue runs in packed
  * fp16x2.  Its range limit is |log2(e) x pre-activation| < 6.5e4, far above anything a trained u_k produces.
- * DPI_PREC_BF16 is kept as an alias of the same path for callers written against the first revision. */
+ * DPI_PREC_BF16 is kept as an alias of the same path for callers written against the first revision.
+ * Which paths DPI_PREC_F16 selects: Cha with the MLP [1+d,128,128,128,128,1], d <= 1024 (chunked first layer above 128);
+ * GBM/SDGD with hidden width 64, v <= 127 (fp16 2-jets); PISGradNet/OU with its wide GEMMs on the tensor cores in
+ * TF32 (fp32 operands in memory, 10-bit mantissa in the multiply, fp32 accumulate).  Anything else: DPI_ERR_UNSUPPORTED. */
 typedef enum { DPI_PREC_FP32 = 0, DPI_PREC_F16 = 1, DPI_PREC_BF16 = 1 } dpi_precision;
 
 /* Equation parameters.  All array pointers are HOST pointers (tiny), copied by dpi_set_problem. */
