@@ -1,21 +1,32 @@
 #!/usr/bin/env python
 """bench.py — labelled collocation points/sec of the DPI Monte Carlo label generator on B200.
 
-One "step" = one pass of the hot path (terminal estimator + integral estimator with u_k value/tangent evaluation
-+ MC reduction) over one batch of synthetic collocation points.  Workload at N=1: BASELINE.json configs[1]
-(`scripts/burgers/base_100d_T1.0_w1.0_0.yaml`): Cha nx=100, MLP [101,128,128,128,128,1] ELU, M_T=M_I=4096,
-4096 points per step per GPU (one Picard iteration's DATA_SIZE).  Points shard across ranks with no data-path
-collective (weak scaling: every rank labels `--points` points per step; Philox counters are keyed by the global
-point index).
+One "step" = one pass of the hot path (terminal estimator + integral estimator with the u_k value/derivative
+evaluation + MC reduction) over one batch of synthetic collocation points.  Workloads (`--workload`), one per
+BASELINE.json config:
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--precision f16|fp32]
+  burgers100d   configs[0]/[1]  scripts/burgers/base_100d_T1.0_w{0.0,1.0}_0.yaml: Cha nx=100, MLP [101,128x4,1], M=4096,
+                                4096 points per step per GPU (one Picard iteration's DATA_SIZE)            [default]
+  hjb100d       configs[2]      scripts/hjb/base_100d_T1.0_w0.1_0.yaml: OU nx=100 (GMM K=5), PISGradNet 4x512, M=4096, 4096 pts
+  gbm100d       configs[3]      scripts/fully_nonlinear/case_1/base_100d_T1.0_w0.0_nov_0.yaml: GBM nx=100, MLP [101,64x3,1],
+                                M=1024, SDGD v=100, 2048 pts
+  burgers1000d  configs[4]      synthetic sweep: Cha nx=1000, MLP [1001,128x4,1], 2^20 points sharded over the GPUs
+                                (contiguous blocks), `--mc` in {256,512,1024,2048,4096} paths per point
+
+Points shard across ranks with no data-path collective; Philox counters are keyed by the global point index.
+`--scaling weak` (default for the 100d workloads): every rank labels `--points` points per step; `--scaling strong`:
+the GLOBAL point count is fixed and split over the ranks (always the case for burgers1000d).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload W] [--precision P]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Prints ONE JSON line (rank 0).  `value` is device-resident throughput; `e2e` goes through the host-buffer C-ABI
-call (`dpi_label_gen_host`: pinned host tx -> H2D -> kernels -> D2H y -> sync); `roofline` is the integral
-(MLP-over-paths) kernel timed by CUDA events on its own stream inside the same run; `cpu_baseline` is the CPU
-restatement of the reference (oracle/dpi_oracle.py, mode="autograd" = what the reference executes, fp64) timed on
-this box's host cores on a bounded sample.  `--impl reference` times only that CPU arm.
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput; `e2e` goes through the host-buffer C-ABI call
+(`dpi_label_gen_host`: pinned host tx -> H2D -> kernels -> D2H y -> sync -> label check); `roofline` is the integral
+(u_k over paths) stage timed by CUDA events on its own stream inside the same run, against the MEASURED bf16 peak:
+burst when the SM clock stayed at its maximum through the timed region, sustained otherwise (both fractions are
+printed); `cpu_baseline` is the CPU restatement of the reference's torch path (oracle/dpi_oracle.py,
+mode="autograd" = the ops the reference executes, fp64) on this box's host cores on a bounded sample.
+`--impl reference` times only that CPU arm.
 """
 from __future__ import annotations
 
@@ -36,31 +47,86 @@ METRIC = "labelled collocation points/sec"
 UNIT = "points/s"
 
 WORKLOADS = {
-    # name: (nx, hidden, M, default points per GPU per step, BASELINE config it restates)
-    "burgers100d": dict(nx=100, hidden=[128] * 4, M=4096, points=4096, cha_k=5.0,
+    "burgers100d": dict(eq="Cha", nx=100, net="mlp", hidden=[128] * 4, M=4096, points=4096, cha_k=5.0, v=0,
+                        precision="f16", scaling="weak", steps=50, cpu_points=32,
                         config="scripts/burgers/base_100d_T1.0_w1.0_0.yaml"),
-    "burgers1000d": dict(nx=1000, hidden=[128] * 4, M=256, points=16384, cha_k=5.0,
-                         config="synthetic Burgers 1000d DPI scaling sweep"),
+    "hjb100d": dict(eq="OU", nx=100, net="pisgrad", hidden=[512] * 4, M=4096, points=4096, v=0,
+                    precision="tf32", scaling="weak", steps=4, cpu_points=4,
+                    config="scripts/hjb/base_100d_T1.0_w0.1_0.yaml"),
+    "gbm100d": dict(eq="GBM", nx=100, net="mlp", hidden=[64] * 3, M=1024, points=2048, v=100,
+                    precision="f16", scaling="weak", steps=10, cpu_points=2,
+                    config="scripts/fully_nonlinear/case_1/base_100d_T1.0_w0.0_nov_0.yaml"),
+    "burgers1000d": dict(eq="Cha", nx=1000, net="mlp", hidden=[128] * 4, M=256, points=1 << 20, cha_k=5.0, v=0,
+                         precision="f16", scaling="strong", steps=3, cpu_points=16,
+                         config="synthetic Burgers 1000d DPI scaling sweep (SURVEY.md 8d config 5)"),
 }
 
 
-def flops_per_point(nx: int, hidden, M_I: int) -> float:
-    """F_point = (M_I + 1) * F_row; F_row = 2 * (forward MACs + tangent MACs); the first-layer
-    tangent along a fixed direction is a constant vector (0 flops)."""
-    dims = [1 + nx] + list(hidden) + [1]
-    fwd = sum(dims[i] * dims[i + 1] for i in range(len(dims) - 1))
-    jvp = sum(dims[i] * dims[i + 1] for i in range(1, len(dims) - 1))
-    return float((M_I + 1) * 2 * (fwd + jvp))
+def flops_per_point(wl, M_I: int) -> float:
+    """F_point = (M_I + 1) * F_row, 2 flops per MAC, un-padded dims.
+    Cha: forward + one tangent (the first-layer tangent along a fixed direction is a constant vector: 0 flops);
+    GBM: forward + v two-jets (2 GEMM rows per hidden layer per direction + the output dot);
+    OU/PISGradNet: nn_module forward + VJP back to x + the two time nets."""
+    nx, hid = wl["nx"], list(wl["hidden"])
+    if wl["eq"] == "Cha":
+        dims = [1 + nx] + hid + [1]
+        fwd = sum(dims[i] * dims[i + 1] for i in range(len(dims) - 1))
+        jvp = sum(dims[i] * dims[i + 1] for i in range(1, len(dims) - 1))
+        row = 2 * (fwd + jvp)
+    elif wl["eq"] == "GBM":
+        dims = [1 + nx] + hid + [1]
+        fwd = sum(dims[i] * dims[i + 1] for i in range(len(dims) - 1))
+        jet = 2 * sum(dims[i] * dims[i + 1] for i in range(1, len(dims) - 2)) + dims[-2]
+        row = 2 * (fwd + wl["v"] * jet)
+    else:
+        dims = [64 + nx] + hid + [nx]
+        fwd = sum(dims[i] * dims[i + 1] for i in range(len(dims) - 1))
+        vjp = nx * hid[0] + sum(dims[i] * dims[i + 1] for i in range(1, len(dims) - 1))
+        t_enc = 128 * 64 + 64 * 64
+        smooth = 128 * 64 + (len(hid)) * 64 * 64 + 64 * 1  # only output 0 of the last layer is used
+        row = 2 * (fwd + vjp + t_enc + smooth)
+    return float((M_I + 1) * row)
 
 
-def make_weights(nx: int, hidden, seed: int = 0):
-    """torch.nn.Linear default init under a fixed seed (a trained net is not needed to measure throughput)."""
+def _linear_init(n_in, n_out, gen):
+    """torch.nn.Linear default init (U(-1/sqrt(in), 1/sqrt(in))) from an explicit generator."""
     import torch
 
-    torch.manual_seed(seed)
-    dims = [1 + nx] + list(hidden) + [1]
-    lins = [torch.nn.Linear(dims[i], dims[i + 1]) for i in range(len(dims) - 1)]
-    return [(l.weight.detach().float().clone(), l.bias.detach().float().clone()) for l in lins]
+    b = 1.0 / n_in ** 0.5
+    return ((torch.rand(n_out, n_in, generator=gen) * 2 - 1) * b, (torch.rand(n_out, generator=gen) * 2 - 1) * b)
+
+
+def make_network(wl, seed: int = 0):
+    """Random-init weights of the architecture the config names (a trained net is not needed to measure throughput)."""
+    import torch
+
+    g = torch.Generator().manual_seed(seed)
+    nx, hid = wl["nx"], list(wl["hidden"])
+
+    def chain(dims):
+        return [_linear_init(dims[i], dims[i + 1], g) for i in range(len(dims) - 1)]
+
+    if wl["net"] == "mlp":
+        return dict(kind="mlp", main=chain([1 + nx] + hid + [1]))
+    return dict(kind="pisgrad", t_encoder=chain([128, 64, 64]), smooth_net=chain([128] + [64] * (len(hid) + 1) + [nx]),
+                main=chain([nx + 64] + hid + [nx]), phase=torch.zeros(1, 64),
+                coeff=torch.linspace(0.1, 100.0, 64).unsqueeze(0))
+
+
+def problem_instance(wl):
+    """Equation parameters.  GBM / OU use the reference's SHIPPED problem instance (scripts/**/gbm_2nodes_{w,v}_100d.pt,
+    scripts/hjb/{mean,pi}_100d_*.pt), carried by the committed golden fixtures (the reference tree is not on the GPU box)."""
+    import numpy as np
+
+    if wl["eq"] == "Cha":
+        return dict(cha_k=wl["cha_k"])
+    gold = os.path.join(ROOT, "tests", "golden")
+    if wl["eq"] == "GBM":
+        z = np.load(os.path.join(gold, "gbm_100d_mlp64_sdgd.npz"))
+        return dict(gbm_w=z["gbm_w"], gbm_v=z["gbm_v"], sdgd_v=wl["v"])
+    z = np.load(os.path.join(gold, "hjb_100d_pisgrad.npz"))
+    return dict(ou_mean=z["ou_mean"], ou_diagvar=z["ou_diagvar"], ou_pi=z["ou_pi"], ou_theta=1.0, ou_mu=0.0,
+                ou_alpha_init=4.0)
 
 
 def load_peaks():
@@ -127,29 +193,53 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def describe(wl, M):
+    dims = ([1 + wl["nx"]] + wl["hidden"] + [1]) if wl["net"] == "mlp" else ([64 + wl["nx"]] + wl["hidden"] + [wl["nx"]])
+    d = {"equation": {"Cha": "Cha", "GBM": "GBMEquationComplexExact", "OU": "OUProcessEquation"}[wl["eq"]],
+         "nx": wl["nx"], "network": "MLP" if wl["net"] == "mlp" else "PISGradNet", "layers": dims, "M_T": M, "M_I": M}
+    if wl["v"]:
+        d["sdgd_v"] = wl["v"]
+    return d
+
+
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the restatement of the reference's torch path (oracle), all host threads, fp64
 # ------------------------------------------------------------------------------------------------
-def cpu_arm(wl, weights, n_sample: int, steps: int, warmup: int):
+def cpu_arm(wl, net, M: int, n_sample: int, steps: int, warmup: int):
     import torch
     from oracle import dpi_oracle as orc
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    eq = orc.Cha(wl["nx"], 1.0, wl["cha_k"], 1.0)
-    net = orc.MLP([W.double() for W, _ in weights], [b.double() for _, b in weights])
+    inst = problem_instance(wl)
+    dd = lambda lins: [(W.double(), b.double()) for W, b in lins]
+    if wl["eq"] == "Cha":
+        eq = orc.Cha(wl["nx"], 1.0, wl["cha_k"], 1.0)
+    elif wl["eq"] == "GBM":
+        eq = orc.GBM(wl["nx"], torch.from_numpy(inst["gbm_w"]).double(), torch.from_numpy(inst["gbm_v"]).double(), 1.0, 1.0)
+    else:
+        eq = orc.OU(wl["nx"], torch.from_numpy(inst["ou_mean"]).double(), torch.from_numpy(inst["ou_diagvar"]).double(),
+                    torch.from_numpy(inst["ou_pi"]).double())
+    if net["kind"] == "mlp":
+        onet = orc.MLP([W.double() for W, _ in net["main"]], [b.double() for _, b in net["main"]])
+    else:
+        onet = orc.PISGradNet(net["phase"].double(), net["coeff"].double(), dd(net["t_encoder"]), dd(net["smooth_net"]),
+                              dd(net["main"]), 1.0)
     gen = torch.Generator().manual_seed(0)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        orc.sample_with_gradients(eq, net, n_sample, wl["M"], wl["M"], None, mode="autograd", generator=gen)
+        orc.sample_with_gradients(eq, onet, n_sample, M, M, wl["v"] or None, mode="autograd", generator=gen)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
     tot = sum(times)
     return dict(value=n_sample * len(times) / tot, unit=UNIT, cores=torch.get_num_threads(), kind="port",
-                sample=f"{n_sample} points/step x {len(times)} steps (+{warmup} warm-up), fp64, M_T=M_I={wl['M']}, "
+                sample=f"{n_sample} points/step x {len(times)} steps (+{warmup} warm-up), fp64, M_T=M_I={M}, "
                        f"oracle/dpi_oracle.py mode=autograd (forward + reverse-mode like picard/data.py:1226-1325)",
+                note="port of a pure-Python reference (uninstallable here: lightning/yacs/h5py absent); on 8 cores the "
+                     "live reference ran 12.7 points/s against 7.4 for this port (Burgers-100d, n=16), so the port does "
+                     "not flatter the CPU side by running faster than the reference",
                 ms_per_step=1e3 * tot / len(times))
 
 
@@ -157,17 +247,19 @@ def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    weights = make_weights(wl["nx"], wl["hidden"])
-    n_sample = args.cpu_points
-    cb = cpu_arm(wl, weights, n_sample, args.steps, args.warmup)
+    M = args.mc or wl["M"]
+    net = make_network(wl)
+    n_sample = args.cpu_points or wl["cpu_points"]
+    steps = args.steps if args.steps is not None else 4
+    cb = cpu_arm(wl, net, M, n_sample, steps, args.warmup)
+    cfg = {"workload": args.workload, "restates": wl["config"], "points_per_step": n_sample,
+           "note": "CPU arm: bounded sample of the same workload (a per-point rate)"}
+    cfg.update(describe(wl, M))
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "restates": wl["config"], "nx": wl["nx"],
-                   "mlp": [1 + wl["nx"]] + wl["hidden"] + [1], "M_T": wl["M"], "M_I": wl["M"],
-                   "points_per_step": n_sample, "note": "CPU arm: bounded sample of the same workload"},
-        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "steps": steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "note")},
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -193,17 +285,26 @@ def run_b200(args, wl):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from deeppicarditeration_b200.engine import LabelEngine
+    from deeppicarditeration_b200.sharding import shard_range
 
-    nx, M, n = wl["nx"], wl["M"], args.points or wl["points"]
-    weights = make_weights(nx, wl["hidden"])
+    nx, M = wl["nx"], args.mc or wl["M"]
+    scaling = args.scaling or wl["scaling"]
+    if scaling == "strong":
+        n_global = args.points or wl["points"]
+        base, n = shard_range(n_global, rank, world)  # contiguous block of the global point index range
+    else:
+        n = args.points or wl["points"]
+        n_global, base = world * n, rank * n
+    steps = args.steps if args.steps is not None else wl["steps"]
+    net = make_network(wl)
     eng = LabelEngine(f"cuda:{local}")
-    eng.set_problem("Cha", nx, 1.0, 1.0, cha_k=wl["cha_k"])
-    eng.set_network("mlp", main=weights)
-    prec = args.precision
-    base = rank * n  # contiguous shard of the global point index range
+    eng.set_problem(wl["eq"], nx, 1.0, 1.0, **problem_instance(wl))
+    eng.set_network(**net)
+    prec = args.precision or wl["precision"]
     tx = eng.sample_tx(n, seed=0, point_index_base=base)
-    tx_host = tx.cpu().pin_memory()
-    y_host = torch.empty_like(tx_host).pin_memory()
+    tx_host = torch.empty(tx.shape, dtype=torch.float32, pin_memory=True)
+    tx_host.copy_(tx)
+    y_host = torch.empty(tx.shape, dtype=torch.float32, pin_memory=True)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=tx.device)  # > 126 MB L2
 
     def step_dev(i):
@@ -245,10 +346,10 @@ def run_b200(args, wl):
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    tot_ms, launches, stage_ms = timed(step_dev, args.steps, args.warmup, stage="integral")
+    tot_ms, launches, stage_ms = timed(step_dev, steps, args.warmup, stage="integral")
     clk = clocks.stop() if rank == 0 else None
     eng.set_stage_timing(False)
-    e2e_ms, _, _ = timed(step_host, args.steps, max(3, args.warmup))
+    e2e_ms, _, _ = timed(step_host, steps, max(3, args.warmup))
 
     y = step_dev(0)
     finite = bool(torch.isfinite(y).all())
@@ -260,44 +361,54 @@ def run_b200(args, wl):
         return 0
 
     peaks = load_peaks()
-    ms_step = tot_ms / args.steps
-    value = world * n / (ms_step * 1e-3)
-    e2e_value = world * n / (e2e_ms / args.steps * 1e-3)
-    F = flops_per_point(nx, wl["hidden"], M)
+    ms_step = tot_ms / steps
+    value = n_global / (ms_step * 1e-3)
+    e2e_value = n_global / (e2e_ms / steps * 1e-3)
+    F = flops_per_point(wl, M)
     k_ms = statistics.mean(stage_ms)
     achieved = n * F / (k_ms * 1e-3) / 1e12
+    # burst vs sustained denominator: the burst peak applies when the SM clock held its maximum through the timed region
+    at_max = bool(clk and clk.get("sm_mhz") and clk.get("sm_max_mhz") and clk["sm_mhz"] >= 0.95 * clk["sm_max_mhz"])
+    which = "burst" if at_max else "sustained"
+    dt = "f32" if prec == "fp32" else ("tf32" if wl["net"] == "pisgrad" else "f16")
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         with open(tp) as f:
-            rec = json.load(f).get(f"{args.workload}:{'f16' if prec in ('f16', 'bf16') else prec}")
+            rec = json.load(f).get(f"{args.workload}:{dt}")
             # ncu dram__bytes_read.sum + dram__bytes_write.sum of the integral kernel, valid for the same launch size only
-            if isinstance(rec, dict) and rec.get("launch_points") == n:
+            if isinstance(rec, dict) and rec.get("launch_points") == n and rec.get("M", M) == M:
                 traffic = rec.get("dram_bytes_per_launch")
+    cfg = {"workload": args.workload, "restates": wl["config"]}
+    cfg.update(describe(wl, M))
+    cfg.update({"points_per_gpu_per_step": n, "global_points_per_step": n_global,
+                "parallelism": f"points sharded x{world} (contiguous blocks), no collective",
+                "rng": "on-device Philox4x32-10 keyed by global point index",
+                "l2": "256 MiB buffer written between timed iterations",
+                "weights": "nn.Linear default init, seed 0",
+                "instance": "Cha closed form" if wl["eq"] == "Cha" else "reference's shipped tensors (tests/golden fixture)"})
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f16" if prec in ("f16", "bf16") else "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "restates": wl["config"], "equation": "Cha", "nx": nx,
-                   "mlp": [1 + nx] + wl["hidden"] + [1], "M_T": M, "M_I": M, "points_per_gpu_per_step": n,
-                   "global_points_per_step": world * n, "parallelism": f"points sharded x{world}, no collective",
-                   "rng": "on-device Philox4x32-10 keyed by global point index",
-                   "l2": "256 MiB buffer written between timed iterations",
-                   "weights": "nn.Linear default init, torch.manual_seed(0)"},
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+        "dtype": dt, "data": "synthetic", "config": cfg,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": tx_host.numel() * 4,
                 "d2h_bytes_per_step": y_host.numel() * 4, "api": "dpi_label_gen_host (pinned host buffers)"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["sustained"], "unit": "TFLOP/s",
-                     "frac": achieved / peaks["sustained"], "traffic": traffic,
-                     "kernel": "integral estimator (u_k value+tangent over paths)", "kernel_ms": k_ms,
-                     "kernel_share_of_step": k_ms / ms_step, "flops_per_point": F,
-                     "peak_source": f"{peaks['source']} bf16 dense, sustained (kernel timed inside a long step)",
-                     "peak_burst": peaks["burst"], "frac_burst": achieved / peaks["burst"]},
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks[which], "unit": "TFLOP/s",
+                     "frac": achieved / peaks[which], "traffic": traffic,
+                     "kernel": "integral estimator stage (u_k value + derivative over paths, f, Bismut weights, MC sums)",
+                     "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_step, "flops_per_point": F,
+                     "peak_source": f"{peaks['source']} bf16 dense, {which} "
+                                    f"(median SM clock {clk.get('sm_mhz') if clk else None} of "
+                                    f"{clk.get('sm_max_mhz') if clk else None} MHz during the timed region)",
+                     "peak_burst": peaks["burst"], "frac_burst": achieved / peaks["burst"],
+                     "peak_sustained": peaks["sustained"], "frac_sustained": achieved / peaks["sustained"],
+                     "step_tflops": n * F / (ms_step * 1e-3) / 1e12},
         "clocks": clk, "labels_finite": finite,
     }
     if world == 1 and not args.no_cpu:
-        cb = cpu_arm(wl, weights, args.cpu_points, args.cpu_steps, 1)
-        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cb = cpu_arm(wl, net, M, args.cpu_points or wl["cpu_points"], args.cpu_steps, 1)
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "note")}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
@@ -307,16 +418,19 @@ def run_b200(args, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default: per workload, minutes at most)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="burgers100d", choices=sorted(WORKLOADS))
-    ap.add_argument("--precision", default=os.environ.get("DPI_BENCH_PRECISION", "f16"), choices=["fp32", "f16", "bf16"],
-                    help="f16: tcgen05 path (fp16 operands, fp32 accumulation; labels within 1e-2 of the reference); "
-                         "fp32: CUDA-core path (within 1e-4)")
-    ap.add_argument("--points", type=int, default=0, help="points per GPU per step (default: workload's)")
-    ap.add_argument("--cpu-points", type=int, default=32, help="points per CPU-arm step (bounded sample)")
-    ap.add_argument("--cpu-steps", type=int, default=4)
+    ap.add_argument("--precision", default=os.environ.get("DPI_BENCH_PRECISION"), choices=["fp32", "f16", "tf32"],
+                    help="default per workload: f16 = tcgen05 paths with fp16 operands (tf32 GEMMs for PISGradNet), "
+                         "labels within 1e-2 of the reference; fp32 = CUDA-core paths (within 1e-4)")
+    ap.add_argument("--scaling", default=None, choices=["weak", "strong"],
+                    help="weak: --points per GPU; strong: --points in total, split over the GPUs")
+    ap.add_argument("--points", type=int, default=0, help="points per step (per GPU if weak, global if strong)")
+    ap.add_argument("--mc", type=int, default=0, help="MC paths per point (M_T = M_I); default: the config's")
+    ap.add_argument("--cpu-points", type=int, default=0, help="points per CPU-arm step (bounded sample)")
+    ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

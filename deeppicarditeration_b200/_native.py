@@ -16,13 +16,15 @@ DPI_MAX_LINEAR = 8
 DPI_EQ_CHA, DPI_EQ_GBM, DPI_EQ_OU = 0, 1, 2
 DPI_NET_ZERO, DPI_NET_MLP, DPI_NET_PISGRAD = 0, 1, 2
 DPI_PREC_FP32, DPI_PREC_F16 = 0, 1
-DPI_PREC_BF16 = DPI_PREC_F16  # alias: the 16-bit tensor-core path (fp16 operands)
+DPI_PREC_BF16 = 2  # distinct and rejected (DPI_ERR_UNSUPPORTED): bf16 operands are not built
+DPI_ERR_NONFINITE = -5
 
 EXPORTED_SYMBOLS = (
     "dpi_version", "dpi_last_error", "dpi_create", "dpi_destroy", "dpi_set_problem", "dpi_set_network",
     "dpi_sample_tx", "dpi_label_gen", "dpi_label_gen_host", "dpi_net_eval", "dpi_launch_count",
     "dpi_set_stage_timing", "dpi_stage_ms", "dpi_selftest_umma",
     "dpi_train_init", "dpi_train_param_count", "dpi_train_grad", "dpi_train_adam", "dpi_train_fit", "dpi_train_reset",
+    "dpi_check_labels", "dpi_export_draws",
 )
 
 
@@ -90,6 +92,9 @@ def load() -> C.CDLL:
                                   C.c_void_p, C.c_void_p]
     lib.dpi_label_gen_host.argtypes = [H, C.c_void_p, C.c_int64, C.POINTER(dpi_label_config), C.c_void_p, C.c_void_p,
                                        C.c_void_p]
+    lib.dpi_check_labels.argtypes = [H, C.c_void_p]
+    lib.dpi_export_draws.argtypes = [H, C.c_int64, C.POINTER(dpi_label_config), C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p]
     lib.dpi_net_eval.argtypes = [H, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.dpi_launch_count.argtypes = [H]
     lib.dpi_launch_count.restype = C.c_int64
@@ -116,4 +121,6 @@ def check(rc: int, what: str) -> None:
         msg = load().dpi_last_error().decode("utf-8", "replace")
         if rc == -3:
             raise NotImplementedError(f"{what}: {msg}")
+        if rc == DPI_ERR_NONFINITE:
+            raise FloatingPointError(f"{what}: {msg}")
         raise RuntimeError(f"{what} failed (status {rc}): {msg}")

@@ -68,6 +68,7 @@ struct dpi_handle {
   float* stage_y = nullptr;
   int64_t stage_floats = 0;
   int64_t launches = 0;
+  int* nonfinite_flag = nullptr;  // device: set by the label kernels' final check when a label is inf / NaN
   // optional per-stage timing (dpi_set_stage_timing)
   bool timing = false;
   cudaEvent_t ev[DPI_STAGE_COUNT][2] = {};
@@ -152,6 +153,22 @@ constexpr int64_t kHjbScratchBudget = 6LL << 30;
 
 int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+// Private copy of one Linear layer (picard/data.py:407-412 freezes `solution`: the label path must not see the
+// caller's tensors again -- they may be trained in place or freed once dpi_set_network returns).
+int freeze_linear(std::vector<void*>& owner, const dpi_linear& src, dpi_linear* dst, cudaStream_t st) {
+  float *W = nullptr, *b = nullptr;
+  const size_t nw = (size_t)src.n_out * src.n_in;
+  int rc;
+  if ((rc = dev_alloc(owner, nw, &W))) return rc;
+  if ((rc = dev_alloc(owner, (size_t)src.n_out, &b))) return rc;
+  DPI_CUDA_CHECK(cudaMemcpyAsync(W, src.W, sizeof(float) * nw, cudaMemcpyDeviceToDevice, st));
+  DPI_CUDA_CHECK(cudaMemcpyAsync(b, src.b, sizeof(float) * src.n_out, cudaMemcpyDeviceToDevice, st));
+  *dst = src;
+  dst->W = W;
+  dst->b = b;
+  return DPI_OK;
+}
+
 // RAII bracket: records the stage's start event now and its end event when it goes out of scope.
 struct StageTimer {
   dpi_handle* h;
@@ -200,6 +217,12 @@ int dpi_create(int device, dpi_handle** out) {
   DPI_CUDA_CHECK(cudaSetDevice(device));
   dpi_handle* h = new dpi_handle();
   h->device = device;
+  if (cudaMalloc((void**)&h->nonfinite_flag, sizeof(int)) != cudaSuccess ||
+      cudaMemset(h->nonfinite_flag, 0, sizeof(int)) != cudaSuccess) {
+    set_error("dpi_create: cannot allocate the status word: %s", cudaGetErrorString(cudaGetLastError()));
+    delete h;
+    return DPI_ERR_CUDA;
+  }
   *out = h;
   return DPI_OK;
 }
@@ -217,6 +240,7 @@ int dpi_destroy(dpi_handle* h) {
   if (h->tc_zring) cudaFree(h->tc_zring);
   if (h->partF) cudaFree(h->partF);
   if (h->hjb_scratch) cudaFree(h->hjb_scratch);
+  if (h->nonfinite_flag) cudaFree(h->nonfinite_flag);
   if (h->train_m) cudaFree(h->train_m);
   if (h->train_v) cudaFree(h->train_v);
   if (h->train_scratch) cudaFree(h->train_scratch);
@@ -398,11 +422,14 @@ int dpi_set_network(dpi_handle* h, const dpi_network* net, void* stream) {
       M.bh[l] = bh[l];
     }
     h->mlp = M;
-    for (int l = 0; l < L; ++l) h->mlp_raw[l] = net->main[l];
+    // dpi_net_eval (value + full input gradient) reads torch-layout weights: keep a private copy, not the caller's
+    for (int l = 0; l < L; ++l)
+      if ((rc = freeze_linear(h->net_bufs, net->main[l], &h->mlp_raw[l], st))) return rc;
     h->n_mlp_raw = L;
     // bf16 tensor-core packing (tcgen05 path) when the shape qualifies
     rc = tc_pack_network(*net, h->P, M, h->net_bufs, &h->tc, &h->tc_ready, &h->launches, st);
     if (rc) return rc;
+    DPI_CUDA_CHECK(cudaStreamSynchronize(st));  // the caller's tensors are not read after this call returns
     h->has_net = true;
     return DPI_OK;
   }
@@ -430,26 +457,35 @@ int dpi_set_network(dpi_handle* h, const dpi_network* net, void* stream) {
     PisDev N{};
     N.n_main = net->n_main, N.n_t_encoder = net->n_t_encoder, N.n_smooth = net->n_smooth;
     N.hmax = 0;
+    int rc_f;
     for (int l = 0; l < net->n_main; ++l) {
-      N.main[l] = net->main[l];
+      if ((rc_f = freeze_linear(h->net_bufs, net->main[l], &N.main[l], st))) return rc_f;
       if (l < net->n_main - 1 && net->main[l].n_out > N.hmax) N.hmax = net->main[l].n_out;
     }
-    for (int l = 0; l < net->n_t_encoder; ++l) N.t_encoder[l] = net->t_encoder[l];
-    for (int l = 0; l < net->n_smooth; ++l) N.smooth_net[l] = net->smooth_net[l];
-    N.phase = net->timestep_phase, N.coeff = net->timestep_coeff;
+    for (int l = 0; l < net->n_t_encoder; ++l)
+      if ((rc_f = freeze_linear(h->net_bufs, net->t_encoder[l], &N.t_encoder[l], st))) return rc_f;
+    for (int l = 0; l < net->n_smooth; ++l)
+      if ((rc_f = freeze_linear(h->net_bufs, net->smooth_net[l], &N.smooth_net[l], st))) return rc_f;
+    {
+      float* pc = nullptr;  // [phase 64 | coeff 64]
+      if ((rc_f = dev_alloc(h->net_bufs, 128, &pc))) return rc_f;
+      DPI_CUDA_CHECK(cudaMemcpyAsync(pc, net->timestep_phase, 64 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      DPI_CUDA_CHECK(cudaMemcpyAsync(pc + 64, net->timestep_coeff, 64 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      N.phase = pc, N.coeff = pc + 64;
+    }
     // K-major ([n_in][n_out]) copies of the nn_module weights: the VJP GEMMs of the tensor-core path then load both
     // operands with 16-byte copies instead of transposing a [K][N] weight element by element
     for (int l = 0; l < net->n_main; ++l) {
       float* wt = nullptr;
       DPI_CUDA_CHECK(cudaMalloc((void**)&wt, sizeof(float) * (size_t)net->main[l].n_out * net->main[l].n_in));
       h->net_bufs.push_back(wt);
-      if (int rc_t = gemm_transpose(net->main[l].W, net->main[l].n_out, net->main[l].n_in, wt, st)) return rc_t;
+      if (int rc_t = gemm_transpose(N.main[l].W, net->main[l].n_out, net->main[l].n_in, wt, st)) return rc_t;
       N.main_t[l] = wt;
     }
     h->launches += net->n_main;
     h->pis = N;
+    DPI_CUDA_CHECK(cudaStreamSynchronize(st));  // the caller's tensors are not read after this call returns
     h->has_net = true;
-    (void)st;
     return DPI_OK;
   }
   set_error("dpi_set_network: unknown network kind %d", net->kind);
@@ -465,6 +501,11 @@ int dpi_sample_tx(dpi_handle* h, int64_t n, int64_t point_index_base, uint64_t s
     set_error("dpi_sample_tx: bad n/tx");
     return DPI_ERR_INVALID;
   }
+  if (point_index_base < 0 || point_index_base > (1LL << 48) - n) {
+    set_error("dpi_sample_tx: point_index_base %lld + n %lld leaves the 48-bit range of the Philox counter",
+              (long long)point_index_base, (long long)n);
+    return DPI_ERR_INVALID;
+  }
   DPI_CUDA_CHECK(cudaSetDevice(h->device));
   // eps = 0.01: default ESTIMATE_TERMINAL "OU_ByGx" (config.py:100, data.py:134-137)
   int rc = launch_sample_tx(h->P, n, point_index_base, seed, 0.01f, tx, reinterpret_cast<cudaStream_t>(stream));
@@ -472,8 +513,76 @@ int dpi_sample_tx(dpi_handle* h, int64_t n, int64_t point_index_base, uint64_t s
   return rc;
 }
 
+static int label_gen_body(dpi_handle* h, const float* tx, int64_t n, const dpi_label_config* cfg, const dpi_draws* draws,
+                          float* y, void* stream);
+
+// Philox counters hold 48 bits of the global point index (dpi_common.cuh: philox_counter)
+static bool point_range_ok(int64_t base, int64_t n) { return base >= 0 && n >= 0 && base <= (1LL << 48) - n; }
+
 int dpi_label_gen(dpi_handle* h, const float* tx, int64_t n, const dpi_label_config* cfg, const dpi_draws* draws,
                   float* y, void* stream) {
+  if (!h || !cfg) {
+    set_error("dpi_label_gen: NULL argument");
+    return DPI_ERR_INVALID;
+  }
+  if (cfg->precision != DPI_PREC_FP32 && cfg->precision != DPI_PREC_F16) {
+    set_error("dpi_label_gen: precision %d is not built (DPI_PREC_BF16 operands are not implemented: use DPI_PREC_F16, "
+              "same operand width with three more mantissa bits, or DPI_PREC_FP32)", cfg->precision);
+    return DPI_ERR_UNSUPPORTED;
+  }
+  if (!draws && !point_range_ok(cfg->point_index_base, n)) {
+    set_error("dpi_label_gen: point_index_base %lld + n %lld leaves the 48-bit range of the Philox counter",
+              (long long)cfg->point_index_base, (long long)n);
+    return DPI_ERR_INVALID;
+  }
+  int rc = label_gen_body(h, tx, n, cfg, draws, y, stream);
+  if (rc || n <= 0) return rc;
+  // the tensor-core finish kernel checks its own output; every other path gets one small sweep over y
+  const bool tc_cha = h->net_kind == DPI_NET_MLP && h->P.eq == DPI_EQ_CHA && cfg->precision == DPI_PREC_F16;
+  if (!tc_cha) {
+    rc = launch_check_finite(y, n * (int64_t)(1 + h->P.nx), h->nonfinite_flag, reinterpret_cast<cudaStream_t>(stream));
+    if (!rc) h->launches += 1;
+  }
+  return rc;
+}
+
+int dpi_check_labels(dpi_handle* h, void* stream) {
+  if (!h) {
+    set_error("dpi_check_labels: NULL handle");
+    return DPI_ERR_INVALID;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  DPI_CUDA_CHECK(cudaSetDevice(h->device));
+  int flag = 0;
+  DPI_CUDA_CHECK(cudaMemcpyAsync(&flag, h->nonfinite_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  DPI_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (flag) {
+    DPI_CUDA_CHECK(cudaMemsetAsync(h->nonfinite_flag, 0, sizeof(int), st));
+    set_error("non-finite labels: the frozen network leaves the range of the selected arithmetic (fp16 operands hold "
+              "|log2(e) * pre-activation| < 6.5e4) or the inputs were not finite; re-run with DPI_PREC_FP32");
+    return DPI_ERR_NONFINITE;
+  }
+  return DPI_OK;
+}
+
+int dpi_export_draws(dpi_handle* h, int64_t n, const dpi_label_config* cfg, float* zT, float* u_s, float* zS,
+                     int32_t* idx, void* stream) {
+  if (!h || !cfg || !h->has_problem) {
+    set_error("dpi_export_draws: problem not set / NULL argument");
+    return DPI_ERR_STATE;
+  }
+  if (n < 0 || cfg->M_T < 1 || cfg->M_I < 1 || !point_range_ok(cfg->point_index_base, n)) {
+    set_error("dpi_export_draws: bad arguments (n=%lld M_T=%d M_I=%d base=%lld)", (long long)n, cfg->M_T, cfg->M_I,
+              (long long)cfg->point_index_base);
+    return DPI_ERR_INVALID;
+  }
+  DPI_CUDA_CHECK(cudaSetDevice(h->device));
+  return launch_export_draws(h->P, n, cfg->M_T, cfg->M_I, cfg->seed, cfg->point_index_base, zT, u_s, zS, idx,
+                             reinterpret_cast<cudaStream_t>(stream), &h->launches);
+}
+
+static int label_gen_body(dpi_handle* h, const float* tx, int64_t n, const dpi_label_config* cfg, const dpi_draws* draws,
+                          float* y, void* stream) {
   if (!h || !cfg) {
     set_error("dpi_label_gen: NULL argument");
     return DPI_ERR_INVALID;
@@ -575,7 +684,7 @@ int dpi_label_gen(dpi_handle* h, const float* tx, int64_t n, const dpi_label_con
                                 draws ? draws->zS + p0 * (int64_t)cfg->M_I * d : nullptr, h->fb + p0,
                                 h->c0 + p0 * h->mlp.HP, bound, h->partG, h->partF,
                                 reinterpret_cast<int*>(h->partF + h->part_units * kTcPartFFloatsPerUnit), h->tc_zring,
-                                y + p0 * (1 + d), st);
+                                h->nonfinite_flag, y + p0 * (1 + d), st);
         if (rc) return rc;
         h->launches += 2;
       }
@@ -591,7 +700,7 @@ int dpi_label_gen(dpi_handle* h, const float* tx, int64_t n, const dpi_label_con
     PisDev pis = h->pis;
     pis.tf32 = cfg->precision != DPI_PREC_FP32;
     const int64_t ppc = std::min<int64_t>(n, hjb_points_per_chunk(h->pis, P.nx, cfg->M_I, kHjbScratchBudget));
-    if ((rc = ensure_hjb_scratch(h, hjb_scratch_floats(h->pis, P.nx, ppc * (cfg->M_I + 1))))) return rc;
+    if ((rc = ensure_hjb_scratch(h, hjb_scratch_floats(h->pis, P.nx, ppc * (cfg->M_I + 1), ppc)))) return rc;
     StageTimer tm(h, DPI_STAGE_INTEGRAL, st);
     return launch_hjb_paths(P, pis, tx, n, cfg->M_I, cfg->seed, cfg->point_index_base, draws ? draws->u_s : nullptr,
                             draws ? draws->zS : nullptr, bound, h->hjb_scratch, ppc, y, st, &h->launches);
@@ -627,8 +736,7 @@ int dpi_label_gen_host(dpi_handle* h, const float* tx_in_host, int64_t n, const 
   DPI_CUDA_CHECK(cudaMemcpyAsync(y_host, h->stage_y, sizeof(float) * floats, cudaMemcpyDeviceToHost, st));
   if (tx_out_host)
     DPI_CUDA_CHECK(cudaMemcpyAsync(tx_out_host, h->stage_tx, sizeof(float) * floats, cudaMemcpyDeviceToHost, st));
-  DPI_CUDA_CHECK(cudaStreamSynchronize(st));
-  return DPI_OK;
+  return dpi_check_labels(h, stream);  // synchronises the stream; DPI_ERR_NONFINITE instead of silent inf / NaN labels
 }
 
 int dpi_net_eval(dpi_handle* h, const float* tx, int64_t n, float* u, float* du, void* stream) {
@@ -660,9 +768,9 @@ int dpi_net_eval(dpi_handle* h, const float* tx, int64_t n, float* u, float* du,
     return DPI_OK;
   }
   if (h->net_kind == DPI_NET_PISGRAD && h->P.eq == DPI_EQ_OU) {
-    const int64_t per_row = hjb_scratch_floats(h->pis, h->P.nx, 1) * (int64_t)sizeof(float);
+    const int64_t per_row = hjb_scratch_floats(h->pis, h->P.nx, 1, 0) * (int64_t)sizeof(float);
     const int64_t rpc = std::max<int64_t>(1, std::min<int64_t>(n, kHjbScratchBudget / per_row));
-    int rc = ensure_hjb_scratch(h, hjb_scratch_floats(h->pis, h->P.nx, rpc));
+    int rc = ensure_hjb_scratch(h, hjb_scratch_floats(h->pis, h->P.nx, rpc, 0));
     if (rc) return rc;
     return launch_hjb_eval(h->P, h->pis, tx, n, h->hjb_scratch, rpc, u, du, st, &h->launches);
   }

@@ -102,8 +102,13 @@ __device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5
 // Box-Muller on the MUFU pipe, 16 + 16 random bits -> 2 normals (13 instructions): radius from
 // u = (k + 1/2) 2^-16 in (0, 1), angle 2 pi (k' + 1/2) 2^-16.  One Philox4x32 block therefore yields EIGHT normals.
 // The pair (z0, z1) takes 2^32 distinct values; the radius is a midpoint rule with 65536 equiprobable cells
-// (|z| <= 4.86: the missing tail has probability 1.2e-6, its contribution to E[z^2] is 3e-5), the angle an equispaced
-// rule with 65536 nodes, which is spectrally accurate for the smooth periodic integrands it feeds.
+// (|z| <= 4.86: the missing tail has probability 1.2e-6), the angle an equispaced rule with 65536 nodes, which is
+// spectrally accurate for the smooth periodic integrands it feeds.  The midpoint rule alone leaves E[r^2] at
+// 1.9999894 instead of 2 (a SYSTEMATIC 5.3e-6 deficit in the variance of every increment, invisible to
+// deterministic-mode parity), so the radius constant is calibrated: kBmRadius = -2 ln2 * 2 / mean_k(-2 ln u_k)
+// makes E[z^2] = 1 exactly over the 2^32 pairs (E[z^4] = 2.99982); tests/test_gpu_rng.py bounds the effect on a
+// label against Gauss-Hermite quadrature.
+constexpr float kBmRadius = -1.3863016922764049f;
 #ifdef DPI_BM_LOP3
 constexpr bool kBmLop3Default = true;
 #else
@@ -131,11 +136,11 @@ __device__ __forceinline__ void box_muller16(uint32_t w, float& z0, float& z1) {
   }
   const float u = xr - 0.99999237060546875f;                 // (k + 1/2) 2^-16
 #ifdef DPI_DBG_BM_NOXU  // sensitivity builds only: same instruction count without the four MUFU ops (wrong numbers)
-  const float r = fmaf(-1.3862943611198906f, fmaf(u, 0.5f, 0.25f), 2.f) * 0.7f;
+  const float r = fmaf(kBmRadius, fmaf(u, 0.5f, 0.25f), 2.f) * 0.7f;
   const float ang = fmaf(xa, 6.283185307179586f, -6.283137370279964f) * 0.15915494f;
   float s = fmaf(ang, 0.5f, -0.25f), c = fmaf(ang, -0.5f, 0.25f);
 #else
-  const float r = sqrtf(-1.3862943611198906f * __log2f(u));  // sqrt(-2 ln u) = sqrt(-2 ln2 log2 u)
+  const float r = sqrtf(kBmRadius * __log2f(u));  // sqrt(-2 ln u) = sqrt(-2 ln2 log2 u), calibrated (see above)
   float s, c;
   __sincosf(fmaf(xa, 6.283185307179586f, -6.283137370279964f), &s, &c);  // 2 pi (k' + 1/2) 2^-16
 #endif

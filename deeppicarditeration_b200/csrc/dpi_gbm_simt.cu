@@ -311,7 +311,8 @@ gbm_simt_kernel(const ProblemDev P, const MlpDev N, const float* __restrict__ tx
       int jj[4];
       if (det) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) jj[q] = (4 * lane + q < v) ? __ldg(idx_in + ((int64_t)p * M_I + m) * v + 4 * lane + q) : 0;
+        for (int q = 0; q < 4; ++q)  // caller-supplied coordinates are clamped into [0, d): never index shared memory out of range
+          jj[q] = (4 * lane + q < v) ? min(max(__ldg(idx_in + ((int64_t)p * M_I + m) * v + 4 * lane + q), 0), d - 1) : 0;
       } else {
         const uint4 r = philox_at(seed, gp, kStreamIdx, (uint32_t)m, (uint32_t)lane);
         jj[0] = (int)__umulhi(r.x, (uint32_t)d), jj[1] = (int)__umulhi(r.y, (uint32_t)d);

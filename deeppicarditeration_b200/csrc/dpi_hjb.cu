@@ -677,10 +677,16 @@ int eval_rows(const PisDev& N, int d, const Scratch& S, int64_t R, cudaStream_t 
 
 int gemm(const GemmArgs& g, cudaStream_t st, int64_t* launches) { return gemm_impl(g, st, launches); }
 
-int64_t hjb_scratch_floats(const PisDev& N, int d, int64_t rows) { return (rows + 1) * floats_per_row(N, d) + 64; }
+// rows of activations (+ the lambda = 0 row, + alignment slack of carve) and, behind them, the slice partials of the MC
+// reduction: kRedSlices x (1 + d) floats per point.  (The partials used to alias the hA activation buffer, which is
+// too small for narrow networks with few samples: 8 (1 + d) > (M_I + 1) hmax.)
+int64_t hjb_scratch_floats(const PisDev& N, int d, int64_t rows, int64_t points) {
+  return (rows + 1) * floats_per_row(N, d) + 64 + points * (int64_t)kRedSlices * (1 + d);
+}
 
 int64_t hjb_points_per_chunk(const PisDev& N, int d, int M_I, int64_t budget_bytes) {
-  const int64_t per_point = (int64_t)(M_I + 1) * floats_per_row(N, d) * (int64_t)sizeof(float);
+  const int64_t per_point =
+      ((int64_t)(M_I + 1) * floats_per_row(N, d) + (int64_t)kRedSlices * (1 + d)) * (int64_t)sizeof(float);
   int64_t pc = budget_bytes / per_point;
   return pc < 1 ? 1 : pc;
 }
@@ -704,10 +710,11 @@ int launch_hjb_paths(const ProblemDev& P, const PisDev& N, const float* tx, int6
     F.in = S.rows.in, F.nout = S.nout, F.jtx = S.jtx, F.sraw = S.sraw, F.sa = S.rows.sa, F.f = S.f, F.R = R;
     hjb_final_kernel<<<(unsigned)((R + 7) / 8), 256, 0, st>>>(P, F);
     DPI_CUDA_CHECK(cudaGetLastError());
-    // slice partials live in hA (free once the VJP is done): np x kRedSlices x (1 + d) floats
+    // slice partials: np x kRedSlices x (1 + d) floats behind the carved activation buffers of this chunk
+    float* part = scratch + hjb_scratch_floats(N, d, R, 0);
     hjb_reduce_kernel<<<dim3((unsigned)np, kRedSlices), 128 * kRedGroups, 0, st>>>(P, tx + p0 * (1 + d), M_I, S.f, S.rows.z,
-                                                                                S.rows.sa, S.hA);
-    hjb_reduce_finish_kernel<<<(unsigned)np, 128, 0, st>>>(P, tx + p0 * (1 + d), M_I, S.hA, bound, y + p0 * (1 + d));
+                                                                                S.rows.sa, part);
+    hjb_reduce_finish_kernel<<<(unsigned)np, 128, 0, st>>>(P, tx + p0 * (1 + d), M_I, part, bound, y + p0 * (1 + d));
     DPI_CUDA_CHECK(cudaGetLastError());
     *launches += 3;
   }

@@ -82,7 +82,8 @@ constexpr int64_t kTcPartFFloatsPerUnit = 8;  // [slot][lane quarter]
 // partG [n*units][32][128], partF [n*units][8]: scratch for the unit partial sums
 int launch_cha_tc_path(const ProblemDev& P, const TcNetDev& net, const float* tx, int64_t n, int M_I, uint64_t seed,
                        int64_t base, const float* u_s, const float* zS, const float* fb, const float* c0, float bound,
-                       float* partG, float* partF, int* unit_counter, void* zring, float* y, cudaStream_t st);
+                       float* partG, float* partF, int* unit_counter, void* zring, int* nonfinite, float* y,
+                       cudaStream_t st);
 // bytes of the increment ring of the chunked (d > 128) tensor-core kernel: 4 tiles x chunks x 32 KB per SM
 inline size_t tc_zring_bytes(const TcNetDev& net) { return net.nchunks > 1 ? (size_t)net.num_sms * 4 * net.nchunks * 32768 : 0; }
 // D[128x128] = A[128x128] . B[128x128]^T (fp32 row-major device buffers, rounded to bf16) through tcgen05
@@ -137,7 +138,7 @@ struct PisDev {
   int tf32;            // 1: eligible GEMMs on the tensor cores (TF32 operands, fp32 accumulate; dpi_gemm_tc.cu)
   const float* main_t[DPI_MAX_LINEAR];  // main[l].W transposed ([n_in][n_out]): K-major operands for the VJP GEMMs
 };
-int64_t hjb_scratch_floats(const PisDev& net, int d, int64_t rows);
+int64_t hjb_scratch_floats(const PisDev& net, int d, int64_t rows, int64_t points);
 int64_t hjb_points_per_chunk(const PisDev& net, int d, int M_I, int64_t budget_bytes);
 // y += integral part (paths + baseline row per point through the network), then clip
 int launch_hjb_paths(const ProblemDev& P, const PisDev& net, const float* tx, int64_t n, int M_I, uint64_t seed,
@@ -171,6 +172,13 @@ int launch_train_adam(const dpi_linear* L, int n_lin, const float* grad_flat, fl
 
 int launch_train_adam_dev(const dpi_linear* L, int n_lin, const float* grad_flat, float* m, float* v, float lr, float b1,
                           float b2, float eps, long long* step_dev, cudaStream_t st, int64_t* launches);
+
+// ---- draws and status (dpi_draws.cu) --------------------------------------------------------------------------
+// the Philox draws of a call in the reference's layout (any pointer may be null = skip)
+int launch_export_draws(const ProblemDev& P, int64_t n, int M_T, int M_I, uint64_t seed, int64_t base, float* zT,
+                        float* u_s, float* zS, int32_t* idx, cudaStream_t st, int64_t* launches);
+// *flag |= 1 if any of y[0..count) is inf / NaN
+int launch_check_finite(const float* y, int64_t count, int* flag, cudaStream_t st);
 
 // y = clip(y + add, +-bound) elementwise helpers used by the Zero-network shortcuts
 int launch_finish_zero(const ProblemDev& P, const float* tx, int64_t n, float bound, float* y, cudaStream_t st);

@@ -910,12 +910,13 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
 // y[p] += (sum of the unit partials in a fixed order) / M_I, then clip (data.py:222)
 __global__ void __launch_bounds__(128)
 cha_tc_finish_kernel(const float* __restrict__ partG, const float* __restrict__ partF, int units_per_point, int cls, int d,
-                     int M_I, float bound, float* __restrict__ y) {
+                     int M_I, float bound, float* __restrict__ y, int* __restrict__ nonfinite) {
   const int64_t p = blockIdx.x;
   const int j = threadIdx.x;
   const float invM = 1.f / (float)M_I;
   const bool clip = bound > 0.f && isfinite(bound);
   float* yp = y + p * (int64_t)(1 + d);
+  bool bad = false;
   if (j < d) {
     float s = 0.f;
     for (int g = 0; g < units_per_point; ++g)
@@ -923,6 +924,7 @@ cha_tc_finish_kernel(const float* __restrict__ partG, const float* __restrict__ 
     float v = yp[1 + j] + s * invM;
     if (clip) v = fminf(fmaxf(v, -bound), bound);
     yp[1 + j] = v;
+    bad |= !isfinite(v);
   }
   if (j == 0) {
     float s = 0.f;
@@ -932,17 +934,21 @@ cha_tc_finish_kernel(const float* __restrict__ partG, const float* __restrict__ 
     float v = yp[0] + s * invM;
     if (clip) v = fminf(fmaxf(v, -bound), bound);
     yp[0] = v;
+    bad |= !isfinite(v);
   }
+  // an overflowing 16-bit operand (inf -> NaN through the MMA) ends up here: report it instead of returning NaN labels
+  if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(nonfinite, 1);
 }
 
 // the same for the chunked layout (d > 128): unit partials are [chunk][row parity][128]
 __global__ void __launch_bounds__(128)
 cha_tc_finish_multi_kernel(const float* __restrict__ partG, const float* __restrict__ partF, int units_per_point, int d,
-                           int M_I, float bound, float* __restrict__ y) {
+                           int M_I, float bound, float* __restrict__ y, int* __restrict__ nonfinite) {
   const int64_t p = blockIdx.x;
   const float invM = 1.f / (float)M_I;
   const bool clip = bound > 0.f && isfinite(bound);
   float* yp = y + p * (int64_t)(1 + d);
+  bool bad = false;
   for (int j = threadIdx.x; j < d; j += 128) {
     const int cch = j >> 7, jj = j & 127;
     float s = 0.f;
@@ -952,6 +958,7 @@ cha_tc_finish_multi_kernel(const float* __restrict__ partG, const float* __restr
     float v = yp[1 + j] + s * invM;
     if (clip) v = fminf(fmaxf(v, -bound), bound);
     yp[1 + j] = v;
+    bad |= !isfinite(v);
   }
   if (threadIdx.x == 0) {
     float s = 0.f;
@@ -961,7 +968,9 @@ cha_tc_finish_multi_kernel(const float* __restrict__ partG, const float* __restr
     float v = yp[0] + s * invM;
     if (clip) v = fminf(fmaxf(v, -bound), bound);
     yp[0] = v;
+    bad |= !isfinite(v);
   }
+  if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(nonfinite, 1);
 }
 
 // dst = fp16 SWIZZLE_128B K-major image of W[n][col_off + k] (n < n_valid, k < k_valid; zero elsewhere)
@@ -1090,10 +1099,12 @@ int64_t tc_units_per_point(int M_I) {
 
 int launch_cha_tc_path(const ProblemDev& P, const TcNetDev& N, const float* tx, int64_t n, int M_I, uint64_t seed,
                        int64_t base, const float* u_s, const float* zS, const float* fb, const float* c0, float bound,
-                       float* partG, float* partF, int* unit_counter, void* zring, float* y, cudaStream_t st) {
+                       float* partG, float* partF, int* unit_counter, void* zring, int* nonfinite, float* y,
+                       cudaStream_t st) {
   if (n <= 0) return DPI_OK;
   if (n * tc_units_per_point(M_I) > 0x7fffff00LL) {
-    fprintf(stderr, "dpi tc: too many units in one launch\n");
+    set_error("tensor-core path: %lld points x %lld units exceed one launch; shard the call", (long long)n,
+              (long long)tc_units_per_point(M_I));
     return DPI_ERR_INVALID;
   }
   TcArgs A{};
@@ -1186,9 +1197,9 @@ int launch_cha_tc_path(const ProblemDev& P, const TcNetDev& N, const float* tx, 
   }
 #endif
   if (N.nchunks > 1)
-    cha_tc_finish_multi_kernel<<<(unsigned)n, 128, 0, st>>>(partG, partF, A.units_per_point, P.nx, M_I, bound, y);
+    cha_tc_finish_multi_kernel<<<(unsigned)n, 128, 0, st>>>(partG, partF, A.units_per_point, P.nx, M_I, bound, y, nonfinite);
   else
-    cha_tc_finish_kernel<<<(unsigned)n, 128, 0, st>>>(partG, partF, A.units_per_point, N.cls, P.nx, M_I, bound, y);
+    cha_tc_finish_kernel<<<(unsigned)n, 128, 0, st>>>(partG, partF, A.units_per_point, N.cls, P.nx, M_I, bound, y, nonfinite);
   DPI_CUDA_CHECK(cudaGetLastError());
   return DPI_OK;
 }

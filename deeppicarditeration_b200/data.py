@@ -8,7 +8,8 @@ Differences that are deliberate and visible:
   * labels are float32 tensors (the reference's configs run in float64); pass `out_dtype=torch.float64` to get
     them cast for a float64 trainer.  Arithmetic: fp32 CUDA-core path (`precision="fp32"`, within 1e-4 rel of the
     fp64 reference on replayed draws) or the 16-bit tcgen05 tensor-core path with fp32 accumulation (`precision="f16"`:
-    fp16 operands, within 1e-2; `"bf16"` is accepted as an alias of the same path).
+    fp16 operands, within 1e-2).  `"bf16"` is rejected (not built) rather than aliased; labels that come out inf / NaN
+    (a network outside fp16's range) raise FloatingPointError instead of being returned.
   * randomness is a counter-based Philox stream keyed by (`seed`, global point index) instead of torch's global
     generator, so the labels of a point do not depend on the batch size, the call pattern or the GPU count.
     Successive `sample*` calls advance the point index; `rank`/`world_size` give each GPU a disjoint index range.
@@ -73,7 +74,12 @@ class OnlineDataGenerator(DataGenerator):
             raise NotImplementedError("t ~ U[0,T] without the epsilon margin (ESTIMATE_TERMINAL without 'ByGx') is "
                                       "not built: sqrt(T-t) -> 0 at the boundary")
         self.precision, self.seed, self.out_dtype = precision, int(seed), out_dtype
+        # disjoint blocks of the global point index per rank; the Philox counter holds 48 bits of it
+        if not (0 <= int(rank) < int(world_size)) or (int(rank) + 1) * int(points_per_rank) > (1 << 48):
+            raise ValueError(f"rank {rank} of {world_size} with {points_per_rank} points per rank leaves the 48-bit "
+                             "point index range of the Philox counter")
         self._base = int(rank) * int(points_per_rank)
+        self._limit = int(points_per_rank)
         self._drawn = 0
         self._device = torch.device(device)
         self._engine: Optional[LabelEngine] = None
@@ -113,20 +119,42 @@ class OnlineDataGenerator(DataGenerator):
         return t if self.out_dtype is None else t.to(self.out_dtype)
 
     # ------------------------------------------------------------------------------------------
+    def _advance(self, n: int) -> int:
+        """Reserve n global point indices for a call: successive calls never share Philox streams."""
+        if self._drawn + n > self._limit:
+            raise RuntimeError("this rank's block of the global point index range is exhausted")
+        base = self._base + self._drawn
+        self._drawn += n
+        return base
+
+    def _label(self, tx: torch.Tensor, base: int, bound: float, draws: Optional[dict]) -> torch.Tensor:
+        """One call of the custom op `picard_b200::label_gen` (engine.py) = one dpi_label_gen through the C ABI."""
+        d = draws or {}
+        y = torch.ops.picard_b200.label_gen(
+            tx.to(self._device, torch.float32).contiguous(), self._engine.id, self.n_estimate_terminal,
+            self.n_estimate_integral, self.precision, float(bound) if math.isfinite(bound) else 0.0, self.seed, int(base),
+            d.get("zT"), d.get("u_s"), d.get("zS"), d.get("idx"))
+        self._engine.check_labels()  # raises FloatingPointError instead of handing out inf / NaN labels
+        return y
+
     def generate_with_gradients(self, tx: torch.Tensor, draws: Optional[dict] = None, point_index_base=None):
-        """data.py:1208-1218 (terminal + integral estimator, non-TD branch) -> y [n, 1+nx]."""
-        base = self._base + self._drawn if point_index_base is None else point_index_base
-        y = self._engine.label_gen(tx, self.n_estimate_terminal, self.n_estimate_integral, precision=self.precision,
-                                   sample_bound=self.sample_bound, seed=self.seed, point_index_base=base, draws=draws)
-        return self._out(y)
+        """data.py:1208-1218 (terminal + integral estimator, non-TD branch) -> y [n, 1+nx], UNCLIPPED like the
+        reference's (the clip belongs to sample_with_gradients, data.py:222)."""
+        if draws is not None:
+            draws = {k: (None if v is None else v.to(self._device)) for k, v in draws.items()}
+            if draws.get("idx") is not None:
+                draws["idx"] = draws["idx"].to(torch.int32)
+            base = 0 if point_index_base is None else point_index_base
+        else:
+            base = self._advance(tx.shape[0]) if point_index_base is None else point_index_base
+        return self._out(self._label(tx, base, float("inf"), draws))
 
     def sample_with_gradients(self, n_batch: int):
         """data.py:211-223: draw (t, x), label, clip -> (tx [n,1+nx], u_ux [n,1+nx])."""
-        base = self._base + self._drawn
+        base = self._advance(n_batch)
         tx = self._engine.sample_tx(n_batch, seed=self.seed, point_index_base=base)
-        y = self.generate_with_gradients(tx, point_index_base=base)
-        self._drawn += n_batch
-        return self._out(tx), y
+        y = self._label(tx, base, self.sample_bound, None)  # clip fused into the kernels' final write
+        return self._out(tx), self._out(y)
 
     def generate(self, tx):  # data.py:1203-1206 -> estimate_integral -> equation.f, which raises for every shipped
         raise NotImplementedError("The equation has dependence on z, use fff or ff instead.")  # equation (F3)
@@ -138,8 +166,7 @@ class OnlineDataGenerator(DataGenerator):
         raise NotImplementedError("Hessian labels (estimate_*_and_hessians_double) are not built yet")
 
     def sample_exact_with_gradients(self, n_batch):  # data.py:251-262
-        tx = self._engine.sample_tx(n_batch, seed=self.seed, point_index_base=self._base + self._drawn)
-        self._drawn += n_batch
+        tx = self._engine.sample_tx(n_batch, seed=self.seed, point_index_base=self._advance(n_batch))
         t, x = tx[:, :1], tx[:, 1:]
         eq = self.equation.to(tx.device) if hasattr(self.equation, "to") else self.equation
         u, ux = eq.u_u_x(t, x)

@@ -1,73 +1,214 @@
-"""Mirror of the boundary caller `IterableDatasetWithInternalBatch` (picard/dataset.py:20-137).
+"""Label plumbing between the generator and the trainer: the boundary caller and the per-iteration label cache.
 
-Only the call contract is kept: the dataset calls `batch_data_generator(n_samples_each_call) -> (tx, y)` and yields
-`batch_size`-row views.  The reference's chunking of a buffer into several generator calls exists to dodge the
-HBM blow-up of materialised [n*M, 1+nx] path tensors; the fused kernels never materialise them, so a fractional
-`n_batch_buffer` is honoured for compatibility but buys nothing here.
+The reference wraps the generator in `IterableDatasetWithInternalBatch` (picard/dataset.py:20-137), whose
+`refresh_buffer` (:107-116) is the one call site of the hot path, and caches an iteration's labels on the HOST
+(`CacheToMemoryWrapper` + `InMemorySaver`, picard/dataset.py:203-255, picard/data_saver.py:69-83) or in HDF5
+(`H5Saver`, picard/data_saver.py:25-54) so that N_EPOCHS passes reuse them.  Its buffer/call arithmetic exists to keep
+the materialised [n*M, 1+nx] path tensors inside HBM; the fused kernels never build those tensors, so here
+
+  * a refresh is ONE generator call for the whole buffer, whatever `n_batch_buffer` says (a fractional value, which
+    makes the reference split one batch over several calls, only fixes the buffer at one batch);
+  * the cache (`LabelStore`) is preallocated on the generator's device and handed to the trainer as views -- labels
+    never visit the host unless a file is asked for;
+  * files keep the reference's dataset names (`tx`, `u_ux`; picard/data.py:1513-1521): HDF5 when `h5py` is
+    importable, else an `.npz` with the same keys.
+
+Class and method names the reference's `PicardDataModule` touches are kept (`IterableDatasetWithInternalBatch`,
+`attach_saver`, `set_size`, `CacheToMemoryWrapper.init`, `InMemorySaver.save/create_torch_dataset`).
 """
 from __future__ import annotations
 
-from typing import Callable, Tuple, Union
+from fractions import Fraction
+from typing import Callable, Iterator, List, Optional, Sequence, Tuple, Union
 
 import torch
 
 
+class LabelStore:
+    """Device-resident columns of one label set, filled front to back; the role of `InMemorySaver`."""
+
+    def __init__(self, n_total: int, widths: Sequence[int], device=None, dtype=None):
+        self.capacity, self.filled = int(n_total), 0
+        self.widths, self.device, self.dtype = [int(w) for w in widths], device, dtype
+        self.columns: List[torch.Tensor] = []  # allocated at the first save, on the device the labels live on
+
+    def _allocate(self, like: torch.Tensor) -> None:
+        device = self.device if self.device is not None else like.device
+        dtype = self.dtype if self.dtype is not None else like.dtype
+        self.columns = [torch.empty(self.capacity, w, device=device, dtype=dtype) for w in self.widths]
+
+    # Saver protocol of the reference (picard/data_saver.py:11-22): save(sequence of tensors, row count), close()
+    def save(self, data: Sequence[torch.Tensor], length: int) -> None:
+        if self.filled + length > self.capacity:
+            raise ValueError(f"label store overflow: {self.filled} + {length} > {self.capacity}")
+        if not self.columns:
+            self._allocate(data[0])
+        for col, block in zip(self.columns, data):
+            col[self.filled:self.filled + length].copy_(block, non_blocking=True)
+        self.filled += length
+
+    def close(self) -> None:
+        pass
+
+    @property
+    def data(self) -> List[torch.Tensor]:
+        return self.columns
+
+    @property
+    def complete(self) -> bool:
+        return self.filled == self.capacity
+
+    def batches(self, batch_size: int, shuffle: bool = False, drop_last: bool = False,
+                generator: Optional[torch.Generator] = None) -> "StoredBatches":
+        if not self.complete:
+            raise ValueError("Not all data are filled.")
+        return StoredBatches(self.columns, batch_size, shuffle, drop_last, generator)
+
+    def create_torch_dataset(self, batch_size: int, shuffle: bool = False, drop_last: bool = False, **_ignored):
+        """Name used by the reference's wrapper (picard/data_saver.py:80-83); DataLoader kwargs other than
+        shuffle / drop_last have no meaning for device-resident views and are ignored."""
+        return self.batches(batch_size, shuffle=shuffle, drop_last=drop_last)
+
+    def write(self, path: str, labels: Sequence[str] = ("tx", "u_ux")) -> str:
+        """One host copy, on request: HDF5 datasets named like the reference's split files, or npz without h5py."""
+        if not self.complete:
+            raise ValueError("Not all data are filled.")
+        arrays = {name: col.detach().cpu().numpy() for name, col in zip(labels, self.columns)}
+        try:
+            import h5py  # noqa: WPS433 (optional dependency, absent from the build image)
+        except ImportError:
+            import numpy as np
+
+            out = path if path.endswith(".npz") else path + ".npz"
+            np.savez(out, **arrays)
+            return out
+        with h5py.File(path, "w") as f:
+            for name, arr in arrays.items():
+                f.create_dataset(name, data=arr)
+        return path
+
+
+InMemorySaver = LabelStore  # the reference's name for the same role
+
+
+class StoredBatches(torch.utils.data.IterableDataset):
+    """Mini-batch views of a complete LabelStore (unshuffled by default: config.py:90)."""
+
+    def __init__(self, columns, batch_size, shuffle, drop_last, generator):
+        self.columns, self.batch_size, self.shuffle, self.drop_last = columns, int(batch_size), shuffle, drop_last
+        self.generator = generator
+        n = columns[0].shape[0]
+        self._count = n // self.batch_size if drop_last else -(-n // self.batch_size)
+
+    def __len__(self) -> int:
+        return self._count
+
+    def __iter__(self) -> Iterator[Tuple[torch.Tensor, ...]]:
+        n = self.columns[0].shape[0]
+        if self.shuffle:
+            perm = torch.randperm(n, device=self.columns[0].device, generator=self.generator)
+            cols = [c[perm] for c in self.columns]
+        else:
+            cols = self.columns
+        for k in range(self._count):
+            lo = k * self.batch_size
+            yield tuple(c[lo:lo + self.batch_size] for c in cols)
+
+
 class IterableDatasetWithInternalBatch(torch.utils.data.IterableDataset):
+    """Boundary caller of the hot path: `batch_data_generator(n_points) -> (tx, y)` once per refresh, batches out.
+
+    Constructor arguments as in the reference (picard/dataset.py:27-43).  Use with `DataLoader(batch_size=None)`.
+    """
+
     def __init__(self, n: int, n_batch_buffer: Union[int, float], batch_size: int, batch_data_generator: Callable):
         super().__init__()
-        (self.n_batch_buffer, self.n_samples_each_buffer, self._n_calls_to_generator_each_buffer,
-         self._n_samples_each_call) = self._get_sampling_number_info(n_batch_buffer, batch_size)
-        self.batch_size = batch_size
-        self.n_buffer_refresh = self._get_n_refresh(n)
+        self.batch_size = int(batch_size)
+        self.n_batch_buffer = self._batches_per_refresh(n_batch_buffer)
+        self.n_samples_each_buffer = self.n_batch_buffer * self.batch_size
         self.batch_data_generator = batch_data_generator
         self.saver = None
+        self.set_size(n)
 
     @staticmethod
-    def _get_sampling_number_info(n_batch_buffer, batch_size) -> Tuple[int, int, int, int]:  # dataset.py:55-78
-        if abs(round(n_batch_buffer) - n_batch_buffer) < 1e-5:
-            n_batch_buffer = round(n_batch_buffer)
-        if isinstance(n_batch_buffer, int):
-            return n_batch_buffer, n_batch_buffer * batch_size, 1, n_batch_buffer * batch_size
-        assert isinstance(n_batch_buffer, float) and 0 < n_batch_buffer < 1
-        calls = round(1 / n_batch_buffer)
-        each = batch_size // calls
-        assert each * calls == batch_size, f"batch_size {batch_size} must be a multiple of {calls}"
-        return 1, batch_size, calls, each
+    def _batches_per_refresh(n_batch_buffer: Union[int, float]) -> int:
+        frac = Fraction(n_batch_buffer).limit_denominator(1 << 16)
+        if frac >= 1:
+            if frac.denominator != 1:
+                raise ValueError(f"n_batch_buffer={n_batch_buffer}: a value above 1 must be a whole number of batches")
+            return int(frac)
+        if frac <= 0 or frac.numerator != 1:
+            raise ValueError(f"n_batch_buffer={n_batch_buffer}: a fraction must be 1/k (picard/dataset.py:33-35)")
+        return 1  # the reference would split one batch into k generator calls; one fused call needs no split
 
-    def _get_n_refresh(self, n: int) -> int:  # dataset.py:80-99
-        k = n // self.n_samples_each_buffer
-        assert k * self.n_samples_each_buffer == n, (
-            f"Total number of data {n} must be a multiple of batch_size({self.batch_size})*"
-            f"n_batch_buffer({self.n_batch_buffer})={self.n_samples_each_buffer}")
-        return k
+    def set_size(self, n: int) -> None:
+        refreshes, rest = divmod(int(n), self.n_samples_each_buffer)
+        if rest or refreshes < 1:
+            raise ValueError(f"Total number of data {n} must be a positive multiple of batch_size({self.batch_size})*"
+                             f"n_batch_buffer({self.n_batch_buffer})={self.n_samples_each_buffer}")
+        self.n_buffer_refresh = refreshes
 
-    def set_size(self, n):
-        self.n_buffer_refresh = self._get_n_refresh(n)
-
-    def attach_saver(self, saver):
-        assert self.saver is None, "Saver can only be attached once"
+    def attach_saver(self, saver) -> None:
+        if self.saver is not None:
+            raise RuntimeError("Saver can only be attached once")
         self.saver = saver
 
-    def refresh_buffer(self):  # dataset.py:107-116
-        xs, ys = [], []
-        for _ in range(self._n_calls_to_generator_each_buffer):
-            x, y = self.batch_data_generator(self._n_samples_each_call)
-            xs.append(x)
-            ys.append(y)
-        return (xs[0], ys[0]) if len(xs) == 1 else (torch.cat(xs, 0), torch.cat(ys, 0))
+    def refresh_buffer(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        """picard/dataset.py:107-116, as a single call of the fused generator."""
+        return self.batch_data_generator(self.n_samples_each_buffer)
 
-    def __iter__(self):  # dataset.py:118-129
+    def __iter__(self):
         for _ in range(self.n_buffer_refresh):
-            buffer = self.refresh_buffer()
+            tx, y = self.refresh_buffer()
             if self.saver is not None:
-                self.saver.save(buffer, self.n_samples_each_buffer)
-            x, y = buffer
-            x = x.view(self.n_batch_buffer, self.batch_size, -1)
-            y = y.view(self.n_batch_buffer, self.batch_size, -1)
-            for i in range(self.n_batch_buffer):
-                yield x[i], y[i]
+                self.saver.save((tx, y), self.n_samples_each_buffer)
+            yield from zip(tx.split(self.batch_size), y.split(self.batch_size))
         if self.saver is not None:
             self.saver.close()
 
-    def __len__(self):
+    def __len__(self) -> int:
         return self.n_buffer_refresh * self.n_batch_buffer
+
+
+class CacheToMemoryWrapper(torch.utils.data.IterableDataset):
+    """Generate an iteration's labels once, replay them every epoch (picard/dataset.py:203-255) -- on the device."""
+
+    def __init__(self, dataset: IterableDatasetWithInternalBatch, batch_size: Optional[int] = None, **batching):
+        self.dataset = dataset
+        self.batch_size = int(batch_size or dataset.batch_size)
+        self.batching = {k: batching[k] for k in ("shuffle", "drop_last") if k in batching}
+        self.saver: Optional[LabelStore] = None
+        self._replay: Optional[StoredBatches] = None
+        self._file: Optional[Tuple[str, Sequence[str]]] = None
+
+    def enable_save_to_file(self, path: str, labels: Sequence[str] = ("tx", "u_ux")) -> None:
+        self._file = (path, labels)
+
+    def init(self, n_total: int, n_dims: Sequence[int], preload: bool = False, device=None,
+             dtype=None) -> None:
+        self.dataset.set_size(n_total)
+        self.saver = LabelStore(n_total, n_dims, device=device, dtype=dtype)
+        self.dataset.attach_saver(self.saver)
+        if preload or self._file is not None or self.batch_size != self.dataset.batch_size:
+            for _ in self.dataset:  # ALL labels of the iteration are generated here
+                pass
+            self._finish()
+
+    def _finish(self) -> None:
+        self._replay = self.saver.batches(self.batch_size, **self.batching)
+        if self._file is not None:
+            self.saver.write(*self._file)
+
+    def __iter__(self):
+        if self.saver is None:
+            raise RuntimeError("Must call init() before using the iterator")
+        if self._replay is not None:
+            return iter(self._replay)
+        return self._first_pass()
+
+    def _first_pass(self):
+        yield from self.dataset
+        self._finish()
+
+    def __len__(self) -> int:
+        return len(self._replay) if self._replay is not None else len(self.dataset)

@@ -90,6 +90,7 @@ class LabelEngine:
             nat.check(self.lib.dpi_set_problem(self.h, C.byref(p)), "dpi_set_problem")
         self.nx = int(nx)
         self.kind = kind
+        self.sdgd_v = int(sdgd_v)
 
     def _fill_chain(self, arr, lins: Sequence[Tuple[torch.Tensor, torch.Tensor]]) -> int:
         if len(lins) > nat.DPI_MAX_LINEAR:
@@ -129,15 +130,20 @@ class LabelEngine:
     def _cfg(M_T, M_I, precision, bound, seed, base):
         cfg = nat.dpi_label_config()
         cfg.M_T, cfg.M_I = int(M_T), int(M_I)
+        # "tf32" names what the reduced-precision flag selects on the PISGradNet path (TF32 GEMMs); "bf16" maps to the
+        # distinct DPI_PREC_BF16 value, which the library rejects (bf16 operands are not built) instead of aliasing fp16
         cfg.precision = {"fp32": nat.DPI_PREC_FP32, "f16": nat.DPI_PREC_F16, "fp16": nat.DPI_PREC_F16,
-                         "bf16": nat.DPI_PREC_F16, "tf32": nat.DPI_PREC_F16}[precision]  # aliases of the reduced-precision tensor-core paths
+                         "tf32": nat.DPI_PREC_F16, "bf16": nat.DPI_PREC_BF16}[precision]
         cfg.sample_bound = float(bound) if bound is not None and math.isfinite(bound) else 0.0
         cfg.seed = seed & (2**64 - 1)
         cfg.point_index_base = int(base)
         return cfg
 
     def label_gen(self, tx: torch.Tensor, M_T: int, M_I: int, *, precision: str = "fp32", sample_bound=None,
-                  seed: int = 0, point_index_base: int = 0, draws: Optional[dict] = None) -> torch.Tensor:
+                  seed: int = 0, point_index_base: int = 0, draws: Optional[dict] = None,
+                  check: bool = False) -> torch.Tensor:
+        """dpi_label_gen on device tensors (asynchronous).  check=True additionally synchronises and raises
+        FloatingPointError if a label is inf / NaN (dpi_check_labels), e.g. a network outside fp16's range."""
         tx = _f32c(tx, self.device)
         n = tx.shape[0]
         assert tx.shape[1] == 1 + self.nx
@@ -153,6 +159,8 @@ class LabelEngine:
             dr.zT, dr.u_s, dr.zS = zT.data_ptr(), u_s.data_ptr(), zS.data_ptr()
             if draws.get("idx") is not None:
                 idx = draws["idx"].to(device=self.device, dtype=torch.int32).contiguous()
+                assert idx.numel() == 0 or (int(idx.min()) >= 0 and int(idx.max()) < self.nx), \
+                    "SDGD coordinates must lie in [0, nx)"
                 keep.append(idx)
                 dr.idx = idx.data_ptr()
         with torch.cuda.device(self.device):
@@ -160,7 +168,35 @@ class LabelEngine:
                                              _ptr(y), self._stream()), "dpi_label_gen")
         if keep:  # draws must outlive the asynchronous launch
             torch.cuda.current_stream(self.device).synchronize()
+        if check:
+            self.check_labels()
         return y
+
+    def check_labels(self) -> None:
+        """Synchronise and raise FloatingPointError if a label written since the last check was inf / NaN."""
+        with torch.cuda.device(self.device):
+            nat.check(self.lib.dpi_check_labels(self.h, self._stream()), "dpi_check_labels")
+
+    def export_draws(self, n: int, M_T: int, M_I: int, *, seed: int = 0, point_index_base: int = 0,
+                     want=("zT", "u_s", "zS", "idx")) -> dict:
+        """The Philox draws a label_gen(seed, point_index_base) call consumes, in the reference's layout
+        (zT [n*M_T,nx], u_s [n*M_I,1], zS [n*M_I,nx], idx [n*M_I,v]); usable as `draws=` or by the reference itself."""
+        cfg = self._cfg(M_T, M_I, "fp32", None, seed, point_index_base)
+        out = {}
+        if "zT" in want:
+            out["zT"] = torch.empty(n * M_T, self.nx, device=self.device, dtype=torch.float32)
+        if "u_s" in want:
+            out["u_s"] = torch.empty(n * M_I, 1, device=self.device, dtype=torch.float32)
+        if "zS" in want:
+            out["zS"] = torch.empty(n * M_I, self.nx, device=self.device, dtype=torch.float32)
+        if "idx" in want and getattr(self, "sdgd_v", 0) > 0:
+            out["idx"] = torch.empty(n * M_I, self.sdgd_v, device=self.device, dtype=torch.int32)
+        with torch.cuda.device(self.device):
+            nat.check(self.lib.dpi_export_draws(self.h, n, C.byref(cfg), _ptr(out.get("zT")), _ptr(out.get("u_s")),
+                                                _ptr(out.get("zS")), _ptr(out.get("idx")), self._stream()),
+                      "dpi_export_draws")
+        out.setdefault("idx", None)
+        return out
 
     def label_gen_host(self, n: int, M_T: int, M_I: int, *, tx_host: Optional[torch.Tensor] = None,
                        y_host: Optional[torch.Tensor] = None, tx_out_host: Optional[torch.Tensor] = None,
@@ -216,15 +252,17 @@ class LabelEngine:
 # torch custom op: thin shim so the label generator composes with torch code (streams, graphs capture-free).
 # ------------------------------------------------------------------------------------------------
 @torch.library.custom_op("picard_b200::label_gen", mutates_args=(), device_types="cuda")
-def label_gen_op(tx: torch.Tensor, engine_id: int, M_T: int, M_I: int, f16: bool, sample_bound: float, seed: int,
+def label_gen_op(tx: torch.Tensor, engine_id: int, M_T: int, M_I: int, precision: str, sample_bound: float, seed: int,
                  point_index_base: int, zT: Optional[torch.Tensor] = None, u_s: Optional[torch.Tensor] = None,
                  zS: Optional[torch.Tensor] = None, idx: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """`torch.ops.picard_b200.label_gen`: what `OnlineDataGenerator.generate_with_gradients` calls.  `engine_id` names
+    the LabelEngine (handle with the packed equation and frozen u_k); the body is the C-ABI call, nothing else."""
     eng = _ENGINES[engine_id]
     draws = None if zT is None else {"zT": zT, "u_s": u_s, "zS": zS, "idx": idx}
-    return eng.label_gen(tx, M_T, M_I, precision="f16" if f16 else "fp32", sample_bound=sample_bound, seed=seed,
+    return eng.label_gen(tx, M_T, M_I, precision=precision, sample_bound=sample_bound, seed=seed,
                          point_index_base=point_index_base, draws=draws)
 
 
 @label_gen_op.register_fake
-def _(tx, engine_id, M_T, M_I, f16, sample_bound, seed, point_index_base, zT=None, u_s=None, zS=None, idx=None):
+def _(tx, engine_id, M_T, M_I, precision, sample_bound, seed, point_index_base, zT=None, u_s=None, zS=None, idx=None):
     return torch.empty_like(tx, dtype=torch.float32)

@@ -50,7 +50,8 @@ typedef enum {
   DPI_ERR_INVALID = -1,     /* bad argument / unsupported combination */
   DPI_ERR_CUDA = -2,        /* CUDA runtime error (message has the cudaError string) */
   DPI_ERR_UNSUPPORTED = -3, /* valid in the reference, not built yet in this library */
-  DPI_ERR_STATE = -4        /* problem / network not set */
+  DPI_ERR_STATE = -4,       /* problem / network not set */
+  DPI_ERR_NONFINITE = -5    /* a label came out inf / NaN (dpi_check_labels, dpi_label_gen_host) */
 } dpi_status;
 
 typedef enum { DPI_EQ_CHA = 0, DPI_EQ_GBM = 1, DPI_EQ_OU = 2 } dpi_equation_kind;
@@ -58,12 +59,15 @@ typedef enum { DPI_NET_ZERO = 0, DPI_NET_MLP = 1, DPI_NET_PISGRAD = 2 } dpi_netw
 /* arithmetic of the u_k GEMM chain: fp32 FMA (labels within 1e-4 rel of the fp64 reference) or the 16-bit tcgen05
  * tensor-core path with fp32 accumulation (within 1e-2 rel; measured 6e-5).  The tensor-core operands are IEEE fp16,
  * not bf16: three more mantissa bits at the same operand width, and the bias/ELU/ELU' epilogue runs in packed
- * fp16x2.  Its range limit is |log2(e) x pre-activation| < 6.5e4, far above anything a trained u_k produces.
- * DPI_PREC_BF16 is kept as an alias of the same path for callers written against the first revision.
+ * fp16x2.  Its range limit is |log2(e) x pre-activation| < 6.5e4, far above anything a trained u_k produces; a network
+ * that does leave it yields inf / NaN, which the label kernels' final pass records in a status word:
+ * dpi_label_gen_host returns DPI_ERR_NONFINITE and dpi_check_labels reports it for the asynchronous dpi_label_gen.
+ * DPI_PREC_BF16 (bf16 operands: fp32's range, 8 mantissa bits) is NOT built: it is a distinct value that every entry
+ * point rejects with DPI_ERR_UNSUPPORTED, so a caller asking for bf16's range is never silently given fp16's.
  * Which paths DPI_PREC_F16 selects: Cha with the MLP [1+d,128,128,128,128,1], d <= 1024 (chunked first layer above 128);
  * GBM/SDGD with hidden width 64, v <= 127 (fp16 2-jets); PISGradNet/OU with its wide GEMMs on the tensor cores in
  * TF32 (fp32 operands in memory, 10-bit mantissa in the multiply, fp32 accumulate).  Anything else: DPI_ERR_UNSUPPORTED. */
-typedef enum { DPI_PREC_FP32 = 0, DPI_PREC_F16 = 1, DPI_PREC_BF16 = 1 } dpi_precision;
+typedef enum { DPI_PREC_FP32 = 0, DPI_PREC_F16 = 1, DPI_PREC_BF16 = 2 } dpi_precision;
 
 /* Equation parameters.  All array pointers are HOST pointers (tiny), copied by dpi_set_problem. */
 typedef struct {
@@ -128,7 +132,8 @@ typedef struct {
   float sample_bound;     /* clip(y, +-bound); <=0 or inf = off (data.py:123-128,222) */
   uint64_t seed;          /* Philox key (ignored when draws != NULL) */
   int64_t point_index_base; /* global index of tx row 0: Philox counters are keyed by the GLOBAL point
-                               index so labels do not depend on the shard size or GPU count */
+                               index so labels do not depend on the shard size or GPU count;
+                               0 <= point_index_base, point_index_base + n <= 2^48 */
 } dpi_label_config;
 
 int dpi_version(void);
@@ -138,7 +143,9 @@ int dpi_create(int device, dpi_handle** out);
 int dpi_destroy(dpi_handle* h);
 
 int dpi_set_problem(dpi_handle* h, const dpi_problem* p);
-/* (Re)pack the frozen network for the kernels. Reads the weight tensors on `stream`. */
+/* Freeze u_k: every tensor of `net` is copied / repacked into handle-owned memory on `stream`, and the stream is
+ * synchronised before the call returns.  Afterwards the label path and dpi_net_eval never read the caller's tensors
+ * again: they may be trained in place (the next Picard iterate) or freed (picard/data.py:407-412 semantics). */
 int dpi_set_network(dpi_handle* h, const dpi_network* net, void* stream);
 
 /* tx [n, 1+nx] device, written.  t ~ U[eps, T-eps] (eps=0.01), x = x0 + sqrt(t*alpha) Z. */
@@ -148,8 +155,21 @@ int dpi_sample_tx(dpi_handle* h, int64_t n, int64_t point_index_base, uint64_t s
 int dpi_label_gen(dpi_handle* h, const float* tx, int64_t n, const dpi_label_config* cfg,
                   const dpi_draws* draws /* nullable: Philox mode */, float* y, void* stream);
 
-/* Same, with HOST buffers (pinned for full speed): copies tx in, y out, and synchronises. If tx_in_host is
- * NULL the points are drawn on the device (dpi_sample_tx) and returned in tx_out_host. */
+/* Synchronises `stream` and returns DPI_ERR_NONFINITE if any label written by dpi_label_gen on this handle since the
+ * last check was inf / NaN (the status word is then cleared), DPI_OK otherwise. */
+int dpi_check_labels(dpi_handle* h, void* stream);
+
+/* The Philox draws a dpi_label_gen call with the same (cfg->seed, cfg->point_index_base, M_T, M_I) consumes, written
+ * in the reference's layout (row = point * M + sample): zT [n*M_T, nx], u_s [n*M_I], zS [n*M_I, nx],
+ * idx [n*M_I, sdgd_v] (int32).  DEVICE pointers, any of them NULL = skip.  Feeding them back through `draws`
+ * reproduces the Philox-mode labels; feeding them to the reference reproduces them there (deterministic mode,
+ * picard/data.py:914,359-360,501).  Not on the label path: the label kernels never materialise their increments. */
+int dpi_export_draws(dpi_handle* h, int64_t n, const dpi_label_config* cfg, float* zT, float* u_s, float* zS,
+                     int32_t* idx, void* stream);
+
+/* Same, with HOST buffers (pinned for full speed): copies tx in, y out, synchronises, and checks the labels
+ * (DPI_ERR_NONFINITE). If tx_in_host is NULL the points are drawn on the device (dpi_sample_tx) and returned in
+ * tx_out_host. */
 int dpi_label_gen_host(dpi_handle* h, const float* tx_in_host, int64_t n, const dpi_label_config* cfg,
                        float* tx_out_host /* nullable */, float* y_host, void* stream);
 

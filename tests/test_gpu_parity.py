@@ -292,15 +292,6 @@ def test_bf16_shard_invariance_and_determinism():
     e.close()
 
 
-def test_bf16_alias_selects_the_same_path():
-    from tests.gpu_util import engine_for
-    eq = orc.Cha(100, 1.0, 5.0, 1.0)
-    e = engine_for(eq, orc.make_mlp(101, [128] * 4, seed=5))
-    tx = e.sample_tx(8, seed=1)
-    assert torch.equal(e.label_gen(tx, 32, 256, precision="f16", seed=2), e.label_gen(tx, 32, 256, precision="bf16", seed=2))
-    e.close()
-
-
 def test_bf16_rejects_unsupported_network_loudly():
     from tests.gpu_util import engine_for
     eq = orc.Cha(100, 1.0, 5.0, 1.0)

@@ -137,6 +137,7 @@ def test_pisgradnet_mirror_matches_oracle_forward():
 
 
 def test_dataset_contract():
+    """Boundary caller (picard/dataset.py:20-137): one fused generator call per refresh, batch views out."""
     calls = []
 
     def gen(n):
@@ -151,10 +152,60 @@ def test_dataset_contract():
     assert all(x.shape == (16, 3) and torch.equal(y, 2 * x) for x, y in batches)
     assert torch.equal(torch.cat([x for x, _ in batches])[:, 0], torch.arange(64.))
     calls.clear()
-    d2 = ds.IterableDatasetWithInternalBatch(32, 0.25, 16, gen)  # fractional buffer: 4 generator calls per batch
-    assert len(list(d2)) == 2 and calls == [4] * 8
-    with pytest.raises(AssertionError):
-        ds.IterableDatasetWithInternalBatch(40, 1, 16, gen)
+    # fractional buffer (the reference splits one batch into 1/f generator calls to bound its path tensors): the
+    # buffer is one batch, generated by ONE call
+    d2 = ds.IterableDatasetWithInternalBatch(32, 0.25, 16, gen)
+    assert len(d2) == 2 and len(list(d2)) == 2 and calls == [16, 16]
+    for bad in ((40, 1, 16), (32, 0.3, 16), (32, 1.5, 16)):
+        with pytest.raises(ValueError):
+            ds.IterableDatasetWithInternalBatch(*bad, gen)
+
+
+def test_label_cache_replays_epochs_without_regenerating(tmp_path):
+    """Label caching (picard/dataset.py:203-255, data_saver.py:69-83): labels are generated once per iteration,
+    every epoch replays the stored set, other batch sizes re-slice it, and the on-disk copy keeps the reference's
+    dataset names `tx` / `u_ux` (picard/data.py:1513-1521)."""
+    calls = []
+
+    def gen(n):
+        calls.append(n)
+        base = sum(calls[:-1])
+        x = torch.arange(base, base + n, dtype=torch.float32).view(-1, 1).repeat(1, 3)
+        return x, torch.cat([2 * x, x[:, :1]], 1)
+
+    inner = ds.IterableDatasetWithInternalBatch(16, 1, 16, gen)
+    cache = ds.CacheToMemoryWrapper(inner)
+    with pytest.raises(RuntimeError):
+        iter(cache)
+    cache.init(64, [3, 4])  # the data module sets the real size here (picard/data.py:1735-1760)
+    first = list(cache)  # generation pass: streams batches while filling the store
+    assert calls == [16] * 4 and len(first) == 4 and cache.saver.complete
+    for _ in range(3):  # later epochs: no generator call
+        again = list(cache)
+        assert len(again) == len(cache) == 4
+        assert all(torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) for a, b in zip(first, again))
+    assert calls == [16] * 4
+    # preload + a different trainer batch size + file
+    calls.clear()
+    c2 = ds.CacheToMemoryWrapper(ds.IterableDatasetWithInternalBatch(32, 2, 16, gen), batch_size=8, shuffle=False)
+    c2.enable_save_to_file(str(tmp_path / "split_00"))
+    c2.init(64, [3, 4], preload=True)
+    assert calls == [32, 32] and len(c2) == 8
+    b = list(c2)
+    assert b[0][0].shape == (8, 3) and torch.equal(torch.cat([x for x, _ in b])[:, 0], torch.arange(64.))
+    import glob
+
+    import numpy as np
+    (path,) = glob.glob(str(tmp_path / "split_00*"))
+    if path.endswith(".npz"):
+        z = np.load(path)
+        assert z["tx"].shape == (64, 3) and z["u_ux"].shape == (64, 4)
+    shuffled = ds.LabelStore(8, [1])
+    shuffled.save((torch.arange(8.).view(-1, 1),), 8)
+    got = torch.cat([x for (x,) in shuffled.batches(4, shuffle=True, generator=torch.Generator().manual_seed(0))])
+    assert sorted(got.view(-1).tolist()) == list(range(8))
+    with pytest.raises(ValueError):
+        ds.LabelStore(8, [1]).batches(4)
 
 
 def test_shard_range_partitions():
