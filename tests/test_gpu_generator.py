@@ -69,9 +69,13 @@ def test_sample_with_gradients_contract_and_streams():
     # ranks own disjoint index ranges
     gen_r1 = _generator(g, seed=3, rank=1, world_size=2, points_per_rank=64)
     tx_r1, _ = gen_r1.sample_with_gradients(8)
+    gen_all = _generator(g, seed=3)  # one rank owning the whole index range: its points 64.. are rank 1's block
+    tx_all, _ = gen_all.sample_with_gradients(72)
+    assert torch.equal(tx_all[64:], tx_r1)
     gen_r0 = _generator(g, seed=3, rank=0, world_size=2, points_per_rank=64)
-    tx_r0, _ = gen_r0.sample_with_gradients(72)
-    assert torch.equal(tx_r0[64:], tx_r1)
+    gen_r0.sample_with_gradients(64)
+    with pytest.raises(RuntimeError):
+        gen_r0.sample_with_gradients(1)  # a rank never spills into its neighbour's block
 
 
 def test_dataset_with_gradients_iterates_batches():

@@ -273,5 +273,5 @@ def test_custom_op_is_the_generator_path_and_streams_advance():
     assert torch.equal(y1, y_op) and not torch.equal(y1, y2)  # independent MC noise on the second call
     assert float(y1.abs().max()) > 0.3  # generate_with_gradients does not clip ...
     _, ys = gen.sample_with_gradients(8)
-    assert float(ys.abs().max()) <= 0.3  # ... sample_with_gradients does
+    assert float(ys.abs().max()) <= 0.3 + 1e-6  # ... sample_with_gradients does (0.3 rounded to fp32)
     gen.engine.close()

@@ -11,7 +11,7 @@ nx = int(sys.argv[4]) if len(sys.argv) > 4 else 100
 if prec == "err":
     g = Golden("burgers_100d_mlp128")
     e = engine_for(g.eq, g.net, g.v)
-    for pr in ("fp32", "bf16"):
+    for pr in ("fp32", "f16"):
         y = e.label_gen(g.tx, g.M_T, g.M_I, precision=pr, draws=draws_dict(g.draws)).double().cpu()
         print(pr, "rel-L2 all %.3e value %.3e grad %.3e integral-only %.3e" % (
             orc.rel_l2(y, g.y), orc.rel_l2(y[:, :1], g.y[:, :1]), orc.rel_l2(y[:, 1:], g.y[:, 1:]),

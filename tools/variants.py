@@ -28,6 +28,6 @@ else:
     libs = sorted(f for f in os.listdir(VDIR) if f.endswith(".so"))
     for lib in libs:
         env = dict(os.environ, DPI_B200_LIB=os.path.join(VDIR, lib))
-        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "quick_bench.py"), "bf16", n, M], env=env,
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "quick_bench.py"), "f16", n, M], env=env,
                            capture_output=True, text=True, timeout=300)
         print(lib, (r.stdout.strip().splitlines() or [r.stderr[-300:]])[-1])
