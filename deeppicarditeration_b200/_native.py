@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = (
     "dpi_sample_tx", "dpi_label_gen", "dpi_label_gen_host", "dpi_net_eval", "dpi_launch_count",
     "dpi_set_stage_timing", "dpi_stage_ms", "dpi_selftest_umma",
     "dpi_train_init", "dpi_train_param_count", "dpi_train_grad", "dpi_train_adam", "dpi_train_fit", "dpi_train_reset",
-    "dpi_check_labels", "dpi_export_draws",
+    "dpi_check_labels", "dpi_export_draws", "dpi_sample_tx_ex", "dpi_net_hessian_diag",
 )
 
 
@@ -92,6 +92,8 @@ def load() -> C.CDLL:
                                   C.c_void_p, C.c_void_p]
     lib.dpi_label_gen_host.argtypes = [H, C.c_void_p, C.c_int64, C.POINTER(dpi_label_config), C.c_void_p, C.c_void_p,
                                        C.c_void_p]
+    lib.dpi_sample_tx_ex.argtypes = [H, C.c_int64, C.c_int64, C.c_uint64, C.c_int32, C.c_float, C.c_void_p, C.c_void_p]
+    lib.dpi_net_hessian_diag.argtypes = [H, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     lib.dpi_check_labels.argtypes = [H, C.c_void_p]
     lib.dpi_export_draws.argtypes = [H, C.c_int64, C.POINTER(dpi_label_config), C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p]

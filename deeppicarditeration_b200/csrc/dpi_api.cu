@@ -493,6 +493,11 @@ int dpi_set_network(dpi_handle* h, const dpi_network* net, void* stream) {
 }
 
 int dpi_sample_tx(dpi_handle* h, int64_t n, int64_t point_index_base, uint64_t seed, float* tx, void* stream) {
+  return dpi_sample_tx_ex(h, n, point_index_base, seed, 0, 0.01f, tx, stream);
+}
+
+int dpi_sample_tx_ex(dpi_handle* h, int64_t n, int64_t point_index_base, uint64_t seed, int32_t n_factors, float eps,
+                     float* tx, void* stream) {
   if (!h || !h->has_problem) {
     set_error("dpi_sample_tx: problem not set");
     return DPI_ERR_STATE;
@@ -507,8 +512,11 @@ int dpi_sample_tx(dpi_handle* h, int64_t n, int64_t point_index_base, uint64_t s
     return DPI_ERR_INVALID;
   }
   DPI_CUDA_CHECK(cudaSetDevice(h->device));
-  // eps = 0.01: default ESTIMATE_TERMINAL "OU_ByGx" (config.py:100, data.py:134-137)
-  int rc = launch_sample_tx(h->P, n, point_index_base, seed, 0.01f, tx, reinterpret_cast<cudaStream_t>(stream));
+  if (n_factors < 0 || n_factors > 4096 || !(eps >= 0.f) || !(2.f * eps < h->P.T)) {
+    set_error("dpi_sample_tx: bad sampler parameters (n_factors=%d eps=%g)", n_factors, eps);
+    return DPI_ERR_INVALID;
+  }
+  int rc = launch_sample_tx(h->P, n, point_index_base, seed, eps, n_factors, tx, reinterpret_cast<cudaStream_t>(stream));
   if (!rc && n > 0) h->launches += 1;
   return rc;
 }
@@ -776,6 +784,31 @@ int dpi_net_eval(dpi_handle* h, const float* tx, int64_t n, float* u, float* du,
   }
   set_error("dpi_net_eval: full input gradient not built yet");
   return DPI_ERR_UNSUPPORTED;
+}
+
+int dpi_net_hessian_diag(dpi_handle* h, const float* tx, int64_t n, float* d2u, void* stream) {
+  if (!h || !h->has_problem || !h->has_net) {
+    set_error("dpi_net_hessian_diag: problem/network not set");
+    return DPI_ERR_STATE;
+  }
+  if (n <= 0) return DPI_OK;
+  if (!tx || !d2u) {
+    set_error("dpi_net_hessian_diag: NULL buffer");
+    return DPI_ERR_INVALID;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  DPI_CUDA_CHECK(cudaSetDevice(h->device));
+  if (h->net_kind == DPI_NET_ZERO) {
+    DPI_CUDA_CHECK(cudaMemsetAsync(d2u, 0, sizeof(float) * n * h->P.nx, st));
+    return DPI_OK;
+  }
+  if (h->net_kind != DPI_NET_MLP) {
+    set_error("dpi_net_hessian_diag: built for plain MLPs (the fully nonlinear config)");
+    return DPI_ERR_UNSUPPORTED;
+  }
+  int rc = launch_mlp_hess_diag(h->P, h->mlp, tx, n, d2u, st);
+  if (!rc) h->launches += 1;
+  return rc;
 }
 
 int dpi_train_init(dpi_handle* h, const dpi_network* net, int64_t max_batch, void* stream) {

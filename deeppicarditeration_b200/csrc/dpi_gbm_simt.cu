@@ -363,6 +363,52 @@ gbm_simt_kernel(const ProblemDev P, const MlpDev N, const float* __restrict__ tx
   }
 }
 
+
+// Hessian diagonal of the MLP u_k at the rows of tx (the evaluation callback's TEST_HESSIAN metric on its diagonal,
+// picard/utils.py:329-478,579-591): the baseline tile of the label kernel on its own -- one CTA per point, forward
+// value chain at (t, x), then the 2-jets of all d coordinate directions.
+__global__ void __launch_bounds__(kThreads, 1)
+mlp_hess_diag_kernel(const ProblemDev P, const MlpDev N, const float* __restrict__ tx, float* __restrict__ diag) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  GbmSmem& S = *reinterpret_cast<GbmSmem*>(smem_raw);
+  const int tid = threadIdx.x, d = P.nx;
+  const int64_t p = blockIdx.x;
+  const float* txp = tx + p * (int64_t)(1 + d);
+  const float t = __ldg(txp);
+  for (int i = tid; i < 128; i += kThreads) {
+    S.xs[i] = (i < d) ? __ldg(txp + 1 + i) : 0.f;
+    S.zs[i] = 0.f;
+  }
+  const int n_hidden = N.n_linear - 2;
+  for (int i = tid; i < 128 * kH; i += kThreads) {
+    const int j = i / kH, h = i - j * kH;
+    S.Wt1[j * kLDW1 + h] = N.Wt1[i];
+  }
+  for (int l = 0; l < n_hidden; ++l) {
+    for (int i = tid; i < kH * kH; i += kThreads) S.Wh[l][i] = N.Wth[l][i];
+    if (tid < kH) S.bh[l][tid] = N.bh[l][tid];
+  }
+  if (tid < kH) {
+    S.wt[tid] = N.wt[tid];
+    S.wout[tid] = N.wout[tid];
+  }
+  const float bout = __ldg(N.bout);
+  __syncthreads();
+  {
+    const int col = tid & 63, part = tid >> 6;
+    float acc = 0.f;
+    for (int j = part; j < d; j += 4) acc = fmaf(S.Wt1[j * kLDW1 + col], S.xs[j], acc);
+    S.part[part][col] = acc;
+    __syncthreads();
+    if (tid < kH) S.c0[tid] = N.b1[tid] + S.part[0][tid] + S.part[1][tid] + S.part[2][tid] + S.part[3][tid];
+    __syncthreads();
+  }
+  if (tid < kDirs) S.idx[tid] = tid;
+  forward_row(S, N, d, t, 0.f, bout, false);
+  jet_tile(S, N, d);
+  if (tid < d) diag[p * (int64_t)d + tid] = S.red[0][tid];
+}
+
 }  // namespace
 
 int launch_gbm_simt(const ProblemDev& P, const MlpDev& N, bool zero_net, const float* tx, int64_t n, int M_I,
@@ -394,4 +440,19 @@ int launch_gbm_simt(const ProblemDev& P, const MlpDev& N, bool zero_net, const f
   return DPI_OK;
 }
 
+}  // namespace dpi
+
+namespace dpi {
+int launch_mlp_hess_diag(const ProblemDev& P, const MlpDev& N, const float* tx, int64_t n, float* diag, cudaStream_t st) {
+  if (n <= 0) return DPI_OK;
+  if (P.nx > 128 || N.HP != 64 || N.n_linear - 2 > kMaxHidden || N.n_linear < 3 || N.d_pad != 128) {
+    set_error("Hessian diagonal: built for MLPs with 1..%d hidden GEMM layers of width <= 64 and nx <= 128", kMaxHidden);
+    return DPI_ERR_UNSUPPORTED;
+  }
+  const size_t smem = sizeof(GbmSmem);
+  DPI_CUDA_CHECK(cudaFuncSetAttribute(mlp_hess_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mlp_hess_diag_kernel<<<(unsigned)n, kThreads, smem, st>>>(P, N, tx, diag);
+  DPI_CUDA_CHECK(cudaGetLastError());
+  return DPI_OK;
+}
 }  // namespace dpi

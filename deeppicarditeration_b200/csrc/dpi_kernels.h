@@ -23,7 +23,8 @@ struct MlpDev {
   const float* bout;  // [1] device
 };
 
-int launch_sample_tx(const ProblemDev& P, int64_t n, int64_t base, uint64_t seed, float eps, float* tx,
+// n_factors = 0: t = (T - 2 eps)(1 - U) + eps (data.py:161-167); n_factors >= 1: t = T (1 - prod of n_factors uniforms) (data.py:149-159)
+int launch_sample_tx(const ProblemDev& P, int64_t n, int64_t base, uint64_t seed, float eps, int n_factors, float* tx,
                      cudaStream_t st);
 int launch_terminal(const ProblemDev& P, const float* tx, int64_t n, int M_T, uint64_t seed, int64_t base,
                     const float* zT, float* y, cudaStream_t st);
@@ -46,6 +47,9 @@ int launch_cha_simt_path(const ProblemDev& P, const MlpDev& net, const float* tx
 int launch_gbm_simt(const ProblemDev& P, const MlpDev& net, bool zero_net, const float* tx, int64_t n, int M_I,
                     uint64_t seed, int64_t base, const float* u_s, const float* zS, const int32_t* idx, float bound,
                     float* y, cudaStream_t st);
+
+// Hessian diagonal [n, nx] of the MLP at the rows of tx (hidden width <= 64, nx <= 128)
+int launch_mlp_hess_diag(const ProblemDev& P, const MlpDev& net, const float* tx, int64_t n, float* diag, cudaStream_t st);
 
 // same on the tensor cores (dpi_gbm_tc.cu): fp16 jets through the hidden layers, nx <= 127, v <= 127
 int launch_gbm_tc(const ProblemDev& P, const MlpDev& net, const float* tx, int64_t n, int M_I, uint64_t seed, int64_t base,

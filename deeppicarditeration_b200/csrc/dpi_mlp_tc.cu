@@ -53,7 +53,7 @@ constexpr int kTcThreads = 640;
 // (B300_MICROARCH.md, multi-warp arbiter), and the epilogue is the critical path of a tile while a producer that polls
 // a barrier is not: with DPI_TC_ROLE_SWAP the epilogue takes warps 8-15 and the producers warps 0-7.
 #ifndef DPI_TC_ROLE_SWAP
-#define DPI_TC_ROLE_SWAP 1
+#define DPI_TC_ROLE_SWAP 0
 #endif
 constexpr int kProdWarp0 = DPI_TC_ROLE_SWAP ? 0 : 8, kEpiWarp0 = DPI_TC_ROLE_SWAP ? 8 : 0, kMmaWarp = 16, kTmaWarp = 17;
 #ifndef DPI_EPI_REGS
@@ -151,6 +151,11 @@ constexpr int kEpiUnroll = DPI_EPI_UNROLL;  // chunks per loop iteration of an e
 #ifndef DPI_EPI_DB
 #define DPI_EPI_DB 0
 #endif
+#ifndef DPI_EPI_POLY
+#define DPI_EPI_POLY 0x0
+#endif
+// which of the four column pairs of every 8-column group take the FMA-pipe exponential (h2_ex2_poly) instead of MUFU
+constexpr int kEpiPolyMask = DPI_EPI_POLY;
 constexpr int kEpiCW = DPI_EPI_CW;       // accumulator columns per tcgen05.ld (8 or 16)
 constexpr bool kEpiDB = DPI_EPI_DB != 0; // prefetch the next chunk under the arithmetic of the current one
 static_assert(kEpiCW == 8 || kEpiCW == 16 || kEpiCW == 32, "chunk width");
@@ -214,7 +219,8 @@ __device__ __forceinline__ void epi_pass(const TcConsts& C, uint32_t tacc, uint8
                      MODE == kPassHidden ? bias[col / 2] : C.b16[2][col / 2]);
           tg = pack_f16x2(__uint_as_float(tt[k2]), __uint_as_float(tt[k2 + 1]));
         }
-        const uint32_t e = h2_ex2(h2_min(z, kZero));           // ELU'(z) = 2^min(z',0)
+        const uint32_t zneg = h2_min(z, kZero);
+        const uint32_t e = ((kEpiPolyMask >> (k2 / 2)) & 1) ? h2_ex2_poly(zneg) : h2_ex2(zneg);  // ELU'(z) = 2^min(z',0)
         const uint32_t h = h2_max(z, h2_fma(e, kL, kNegL));    // log2e ELU(z)
         const uint32_t dh = h2_mul(e, tg);
         if (MODE == kPassOut) {

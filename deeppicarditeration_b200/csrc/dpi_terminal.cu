@@ -242,16 +242,32 @@ terminal_kernel(const ProblemDev P, const float* __restrict__ tx, int M_T, const
   }
 }
 
-// t = (T-2eps)(1-U)+eps ; x = x0 + sqrt(t) sigma Z  (one warp per point)
+// t = (T-2eps)(1-U)+eps, or T (1 - U_1 ... U_k) when n_factors = k >= 1 (the default sampler of the reference,
+// data.py:149-159: k = N - i + 1 uniforms per point, Philox block b of stream T holds factors 4b..4b+3);
+// x = x0 + sqrt(t) sigma Z  (one warp per point)
 __global__ void __launch_bounds__(256)
-sample_tx_kernel(const ProblemDev P, int64_t n, int64_t point_base, uint64_t seed, float eps, float* __restrict__ tx) {
+sample_tx_kernel(const ProblemDev P, int64_t n, int64_t point_base, uint64_t seed, float eps, int n_factors,
+                 float* __restrict__ tx) {
   const int lane = threadIdx.x & 31;
   const int64_t p = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (p >= n) return;
   const int d = P.nx;
   const uint64_t gp = (uint64_t)(point_base + p);
-  const uint4 r = philox_at(seed, gp, kStreamT, 0u, 0u);
-  const float t = (P.T - 2.f * eps) * (1.f - u01(r.x)) + eps;
+  float t;
+  if (n_factors <= 0) {
+    const uint4 r = philox_at(seed, gp, kStreamT, 0u, 0u);
+    t = (P.T - 2.f * eps) * (1.f - u01(r.x)) + eps;
+  } else {
+    float prod = 1.f;  // every lane computes the same product (warp-uniform, a few Philox blocks)
+    for (int b = 0; 4 * b < n_factors; ++b) {
+      const uint4 r = philox_at(seed, gp, kStreamT, 0u, (uint32_t)b);
+      const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (4 * b + q < n_factors) prod *= u01(w[q]);
+    }
+    t = P.T * (1.f - prod);
+  }
   float* row = tx + p * (int64_t)(1 + d);
   if (lane == 0) row[0] = t;
   const float a = sqrtf(t) * P.sigma;
@@ -315,11 +331,11 @@ int launch_terminal(const ProblemDev& P, const float* tx, int64_t n, int M_T, ui
   return DPI_ERR_INVALID;
 }
 
-int launch_sample_tx(const ProblemDev& P, int64_t n, int64_t base, uint64_t seed, float eps, float* tx,
+int launch_sample_tx(const ProblemDev& P, int64_t n, int64_t base, uint64_t seed, float eps, int n_factors, float* tx,
                      cudaStream_t st) {
   if (n <= 0) return DPI_OK;
   const int wpb = 8;
-  sample_tx_kernel<<<(unsigned)((n + wpb - 1) / wpb), wpb * 32, 0, st>>>(P, n, base, seed, eps, tx);
+  sample_tx_kernel<<<(unsigned)((n + wpb - 1) / wpb), wpb * 32, 0, st>>>(P, n, base, seed, eps, n_factors, tx);
   DPI_CUDA_CHECK(cudaGetLastError());
   return DPI_OK;
 }

@@ -54,9 +54,9 @@ class OnlineDataGenerator(DataGenerator):
         if hasattr(solution, "eval"):
             solution.eval()
         assert getattr(equation, "nu", 1) == 1, "Currently only nu=1 is supported"  # data.py:431
-        if not t_always_uniform:
-            # data.py:149-159 (T(1 - prod of N-i+1 uniforms)): SURVEY.md 8f-4, not selected by any BASELINE config
-            raise NotImplementedError("t_always_uniform=False (product-of-uniforms t sampler) is not built yet")
+        # data.py:108-111: t_always_uniform selects U[eps, T - eps]; otherwise t = T (1 - prod of N - i + 1 uniforms)
+        self.t_always_uniform = bool(t_always_uniform)
+        self._t_factors = 0 if self.t_always_uniform else max(1, int(N) - int(i) + 1)
         if estimate_delta_t and estimate_delta_t > 0:
             raise NotImplementedError("ESTIMATE_DELTA_T > 0 (TD estimators, data.py:529-575,928-952) is not built yet")
         method = getattr(hessian_approximation, "method", None) if hessian_approximation is not None else None
@@ -70,9 +70,7 @@ class OnlineDataGenerator(DataGenerator):
         self.estimate_terminal_type, self.estimate_integral_type = estimate_terminal, estimate_integral
         # data.py:134-137: epsilon = 0.01 iff "ByGx" in ESTIMATE_TERMINAL or "Joint" in ESTIMATE_INTEGRAL
         eps_on = ("ByGx" in (estimate_terminal or "")) or ("Joint" in (estimate_integral or ""))
-        if not eps_on:
-            raise NotImplementedError("t ~ U[0,T] without the epsilon margin (ESTIMATE_TERMINAL without 'ByGx') is "
-                                      "not built: sqrt(T-t) -> 0 at the boundary")
+        self.generate_t_uniform_epsilon = 0.01 if eps_on else 0.0
         self.precision, self.seed, self.out_dtype = precision, int(seed), out_dtype
         # disjoint blocks of the global point index per rank; the Philox counter holds 48 bits of it
         if not (0 <= int(rank) < int(world_size)) or (int(rank) + 1) * int(points_per_rank) > (1 << 48):
@@ -119,6 +117,11 @@ class OnlineDataGenerator(DataGenerator):
         return t if self.out_dtype is None else t.to(self.out_dtype)
 
     # ------------------------------------------------------------------------------------------
+    def _sample_tx(self, n: int, base: int) -> torch.Tensor:
+        """t_sampler + equation.sample_x (data.py:149-167, 211-219) on the device."""
+        return self._engine.sample_tx(n, seed=self.seed, point_index_base=base, n_factors=self._t_factors,
+                                      eps=self.generate_t_uniform_epsilon)
+
     def _advance(self, n: int) -> int:
         """Reserve n global point indices for a call: successive calls never share Philox streams."""
         if self._drawn + n > self._limit:
@@ -152,7 +155,7 @@ class OnlineDataGenerator(DataGenerator):
     def sample_with_gradients(self, n_batch: int):
         """data.py:211-223: draw (t, x), label, clip -> (tx [n,1+nx], u_ux [n,1+nx])."""
         base = self._advance(n_batch)
-        tx = self._engine.sample_tx(n_batch, seed=self.seed, point_index_base=base)
+        tx = self._sample_tx(n_batch, base)
         y = self._label(tx, base, self.sample_bound, None)  # clip fused into the kernels' final write
         return self._out(tx), self._out(y)
 
@@ -166,7 +169,7 @@ class OnlineDataGenerator(DataGenerator):
         raise NotImplementedError("Hessian labels (estimate_*_and_hessians_double) are not built yet")
 
     def sample_exact_with_gradients(self, n_batch):  # data.py:251-262
-        tx = self._engine.sample_tx(n_batch, seed=self.seed, point_index_base=self._advance(n_batch))
+        tx = self._sample_tx(n_batch, self._advance(n_batch))
         t, x = tx[:, :1], tx[:, 1:]
         eq = self.equation.to(tx.device) if hasattr(self.equation, "to") else self.equation
         u, ux = eq.u_u_x(t, x)

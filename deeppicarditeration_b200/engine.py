@@ -119,11 +119,14 @@ class LabelEngine:
         self.net_kind = kind
 
     # ------------------------------------------------------------------------------------------
-    def sample_tx(self, n: int, seed: int = 0, point_index_base: int = 0) -> torch.Tensor:
+    def sample_tx(self, n: int, seed: int = 0, point_index_base: int = 0, *, n_factors: int = 0,
+                  eps: float = 0.01) -> torch.Tensor:
+        """(t, x) points.  n_factors = 0: t ~ U[eps, T - eps] (data.py:161-167); n_factors = k >= 1: the reference's
+        default `sample_t`, t = T (1 - product of k uniforms) with k = N - i + 1 (data.py:149-159)."""
         tx = torch.empty(n, 1 + self.nx, device=self.device, dtype=torch.float32)
         with torch.cuda.device(self.device):
-            nat.check(self.lib.dpi_sample_tx(self.h, n, point_index_base, C.c_uint64(seed & (2**64 - 1)), _ptr(tx),
-                                             self._stream()), "dpi_sample_tx")
+            nat.check(self.lib.dpi_sample_tx_ex(self.h, n, point_index_base, C.c_uint64(seed & (2**64 - 1)),
+                                                int(n_factors), float(eps), _ptr(tx), self._stream()), "dpi_sample_tx_ex")
         return tx
 
     @staticmethod
@@ -222,6 +225,15 @@ class LabelEngine:
         with torch.cuda.device(self.device):
             nat.check(self.lib.dpi_net_eval(self.h, _ptr(tx), n, _ptr(u), _ptr(du), self._stream()), "dpi_net_eval")
         return u, du
+
+    def net_hessian_diag(self, tx: torch.Tensor) -> torch.Tensor:
+        """diag of the Hessian of u_k in x at the rows of tx: [n, nx] (dpi_net_hessian_diag)."""
+        tx = _f32c(tx, self.device)
+        d2 = torch.empty(tx.shape[0], self.nx, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            nat.check(self.lib.dpi_net_hessian_diag(self.h, _ptr(tx), tx.shape[0], _ptr(d2), self._stream()),
+                      "dpi_net_hessian_diag")
+        return d2
 
     def launch_count(self) -> int:
         return int(self.lib.dpi_launch_count(self.h))

@@ -28,16 +28,11 @@ class _HA:
 
 
 def evaluate(generator: OnlineDataGenerator, equation, n_points: int, seed: int = 12345) -> Dict[str, float]:
-    """rRMSE of u and of grad_x u against the exact solution (utils.py:405-456), on the device."""
-    eng = generator.engine
-    tx = eng.sample_tx(n_points, seed=seed)
-    u, du = eng.net_eval(tx, want_grad=True)
-    t, x = tx[:, :1].double(), tx[:, 1:].double()
-    eq = equation.to(tx.device) if hasattr(equation, "to") else equation
-    u_ex, ux_ex = eq.u_u_x(t, x)
-    err = (u.double().view(-1, 1) - u_ex).norm() / u_ex.norm()
-    errg = ((du.double() - ux_ex).norm(dim=0) / ux_ex.norm(dim=0)).mean()
-    return {"rRMSE": float(err), "rRMSEg": float(errg)}
+    """rRMSE of u and of grad_x u against the exact solution, the reference's EvalCallback metrics on its points
+    (t = linspace(0, T, n), x = sample_x(t); picard/utils.py:362-452) -- see evaluation.py."""
+    from .evaluation import EvalCallback
+    cb = EvalCallback({"L2_N_POINTS": n_points, "TEST_GRAD": True}, equation, seed=seed)
+    return cb(generator.engine)
 
 
 def run_picard(equation, neurons: Sequence[int], n_iterations: int, *, data_size: int = 4096, n_mc: int = 4096,

@@ -151,6 +151,13 @@ int dpi_set_network(dpi_handle* h, const dpi_network* net, void* stream);
 /* tx [n, 1+nx] device, written.  t ~ U[eps, T-eps] (eps=0.01), x = x0 + sqrt(t*alpha) Z. */
 int dpi_sample_tx(dpi_handle* h, int64_t n, int64_t point_index_base, uint64_t seed, float* tx, void* stream);
 
+/* General form of the point sampler: n_factors = 0 is dpi_sample_tx with the margin eps (the reference uses 0.01 when
+ * ESTIMATE_TERMINAL contains "ByGx", else 0: data.py:134-137); n_factors = k >= 1 is the reference's default sampler
+ * `sample_t` (data.py:149-159): t = T (1 - U_1 U_2 ... U_k) with k = N - i + 1 uniforms, which concentrates the points
+ * of late Picard iterations near t = 0. */
+int dpi_sample_tx_ex(dpi_handle* h, int64_t n, int64_t point_index_base, uint64_t seed, int32_t n_factors, float eps,
+                     float* tx, void* stream);
+
 /* y [n, 1+nx] device, written: column 0 the value label, columns 1.. the gradient label. */
 int dpi_label_gen(dpi_handle* h, const float* tx, int64_t n, const dpi_label_config* cfg,
                   const dpi_draws* draws /* nullable: Philox mode */, float* y, void* stream);
@@ -175,6 +182,11 @@ int dpi_label_gen_host(dpi_handle* h, const float* tx_in_host, int64_t n, const 
 
 /* u_k and its input gradient on rows of tx: u [n], du [n, nx] (either may be NULL). fp32 path. */
 int dpi_net_eval(dpi_handle* h, const float* tx, int64_t n, float* u, float* du, void* stream);
+
+/* Diagonal of the Hessian of u_k with respect to x on rows of tx: d2u [n, nx] (forward 2-jets along the coordinate
+ * directions, the construction the SDGD label kernel uses).  For the evaluation callback's Hessian metric
+ * (picard/utils.py:329-478 with get_hessian :579-591, restricted to the diagonal).  Plain MLPs, hidden width <= 64. */
+int dpi_net_hessian_diag(dpi_handle* h, const float* tx, int64_t n, float* d2u, void* stream);
 
 /* ---- regression step (the trainer's inner loop) -------------------------------------------
  *   dpi_train_init  <- PicardSolutionGradientWrapper.__init__ + configure_optimizers   picard/solution_jac.py:125-146,

@@ -96,9 +96,6 @@ def test_unreachable_paths_raise_like_the_reference():
     from deeppicarditeration_b200.data import OnlineDataGenerator
     eq = eqs.Cha(nx=10, alpha=1.0, k=5.0)
     with pytest.raises(NotImplementedError):
-        OnlineDataGenerator(eq, sol.ZeroSolution(), 10, 1, device="cuda", t_always_uniform=False,
-                            hessian_approximation=_HA())
-    with pytest.raises(NotImplementedError):
         OnlineDataGenerator(eq, sol.ZeroSolution(), 10, 1, device="cuda", t_always_uniform=True,
                             hessian_approximation=_HA(), estimate_delta_t=0.1)
     with pytest.raises(AssertionError):
