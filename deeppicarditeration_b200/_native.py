@@ -18,6 +18,7 @@ DPI_NET_ZERO, DPI_NET_MLP, DPI_NET_PISGRAD = 0, 1, 2
 DPI_PREC_FP32, DPI_PREC_F16 = 0, 1
 DPI_PREC_BF16 = 2  # distinct and rejected (DPI_ERR_UNSUPPORTED): bf16 operands are not built
 DPI_ERR_NONFINITE = -5
+DPI_DP_HANDLE_BYTES = 64
 
 EXPORTED_SYMBOLS = (
     "dpi_version", "dpi_last_error", "dpi_create", "dpi_destroy", "dpi_set_problem", "dpi_set_network",
@@ -25,6 +26,7 @@ EXPORTED_SYMBOLS = (
     "dpi_set_stage_timing", "dpi_stage_ms", "dpi_selftest_umma",
     "dpi_train_init", "dpi_train_param_count", "dpi_train_grad", "dpi_train_adam", "dpi_train_fit", "dpi_train_reset",
     "dpi_check_labels", "dpi_export_draws", "dpi_sample_tx_ex", "dpi_net_hessian_diag",
+    "dpi_train_dp_export", "dpi_train_dp_connect",
 )
 
 
@@ -94,6 +96,8 @@ def load() -> C.CDLL:
                                        C.c_void_p]
     lib.dpi_sample_tx_ex.argtypes = [H, C.c_int64, C.c_int64, C.c_uint64, C.c_int32, C.c_float, C.c_void_p, C.c_void_p]
     lib.dpi_net_hessian_diag.argtypes = [H, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    lib.dpi_train_dp_export.argtypes = [H, C.c_void_p]
+    lib.dpi_train_dp_connect.argtypes = [H, C.c_int32, C.c_int32, C.c_void_p]
     lib.dpi_check_labels.argtypes = [H, C.c_void_p]
     lib.dpi_export_draws.argtypes = [H, C.c_int64, C.POINTER(dpi_label_config), C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p]

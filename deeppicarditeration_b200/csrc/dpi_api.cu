@@ -45,6 +45,7 @@ struct dpi_handle {
   cudaGraphExec_t train_graph = nullptr;
   int64_t train_graph_batch = 0, train_graph_nodes = 0;
   dpi_train_config train_graph_cfg{};
+  DpLinks dp;  // data-parallel peers (dpi_train_dp_connect); world == 1: single device
   dpi_linear mlp_raw[DPI_MAX_LINEAR] = {};  // the caller's MLP tensors (torch layout), for dpi_net_eval
   int n_mlp_raw = 0;
   // activations of one chunk of rows of the batched-GEMM (PISGradNet) path
@@ -244,6 +245,8 @@ int dpi_destroy(dpi_handle* h) {
   if (h->train_m) cudaFree(h->train_m);
   if (h->train_v) cudaFree(h->train_v);
   if (h->train_scratch) cudaFree(h->train_scratch);
+  for (int r = 0; r < DPI_DP_MAX_WORLD; ++r)
+    if (h->dp.mapped[r]) cudaIpcCloseMemHandle(h->dp.mapped[r]);
   if (h->train_grad) cudaFree(h->train_grad);
   if (h->train_graph) cudaGraphExecDestroy(h->train_graph);
   if (h->train_stage_tx) cudaFree(h->train_stage_tx);
@@ -838,6 +841,9 @@ int dpi_train_init(dpi_handle* h, const dpi_network* net, int64_t max_batch, voi
   if (h->train_m) cudaFree(h->train_m);
   if (h->train_v) cudaFree(h->train_v);
   if (h->train_scratch) cudaFree(h->train_scratch);
+  for (int r = 0; r < DPI_DP_MAX_WORLD; ++r)
+    if (h->dp.mapped[r]) cudaIpcCloseMemHandle(h->dp.mapped[r]);
+  h->dp = DpLinks{};
   if (h->train_grad) cudaFree(h->train_grad);
   if (h->train_graph) cudaGraphExecDestroy(h->train_graph);
   if (h->train_stage_tx) cudaFree(h->train_stage_tx);
@@ -853,7 +859,10 @@ int dpi_train_init(dpi_handle* h, const dpi_network* net, int64_t max_batch, voi
   DPI_CUDA_CHECK(cudaMalloc((void**)&h->train_m, sizeof(float) * h->train_params));
   DPI_CUDA_CHECK(cudaMalloc((void**)&h->train_v, sizeof(float) * h->train_params));
   DPI_CUDA_CHECK(cudaMalloc((void**)&h->train_scratch, sizeof(float) * train_scratch_floats(h->train_lin, L, max_batch)));
-  DPI_CUDA_CHECK(cudaMalloc((void**)&h->train_grad, sizeof(float) * (h->train_params + 4)));
+  // [gradient P | loss terms 4 | pad 4 | flag, epoch, done (ints) ...]: one block, so that peers map all of it at once
+  DPI_CUDA_CHECK(cudaMalloc((void**)&h->train_grad, sizeof(float) * (h->train_params + 16)));
+  DPI_CUDA_CHECK(cudaMemset(h->train_grad, 0, sizeof(float) * (h->train_params + 16)));
+  h->dp = DpLinks{};
   DPI_CUDA_CHECK(cudaMalloc((void**)&h->train_stage_tx, sizeof(float) * max_batch * net->main[0].n_in));
   DPI_CUDA_CHECK(cudaMalloc((void**)&h->train_stage_y, sizeof(float) * max_batch * net->main[0].n_in));
   if (!h->train_step_dev) DPI_CUDA_CHECK(cudaMalloc((void**)&h->train_step_dev, sizeof(long long)));
@@ -954,8 +963,11 @@ int dpi_train_fit(dpi_handle* h, const float* tx, const float* y, int64_t n, int
           int rc = launch_train_grad(h->train_lin, h->n_train_lin, h->train_stage_tx, h->train_stage_y, b, cfg->loss_beta,
                                      cfg->fixed_weight, h->train_scratch, h->train_grad, losses, ts, &nodes, &h->train_aux);
           if (!rc)
-            rc = launch_train_adam_dev(h->train_lin, h->n_train_lin, h->train_grad, h->train_m, h->train_v, cfg->lr,
-                                       cfg->beta1, cfg->beta2, cfg->eps, h->train_step_dev, ts, &nodes);
+            rc = h->dp.world > 1
+                     ? launch_train_dp_reduce_adam(h->train_lin, h->n_train_lin, h->dp, h->train_m, h->train_v, cfg->lr,
+                                                   cfg->beta1, cfg->beta2, cfg->eps, h->train_step_dev, ts, &nodes)
+                     : launch_train_adam_dev(h->train_lin, h->n_train_lin, h->train_grad, h->train_m, h->train_v, cfg->lr,
+                                             cfg->beta1, cfg->beta2, cfg->eps, h->train_step_dev, ts, &nodes);
           cudaError_t ce = cudaStreamEndCapture(ts, &graph);
           if (rc) {
             if (graph) cudaGraphDestroy(graph);
@@ -974,8 +986,11 @@ int dpi_train_fit(dpi_handle* h, const float* tx, const float* y, int64_t n, int
         int rc = launch_train_grad(h->train_lin, h->n_train_lin, h->train_stage_tx, h->train_stage_y, b, cfg->loss_beta,
                                    cfg->fixed_weight, h->train_scratch, h->train_grad, losses, ts, &h->launches, &h->train_aux);
         if (rc) return rc;
-        rc = launch_train_adam_dev(h->train_lin, h->n_train_lin, h->train_grad, h->train_m, h->train_v, cfg->lr, cfg->beta1,
-                                   cfg->beta2, cfg->eps, h->train_step_dev, ts, &h->launches);
+        rc = h->dp.world > 1
+                 ? launch_train_dp_reduce_adam(h->train_lin, h->n_train_lin, h->dp, h->train_m, h->train_v, cfg->lr, cfg->beta1,
+                                               cfg->beta2, cfg->eps, h->train_step_dev, ts, &h->launches)
+                 : launch_train_adam_dev(h->train_lin, h->n_train_lin, h->train_grad, h->train_m, h->train_v, cfg->lr, cfg->beta1,
+                                         cfg->beta2, cfg->eps, h->train_step_dev, ts, &h->launches);
         if (rc) return rc;
       }
     }
@@ -983,6 +998,57 @@ int dpi_train_fit(dpi_handle* h, const float* tx, const float* y, int64_t n, int
     DPI_CUDA_CHECK(cudaMemcpyAsync(losses_last, losses, 3 * sizeof(float), cudaMemcpyDeviceToDevice, ts));
   DPI_CUDA_CHECK(cudaEventRecord(h->train_ev_out, ts));
   DPI_CUDA_CHECK(cudaStreamWaitEvent(st, h->train_ev_out, 0));
+  return DPI_OK;
+}
+
+int dpi_train_dp_export(dpi_handle* h, void* handle_out) {
+  if (!h || !h->n_train_lin || !handle_out) {
+    set_error("dpi_train_dp_export: call dpi_train_init first");
+    return DPI_ERR_STATE;
+  }
+  DPI_CUDA_CHECK(cudaSetDevice(h->device));
+  static_assert(sizeof(cudaIpcMemHandle_t) == DPI_DP_HANDLE_BYTES, "IPC handle size");
+  cudaIpcMemHandle_t mh;
+  DPI_CUDA_CHECK(cudaIpcGetMemHandle(&mh, h->train_grad));
+  std::memcpy(handle_out, &mh, sizeof(mh));
+  return DPI_OK;
+}
+
+int dpi_train_dp_connect(dpi_handle* h, int32_t rank, int32_t world, const void* handles) {
+  if (!h || !h->n_train_lin || !handles) {
+    set_error("dpi_train_dp_connect: call dpi_train_init first");
+    return DPI_ERR_STATE;
+  }
+  if (world < 1 || world > DPI_DP_MAX_WORLD || rank < 0 || rank >= world) {
+    set_error("dpi_train_dp_connect: rank %d of %d (at most %d ranks of one node)", rank, world, DPI_DP_MAX_WORLD);
+    return DPI_ERR_INVALID;
+  }
+  DPI_CUDA_CHECK(cudaSetDevice(h->device));
+  DPI_CUDA_CHECK(cudaDeviceSynchronize());
+  for (int r = 0; r < DPI_DP_MAX_WORLD; ++r)
+    if (h->dp.mapped[r]) cudaIpcCloseMemHandle(h->dp.mapped[r]);
+  h->dp = DpLinks{};
+  if (h->train_graph) cudaGraphExecDestroy(h->train_graph);  // the captured step names the optimiser kernel
+  h->train_graph = nullptr;
+  h->train_graph_batch = 0;
+  const int64_t P = h->train_params;
+  int* ctl = reinterpret_cast<int*>(h->train_grad + P + 8);
+  DPI_CUDA_CHECK(cudaMemset(ctl, 0, 8 * sizeof(int)));
+  h->dp.world = world, h->dp.rank = rank;
+  h->dp.epoch = ctl + 1, h->dp.done = ctl + 2;
+  for (int r = 0; r < world; ++r) {
+    float* base = h->train_grad;
+    if (r != rank) {
+      cudaIpcMemHandle_t mh;
+      std::memcpy(&mh, reinterpret_cast<const char*>(handles) + (size_t)r * sizeof(mh), sizeof(mh));
+      void* p = nullptr;
+      DPI_CUDA_CHECK(cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
+      h->dp.mapped[r] = p;
+      base = reinterpret_cast<float*>(p);
+    }
+    h->dp.grad[r] = base;
+    h->dp.flag[r] = reinterpret_cast<int*>(base + P + 8);
+  }
   return DPI_OK;
 }
 

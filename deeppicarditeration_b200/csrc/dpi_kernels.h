@@ -176,6 +176,19 @@ int launch_train_adam(const dpi_linear* L, int n_lin, const float* grad_flat, fl
 
 int launch_train_adam_dev(const dpi_linear* L, int n_lin, const float* grad_flat, float* m, float* v, float lr, float b1,
                           float b2, float eps, long long* step_dev, cudaStream_t st, int64_t* launches);
+// data-parallel ranks of one node: every rank's gradient block mapped through CUDA IPC (own block at index `rank`)
+constexpr int DPI_DP_MAX_WORLD = 16;
+struct DpLinks {
+  int world = 1, rank = 0;
+  const float* grad[DPI_DP_MAX_WORLD] = {};
+  int* flag[DPI_DP_MAX_WORLD] = {};
+  int* epoch = nullptr;  // device launch counter of the fused reduce + Adam kernel
+  int* done = nullptr;   // device block counter
+  void* mapped[DPI_DP_MAX_WORLD] = {};  // peer base pointers to cudaIpcCloseMemHandle
+};
+// gradient all-reduce over NVLink peer memory fused with the Adam update (one kernel per step, graph-capturable)
+int launch_train_dp_reduce_adam(const dpi_linear* L, int n_lin, const DpLinks& dp, float* m, float* v, float lr, float b1,
+                                float b2, float eps, long long* step_dev, cudaStream_t st, int64_t* launches);
 
 // ---- draws and status (dpi_draws.cu) --------------------------------------------------------------------------
 // the Philox draws of a call in the reference's layout (any pointer may be null = skip)

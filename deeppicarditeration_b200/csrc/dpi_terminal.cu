@@ -266,7 +266,9 @@ sample_tx_kernel(const ProblemDev P, int64_t n, int64_t point_base, uint64_t see
       for (int q = 0; q < 4; ++q)
         if (4 * b + q < n_factors) prod *= u01(w[q]);
     }
-    t = P.T * (1.f - prod);
+    // tx carries t in fp32: keep T - t representable (>= 2^-21 T).  With many factors the product underflows the fp32
+    // spacing below T in ~1 % of the points; the fp64 reference keeps T - t ~ 1e-16 there, fp32 would get 0 and divide by it.
+    t = P.T * (1.f - fmaxf(prod, 4.76837158203125e-7f));
   }
   float* row = tx + p * (int64_t)(1 + d);
   if (lane == 0) row[0] = t;

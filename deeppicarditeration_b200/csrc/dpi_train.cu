@@ -169,6 +169,87 @@ __global__ void train_adam_dev_kernel(const AdamTable T, const float* __restrict
 }
 __global__ void train_step_inc_kernel(long long* step) { *step += 1; }
 
+// ---- data-parallel step over NVLink peer memory: gradient all-reduce fused with Adam -----------------------------
+// Every rank's flat gradient lives in a cudaMalloc'd block that its peers have mapped (CUDA IPC).  One kernel per
+// optimiser step and rank:
+//   barrier 1  own flag <- 2e+1 (release, system scope); wait until every peer's flag >= 2e+1: all gradients written
+//   reduce     g_i = (sum over ranks r = 0..W-1, in rank order, of grad_r[i]) / W, read through NVLink (ld.cg: remote
+//              lines are never cached in the local L2) -- the same order on every rank, so the replicas stay BITWISE
+//              identical without a broadcast -- followed by the Adam update of the local replica
+//   barrier 2  last block: own flag <- 2e+2; wait for the peers' flags >= 2e+2: nobody still reads this rank's
+//              gradient when the next step's kernels overwrite it
+// e is a device-side launch counter (never reset, identical on every rank because all ranks run the same schedule),
+// so the kernel replays from a CUDA graph.  Waits trap after ~4 s instead of hanging the box.
+struct DpPeers {
+  const float* grad[DPI_DP_MAX_WORLD];
+  int* flag[DPI_DP_MAX_WORLD];
+  int world, rank;
+};
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void dp_wait_peers(const DpPeers& D, int target) {
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (int r = 0; r < D.world; ++r) {
+    if (r == D.rank) continue;
+    unsigned spins = 0;
+    while (ld_acquire_sys(D.flag[r]) - target < 0) {  // wrap-safe comparison of launch counters
+      if ((++spins & 1023u) == 0) {
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 4000000000ull) __trap();
+      }
+    }
+  }
+}
+__global__ void __launch_bounds__(256)
+train_dp_reduce_adam_kernel(const AdamTable T, const DpPeers D, float* __restrict__ m, float* __restrict__ v, float lr,
+                            float b1, float b2, float eps, const long long* __restrict__ step, int* __restrict__ epoch,
+                            int* __restrict__ done, int64_t total) {
+  const int e = *epoch;  // written only by the last block of the previous launch
+  if (threadIdx.x == 0) {
+    if (blockIdx.x == 0) {
+      __threadfence_system();
+      st_release_sys(D.flag[D.rank], 2 * e + 1);
+    }
+    dp_wait_peers(D, 2 * e + 1);
+  }
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total) {
+    float gi = 0.f;
+    for (int r = 0; r < D.world; ++r) gi += __ldcg(D.grad[r] + i);
+    gi *= 1.f / (float)D.world;
+    const float st = (float)(*step);
+    const float bc1 = 1.f - powf(b1, st), bc2 = 1.f - powf(b2, st);
+    int s = 0;
+    while (s + 1 < T.n_seg && i >= T.seg[s + 1].off) ++s;
+    float* p = T.seg[s].p + (i - T.seg[s].off);
+    const float mi = fmaf(b1, m[i], (1.f - b1) * gi);
+    const float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);
+    m[i] = mi;
+    v[i] = vi;
+    *p -= (lr / bc1) * mi / (sqrtf(vi / bc2) + eps);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(done, 1) == (int)gridDim.x - 1) {  // last block of this rank: every read of the peers' gradients is done
+      *done = 0;
+      __threadfence_system();
+      st_release_sys(D.flag[D.rank], 2 * e + 2);
+      dp_wait_peers(D, 2 * e + 2);
+      *epoch = e + 1;
+    }
+  }
+}
+
 }  // namespace
 
 int64_t train_param_count(const dpi_linear* L, int n_lin) {
@@ -368,6 +449,28 @@ int launch_train_adam_dev(const dpi_linear* L, int n_lin, const float* grad_flat
     off += L[l].n_out;
   }
   train_adam_dev_kernel<<<(unsigned)((off + 255) / 256), 256, 0, st>>>(T, grad_flat, m, v, lr, b1, b2, eps, step_dev, off);
+  train_step_inc_kernel<<<1, 1, 0, st>>>(step_dev);
+  DPI_CUDA_CHECK(cudaGetLastError());
+  *launches += 2;
+  return DPI_OK;
+}
+
+int launch_train_dp_reduce_adam(const dpi_linear* L, int n_lin, const DpLinks& dp, float* m, float* v, float lr, float b1,
+                                float b2, float eps, long long* step_dev, cudaStream_t st, int64_t* launches) {
+  AdamTable T{};
+  int64_t off = 0;
+  T.n_seg = 0;
+  for (int l = 0; l < n_lin; ++l) {
+    T.seg[T.n_seg++] = AdamSeg{const_cast<float*>(L[l].W), off, (int64_t)L[l].n_out * L[l].n_in};
+    off += (int64_t)L[l].n_out * L[l].n_in;
+    T.seg[T.n_seg++] = AdamSeg{const_cast<float*>(L[l].b), off, (int64_t)L[l].n_out};
+    off += L[l].n_out;
+  }
+  DpPeers D{};
+  D.world = dp.world, D.rank = dp.rank;
+  for (int r = 0; r < dp.world; ++r) D.grad[r] = dp.grad[r], D.flag[r] = dp.flag[r];
+  train_dp_reduce_adam_kernel<<<(unsigned)((off + 255) / 256), 256, 0, st>>>(T, D, m, v, lr, b1, b2, eps, step_dev, dp.epoch,
+                                                                          dp.done, off);
   train_step_inc_kernel<<<1, 1, 0, st>>>(step_dev);
   DPI_CUDA_CHECK(cudaGetLastError());
   *launches += 2;

@@ -3,9 +3,14 @@
 `RegressionTrainer` plays the role of `PicardSolutionGradientWrapper.training_step` + `loss.backward()` +
 `torch.optim.Adam.step()` (picard/solution_jac.py:172-216, picard/solution.py:93-97) for a scalar-output MLP with
 `FixedLossScaler`: same loss, same optimiser, fp32 master weights held in the solution's own `nn.Linear` tensors and
-updated in place by the library (no torch autograd on this path).  Data-parallel runs all-reduce the flat gradient
-between `dpi_train_grad` and `dpi_train_adam` (NCCL through torch.distributed), which keeps every rank's replica of
-`u_k` identical without a separate broadcast.
+updated in place by the library (no torch autograd on this path).
+
+Data parallel (one process per GPU of a node, torch.distributed initialised): `enable_data_parallel()` exchanges CUDA
+IPC handles of the ranks' gradient blocks once; from then on `fit` stays the native, graph-replayed inner loop and
+the gradient all-reduce happens INSIDE the optimiser kernel over NVLink peer memory (`dpi_train_dp_*`, dpi_train.cu):
+every rank sums the peers' gradients in rank order, so the replicas of `u_k` stay bitwise identical without a
+broadcast.  `step()` (one mini-batch from Python) keeps the plain NCCL all-reduce between `dpi_train_grad` and
+`dpi_train_adam`.
 """
 from __future__ import annotations
 
@@ -21,7 +26,8 @@ from .solution import _linears
 
 class RegressionTrainer:
     def __init__(self, solution, *, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, loss_beta: float = 0.0,
-                 fixed_weight: float = 1.0, max_batch: int = 4096, device="cuda", process_group=None):
+                 fixed_weight: float = 1.0, max_batch: int = 4096, device="cuda", process_group=None,
+                 data_parallel: Optional[bool] = None):
         model = getattr(solution, "model", solution)
         if not isinstance(model, torch.nn.Sequential):
             raise NotImplementedError("the B200 regression step is built for plain MLPs (Linear + ELU)")
@@ -50,6 +56,32 @@ class RegressionTrainer:
         self.losses = torch.zeros(3, device=self.device, dtype=torch.float32)
         self.step_count = 0
         self.pg = process_group
+        self.dp_world = 1
+        self._dp_wanted = data_parallel  # None: data parallel iff torch.distributed runs with more than one rank
+        if self._distributed():
+            self.enable_data_parallel()
+
+    def _distributed(self) -> bool:
+        if self._dp_wanted is False:
+            return False
+        d = torch.distributed
+        return self.pg is not None or (d.is_available() and d.is_initialized() and d.get_world_size() > 1)
+
+    def enable_data_parallel(self) -> None:
+        """All-gather the ranks' IPC handles and map the peers' gradient blocks (ranks of one node)."""
+        d = torch.distributed
+        rank, world = d.get_rank(self.pg), d.get_world_size(self.pg)
+        e = self.engine
+        buf = (C.c_ubyte * nat.DPI_DP_HANDLE_BYTES)()
+        with torch.cuda.device(self.device):
+            nat.check(e.lib.dpi_train_dp_export(e.h, buf), "dpi_train_dp_export")
+        mine = torch.tensor(list(buf), dtype=torch.uint8, device=self.device if d.get_backend(self.pg) == "nccl" else "cpu")
+        allh = [torch.empty_like(mine) for _ in range(world)]
+        d.all_gather(allh, mine, group=self.pg)
+        raw = bytes(torch.cat(allh).cpu().tolist())
+        with torch.cuda.device(self.device):
+            nat.check(e.lib.dpi_train_dp_connect(e.h, rank, world, C.c_char_p(raw)), "dpi_train_dp_connect")
+        self.dp_world = world
 
     def close(self):
         self.engine.close()
@@ -90,10 +122,9 @@ class RegressionTrainer:
     def fit(self, tx: torch.Tensor, y: torch.Tensor, batch_size: int, n_epochs: int) -> Optional[torch.Tensor]:
         """The reference's inner loop over one iteration's label set: unshuffled mini-batches (config.py:90), n_epochs passes."""
         n = tx.shape[0]
-        distributed = self.pg is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
-                                              and torch.distributed.get_world_size() > 1)
-        if not distributed:
-            # single device: the whole inner loop runs natively (no host round trip between the steps)
+        if not self._distributed() or self.dp_world > 1:
+            # the whole inner loop runs natively (no host round trip between the steps); with peers connected the
+            # captured step ends in the fused NVLink reduce + Adam kernel and batch_size is this rank's share
             tx = tx.detach().to(self.device, torch.float32).contiguous()
             y = y.detach().to(self.device, torch.float32).contiguous()
             e = self.engine

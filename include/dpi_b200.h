@@ -219,6 +219,20 @@ int dpi_train_adam(dpi_handle* h, const float* grad_flat, const dpi_train_config
 int dpi_train_fit(dpi_handle* h, const float* tx, const float* y, int64_t n, int64_t batch, int64_t n_epochs,
                   const dpi_train_config* cfg, int64_t first_step, float* losses_last, void* stream);
 
+/* ---- data-parallel regression over NVLink (one process per GPU of one node) ------------------------------------------
+ * The reference's trainer would all-reduce the MLP gradients between backward and optimiser step (DDP under
+ * pl.Trainer).  Here the exchange is part of the optimiser kernel: every rank's gradient block is mapped
+ * into its peers (CUDA IPC), and ONE kernel per step waits until all ranks' gradients are written, sums them over peer
+ * memory in rank order (bitwise identical replicas, no broadcast), applies Adam, and holds until all peers have read.
+ * It replaces the Adam kernel inside dpi_train_fit's captured step, so the inner loop stays native and graph-replayed.
+ *   dpi_train_dp_export : handle_out receives DPI_DP_HANDLE_BYTES bytes naming this rank's block (after dpi_train_init);
+ *   dpi_train_dp_connect: `handles` = world x DPI_DP_HANDLE_BYTES bytes, rank order (all-gathered by the caller, e.g.
+ *                         over torch.distributed); every rank then calls dpi_train_fit with its share of each global
+ *                         mini-batch (batch / world rows) and the same n, n_epochs, first_step. */
+#define DPI_DP_HANDLE_BYTES 64
+int dpi_train_dp_export(dpi_handle* h, void* handle_out);
+int dpi_train_dp_connect(dpi_handle* h, int32_t rank, int32_t world, const void* handles);
+
 /* Kernels launched by this handle since creation (for bench.py's gpu_launches). */
 int64_t dpi_launch_count(const dpi_handle* h);
 

@@ -67,7 +67,9 @@ def test_eval_callback_metrics_match_a_host_restatement():
     assert abs(error_metrics(u, ue, gx, gxe, hx, hxe)["rRMSE"] - m["rRMSE"]) < 1e-12
     # network side of those arrays vs autograd of the oracle net at the same points is covered by the net_eval tests;
     # here: the exact side must be the closed forms of equations.py
-    assert np.isfinite(list(m.values())).all() and 0.5 < m["rRMSE"] < 5.0  # random-init net: O(1) relative error
+    # (MArE divides by |u_exact|, which is 0 at the point t = 0, x = 0 of the linspace grid: inf there, as upstream)
+    assert all(np.isfinite(m[k]) for k in ("MSE", "rRMSE", "rMAE", "rRMSEg", "rMAEg", "rRMSEh", "rMAEh"))
+    assert 0.5 < m["rRMSE"] < 5.0  # random-init net: O(1) relative error
     e.close()
 
 
@@ -114,23 +116,23 @@ PICARD: {N: 2}
 FORCE: true
 DATA:
   FLOAT: double
-  DATA_SIZE: 512
+  DATA_SIZE: 2048
   SAVE: true
   PREFETCH_FACTOR: None
-  kwargs: {t_always_uniform: true, n_estimate_terminal: 256, n_estimate_integral: 256}
+  kwargs: {t_always_uniform: true, n_estimate_terminal: 1024, n_estimate_integral: 256}
 TRAIN:
   N_EPOCHS: 4
-  BATCH_SIZE: 128
+  BATCH_SIZE: 256
   LOSS: {SCALER: {cls: FixedLossScaler, kwargs: {fixed_weight: 1.0}}}
 NETWORK: {NEURONS: [128, 128, 128, 128], ACTIVATIONS: [ELU, ELU, ELU, ELU], BOUND: None, RELOAD: true}
 EVAL: {L2_N_POINTS: 1000, FREQ: 8, TEST_GRAD: true}
 """)
-    (tmp_path / "run.yaml").write_text("BASE: base.yaml\nNAME: run\nTRAIN: {N_EPOCHS: 6}\n")
+    (tmp_path / "run.yaml").write_text("BASE: base.yaml\nNAME: run\nTRAIN: {N_EPOCHS: 24}\n")
     from deeppicarditeration_b200.main import train
     cwd = os.getcwd()
     os.chdir(tmp_path)
     try:
-        hist = train("run.yaml", ["--PICARD.N", "3", "DATA.kwargs.n_estimate_integral", "128"])
+        hist = train("run.yaml", ["--PICARD.N", "3", "DATA.kwargs.n_estimate_integral", "1024"])
     finally:
         os.chdir(cwd)
         torch.set_default_dtype(torch.float32)
@@ -138,7 +140,7 @@ EVAL: {L2_N_POINTS: 1000, FREQ: 8, TEST_GRAD: true}
     assert len(hist) == 3 and (exp / "config.yaml").exists()
     import yaml
     dumped = yaml.safe_load((exp / "config.yaml").read_text())
-    assert dumped["PICARD"]["N"] == 3 and dumped["TRAIN"]["N_EPOCHS"] == 6 and dumped["DATA"]["kwargs"]["n_estimate_integral"] == 128
+    assert dumped["PICARD"]["N"] == 3 and dumped["TRAIN"]["N_EPOCHS"] == 24 and dumped["DATA"]["kwargs"]["n_estimate_integral"] == 1024
     for i in (1, 2, 3):
         sd = torch.load(exp / f"model_{i}.ckpt")["state_dict"]
         assert set(sd) == {f"solution.model.{j}.{p}" for j in (0, 2, 4, 6, 8) for p in ("weight", "bias")}
@@ -150,7 +152,7 @@ EVAL: {L2_N_POINTS: 1000, FREQ: 8, TEST_GRAD: true}
     assert files, list(exp.iterdir())
     if files[0].endswith(".npz"):
         z = np.load(exp / files[0])
-        assert z["tx"].shape == (512, 21) and z["u_ux"].shape == (512, 21)
+        assert z["tx"].shape == (2048, 21) and z["u_ux"].shape == (2048, 21)
     with pytest.raises(FileExistsError):  # no FORCE: refuse to overwrite (picard_iteration.py:131-137)
         os.chdir(tmp_path)
         try:
