@@ -51,7 +51,7 @@ WORKLOADS = {
                         precision="f16", scaling="weak", steps=50, cpu_points=32,
                         config="scripts/burgers/base_100d_T1.0_w1.0_0.yaml"),
     "hjb100d": dict(eq="OU", nx=100, net="pisgrad", hidden=[512] * 4, M=4096, points=4096, v=0,
-                    precision="tf32", scaling="weak", steps=4, cpu_points=4,
+                    precision="f16", scaling="weak", steps=4, cpu_points=4,
                     config="scripts/hjb/base_100d_T1.0_w0.1_0.yaml"),
     "gbm100d": dict(eq="GBM", nx=100, net="mlp", hidden=[64] * 3, M=1024, points=2048, v=100,
                     precision="f16", scaling="weak", steps=10, cpu_points=2,
@@ -370,7 +370,7 @@ def run_b200(args, wl):
     # burst vs sustained denominator: the burst peak applies when the SM clock held its maximum through the timed region
     at_max = bool(clk and clk.get("sm_mhz") and clk.get("sm_max_mhz") and clk["sm_mhz"] >= 0.95 * clk["sm_max_mhz"])
     which = "burst" if at_max else "sustained"
-    dt = "f32" if prec == "fp32" else ("tf32" if wl["net"] == "pisgrad" else "f16")
+    dt = {"fp32": "f32", "tf32": "tf32"}.get(prec, "f16")
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):

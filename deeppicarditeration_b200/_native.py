@@ -17,6 +17,7 @@ DPI_EQ_CHA, DPI_EQ_GBM, DPI_EQ_OU = 0, 1, 2
 DPI_NET_ZERO, DPI_NET_MLP, DPI_NET_PISGRAD = 0, 1, 2
 DPI_PREC_FP32, DPI_PREC_F16 = 0, 1
 DPI_PREC_BF16 = 2  # distinct and rejected (DPI_ERR_UNSUPPORTED): bf16 operands are not built
+DPI_PREC_TF32 = 3  # PISGradNet: layer-by-layer pipeline with TF32 tensor-core GEMMs
 DPI_ERR_NONFINITE = -5
 DPI_DP_HANDLE_BYTES = 64
 

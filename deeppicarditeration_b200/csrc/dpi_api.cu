@@ -31,6 +31,9 @@ struct dpi_handle {
   TcNetDev tc{};
   bool tc_ready = false;
   PisDev pis{};
+  HjbTcNet* hjb_tc = nullptr;   // fused tensor-core packing of the PISGradNet (null: shape not eligible)
+  float* hjb_part = nullptr;    // per-tile partial sums of the fused path
+  int64_t hjb_part_floats = 0;
   // regression step: trainable MLP (caller's tensors), Adam moments, activation scratch
   dpi_linear train_lin[DPI_MAX_LINEAR] = {};
   int n_train_lin = 0;
@@ -241,6 +244,8 @@ int dpi_destroy(dpi_handle* h) {
   if (h->tc_zring) cudaFree(h->tc_zring);
   if (h->partF) cudaFree(h->partF);
   if (h->hjb_scratch) cudaFree(h->hjb_scratch);
+  if (h->hjb_part) cudaFree(h->hjb_part);
+  if (h->hjb_tc) hjb_tc_free(h->hjb_tc);
   if (h->nonfinite_flag) cudaFree(h->nonfinite_flag);
   if (h->train_m) cudaFree(h->train_m);
   if (h->train_v) cudaFree(h->train_v);
@@ -357,6 +362,8 @@ int dpi_set_network(dpi_handle* h, const dpi_network* net, void* stream) {
   DPI_CUDA_CHECK(cudaSetDevice(h->device));
   DPI_CUDA_CHECK(cudaDeviceSynchronize());
   free_all(h->net_bufs);
+  if (h->hjb_tc) hjb_tc_free(h->hjb_tc);
+  h->hjb_tc = nullptr;
   h->has_net = false;
   h->tc_ready = false;
   h->net_kind = net->kind;
@@ -486,6 +493,7 @@ int dpi_set_network(dpi_handle* h, const dpi_network* net, void* stream) {
       N.main_t[l] = wt;
     }
     h->launches += net->n_main;
+    if (int rc_p = hjb_tc_pack(N, nx, h->net_bufs, &h->hjb_tc, &h->launches, st)) return rc_p;
     h->pis = N;
     DPI_CUDA_CHECK(cudaStreamSynchronize(st));  // the caller's tensors are not read after this call returns
     h->has_net = true;
@@ -536,7 +544,8 @@ int dpi_label_gen(dpi_handle* h, const float* tx, int64_t n, const dpi_label_con
     set_error("dpi_label_gen: NULL argument");
     return DPI_ERR_INVALID;
   }
-  if (cfg->precision != DPI_PREC_FP32 && cfg->precision != DPI_PREC_F16) {
+  if (cfg->precision != DPI_PREC_FP32 && cfg->precision != DPI_PREC_F16 &&
+      !(cfg->precision == DPI_PREC_TF32 && h->net_kind == DPI_NET_PISGRAD)) {
     set_error("dpi_label_gen: precision %d is not built (DPI_PREC_BF16 operands are not implemented: use DPI_PREC_F16, "
               "same operand width with three more mantissa bits, or DPI_PREC_FP32)", cfg->precision);
     return DPI_ERR_UNSUPPORTED;
@@ -550,7 +559,8 @@ int dpi_label_gen(dpi_handle* h, const float* tx, int64_t n, const dpi_label_con
   if (rc || n <= 0) return rc;
   // the tensor-core finish kernel checks its own output; every other path gets one small sweep over y
   const bool tc_cha = h->net_kind == DPI_NET_MLP && h->P.eq == DPI_EQ_CHA && cfg->precision == DPI_PREC_F16;
-  if (!tc_cha) {
+  const bool tc_hjb = h->net_kind == DPI_NET_PISGRAD && cfg->precision == DPI_PREC_F16 && h->hjb_tc;
+  if (!tc_cha && !tc_hjb) {
     rc = launch_check_finite(y, n * (int64_t)(1 + h->P.nx), h->nonfinite_flag, reinterpret_cast<cudaStream_t>(stream));
     if (!rc) h->launches += 1;
   }
@@ -707,7 +717,22 @@ static int label_gen_body(dpi_handle* h, const float* tx, int64_t n, const dpi_l
     return rc;
   }
   if (h->net_kind == DPI_NET_PISGRAD && P.eq == DPI_EQ_OU) {
-    // reduced precision here = the wide GEMMs of nn_module on the tensor cores with TF32 operands (fp32 in memory)
+    if (cfg->precision == DPI_PREC_F16 && h->hjb_tc) {
+      // fused tcgen05 kernel: fp16 operands, activations in shared memory / TMEM, weights streamed from L2
+      if ((rc = ensure_scratch(h, n, 64))) return rc;
+      const int64_t pf = hjb_tc_part_floats(n, cfg->M_I, P.nx);
+      if (pf > h->hjb_part_floats) {
+        if (h->hjb_part) cudaFree(h->hjb_part);
+        h->hjb_part = nullptr, h->hjb_part_floats = 0;
+        DPI_CUDA_CHECK(cudaMalloc((void**)&h->hjb_part, sizeof(float) * pf));
+        h->hjb_part_floats = pf;
+      }
+      StageTimer tm(h, DPI_STAGE_INTEGRAL, st);
+      return launch_hjb_tc_paths(P, h->hjb_tc, tx, n, cfg->M_I, cfg->seed, cfg->point_index_base,
+                                 draws ? draws->u_s : nullptr, draws ? draws->zS : nullptr, bound, h->fb, h->hjb_part,
+                                 h->nonfinite_flag, y, st, &h->launches);
+    }
+    // DPI_PREC_TF32 (or an ineligible shape): the batched-GEMM pipeline with its wide GEMMs on tcgen05, TF32 operands
     PisDev pis = h->pis;
     pis.tf32 = cfg->precision != DPI_PREC_FP32;
     const int64_t ppc = std::min<int64_t>(n, hjb_points_per_chunk(h->pis, P.nx, cfg->M_I, kHjbScratchBudget));

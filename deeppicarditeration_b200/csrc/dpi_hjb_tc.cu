@@ -1,0 +1,760 @@
+// Fused tcgen05 integral estimator for the HJB equation `OUProcessEquation` with u_k = PISGradNet (BASELINE config 3).
+//
+// Same mathematics as dpi_hjb.cu (picard/data.py:471-527,350-366,1226-1325; picard/solution.py:211-289;
+// picard/equations.py:657-666; picard/utils.py:852-915) -- closed-form grad_x u = S (n + J_n^T x) + (1 - S) gamma g_x(gamma x)
+// with ONE VJP through nn_module -- but a tile of 128 path rows goes through EVERY layer inside one persistent CTA:
+//
+//   * activations never leave the SM: the A operand of a layer (128 rows x up to 512 fp16, K-major SWIZZLE_128B, 8
+//     panels of 16 KB) lives in shared memory, the layer's fp32 accumulators in TMEM (512 columns = the whole
+//     128 x 512 output), and the epilogue (bias, ELU in packed fp16x2, or the VJP mask) writes the next A operand in
+//     place once the layer's MMAs have completed;
+//   * the 512-wide weights (3.7 MB of fp16 operand images for forward + VJP) do not fit an SM: they are packed once
+//     at dpi_set_network as a stream of [128 n x 64 k] tiles in consumption order, and a TMA warp streams that ring
+//     (6 x 16 KB) from L2 with 1-D bulk copies, running ahead across layer and tile boundaries;
+//   * the only per-row state that does leave the SM is what the VJP needs again: the hidden activations h_l (fp16,
+//     from which ELU'(z_l) = min(1, 1 + ln2 h_l') is recovered) and the network output n, in a per-CTA scratch of
+//     576 KB that is rewritten every tile and therefore stays in L2.  No [rows, 512] tensor exists in HBM;
+//   * the time nets (t_encoder, smooth_net: 64 wide) run as six small MMA steps in front of nn_module, the sin/cos
+//     embedding is computed in the tile set-up with a two-constant Cody-Waite reduction (arguments reach 100 rad);
+//   * the row's f, the Bismut coefficient and the MC sums (value and gradient label) are formed in the last epilogue;
+//     increments are re-drawn from their Philox counters where they are needed again (forward input, VJP cotangent,
+//     Bismut sums) instead of being kept.
+//
+// All activations are carried scaled by log2(e) (see dpi_mlp_tc.cu): biases are pre-scaled, weights are used as they
+// are, the VJP runs on unscaled cotangents.  One partial [1 + d] per (point, 128-sample tile) goes to scratch and
+// hjb_tc_finish_kernel adds them in a fixed order: labels are bitwise independent of the launch geometry.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "dpi_common.cuh"
+#include "dpi_kernels.h"
+#include "dpi_tc_common.cuh"
+
+namespace dpi {
+namespace {
+using namespace tc;
+
+constexpr int kThreads = 320;  // warps 0-7: set-up + epilogue, warp 8: MMA issuer, warp 9: TMA issuer
+constexpr int kEpiWarps = 8, kMmaWarp = 8, kTmaWarp = 9;
+constexpr int kSlots = 6;
+constexpr uint32_t kSlotBytes = 16384;
+constexpr uint32_t kOffA = 0;                             // 8 panels x 16 KB: the current A operand
+constexpr uint32_t kOffRing = 8 * kPanelBytes;            // weight ring
+constexpr uint32_t kOffMisc = kOffRing + kSlots * kSlotBytes;  // S_raw [128]
+constexpr uint32_t kOffBars = kOffMisc + 1024;
+constexpr uint32_t kOffTmemPtr = kOffBars + 8 * (2 * kSlots + 2);
+constexpr uint32_t kSmemBytes = kOffTmemPtr + 16;
+static_assert(kSmemBytes <= 232448, "shared memory budget");
+// FINAL-step scratch inside the (then free) A region
+constexpr uint32_t kFinZ = 0;                      // Zs [128 cols][129] fp32
+constexpr uint32_t kFinRow = 128 * 129 * 4;        // per-row exchange: q[8], dfg, gg, coef, dTf (12 floats per row)
+constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+
+enum Epi : int { kEpiTime1 = 0, kEpiTemb, kEpiSmHid, kEpiSmOut, kEpiFwdHid, kEpiFwdOut, kEpiBwdHid, kEpiFinal };
+constexpr int kMaxSteps = 24;
+
+struct Step {
+  int a_panel0, n_kp, n_chunks, width, acc0, epi, layer, dst_panel;
+};
+
+struct Args {
+  Step steps[kMaxSteps];
+  int n_steps;
+  int H, nh, n_hid;            // hidden width, H / 128, number of hidden layers
+  int d, no;                   // nx, ceil(d / 8)
+  const uint8_t* W;            // packed weight tiles in consumption order
+  uint32_t tile_bytes_total;   // bytes of one pass over the tile stream
+  // constants (device): fp16x2 bias vectors (x log2e) per step, fp32 vectors for the output layers
+  const uint32_t* bias16[kMaxSteps];
+  const float* sm_w0;   // [64] ln2 * smooth_net last layer row 0
+  float sm_b0, S0;      // its bias; smooth_net(emb(0))[0]
+  const float* out_b;   // [128] bias of nn_module's last layer (unscaled)
+  const float* phase;   // [64]
+  const float* coeff;   // [64]
+  // per-CTA global scratch
+  uint4* hs;            // [grid][n_hid][H/8][128] fp16x8
+  float4* nbuf;         // [grid][32][128]
+  // problem instance of the call
+  const float* tx;
+  int64_t n, n_tiles, point_base;
+  int M_I, tiles_pp;
+  int baseline;         // 1: rows are points (t, x) themselves, output fb
+  PhiloxKeys keys;
+  const float* u_s;
+  const float* zS;
+  const float* fb_in;   // [n] control variate (path mode)
+  float* fb_out;        // [n] (baseline mode)
+  float* part;          // [n_tiles][1 + d] (path mode)
+};
+
+__device__ __forceinline__ uint32_t panel_off(int col8, int r) {  // byte offset of the 16-byte chunk `col8` (8 columns) of row r
+  return (uint32_t)(col8 >> 3) * kPanelBytes + (uint32_t)r * 128u + ((((uint32_t)col8 & 7u) ^ ((uint32_t)r & 7u)) << 4);
+}
+
+// row r of the tile -> (point, sample, validity)
+struct RowId {
+  int64_t p;
+  int m;
+  bool valid;
+};
+__device__ __forceinline__ RowId row_of(const Args& A, int64_t tile, int r) {
+  RowId R;
+  if (A.baseline) {
+    R.p = tile * 128 + r;
+    R.m = 0;
+    R.valid = R.p < A.n;
+    if (!R.valid) R.p = A.n - 1;
+  } else {
+    R.p = tile / A.tiles_pp;
+    R.m = (int)(tile - R.p * A.tiles_pp) * 128 + r;
+    R.valid = R.m < A.M_I;
+  }
+  return R;
+}
+
+// increments of dims [8 o, 8 o + 8) of the row (zero in baseline mode / for invalid rows)
+__device__ __forceinline__ void row_z8(const Args& A, const RowId& R, int o, float (&z)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) z[i] = 0.f;
+  if (A.baseline || !R.valid || 8 * o >= A.d) return;
+  if (A.zS) {
+    const float* row = A.zS + (R.p * A.M_I + R.m) * (int64_t)A.d;
+    const float4 a = load_row4(row, 8 * o, A.d, (A.d & 3) == 0), b = load_row4(row, 8 * o + 4, A.d, (A.d & 3) == 0);
+    z[0] = a.x, z[1] = a.y, z[2] = a.z, z[3] = a.w, z[4] = b.x, z[5] = b.y, z[6] = b.z, z[7] = b.w;
+  } else {
+    float4 a, b;
+    normal8(A.keys, (uint64_t)(A.point_base + R.p), kStreamIntegral, (uint32_t)R.m, (uint32_t)o, a, b);
+    z[0] = a.x, z[1] = a.y, z[2] = a.z, z[3] = a.w, z[4] = b.x, z[5] = b.y, z[6] = b.z, z[7] = b.w;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (8 * o + i >= A.d) z[i] = 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+hjb_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ Args A) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  auto bar_full = [&](int s) -> uint32_t { return sbase + kOffBars + 8u * (uint32_t)s; };
+  auto bar_empty = [&](int s) -> uint32_t { return sbase + kOffBars + 8u * (uint32_t)(kSlots + s); };
+  const uint32_t bar_acc = sbase + kOffBars + 8u * (2 * kSlots), bar_ready = bar_acc + 8u;
+
+  if (threadIdx.x == 0) {
+    if (sbase & 1023u) __trap();
+    for (int s = 0; s < kSlots; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_empty(s), 1);
+    }
+    mbar_init(bar_acc, 1);
+    mbar_init(bar_ready, kEpiWarps);
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc(sbase + kOffTmemPtr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + kOffTmemPtr);
+  const int64_t my_tiles = (A.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;  // tiles blockIdx.x, + gridDim.x, ...
+
+  if (warp == kTmaWarp) {
+    // =================================== weight stream ===================================
+    // the same tile sequence for every row tile: walk the packed buffer my_tiles times, up to kSlots tiles ahead
+    const uint32_t leader = elect_one();
+    uint32_t slot = 0, ph = 0, used = 0;
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const uint8_t* src = A.W;
+      for (int si = 0; si < A.n_steps; ++si) {
+        const Step& S = A.steps[si];
+        const uint32_t bytes = (uint32_t)S.width * 128u;
+        const int nt = S.n_chunks * S.n_kp;
+        for (int t = 0; t < nt; ++t) {
+          if (used & (1u << slot)) mbar_wait(bar_empty(slot), (ph >> slot) & 1u, 1);
+          if (used & (1u << slot)) ph ^= 1u << slot;
+          used |= 1u << slot;
+          mbar_arrive_expect_tx_p(bar_full(slot), bytes, leader);
+          bulk_g2s_p(sbase + kOffRing + slot * kSlotBytes, src, bytes, bar_full(slot), leader);
+          src += bytes;
+          slot = (slot + 1 == kSlots) ? 0 : slot + 1;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == kMmaWarp) {
+    // =================================== MMA issuer ===================================
+    const uint32_t leader = elect_one();
+    uint32_t slot = 0, ph_full = 0, ph_ready = 0;
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      for (int si = 0; si < A.n_steps; ++si) {
+        const Step& S = A.steps[si];
+        // the step's A operand is written and the accumulators of the previous step are drained
+        mbar_wait(bar_ready, ph_ready, 2);
+        ph_ready ^= 1u;
+        tc_fence_after();
+        const uint32_t idesc = make_idesc_f16(128, S.width);
+        for (int nc = 0; nc < S.n_chunks; ++nc) {
+          const uint32_t acc = tmem + (uint32_t)(S.acc0 + nc * S.width);
+          for (int kp = 0; kp < S.n_kp; ++kp) {
+            mbar_wait(bar_full(slot), (ph_full >> slot) & 1u, 3);
+            ph_full ^= 1u << slot;
+            tc_fence_after();
+            const uint32_t a_base = sbase + kOffA + (uint32_t)(S.a_panel0 + kp) * kPanelBytes;
+            const uint32_t b_base = sbase + kOffRing + slot * kSlotBytes;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_bf16_p(acc, make_desc_sw128(a_base + ks * 32u), make_desc_sw128(b_base + ks * 32u), idesc,
+                          (uint32_t)((kp | ks) != 0), leader);
+            tc_commit_p(bar_empty(slot), leader);  // the slot may be refilled once these MMAs have read it
+            slot = (slot + 1 == kSlots) ? 0 : slot + 1;
+          }
+        }
+        tc_commit_p(bar_acc, leader);
+      }
+    }
+    __syncwarp();
+  } else {
+    // =================================== set-up + epilogue warps ===================================
+    const int q = warp & 3, hh = warp >> 2;
+    const int r = q * 32 + lane;
+    const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+    float* sraw_s = reinterpret_cast<float*>(smem + kOffMisc);
+    const int d = A.d;
+    uint4* const hs = A.hs + (size_t)blockIdx.x * A.n_hid * (A.H / 8) * 128;
+    float4* const nbuf = A.nbuf + (size_t)blockIdx.x * 32 * 128;
+    uint32_t ph_acc = 0;
+    auto step_done = [&]() {  // A operand of the next step written (generic -> async proxy), accumulators read
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_ready);
+    };
+    const uint32_t kL = h2_const(kLog2e, kLog2e), kNegL = h2_const(-kLog2e, -kLog2e), kZero = 0u;
+    const uint32_t kOne = h2_const(1.f, 1.f), kLn2h = h2_const(kLn2, kLn2);
+
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const int64_t tile = blockIdx.x + it * (int64_t)gridDim.x;
+      const RowId R = row_of(A, tile, r);
+      const float* txp = A.tx + R.p * (int64_t)(1 + d);
+      const float t = __ldg(txp), dT = P.T - t;
+      float uu = 0.5f;
+      if (A.baseline) {
+        uu = 0.f;
+      } else if (R.valid) {
+        uu = A.zS ? __ldg(A.u_s + R.p * A.M_I + R.m)
+                  : u01(philox_at(A.keys, (uint64_t)(A.point_base + R.p), kStreamS, (uint32_t)R.m, 0u).x);
+      }
+      const float s = uu * dT + t, a = sqrtf(uu * dT) * P.sigma, lam = P.T - s;
+
+      // ---------------- set-up: embedding -> panels 6, 7; X' -> panels 1..; nxdot = 0 ----------------
+      {
+        // channels [32 hh, 32 hh + 32): sin -> panel 6, cos -> panel 7 (solution.py:211-229), scaled by log2e
+#pragma unroll 1
+        for (int c8 = 0; c8 < 4; ++c8) {
+          uint32_t sn[4], cs[4];
+#pragma unroll
+          for (int i2 = 0; i2 < 4; ++i2) {
+            float sv[2], cv[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int c = 32 * hh + 8 * c8 + 2 * i2 + e;
+              const float arg = fmaf(__ldg(A.coeff + c), lam, __ldg(A.phase + c));
+              const float k = rintf(arg * 0.15915494309189535f);
+              float rr = fmaf(-k, 6.2831854820251465f, arg);  // Cody-Waite: 2 pi = hi + lo
+              rr = fmaf(-k, -1.7484555314695172e-7f, rr);
+              __sincosf(rr, &sv[e], &cv[e]);
+            }
+            sn[i2] = pack_f16x2(kLog2e * sv[0], kLog2e * sv[1]);
+            cs[i2] = pack_f16x2(kLog2e * cv[0], kLog2e * cv[1]);
+          }
+          const int col8 = 4 * hh + c8;  // chunk inside the panel
+          *reinterpret_cast<uint4*>(smem + kOffA + panel_off(48 + col8, r)) = make_uint4(sn[0], sn[1], sn[2], sn[3]);
+          *reinterpret_cast<uint4*>(smem + kOffA + panel_off(56 + col8, r)) = make_uint4(cs[0], cs[1], cs[2], cs[3]);
+        }
+        // X' = log2e (x + a Z) -> columns 64.. of the nn_module input (panels 1, 2); this half takes octets hh, hh+2, ...
+        for (int o = hh; o < 16; o += 2) {
+          float z[8];
+          row_z8(A, R, o, z);
+          uint32_t w[4];
+#pragma unroll
+          for (int i2 = 0; i2 < 4; ++i2) {
+            const int j = 8 * o + 2 * i2;
+            const float x0 = (j < d) ? fmaf(a, z[2 * i2], __ldg(txp + 1 + j)) : 0.f;
+            const float x1 = (j + 1 < d) ? fmaf(a, z[2 * i2 + 1], __ldg(txp + 2 + j)) : 0.f;
+            w[i2] = pack_f16x2(kLog2e * x0, kLog2e * x1);
+          }
+          *reinterpret_cast<uint4*>(smem + kOffA + panel_off(8 + o, r)) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        step_done();
+      }
+
+      for (int si = 0; si < A.n_steps; ++si) {
+        const Step& S = A.steps[si];
+        mbar_wait(bar_acc, ph_acc, 10);
+        ph_acc ^= 1u;
+        tc_fence_after();
+        const int ncols = S.width * S.n_chunks;  // columns of this step's output
+        const int c0 = hh * (ncols / 2), c1 = c0 + ncols / 2;  // this warp's column range
+        const uint32_t* b16 = A.bias16[si];
+
+        if (S.epi == kEpiTime1 || S.epi == kEpiTemb || S.epi == kEpiSmHid || S.epi == kEpiFwdHid) {
+          // bias (+ ELU) in packed fp16x2 -> next A operand (and, for nn_module's hidden layers, the VJP's copy)
+          const bool elu = S.epi != kEpiTemb;
+          uint4* hsl = (S.epi == kEpiFwdHid) ? hs + (size_t)S.layer * (A.H / 8) * 128 : nullptr;
+          for (int c = c0; c < c1; c += 16) {
+            uint32_t v[16];
+            tmem_ld16(trow + (uint32_t)(S.acc0 + c), v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              const int col8 = (c >> 3) + g;
+              const uint4 bb = __ldg(reinterpret_cast<const uint4*>(b16) + col8);
+              const uint32_t bv[4] = {bb.x, bb.y, bb.z, bb.w};
+              uint32_t o[4];
+#pragma unroll
+              for (int i2 = 0; i2 < 4; ++i2) {
+                const uint32_t z = h2_add(pack_f16x2(__uint_as_float(v[8 * g + 2 * i2]), __uint_as_float(v[8 * g + 2 * i2 + 1])), bv[i2]);
+                if (elu) {
+                  const uint32_t e = h2_ex2(h2_min(z, kZero));
+                  o[i2] = h2_max(z, h2_fma(e, kL, kNegL));
+                } else {
+                  o[i2] = z;
+                }
+              }
+              const uint4 chunk = make_uint4(o[0], o[1], o[2], o[3]);
+              int dst8;
+              if (S.epi == kEpiTime1) dst8 = (col8 < 8) ? 32 + col8 : 40 + (col8 - 8);  // t branch -> panel 4, smooth -> panel 5
+              else dst8 = 8 * S.dst_panel + col8;
+              *reinterpret_cast<uint4*>(smem + kOffA + panel_off(dst8, r)) = chunk;
+              if (hsl) hsl[(size_t)col8 * 128 + r] = chunk;
+            }
+          }
+          step_done();
+        } else if (S.epi == kEpiSmOut) {
+          // last 64 -> 64 layer of smooth_net, then ELU and row 0 of the output layer: S_raw (solution.py:231-254)
+          float acc = 0.f;
+          for (int c = c0; c < c1; c += 16) {
+            uint32_t v[16];
+            tmem_ld16(trow + (uint32_t)(S.acc0 + c), v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i2 = 0; i2 < 8; ++i2) {
+              const float2 b = h2_unpack(__ldg(b16 + ((c >> 1) + i2)));
+              const float z0 = __uint_as_float(v[2 * i2]) + b.x, z1 = __uint_as_float(v[2 * i2 + 1]) + b.y;  // log2e-scaled
+              const float h0 = z0 > 0.f ? z0 : kLog2e * (exp2f(z0) - 1.f), h1 = z1 > 0.f ? z1 : kLog2e * (exp2f(z1) - 1.f);
+              acc = fmaf(__ldg(A.sm_w0 + c + 2 * i2), h0, acc);
+              acc = fmaf(__ldg(A.sm_w0 + c + 2 * i2 + 1), h1, acc);
+            }
+          }
+          if (hh == 0) sraw_s[r] = acc;
+          named_bar_sync(1 + q, 64);
+          if (hh == 1) sraw_s[r] += acc + A.sm_b0;
+          step_done();
+        } else if (S.epi == kEpiFwdOut) {
+          // n = ln2 acc + b (unscaled) -> scratch; cotangent X (unscaled, fp16) -> panels 0, 1.  (u = S <n, x> + (1 - S) g
+          // itself is not formed: ff of this equation depends on grad_x u only, equations.py:657-666.)
+          for (int c = c0; c < c1; c += 16) {
+            uint32_t v[16];
+            tmem_ld16(trow + (uint32_t)(S.acc0 + c), v);
+            tmem_ld_wait();
+            float nn[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) nn[i] = fmaf(kLn2, __uint_as_float(v[i]), __ldg(A.out_b + c + i));
+#pragma unroll
+            for (int g4 = 0; g4 < 4; ++g4)
+              nbuf[(size_t)((c >> 2) + g4) * 128 + r] = make_float4(nn[4 * g4], nn[4 * g4 + 1], nn[4 * g4 + 2], nn[4 * g4 + 3]);
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              const int o = (c >> 3) + g;
+              float z[8];
+              row_z8(A, R, o, z);
+              uint32_t w[4];
+#pragma unroll
+              for (int i2 = 0; i2 < 4; ++i2) {
+                const int j = 8 * o + 2 * i2;
+                const float x0 = (j < d) ? fmaf(a, z[2 * i2], __ldg(txp + 1 + j)) : 0.f;
+                const float x1 = (j + 1 < d) ? fmaf(a, z[2 * i2 + 1], __ldg(txp + 2 + j)) : 0.f;
+                w[i2] = pack_f16x2(x0, x1);
+              }
+              *reinterpret_cast<uint4*>(smem + kOffA + panel_off(o, r)) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+          }
+          step_done();
+        } else if (S.epi == kEpiBwdHid) {
+          // c = acc . ELU'(z_l), ELU' recovered from the stored activation: min(1, 1 + ln2 h')
+          const uint4* hsl = hs + (size_t)S.layer * (A.H / 8) * 128;
+          for (int c = c0; c < c1; c += 16) {
+            uint32_t v[16];
+            tmem_ld16(trow + (uint32_t)(S.acc0 + c), v);
+            const uint4 h0 = __ldcg(hsl + (size_t)(c >> 3) * 128 + r), h1 = __ldcg(hsl + (size_t)((c >> 3) + 1) * 128 + r);
+            tmem_ld_wait();
+            const uint32_t hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+            uint32_t o[8];
+#pragma unroll
+            for (int i2 = 0; i2 < 8; ++i2) {
+              const uint32_t e = h2_min(h2_fma(hv[i2], kLn2h, kOne), kOne);
+              o[i2] = h2_mul(pack_f16x2(__uint_as_float(v[2 * i2]), __uint_as_float(v[2 * i2 + 1])), e);
+            }
+            *reinterpret_cast<uint4*>(smem + kOffA + panel_off(c >> 3, r)) = make_uint4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<uint4*>(smem + kOffA + panel_off((c >> 3) + 1, r)) = make_uint4(o[4], o[5], o[6], o[7]);
+          }
+          step_done();
+        } else {
+          // ---------------- FINAL: jtx in TMEM columns [0, 128); u, grad_x u, f, Bismut sums ----------------
+          // this thread: row r, columns [64 hh, 64 hh + 64).  The A region is free: Zs [col][129] and the per-row exchange.
+          float* Zs = reinterpret_cast<float*>(smem + kOffA + kFinZ);
+          float* rowx = reinterpret_cast<float*>(smem + kOffA + kFinRow) + r * 12;
+          const float Ssm = sraw_s[r] - A.S0;
+          const float gamma = __expf(-0.5f * lam);
+          const int K = P.ou_K;
+          if (hh == 0) {
+#pragma unroll
+            for (int i = 0; i < 12; ++i) rowx[i] = 0.f;
+          }
+          named_bar_sync(1 + q, 64);
+          float X[64], G[64];  // X_j; then n_j + jtx_j
+          float qk[kMaxOuK];
+#pragma unroll
+          for (int k = 0; k < kMaxOuK; ++k) qk[k] = 0.f;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const int o = 8 * hh + g;
+            float z[8];
+            row_z8(A, R, o, z);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int j = 8 * o + i;
+              X[8 * g + i] = (j < d) ? fmaf(a, z[i], __ldg(txp + 1 + j)) : 0.f;
+              Zs[(size_t)j * 129 + r] = z[i];
+              if (j < d) {
+                const float yj = gamma * X[8 * g + i];
+#pragma unroll
+                for (int k = 0; k < kMaxOuK; ++k)
+                  if (k < K) {
+                    const float e = yj - __ldg(P.ou_mean + k * d + j);
+                    qk[k] = fmaf(e * e, __ldg(P.ou_ivar + k * d + j), qk[k]);
+                  }
+              }
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < kMaxOuK; ++k)
+            if (k < K) atomicAdd(&rowx[k], qk[k]);
+          named_bar_sync(1 + q, 64);
+          // GMM at y = gamma X (utils.py:852-915)
+          float l[kMaxOuK], mx = -INFINITY;
+#pragma unroll
+          for (int k = 0; k < kMaxOuK; ++k) {
+            l[k] = (k < K) ? P.ou_lognorm[k] - 0.5f * rowx[k] : -INFINITY;
+            mx = fmaxf(mx, l[k]);
+          }
+          float se = 0.f;
+#pragma unroll
+          for (int k = 0; k < kMaxOuK; ++k) {
+            l[k] = __expf(l[k] - mx);
+            se += l[k];
+          }
+          const float inv_se = 1.f / se;
+          // n + jtx for this half's columns
+#pragma unroll
+          for (int c = 0; c < 64; c += 16) {
+            uint32_t v[16];
+            tmem_ld16(trow + (uint32_t)(S.acc0 + 64 * hh + c), v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int g4 = 0; g4 < 4; ++g4) {
+              const float4 nn = __ldcg(nbuf + (size_t)(((64 * hh + c) >> 2) + g4) * 128 + r);
+              G[c + 4 * g4 + 0] = nn.x + __uint_as_float(v[4 * g4 + 0]);
+              G[c + 4 * g4 + 1] = nn.y + __uint_as_float(v[4 * g4 + 1]);
+              G[c + 4 * g4 + 2] = nn.z + __uint_as_float(v[4 * g4 + 2]);
+              G[c + 4 * g4 + 3] = nn.w + __uint_as_float(v[4 * g4 + 3]);
+            }
+          }
+          float dfg = 0.f, gg = 0.f;
+#pragma unroll
+          for (int i = 0; i < 64; ++i) {
+            const int j = 64 * hh + i;
+            if (j < d) {
+              const float xj = X[i], yj = gamma * xj;
+              float gx = 0.f;
+#pragma unroll
+              for (int k = 0; k < kMaxOuK; ++k)
+                if (k < K) gx = fmaf(l[k] * inv_se, (yj - __ldg(P.ou_mean + k * d + j)) * __ldg(P.ou_ivar + k * d + j), gx);
+              const float grad = Ssm * G[i] + (1.f - Ssm) * gamma * gx;
+              dfg = fmaf(P.ou_theta * (P.ou_mu - xj), grad, dfg);
+              gg = fmaf(grad, grad, gg);
+            }
+          }
+          atomicAdd(&rowx[8], dfg);
+          atomicAdd(&rowx[9], gg);
+          named_bar_sync(1 + q, 64);
+          if (hh == 0) {
+            // f = ff(s, X, u, grad) (equations.py:657-666); u itself does not enter f for this equation
+            const float f = -rowx[8] - 0.5f * P.alpha * rowx[9] - (float)d * P.ou_theta;
+            if (A.baseline) {
+              if (R.valid) A.fb_out[R.p] = f;
+            } else {
+              const float fb = __ldg(A.fb_in + R.p);
+              rowx[10] = R.valid ? dT * (f - fb) / a : 0.f;  // Bismut coefficient
+              rowx[11] = R.valid ? dT * f : 0.f;
+            }
+          }
+          tc_fence_before();
+          named_bar_sync(9, kEpiWarps * 32);  // every row's coefficient and every Zs column are written
+          if (!A.baseline) {
+            const float* rows = reinterpret_cast<const float*>(smem + kOffA + kFinRow);
+            float* out = A.part + tile * (int64_t)(1 + d);
+            const int j = threadIdx.x;
+            if (j < d) {
+              float Gj = 0.f;
+              for (int rr = 0; rr < 128; ++rr) Gj = fmaf(rows[rr * 12 + 10], Zs[(size_t)j * 129 + rr], Gj);
+              out[1 + j] = Gj;
+            } else if (j == 128) {
+              float fs = 0.f;
+              for (int rr = 0; rr < 128; ++rr) fs += rows[rr * 12 + 11];
+              out[0] = fs;
+            }
+          }
+          named_bar_sync(9, kEpiWarps * 32);  // the A region is rewritten by the next tile's set-up
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// y[p] += (sum over the point's tiles, in tile order) / M_I, clip, non-finite check
+__global__ void __launch_bounds__(128)
+hjb_tc_finish_kernel(const float* __restrict__ part, int tiles_pp, int d, int M_I, float bound, float* __restrict__ y,
+                     int* __restrict__ nonfinite) {
+  const int64_t p = blockIdx.x;
+  const float invM = 1.f / (float)M_I;
+  const bool clip = bound > 0.f && isfinite(bound);
+  bool bad = false;
+  for (int j = threadIdx.x; j < 1 + d; j += 128) {
+    float s = 0.f;
+    for (int t = 0; t < tiles_pp; ++t) s += part[(p * tiles_pp + t) * (int64_t)(1 + d) + j];
+    float v = y[p * (int64_t)(1 + d) + j] + s * invM;
+    if (clip) v = fminf(fmaxf(v, -bound), bound);
+    y[p * (int64_t)(1 + d) + j] = v;
+    bad |= !isfinite(v);
+  }
+  if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(nonfinite, 1);
+}
+
+// dst tile [width n x 64 k] fp16 SWIZZLE_128B: element (n, k) = src[(row0 + n) * rs + (col0 + k) * cs] if n < n_valid and
+// k < k_valid, else 0; rows [dst_row0, dst_row0 + rows) of the tile are written (stacked sources)
+__global__ void hjb_pack_tile_kernel(const float* __restrict__ src, int64_t rs, int64_t cs, int row0, int col0, int n_valid,
+                                     int k_valid, int dst_row0, int rows, uint8_t* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * 64) return;
+  const int n = i >> 6, k = i & 63;
+  const float v = (n < n_valid && k < k_valid) ? src[(int64_t)(row0 + n) * rs + (int64_t)(col0 + k) * cs] : 0.f;
+  const uint32_t rn = (uint32_t)(dst_row0 + n);
+  const uint32_t off = rn * 128u + (((((uint32_t)k >> 3) ^ (rn & 7u)) << 4) | (((uint32_t)k & 7u) << 1));
+  *reinterpret_cast<__half*>(dst + off) = __float2half_rn(v);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------
+struct HjbTcNet {
+  Args a{};                    // steps, constant pointers (call-independent part)
+  int num_sms = 0;
+  uint4* hs = nullptr;
+  float4* nbuf = nullptr;
+};
+
+bool hjb_tc_eligible(const PisDev& N, int d) {
+  const int L = N.n_main;
+  if (L < 3 || L > 6 || d > 128 || N.n_t_encoder != 2 || N.n_smooth != L + 1) return false;
+  const int H = N.main[0].n_out;
+  if (H % 128 != 0 || H > 512) return false;
+  for (int l = 0; l < L - 1; ++l)
+    if (N.main[l].n_out != H) return false;
+  for (int l = 1; l < N.n_smooth - 1; ++l)
+    if (N.smooth_net[l].n_in != 64 || N.smooth_net[l].n_out != 64) return false;
+  return N.main[0].n_in == 64 + d && N.main[L - 1].n_out == d;
+}
+
+int hjb_tc_pack(const PisDev& N, int d, std::vector<void*>& owner, HjbTcNet** out, int64_t* launches, cudaStream_t st) {
+  *out = nullptr;
+  if (!hjb_tc_eligible(N, d)) return DPI_OK;
+  HjbTcNet* T = new HjbTcNet();
+  Args& A = T->a;
+  const int L = N.n_main, H = N.main[0].n_out, nh = H / 128, n_hid = L - 1, n_sm_hid = N.n_smooth - 2;
+  A.H = H, A.nh = nh, A.n_hid = n_hid, A.d = d, A.no = (d + 7) / 8;
+  const int k0_panels = (64 + d + 63) / 64;
+  // ---- steps ----
+  int ns = 0;
+  auto add = [&](int a0, int nkp, int nch, int width, int acc0, int epi, int layer, int dstp) {
+    A.steps[ns++] = Step{a0, nkp, nch, width, acc0, epi, layer, dstp};
+  };
+  add(6, 2, 1, 128, 0, kEpiTime1, 0, 4);                                    // t_encoder.0 | smooth_net.0
+  add(4, 1, 1, 64, 0, kEpiTemb, 0, 0);                                      // t_encoder.1 -> t_emb' in panel 0
+  for (int l = 0; l < n_sm_hid; ++l)                                        // smooth_net 64 -> 64 layers, ping-pong 5 -> 4 -> 5 ..
+    add((l & 1) ? 4 : 5, 1, 1, 64, 0, l + 1 < n_sm_hid ? kEpiSmHid : kEpiSmOut, l, (l & 1) ? 5 : 4);
+  add(0, k0_panels, nh, 128, 0, kEpiFwdHid, 0, 0);                           // nn_module layer 1
+  for (int l = 1; l < n_hid; ++l) add(0, H / 64, nh, 128, 0, kEpiFwdHid, l, 0);
+  add(0, H / 64, 1, 128, 0, kEpiFwdOut, 0, 0);                               // output layer -> n
+  add(0, 2, nh, 128, 0, kEpiBwdHid, n_hid - 1, 0);                           // c = (x W_L) . e_{n_hid}
+  for (int l = n_hid - 1; l >= 1; --l) add(0, H / 64, nh, 128, 0, kEpiBwdHid, l - 1, 0);
+  add(0, H / 64, 1, 128, 0, kEpiFinal, 0, 0);                                // jtx = c_1 W_1[:, 64:]
+  A.n_steps = ns;
+  // ---- weight tiles in consumption order ----
+  size_t total = 0;
+  for (int i = 0; i < ns; ++i) total += (size_t)A.steps[i].n_chunks * A.steps[i].n_kp * A.steps[i].width * 128;
+  uint8_t* W = nullptr;
+  DPI_CUDA_CHECK(cudaMalloc((void**)&W, total));
+  owner.push_back(W);
+  DPI_CUDA_CHECK(cudaMemsetAsync(W, 0, total, st));
+  uint8_t* cur = W;
+  auto pack = [&](const float* src, int64_t rs, int64_t cs, int row0, int col0, int nv, int kv, int dst_row0, int rows) {
+    hjb_pack_tile_kernel<<<(rows * 64 + 255) / 256, 256, 0, st>>>(src, rs, cs, row0, col0, nv, kv, dst_row0, rows, cur);
+    ++*launches;
+  };
+  // forward layer y = x W^T: tile (nc, kp) holds W[width nc .., 64 kp ..]; backward c W: the transposed view
+  auto pack_layer = [&](const dpi_linear& Lw, bool transposed, int in_off, int n_total, int k_total, int width, int nch, int nkp) {
+    for (int nc = 0; nc < nch; ++nc)
+      for (int kp = 0; kp < nkp; ++kp) {
+        const int n0 = nc * width, k0 = kp * 64;
+        if (!transposed)  // (n, k) = W[n0 + n][k0 + k]
+          pack(Lw.W, Lw.n_in, 1, n0, k0, std::max(0, std::min(width, n_total - n0)), std::max(0, std::min(64, k_total - k0)), 0, width);
+        else              // (n, k) = W[k0 + k][in_off + n0 + n]
+          pack(Lw.W + in_off, 1, Lw.n_in, n0, k0, std::max(0, std::min(width, n_total - n0)), std::max(0, std::min(64, k_total - k0)), 0, width);
+        cur += (size_t)width * 128;
+      }
+  };
+  {
+    // step 0: rows 0-63 = t_encoder.0, rows 64-127 = smooth_net.0, K = 128
+    for (int kp = 0; kp < 2; ++kp) {
+      pack(N.t_encoder[0].W, 128, 1, 0, 64 * kp, 64, 64, 0, 64);
+      pack(N.smooth_net[0].W, 128, 1, 0, 64 * kp, 64, 64, 64, 64);
+      cur += 128 * 128;
+    }
+    pack_layer(N.t_encoder[1], false, 0, 64, 64, 64, 1, 1);
+    for (int l = 0; l < n_sm_hid; ++l) pack_layer(N.smooth_net[1 + l], false, 0, 64, 64, 64, 1, 1);
+    pack_layer(N.main[0], false, 0, H, 64 + d, 128, nh, k0_panels);
+    for (int l = 1; l < n_hid; ++l) pack_layer(N.main[l], false, 0, H, H, 128, nh, H / 64);
+    pack_layer(N.main[L - 1], false, 0, d, H, 128, 1, H / 64);
+    pack_layer(N.main[L - 1], true, 0, H, d, 128, nh, 2);                    // B[n = hidden][k = output j] = W_L[j][n]
+    for (int l = n_hid - 1; l >= 1; --l) pack_layer(N.main[l], true, 0, H, H, 128, nh, H / 64);
+    pack_layer(N.main[0], true, 64, d, H, 128, 1, H / 64);                   // x columns of W_1
+  }
+  if ((size_t)(cur - W) != total) {
+    set_error("hjb tc pack: tile stream size mismatch");
+    return DPI_ERR_INVALID;
+  }
+  DPI_CUDA_CHECK(cudaGetLastError());
+  A.W = W;
+  A.tile_bytes_total = (uint32_t)total;
+  // ---- constants: biases (x log2e, fp16x2), output vectors; computed on the host from copies of the small tensors ----
+  DPI_CUDA_CHECK(cudaStreamSynchronize(st));
+  auto fetch = [&](const float* p, size_t n) {
+    std::vector<float> v(n);
+    cudaMemcpy(v.data(), p, n * sizeof(float), cudaMemcpyDeviceToHost);
+    return v;
+  };
+  std::vector<uint32_t> b16;
+  std::vector<size_t> b16_off(ns, 0);
+  auto push_bias = [&](int step, const std::vector<float>& b, int padded) {
+    b16_off[step] = b16.size();
+    for (int i = 0; i < padded; i += 2) {
+      const float lo = i < (int)b.size() ? b[i] * kLog2e : 0.f, hi = i + 1 < (int)b.size() ? b[i + 1] * kLog2e : 0.f;
+      b16.push_back(h2_const(lo, hi));
+    }
+    while (b16.size() % 4) b16.push_back(0u);  // 16-byte aligned vectors
+  };
+  int si = 0;
+  {
+    std::vector<float> b = fetch(N.t_encoder[0].b, 64), b2 = fetch(N.smooth_net[0].b, 64);
+    b.insert(b.end(), b2.begin(), b2.end());
+    push_bias(si++, b, 128);
+  }
+  push_bias(si++, fetch(N.t_encoder[1].b, 64), 64);
+  for (int l = 0; l < n_sm_hid; ++l) push_bias(si++, fetch(N.smooth_net[1 + l].b, 64), 64);
+  for (int l = 0; l < n_hid; ++l) push_bias(si++, fetch(N.main[l].b, H), H);
+  // remaining steps carry no fp16 bias
+  uint32_t* b16_dev = nullptr;
+  DPI_CUDA_CHECK(cudaMalloc((void**)&b16_dev, sizeof(uint32_t) * std::max<size_t>(b16.size(), 4)));
+  owner.push_back(b16_dev);
+  DPI_CUDA_CHECK(cudaMemcpy(b16_dev, b16.data(), sizeof(uint32_t) * b16.size(), cudaMemcpyHostToDevice));
+  for (int i = 0; i < ns; ++i) A.bias16[i] = b16_dev + (i < si ? b16_off[i] : 0);
+  // smooth_net output row 0 (x ln2: the activations are log2e-scaled), its bias, and S0 = smooth_net(emb(0))[0]
+  {
+    const dpi_linear& Lo = N.smooth_net[N.n_smooth - 1];
+    std::vector<float> w0 = fetch(Lo.W, 64), b0 = fetch(Lo.b, 1);
+    std::vector<float> fv(64 + 128);
+    for (int i = 0; i < 64; ++i) fv[i] = w0[i] * kLn2;
+    std::vector<float> ob = fetch(N.main[L - 1].b, d);
+    for (int i = 0; i < 128; ++i) fv[64 + i] = i < d ? ob[i] : 0.f;
+    float* fdev = nullptr;
+    DPI_CUDA_CHECK(cudaMalloc((void**)&fdev, sizeof(float) * fv.size()));
+    owner.push_back(fdev);
+    DPI_CUDA_CHECK(cudaMemcpy(fdev, fv.data(), sizeof(float) * fv.size(), cudaMemcpyHostToDevice));
+    A.sm_w0 = fdev, A.out_b = fdev + 64, A.sm_b0 = b0[0];
+    // S0 on the host in double: emb(0) = [sin(phase), cos(phase)], then the ELU chain (solution.py:247-252)
+    std::vector<float> phase = fetch(N.phase, 64);
+    std::vector<double> h(128);
+    for (int c = 0; c < 64; ++c) h[c] = std::sin((double)phase[c]), h[64 + c] = std::cos((double)phase[c]);
+    for (int l = 0; l < N.n_smooth; ++l) {
+      const dpi_linear& Ll = N.smooth_net[l];
+      const int rows = (l == N.n_smooth - 1) ? 1 : Ll.n_out;
+      std::vector<float> Wl = fetch(Ll.W, (size_t)rows * Ll.n_in), bl = fetch(Ll.b, rows);
+      std::vector<double> z(rows);
+      for (int o = 0; o < rows; ++o) {
+        double s = bl[o];
+        for (int k = 0; k < Ll.n_in; ++k) s += (double)Wl[(size_t)o * Ll.n_in + k] * h[k];
+        z[o] = (l == N.n_smooth - 1) ? s : (s > 0 ? s : std::expm1(s));
+      }
+      h.assign(z.begin(), z.end());
+    }
+    A.S0 = (float)h[0];
+  }
+  A.phase = N.phase, A.coeff = N.coeff;
+  int dev = 0;
+  DPI_CUDA_CHECK(cudaGetDevice(&dev));
+  DPI_CUDA_CHECK(cudaDeviceGetAttribute(&T->num_sms, cudaDevAttrMultiProcessorCount, dev));
+  DPI_CUDA_CHECK(cudaMalloc((void**)&T->hs, sizeof(uint4) * (size_t)T->num_sms * n_hid * (H / 8) * 128));
+  owner.push_back(T->hs);
+  DPI_CUDA_CHECK(cudaMalloc((void**)&T->nbuf, sizeof(float4) * (size_t)T->num_sms * 32 * 128));
+  owner.push_back(T->nbuf);
+  A.hs = T->hs, A.nbuf = T->nbuf;
+  DPI_CUDA_CHECK(cudaFuncSetAttribute(hjb_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+  *out = T;
+  return DPI_OK;
+}
+
+void hjb_tc_free(HjbTcNet* T) { delete T; }
+
+int64_t hjb_tc_part_floats(int64_t n, int M_I, int d) { return n * ((M_I + 127) / 128) * (int64_t)(1 + d); }
+
+int launch_hjb_tc_paths(const ProblemDev& P, const HjbTcNet* T, const float* tx, int64_t n, int M_I, uint64_t seed,
+                        int64_t base, const float* u_s, const float* zS, float bound, float* fb, float* part,
+                        int* nonfinite, float* y, cudaStream_t st, int64_t* launches) {
+  if (n <= 0) return DPI_OK;
+  Args A = T->a;
+  A.tx = tx, A.n = n, A.point_base = base, A.M_I = M_I, A.keys = make_philox_keys(seed), A.u_s = u_s, A.zS = zS;
+  // 1) control variate f(t, x) per point through the same arithmetic: tiles of 128 points
+  A.baseline = 1, A.n_tiles = (n + 127) / 128, A.tiles_pp = 1, A.fb_in = nullptr, A.fb_out = fb, A.part = nullptr;
+  int grid = (int)std::min<int64_t>(A.n_tiles, T->num_sms);
+  hjb_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(P, A);
+  // 2) path rows
+  A.baseline = 0, A.tiles_pp = (M_I + 127) / 128, A.n_tiles = n * A.tiles_pp, A.fb_in = fb, A.fb_out = nullptr, A.part = part;
+  grid = (int)std::min<int64_t>(A.n_tiles, T->num_sms);
+  hjb_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(P, A);
+  hjb_tc_finish_kernel<<<(unsigned)n, 128, 0, st>>>(part, A.tiles_pp, P.nx, M_I, bound, y, nonfinite);
+  DPI_CUDA_CHECK(cudaGetLastError());
+  *launches += 3;
+  return DPI_OK;
+}
+
+}  // namespace dpi

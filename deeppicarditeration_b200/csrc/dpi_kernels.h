@@ -152,6 +152,17 @@ int launch_hjb_paths(const ProblemDev& P, const PisDev& net, const float* tx, in
 int launch_hjb_eval(const ProblemDev& P, const PisDev& net, const float* tx, int64_t n, float* scratch,
                     int64_t rows_per_chunk, float* u, float* du, cudaStream_t st, int64_t* launches);
 
+// ---- fused tcgen05 PISGradNet path (dpi_hjb_tc.cu): fp16 operands, activations on chip, weights streamed from L2 ----
+struct HjbTcNet;
+// packs the network when its shape qualifies (equal hidden widths, multiple of 128, <= 512; d <= 128); *out = null otherwise
+int hjb_tc_pack(const PisDev& net, int d, std::vector<void*>& owner, HjbTcNet** out, int64_t* launches, cudaStream_t st);
+void hjb_tc_free(HjbTcNet* net);
+int64_t hjb_tc_part_floats(int64_t n, int M_I, int d);
+// y += integral part, then clip; fb [n] and part [hjb_tc_part_floats] are scratch
+int launch_hjb_tc_paths(const ProblemDev& P, const HjbTcNet* net, const float* tx, int64_t n, int M_I, uint64_t seed,
+                        int64_t base, const float* u_s, const float* zS, float bound, float* fb, float* part,
+                        int* nonfinite, float* y, cudaStream_t st, int64_t* launches);
+
 // plain MLP: u [n] and grad_x u [n, d] (either may be null); weights in torch layout, used in place
 int64_t mlp_eval_scratch_floats(const dpi_linear* L, int n_lin, int64_t rows);
 int launch_mlp_eval(const dpi_linear* L, int n_lin, int d, const float* tx, int64_t n, float* scratch,

@@ -133,10 +133,10 @@ class LabelEngine:
     def _cfg(M_T, M_I, precision, bound, seed, base):
         cfg = nat.dpi_label_config()
         cfg.M_T, cfg.M_I = int(M_T), int(M_I)
-        # "tf32" names what the reduced-precision flag selects on the PISGradNet path (TF32 GEMMs); "bf16" maps to the
-        # distinct DPI_PREC_BF16 value, which the library rejects (bf16 operands are not built) instead of aliasing fp16
+        # "tf32": PISGradNet's layer-by-layer pipeline with TF32 tensor-core GEMMs; "bf16" maps to the distinct
+        # DPI_PREC_BF16 value, which the library rejects (bf16 operands are not built) instead of aliasing fp16
         cfg.precision = {"fp32": nat.DPI_PREC_FP32, "f16": nat.DPI_PREC_F16, "fp16": nat.DPI_PREC_F16,
-                         "tf32": nat.DPI_PREC_F16, "bf16": nat.DPI_PREC_BF16}[precision]
+                         "tf32": nat.DPI_PREC_TF32, "bf16": nat.DPI_PREC_BF16}[precision]
         cfg.sample_bound = float(bound) if bound is not None and math.isfinite(bound) else 0.0
         cfg.seed = seed & (2**64 - 1)
         cfg.point_index_base = int(base)

@@ -97,6 +97,9 @@ def test_hjb_100d_4x512_m512_matches_oracle():
     _check(y32, y_ref, yT, TOL32, tol_integral=5 * TOL32, what="hjb100d fp32")
     y19 = e.label_gen(tx, M, M, precision="tf32", draws=draws_dict(d), check=True)
     _check(y19, y_ref, yT, TOL16, what="hjb100d tf32")
+    y16 = e.label_gen(tx, M, M, precision="f16", draws=draws_dict(d), check=True)  # fused tcgen05 kernel (dpi_hjb_tc.cu)
+    _check(y16, y_ref, yT, TOL16, what="hjb100d f16 fused")
+    assert not torch.equal(y16, y19)
     e.close()
 
 
@@ -154,10 +157,32 @@ def test_philox_mode_gbm_100d_m1024_replays_and_matches_oracle():
 def test_philox_mode_hjb_100d_4x512_replays_and_matches_oracle():
     g = Golden("hjb_100d_pisgrad")
     _philox_roundtrip(g.eq, orc.make_pisgrad(g.nx, [512] * 4, T=g.T, seed=33, phase_scale=0.3), 0, 3, 512, 512,
-                      [("fp32", TOL32), ("tf32", TOL16)], "hjb100d", tol_integral32=5 * TOL32)
+                      [("fp32", TOL32), ("tf32", TOL16), ("f16", TOL16)], "hjb100d", tol_integral32=5 * TOL32)
 
 
 def test_philox_mode_burgers_1000d_m256_replays_and_matches_oracle():
     eq = orc.Cha(1000, 1.0, 5.0, 1.0)
     _philox_roundtrip(eq, orc.make_mlp(1001, [128] * 4, seed=34, gain=1.2), 0, 3, 256, 256,
                       [("fp32", TOL32), ("f16", TOL16)], "burgers1000d")
+
+
+@pytest.mark.parametrize("hidden,M_I,n", [([512] * 4, 300, 5), ([256] * 3, 129, 4), ([128] * 2, 64, 3)])
+def test_hjb_fused_kernel_shapes_ragged_tiles_and_shards(hidden, M_I, n):
+    """The fused PISGradNet kernel on other eligible shapes (hidden width a multiple of 128, 2-4 hidden layers), ragged
+    128-row tiles, deterministic mode against the oracle, and bitwise shard invariance in Philox mode."""
+    from tests.gpu_util import draws_dict, engine_for
+    g = Golden("hjb_100d_pisgrad")
+    net = orc.make_pisgrad(g.nx, hidden, T=g.T, seed=51, phase_scale=0.3)
+    M_T = 32
+    d, tx, yT, y_ref = _oracle(g.eq, net, n, M_T, M_I, None, seed=105)
+    e = engine_for(g.eq, net)
+    y16 = e.label_gen(tx, M_T, M_I, precision="f16", draws=draws_dict(d), check=True)
+    _check(y16, y_ref, yT, TOL16, what=f"hjb fused {hidden} M_I={M_I}")
+    y32 = e.label_gen(tx, M_T, M_I, precision="fp32", draws=draws_dict(d), check=True)
+    assert not torch.equal(y16, y32)  # the fused kernel really ran
+    txp = e.sample_tx(7, seed=2)
+    yp = e.label_gen(txp, M_T, M_I, precision="f16", seed=9)
+    yq = torch.cat([e.label_gen(txp[:3], M_T, M_I, precision="f16", seed=9),
+                    e.label_gen(txp[3:], M_T, M_I, precision="f16", seed=9, point_index_base=3)])
+    assert torch.equal(yp, yq) and torch.isfinite(yp).all()
+    e.close()
