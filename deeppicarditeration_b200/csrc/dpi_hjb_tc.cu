@@ -294,53 +294,56 @@ hjb_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ Args
         mbar_wait(bar_acc, ph_acc, 10);
         ph_acc ^= 1u;
         tc_fence_after();
-        const int ncols = S.width * S.n_chunks;  // columns of this step's output
+        const int epi = S.epi, acc0 = S.acc0;
+        const int ncols = S.width * S.n_chunks;                // columns of this step's output
         const int c0 = hh * (ncols / 2), c1 = c0 + ncols / 2;  // this warp's column range
-        const uint32_t* b16 = A.bias16[si];
+        const uint4* b16 = reinterpret_cast<const uint4*>(A.bias16[si]);
 
-        if (S.epi == kEpiTime1 || S.epi == kEpiTemb || S.epi == kEpiSmHid || S.epi == kEpiFwdHid) {
-          // bias (+ ELU) in packed fp16x2 -> next A operand (and, for nn_module's hidden layers, the VJP's copy)
-          const bool elu = S.epi != kEpiTemb;
-          uint4* hsl = (S.epi == kEpiFwdHid) ? hs + (size_t)S.layer * (A.H / 8) * 128 : nullptr;
+        if (epi <= kEpiSmHid || epi == kEpiFwdHid) {
+          // bias (+ ELU) in packed fp16x2 -> next A operand (and, for nn_module's hidden layers, the VJP's copy).
+          // The bias of the NEXT 16 columns is fetched before the accumulator wait of the current ones.
+          const bool elu = epi != kEpiTemb;
+          uint4* hsl = (epi == kEpiFwdHid) ? hs + (size_t)S.layer * (A.H / 8) * 128 : nullptr;
+          // destination chunk of output chunk col8: Time1 splits its halves over panels 4 / 5, the rest is linear
+          const int dst_base = (epi == kEpiTime1) ? 32 : 8 * S.dst_panel;
+          uint4 bn0 = __ldg(b16 + (c0 >> 3)), bn1 = __ldg(b16 + (c0 >> 3) + 1);
+#pragma unroll 1
           for (int c = c0; c < c1; c += 16) {
             uint32_t v[16];
-            tmem_ld16(trow + (uint32_t)(S.acc0 + c), v);
+            tmem_ld16(trow + (uint32_t)(acc0 + c), v);
+            const uint4 bc0 = bn0, bc1 = bn1;
+            if (c + 16 < c1) bn0 = __ldg(b16 + ((c + 16) >> 3)), bn1 = __ldg(b16 + ((c + 16) >> 3) + 1);
             tmem_ld_wait();
+            const uint32_t bv[8] = {bc0.x, bc0.y, bc0.z, bc0.w, bc1.x, bc1.y, bc1.z, bc1.w};
+            uint32_t o[8];
 #pragma unroll
-            for (int g = 0; g < 2; ++g) {
-              const int col8 = (c >> 3) + g;
-              const uint4 bb = __ldg(reinterpret_cast<const uint4*>(b16) + col8);
-              const uint32_t bv[4] = {bb.x, bb.y, bb.z, bb.w};
-              uint32_t o[4];
-#pragma unroll
-              for (int i2 = 0; i2 < 4; ++i2) {
-                const uint32_t z = h2_add(pack_f16x2(__uint_as_float(v[8 * g + 2 * i2]), __uint_as_float(v[8 * g + 2 * i2 + 1])), bv[i2]);
-                if (elu) {
-                  const uint32_t e = h2_ex2(h2_min(z, kZero));
-                  o[i2] = h2_max(z, h2_fma(e, kL, kNegL));
-                } else {
-                  o[i2] = z;
-                }
-              }
-              const uint4 chunk = make_uint4(o[0], o[1], o[2], o[3]);
-              int dst8;
-              if (S.epi == kEpiTime1) dst8 = (col8 < 8) ? 32 + col8 : 40 + (col8 - 8);  // t branch -> panel 4, smooth -> panel 5
-              else dst8 = 8 * S.dst_panel + col8;
-              *reinterpret_cast<uint4*>(smem + kOffA + panel_off(dst8, r)) = chunk;
-              if (hsl) hsl[(size_t)col8 * 128 + r] = chunk;
+            for (int i2 = 0; i2 < 8; ++i2) {
+              const uint32_t z = h2_add(pack_f16x2(__uint_as_float(v[2 * i2]), __uint_as_float(v[2 * i2 + 1])), bv[i2]);
+              const uint32_t e = h2_ex2(h2_min(z, kZero));
+              o[i2] = elu ? h2_max(z, h2_fma(e, kL, kNegL)) : z;
+            }
+            const int col8 = c >> 3;
+            const uint4 ch0 = make_uint4(o[0], o[1], o[2], o[3]), ch1 = make_uint4(o[4], o[5], o[6], o[7]);
+            *reinterpret_cast<uint4*>(smem + kOffA + panel_off(dst_base + col8, r)) = ch0;
+            *reinterpret_cast<uint4*>(smem + kOffA + panel_off(dst_base + col8 + 1, r)) = ch1;
+            if (hsl) {
+              hsl[(size_t)col8 * 128 + r] = ch0;
+              hsl[(size_t)(col8 + 1) * 128 + r] = ch1;
             }
           }
           step_done();
-        } else if (S.epi == kEpiSmOut) {
+        } else if (epi == kEpiSmOut) {
           // last 64 -> 64 layer of smooth_net, then ELU and row 0 of the output layer: S_raw (solution.py:231-254)
+          const uint32_t* b32 = A.bias16[si];
           float acc = 0.f;
+#pragma unroll 1
           for (int c = c0; c < c1; c += 16) {
             uint32_t v[16];
-            tmem_ld16(trow + (uint32_t)(S.acc0 + c), v);
+            tmem_ld16(trow + (uint32_t)(acc0 + c), v);
             tmem_ld_wait();
 #pragma unroll
             for (int i2 = 0; i2 < 8; ++i2) {
-              const float2 b = h2_unpack(__ldg(b16 + ((c >> 1) + i2)));
+              const float2 b = h2_unpack(__ldg(b32 + ((c >> 1) + i2)));
               const float z0 = __uint_as_float(v[2 * i2]) + b.x, z1 = __uint_as_float(v[2 * i2 + 1]) + b.y;  // log2e-scaled
               const float h0 = z0 > 0.f ? z0 : kLog2e * (exp2f(z0) - 1.f), h1 = z1 > 0.f ? z1 : kLog2e * (exp2f(z1) - 1.f);
               acc = fmaf(__ldg(A.sm_w0 + c + 2 * i2), h0, acc);
@@ -351,20 +354,22 @@ hjb_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ Args
           named_bar_sync(1 + q, 64);
           if (hh == 1) sraw_s[r] += acc + A.sm_b0;
           step_done();
-        } else if (S.epi == kEpiFwdOut) {
+        } else if (epi == kEpiFwdOut) {
           // n = ln2 acc + b (unscaled) -> scratch; cotangent X (unscaled, fp16) -> panels 0, 1.  (u = S <n, x> + (1 - S) g
           // itself is not formed: ff of this equation depends on grad_x u only, equations.py:657-666.)
+#pragma unroll 1
           for (int c = c0; c < c1; c += 16) {
             uint32_t v[16];
-            tmem_ld16(trow + (uint32_t)(S.acc0 + c), v);
+            tmem_ld16(trow + (uint32_t)(acc0 + c), v);
             tmem_ld_wait();
-            float nn[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) nn[i] = fmaf(kLn2, __uint_as_float(v[i]), __ldg(A.out_b + c + i));
-#pragma unroll
-            for (int g4 = 0; g4 < 4; ++g4)
-              nbuf[(size_t)((c >> 2) + g4) * 128 + r] = make_float4(nn[4 * g4], nn[4 * g4 + 1], nn[4 * g4 + 2], nn[4 * g4 + 3]);
-#pragma unroll
+            for (int g4 = 0; g4 < 4; ++g4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(A.out_b + c) + g4);
+              nbuf[(size_t)((c >> 2) + g4) * 128 + r] =
+                  make_float4(fmaf(kLn2, __uint_as_float(v[4 * g4]), b.x), fmaf(kLn2, __uint_as_float(v[4 * g4 + 1]), b.y),
+                              fmaf(kLn2, __uint_as_float(v[4 * g4 + 2]), b.z), fmaf(kLn2, __uint_as_float(v[4 * g4 + 3]), b.w));
+            }
+#pragma unroll 1
             for (int g = 0; g < 2; ++g) {
               const int o = (c >> 3) + g;
               float z[8];
@@ -372,22 +377,29 @@ hjb_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ Args
               uint32_t w[4];
 #pragma unroll
               for (int i2 = 0; i2 < 4; ++i2) {
-                const int j = 8 * o + 2 * i2;
-                const float x0 = (j < d) ? fmaf(a, z[2 * i2], __ldg(txp + 1 + j)) : 0.f;
-                const float x1 = (j + 1 < d) ? fmaf(a, z[2 * i2 + 1], __ldg(txp + 2 + j)) : 0.f;
+                const int jx = 8 * o + 2 * i2;
+                const float x0 = (jx < d) ? fmaf(a, z[2 * i2], __ldg(txp + 1 + jx)) : 0.f;
+                const float x1 = (jx + 1 < d) ? fmaf(a, z[2 * i2 + 1], __ldg(txp + 2 + jx)) : 0.f;
                 w[i2] = pack_f16x2(x0, x1);
               }
               *reinterpret_cast<uint4*>(smem + kOffA + panel_off(o, r)) = make_uint4(w[0], w[1], w[2], w[3]);
             }
           }
           step_done();
-        } else if (S.epi == kEpiBwdHid) {
-          // c = acc . ELU'(z_l), ELU' recovered from the stored activation: min(1, 1 + ln2 h')
-          const uint4* hsl = hs + (size_t)S.layer * (A.H / 8) * 128;
+        } else if (epi == kEpiBwdHid) {
+          // c = acc . ELU'(z_l), ELU' recovered from the stored activation: min(1, 1 + ln2 h').  The activations come
+          // back from L2: the loads of the next 16 columns are in flight under the arithmetic of the current ones.
+          const uint4* hsl = hs + (size_t)S.layer * (A.H / 8) * 128 + r;
+          uint4 hn0 = __ldcg(hsl + (size_t)(c0 >> 3) * 128), hn1 = __ldcg(hsl + (size_t)((c0 >> 3) + 1) * 128);
+#pragma unroll 1
           for (int c = c0; c < c1; c += 16) {
             uint32_t v[16];
-            tmem_ld16(trow + (uint32_t)(S.acc0 + c), v);
-            const uint4 h0 = __ldcg(hsl + (size_t)(c >> 3) * 128 + r), h1 = __ldcg(hsl + (size_t)((c >> 3) + 1) * 128 + r);
+            tmem_ld16(trow + (uint32_t)(acc0 + c), v);
+            const uint4 h0 = hn0, h1 = hn1;
+            if (c + 16 < c1) {
+              hn0 = __ldcg(hsl + (size_t)((c + 16) >> 3) * 128);
+              hn1 = __ldcg(hsl + (size_t)(((c + 16) >> 3) + 1) * 128);
+            }
             tmem_ld_wait();
             const uint32_t hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
             uint32_t o[8];
@@ -401,48 +413,53 @@ hjb_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ Args
           }
           step_done();
         } else {
-          // ---------------- FINAL: jtx in TMEM columns [0, 128); u, grad_x u, f, Bismut sums ----------------
-          // this thread: row r, columns [64 hh, 64 hh + 64).  The A region is free: Zs [col][129] and the per-row exchange.
+          // ---------------- FINAL: jtx in TMEM columns [0, 128); grad_x u, f, Bismut sums ----------------
+          // this thread: row r, columns [64 hh, 64 hh + 64).  The A region is free: Zs [col][129], the per-row exchange
+          // and the GMM constants live there for the duration of this step.
           float* Zs = reinterpret_cast<float*>(smem + kOffA + kFinZ);
-          float* rowx = reinterpret_cast<float*>(smem + kOffA + kFinRow) + r * 12;
+          float* rows_s = reinterpret_cast<float*>(smem + kOffA + kFinRow);
+          float* rowx = rows_s + r * 12;
+          float* gm = rows_s + 128 * 12;        // [K][128] mixture means
+          float* gi = gm + kMaxOuK * 128;       // [K][128] inverse variances (0 for padded dims)
           const float Ssm = sraw_s[r] - A.S0;
           const float gamma = __expf(-0.5f * lam);
           const int K = P.ou_K;
+          for (int i = threadIdx.x; i < K * 128; i += kEpiWarps * 32) {
+            const int k = i >> 7, jj = i & 127;
+            gm[i] = (jj < d) ? __ldg(P.ou_mean + k * d + jj) : 0.f;
+            gi[i] = (jj < d) ? __ldg(P.ou_ivar + k * d + jj) : 0.f;
+          }
           if (hh == 0) {
 #pragma unroll
             for (int i = 0; i < 12; ++i) rowx[i] = 0.f;
           }
-          named_bar_sync(1 + q, 64);
-          float X[64], G[64];  // X_j; then n_j + jtx_j
+          named_bar_sync(9, kEpiWarps * 32);
+          // pass 1: increments -> Zs, mixture quadratic forms at y = gamma X (utils.py:852-880)
           float qk[kMaxOuK];
 #pragma unroll
           for (int k = 0; k < kMaxOuK; ++k) qk[k] = 0.f;
-#pragma unroll
+#pragma unroll 1
           for (int g = 0; g < 8; ++g) {
             const int o = 8 * hh + g;
             float z[8];
             row_z8(A, R, o, z);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const int j = 8 * o + i;
-              X[8 * g + i] = (j < d) ? fmaf(a, z[i], __ldg(txp + 1 + j)) : 0.f;
-              Zs[(size_t)j * 129 + r] = z[i];
-              if (j < d) {
-                const float yj = gamma * X[8 * g + i];
+              const int jj = 8 * o + i;
+              Zs[jj * 129 + r] = z[i];
+              const float yj = gamma * ((jj < d) ? fmaf(a, z[i], __ldg(txp + 1 + jj)) : 0.f);
 #pragma unroll
-                for (int k = 0; k < kMaxOuK; ++k)
-                  if (k < K) {
-                    const float e = yj - __ldg(P.ou_mean + k * d + j);
-                    qk[k] = fmaf(e * e, __ldg(P.ou_ivar + k * d + j), qk[k]);
-                  }
-              }
+              for (int k = 0; k < kMaxOuK; ++k)
+                if (k < K) {
+                  const float e = yj - gm[k * 128 + jj];
+                  qk[k] = fmaf(e * e, gi[k * 128 + jj], qk[k]);
+                }
             }
           }
 #pragma unroll
           for (int k = 0; k < kMaxOuK; ++k)
-            if (k < K) atomicAdd(&rowx[k], qk[k]);
+            if (k < K) atomicAdd(&rowx[k], qk[k]);  // two addends onto 0: order-independent
           named_bar_sync(1 + q, 64);
-          // GMM at y = gamma X (utils.py:852-915)
           float l[kMaxOuK], mx = -INFINITY;
 #pragma unroll
           for (int k = 0; k < kMaxOuK; ++k) {
@@ -456,34 +473,33 @@ hjb_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ Args
             se += l[k];
           }
           const float inv_se = 1.f / se;
-          // n + jtx for this half's columns
 #pragma unroll
-          for (int c = 0; c < 64; c += 16) {
-            uint32_t v[16];
-            tmem_ld16(trow + (uint32_t)(S.acc0 + 64 * hh + c), v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int g4 = 0; g4 < 4; ++g4) {
-              const float4 nn = __ldcg(nbuf + (size_t)(((64 * hh + c) >> 2) + g4) * 128 + r);
-              G[c + 4 * g4 + 0] = nn.x + __uint_as_float(v[4 * g4 + 0]);
-              G[c + 4 * g4 + 1] = nn.y + __uint_as_float(v[4 * g4 + 1]);
-              G[c + 4 * g4 + 2] = nn.z + __uint_as_float(v[4 * g4 + 2]);
-              G[c + 4 * g4 + 3] = nn.w + __uint_as_float(v[4 * g4 + 3]);
-            }
-          }
+          for (int k = 0; k < kMaxOuK; ++k) l[k] *= inv_se;  // responsibilities
+          // pass 2: grad_j = S (n_j + jtx_j) + (1 - S) gamma g_x(gamma X)_j  (utils.py:882-915), f's two sums
           float dfg = 0.f, gg = 0.f;
+#pragma unroll 1
+          for (int c = 64 * hh; c < 64 * hh + 64; c += 16) {
+            uint32_t v[16];
+            tmem_ld16(trow + (uint32_t)(acc0 + c), v);
+            float4 nn[4];
 #pragma unroll
-          for (int i = 0; i < 64; ++i) {
-            const int j = 64 * hh + i;
-            if (j < d) {
-              const float xj = X[i], yj = gamma * xj;
-              float gx = 0.f;
+            for (int g4 = 0; g4 < 4; ++g4) nn[g4] = __ldcg(nbuf + (size_t)((c >> 2) + g4) * 128 + r);
+            tmem_ld_wait();
+            const float nv[16] = {nn[0].x, nn[0].y, nn[0].z, nn[0].w, nn[1].x, nn[1].y, nn[1].z, nn[1].w,
+                                  nn[2].x, nn[2].y, nn[2].z, nn[2].w, nn[3].x, nn[3].y, nn[3].z, nn[3].w};
 #pragma unroll
-              for (int k = 0; k < kMaxOuK; ++k)
-                if (k < K) gx = fmaf(l[k] * inv_se, (yj - __ldg(P.ou_mean + k * d + j)) * __ldg(P.ou_ivar + k * d + j), gx);
-              const float grad = Ssm * G[i] + (1.f - Ssm) * gamma * gx;
-              dfg = fmaf(P.ou_theta * (P.ou_mu - xj), grad, dfg);
-              gg = fmaf(grad, grad, gg);
+            for (int i = 0; i < 16; ++i) {
+              const int jj = c + i;
+              if (jj < d) {
+                const float xj = fmaf(a, Zs[jj * 129 + r], __ldg(txp + 1 + jj)), yj = gamma * xj;
+                float gx = 0.f;
+#pragma unroll
+                for (int k = 0; k < kMaxOuK; ++k)
+                  if (k < K) gx = fmaf(l[k], (yj - gm[k * 128 + jj]) * gi[k * 128 + jj], gx);
+                const float grad = Ssm * (nv[i] + __uint_as_float(v[i])) + (1.f - Ssm) * gamma * gx;
+                dfg = fmaf(P.ou_theta * (P.ou_mu - xj), grad, dfg);
+                gg = fmaf(grad, grad, gg);
+              }
             }
           }
           atomicAdd(&rowx[8], dfg);
@@ -503,16 +519,16 @@ hjb_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ Args
           tc_fence_before();
           named_bar_sync(9, kEpiWarps * 32);  // every row's coefficient and every Zs column are written
           if (!A.baseline) {
-            const float* rows = reinterpret_cast<const float*>(smem + kOffA + kFinRow);
             float* out = A.part + tile * (int64_t)(1 + d);
-            const int j = threadIdx.x;
-            if (j < d) {
+            const int jt = threadIdx.x;
+            if (jt < d) {
               float Gj = 0.f;
-              for (int rr = 0; rr < 128; ++rr) Gj = fmaf(rows[rr * 12 + 10], Zs[(size_t)j * 129 + rr], Gj);
-              out[1 + j] = Gj;
-            } else if (j == 128) {
+#pragma unroll 4
+              for (int rr = 0; rr < 128; ++rr) Gj = fmaf(rows_s[rr * 12 + 10], Zs[jt * 129 + rr], Gj);
+              out[1 + jt] = Gj;
+            } else if (jt == 128) {
               float fs = 0.f;
-              for (int rr = 0; rr < 128; ++rr) fs += rows[rr * 12 + 11];
+              for (int rr = 0; rr < 128; ++rr) fs += rows_s[rr * 12 + 11];
               out[0] = fs;
             }
           }
