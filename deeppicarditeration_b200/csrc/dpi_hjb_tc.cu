@@ -36,20 +36,22 @@ namespace dpi {
 namespace {
 using namespace tc;
 
-constexpr int kThreads = 320;  // warps 0-7: set-up + epilogue, warp 8: MMA issuer, warp 9: TMA issuer
-constexpr int kEpiWarps = 8, kMmaWarp = 8, kTmaWarp = 9;
+// warps 0-15: set-up + epilogue (warp = TMEM lane quarter x one of four column parts), warp 16: MMA issuer, warp 17: TMA issuer
+constexpr int kEpiWarps = 16, kMmaWarp = 16, kTmaWarp = 17, kThreads = 32 * 18, kParts = 4;
 constexpr int kSlots = 6;
 constexpr uint32_t kSlotBytes = 16384;
 constexpr uint32_t kOffA = 0;                             // 8 panels x 16 KB: the current A operand
 constexpr uint32_t kOffRing = 8 * kPanelBytes;            // weight ring
 constexpr uint32_t kOffMisc = kOffRing + kSlots * kSlotBytes;  // S_raw [128]
 constexpr uint32_t kOffBars = kOffMisc + 1024;
-constexpr uint32_t kOffTmemPtr = kOffBars + 8 * (2 * kSlots + 2);
+constexpr uint32_t kOffTmemPtr = kOffBars + 8 * (2 * kSlots + 3);
 constexpr uint32_t kSmemBytes = kOffTmemPtr + 16;
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 // FINAL-step scratch inside the (then free) A region
 constexpr uint32_t kFinZ = 0;                      // Zs [128 cols][129] fp32
-constexpr uint32_t kFinRow = 128 * 129 * 4;        // per-row exchange: q[8], dfg, gg, coef, dTf (12 floats per row)
+constexpr uint32_t kFinRow = 128 * 129 * 4;        // per-row exchange [128][kRowF]: q[8][4 parts], dfg[4], gg[4], coef, dTf
+constexpr int kRowF = 44;
+constexpr uint32_t kOffSrawPart = 3 * kPanelBytes;  // S_raw partials [4 parts][128] in panel 3 (free during the time nets)
 constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
 
 enum Epi : int { kEpiTime1 = 0, kEpiTemb, kEpiSmHid, kEpiSmOut, kEpiFwdHid, kEpiFwdOut, kEpiBwdHid, kEpiFinal };
@@ -140,7 +142,7 @@ hjb_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ Args
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   auto bar_full = [&](int s) -> uint32_t { return sbase + kOffBars + 8u * (uint32_t)s; };
   auto bar_empty = [&](int s) -> uint32_t { return sbase + kOffBars + 8u * (uint32_t)(kSlots + s); };
-  const uint32_t bar_acc = sbase + kOffBars + 8u * (2 * kSlots), bar_ready = bar_acc + 8u;
+  const uint32_t bar_acc = sbase + kOffBars + 8u * (2 * kSlots), bar_ready = bar_acc + 8u, bar_half = bar_acc + 16u;
 
   if (threadIdx.x == 0) {
     if (sbase & 1023u) __trap();
@@ -149,6 +151,7 @@ hjb_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ Args
       mbar_init(bar_empty(s), 1);
     }
     mbar_init(bar_acc, 1);
+    mbar_init(bar_half, 1);
     mbar_init(bar_ready, kEpiWarps);
     fence_barrier_init();
   }
@@ -209,6 +212,9 @@ hjb_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ Args
             tc_commit_p(bar_empty(slot), leader);  // the slot may be refilled once these MMAs have read it
             slot = (slot + 1 == kSlots) ? 0 : slot + 1;
           }
+          // wide layers: the first half of the output columns is complete -> its epilogue arithmetic starts while
+          // the tensor pipe works on the second half
+          if (S.n_chunks >= 2 && nc == S.n_chunks / 2 - 1) tc_commit_p(bar_half, leader);
         }
         tc_commit_p(bar_acc, leader);
       }
@@ -216,14 +222,14 @@ hjb_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ Args
     __syncwarp();
   } else {
     // =================================== set-up + epilogue warps ===================================
-    const int q = warp & 3, hh = warp >> 2;
+    const int q = warp & 3, part = warp >> 2;  // TMEM lane quarter, column part 0..3
     const int r = q * 32 + lane;
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
     float* sraw_s = reinterpret_cast<float*>(smem + kOffMisc);
     const int d = A.d;
     uint4* const hs = A.hs + (size_t)blockIdx.x * A.n_hid * (A.H / 8) * 128;
     float4* const nbuf = A.nbuf + (size_t)blockIdx.x * 32 * 128;
-    uint32_t ph_acc = 0;
+    uint32_t ph_acc = 0, ph_half = 0;
     auto step_done = [&]() {  // A operand of the next step written (generic -> async proxy), accumulators read
       tc_fence_before();
       fence_proxy_async();
@@ -232,6 +238,28 @@ hjb_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ Args
     };
     const uint32_t kL = h2_const(kLog2e, kLog2e), kNegL = h2_const(-kLog2e, -kLog2e), kZero = 0u;
     const uint32_t kOne = h2_const(1.f, 1.f), kLn2h = h2_const(kLn2, kLn2);
+    // 16 accumulator columns -> two 16-byte operand chunks: forward (bias, ELU) and VJP (mask from the stored activation)
+    auto fwd16 = [&](const uint32_t (&v)[16], const uint4& b0, const uint4& b1, bool elu, uint4& o0, uint4& o1) {
+      const uint32_t bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      uint32_t o[8];
+#pragma unroll
+      for (int i2 = 0; i2 < 8; ++i2) {
+        const uint32_t z = h2_add(pack_f16x2(__uint_as_float(v[2 * i2]), __uint_as_float(v[2 * i2 + 1])), bv[i2]);
+        const uint32_t e = h2_ex2(h2_min(z, kZero));
+        o[i2] = elu ? h2_max(z, h2_fma(e, kL, kNegL)) : z;
+      }
+      o0 = make_uint4(o[0], o[1], o[2], o[3]), o1 = make_uint4(o[4], o[5], o[6], o[7]);
+    };
+    auto bwd16 = [&](const uint32_t (&v)[16], const uint4& h0, const uint4& h1, uint4& o0, uint4& o1) {
+      const uint32_t hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+      uint32_t o[8];
+#pragma unroll
+      for (int i2 = 0; i2 < 8; ++i2) {
+        const uint32_t e = h2_min(h2_fma(hv[i2], kLn2h, kOne), kOne);
+        o[i2] = h2_mul(pack_f16x2(__uint_as_float(v[2 * i2]), __uint_as_float(v[2 * i2 + 1])), e);
+      }
+      o0 = make_uint4(o[0], o[1], o[2], o[3]), o1 = make_uint4(o[4], o[5], o[6], o[7]);
+    };
 
     for (int64_t it = 0; it < my_tiles; ++it) {
       const int64_t tile = blockIdx.x + it * (int64_t)gridDim.x;
@@ -247,18 +275,18 @@ hjb_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ Args
       }
       const float s = uu * dT + t, a = sqrtf(uu * dT) * P.sigma, lam = P.T - s;
 
-      // ---------------- set-up: embedding -> panels 6, 7; X' -> panels 1..; nxdot = 0 ----------------
+      // ---------------- set-up: embedding -> panels 6, 7; X' -> panels 1, 2 ----------------
       {
-        // channels [32 hh, 32 hh + 32): sin -> panel 6, cos -> panel 7 (solution.py:211-229), scaled by log2e
+        // channels [16 part, 16 part + 16): sin -> panel 6, cos -> panel 7 (solution.py:211-229), scaled by log2e
 #pragma unroll 1
-        for (int c8 = 0; c8 < 4; ++c8) {
+        for (int c8 = 0; c8 < 2; ++c8) {
           uint32_t sn[4], cs[4];
 #pragma unroll
           for (int i2 = 0; i2 < 4; ++i2) {
             float sv[2], cv[2];
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-              const int c = 32 * hh + 8 * c8 + 2 * i2 + e;
+              const int c = 16 * part + 8 * c8 + 2 * i2 + e;
               const float arg = fmaf(__ldg(A.coeff + c), lam, __ldg(A.phase + c));
               const float k = rintf(arg * 0.15915494309189535f);
               float rr = fmaf(-k, 6.2831854820251465f, arg);  // Cody-Waite: 2 pi = hi + lo
@@ -268,20 +296,21 @@ hjb_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ Args
             sn[i2] = pack_f16x2(kLog2e * sv[0], kLog2e * sv[1]);
             cs[i2] = pack_f16x2(kLog2e * cv[0], kLog2e * cv[1]);
           }
-          const int col8 = 4 * hh + c8;  // chunk inside the panel
+          const int col8 = 2 * part + c8;  // chunk inside the panel
           *reinterpret_cast<uint4*>(smem + kOffA + panel_off(48 + col8, r)) = make_uint4(sn[0], sn[1], sn[2], sn[3]);
           *reinterpret_cast<uint4*>(smem + kOffA + panel_off(56 + col8, r)) = make_uint4(cs[0], cs[1], cs[2], cs[3]);
         }
-        // X' = log2e (x + a Z) -> columns 64.. of the nn_module input (panels 1, 2); this half takes octets hh, hh+2, ...
-        for (int o = hh; o < 16; o += 2) {
+        // X' = log2e (x + a Z) -> columns 64.. of the nn_module input (panels 1, 2); this part takes octets part, part+4, ...
+#pragma unroll 1
+        for (int o = part; o < 16; o += kParts) {
           float z[8];
           row_z8(A, R, o, z);
           uint32_t w[4];
 #pragma unroll
           for (int i2 = 0; i2 < 4; ++i2) {
-            const int j = 8 * o + 2 * i2;
-            const float x0 = (j < d) ? fmaf(a, z[2 * i2], __ldg(txp + 1 + j)) : 0.f;
-            const float x1 = (j + 1 < d) ? fmaf(a, z[2 * i2 + 1], __ldg(txp + 2 + j)) : 0.f;
+            const int jx = 8 * o + 2 * i2;
+            const float x0 = (jx < d) ? fmaf(a, z[2 * i2], __ldg(txp + 1 + jx)) : 0.f;
+            const float x1 = (jx + 1 < d) ? fmaf(a, z[2 * i2 + 1], __ldg(txp + 2 + jx)) : 0.f;
             w[i2] = pack_f16x2(kLog2e * x0, kLog2e * x1);
           }
           *reinterpret_cast<uint4*>(smem + kOffA + panel_off(8 + o, r)) = make_uint4(w[0], w[1], w[2], w[3]);
@@ -291,68 +320,128 @@ hjb_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ Args
 
       for (int si = 0; si < A.n_steps; ++si) {
         const Step& S = A.steps[si];
+        const int epi = S.epi, acc0 = S.acc0;
+        const int ncols = S.width * S.n_chunks;  // columns of this step's output
+        const uint4* b16 = reinterpret_cast<const uint4*>(A.bias16[si]);
+
+        if ((epi == kEpiFwdHid || epi == kEpiBwdHid) && S.n_chunks >= 2) {
+          // ---- wide hidden layer, output columns in two halves.  This thread: 64 (= ncols / 8) columns of each half.
+          // Half 0 is converted while the MMAs of half 1 run; its operand chunks wait in registers (the A operand is
+          // still being read) and are stored once the whole layer has completed.
+          const int per = ncols / 8;  // columns per thread and half: 64 at H = 512, 32 at H = 256
+          const bool fwd = epi == kEpiFwdHid;
+          uint4* hsl = hs + (size_t)S.layer * (A.H / 8) * 128 + r;
+          uint4 held[8];
+          mbar_wait(bar_half, ph_half, 11);
+          ph_half ^= 1u;
+          tc_fence_after();
+#pragma unroll
+          for (int i4 = 0; i4 < 4; ++i4) {
+            const int c = part * per + 16 * i4;
+            if (16 * i4 < per) {
+              uint32_t v[16];
+              tmem_ld16(trow + (uint32_t)(acc0 + c), v);
+              uint4 x0, x1;
+              if (fwd) x0 = __ldg(b16 + (c >> 3)), x1 = __ldg(b16 + (c >> 3) + 1);
+              else x0 = __ldcg(hsl + (size_t)(c >> 3) * 128), x1 = __ldcg(hsl + (size_t)((c >> 3) + 1) * 128);
+              tmem_ld_wait();
+              if (fwd) {
+                fwd16(v, x0, x1, true, held[2 * i4], held[2 * i4 + 1]);
+                hsl[(size_t)(c >> 3) * 128] = held[2 * i4];
+                hsl[(size_t)((c >> 3) + 1) * 128] = held[2 * i4 + 1];
+              } else {
+                bwd16(v, x0, x1, held[2 * i4], held[2 * i4 + 1]);
+              }
+            }
+          }
+          mbar_wait(bar_acc, ph_acc, 10);
+          ph_acc ^= 1u;
+          tc_fence_after();
+#pragma unroll
+          for (int i4 = 0; i4 < 4; ++i4) {
+            const int c = part * per + 16 * i4;
+            if (16 * i4 < per) {
+              *reinterpret_cast<uint4*>(smem + kOffA + panel_off(c >> 3, r)) = held[2 * i4];
+              *reinterpret_cast<uint4*>(smem + kOffA + panel_off((c >> 3) + 1, r)) = held[2 * i4 + 1];
+            }
+          }
+          const int h1c0 = ncols / 2 + part * per;
+          uint4 xn0, xn1;
+          if (fwd) xn0 = __ldg(b16 + (h1c0 >> 3)), xn1 = __ldg(b16 + (h1c0 >> 3) + 1);
+          else xn0 = __ldcg(hsl + (size_t)(h1c0 >> 3) * 128), xn1 = __ldcg(hsl + (size_t)((h1c0 >> 3) + 1) * 128);
+#pragma unroll 1
+          for (int c = h1c0; c < h1c0 + per; c += 16) {
+            uint32_t v[16];
+            tmem_ld16(trow + (uint32_t)(acc0 + c), v);
+            const uint4 x0 = xn0, x1 = xn1;
+            if (c + 16 < h1c0 + per) {
+              if (fwd) xn0 = __ldg(b16 + ((c + 16) >> 3)), xn1 = __ldg(b16 + ((c + 16) >> 3) + 1);
+              else xn0 = __ldcg(hsl + (size_t)((c + 16) >> 3) * 128), xn1 = __ldcg(hsl + (size_t)(((c + 16) >> 3) + 1) * 128);
+            }
+            tmem_ld_wait();
+            uint4 o0, o1;
+            if (fwd) {
+              fwd16(v, x0, x1, true, o0, o1);
+              hsl[(size_t)(c >> 3) * 128] = o0;
+              hsl[(size_t)((c >> 3) + 1) * 128] = o1;
+            } else {
+              bwd16(v, x0, x1, o0, o1);
+            }
+            *reinterpret_cast<uint4*>(smem + kOffA + panel_off(c >> 3, r)) = o0;
+            *reinterpret_cast<uint4*>(smem + kOffA + panel_off((c >> 3) + 1, r)) = o1;
+          }
+          step_done();
+          continue;
+        }
+
         mbar_wait(bar_acc, ph_acc, 10);
         ph_acc ^= 1u;
         tc_fence_after();
-        const int epi = S.epi, acc0 = S.acc0;
-        const int ncols = S.width * S.n_chunks;                // columns of this step's output
-        const int c0 = hh * (ncols / 2), c1 = c0 + ncols / 2;  // this warp's column range
-        const uint4* b16 = reinterpret_cast<const uint4*>(A.bias16[si]);
+        const int c0 = part * (ncols / kParts), c1 = c0 + ncols / kParts;  // this warp's column range (16, 32 or 128 wide)
 
-        if (epi <= kEpiSmHid || epi == kEpiFwdHid) {
-          // bias (+ ELU) in packed fp16x2 -> next A operand (and, for nn_module's hidden layers, the VJP's copy).
-          // The bias of the NEXT 16 columns is fetched before the accumulator wait of the current ones.
-          const bool elu = epi != kEpiTemb;
-          uint4* hsl = (epi == kEpiFwdHid) ? hs + (size_t)S.layer * (A.H / 8) * 128 : nullptr;
-          // destination chunk of output chunk col8: Time1 splits its halves over panels 4 / 5, the rest is linear
-          const int dst_base = (epi == kEpiTime1) ? 32 : 8 * S.dst_panel;
-          uint4 bn0 = __ldg(b16 + (c0 >> 3)), bn1 = __ldg(b16 + (c0 >> 3) + 1);
+        if (epi <= kEpiSmHid || epi == kEpiFwdHid || epi == kEpiBwdHid) {
+          // narrow layers (time nets; nn_module at H = 128): bias (+ ELU) or VJP mask -> next A operand
+          const bool fwd = epi != kEpiBwdHid, elu = epi != kEpiTemb;
+          uint4* hsl = (epi == kEpiFwdHid || epi == kEpiBwdHid) ? hs + (size_t)S.layer * (A.H / 8) * 128 + r : nullptr;
+          const int dst_base = (epi == kEpiTime1) ? 32 : (epi <= kEpiSmHid ? 8 * S.dst_panel : 0);
 #pragma unroll 1
           for (int c = c0; c < c1; c += 16) {
             uint32_t v[16];
             tmem_ld16(trow + (uint32_t)(acc0 + c), v);
-            const uint4 bc0 = bn0, bc1 = bn1;
-            if (c + 16 < c1) bn0 = __ldg(b16 + ((c + 16) >> 3)), bn1 = __ldg(b16 + ((c + 16) >> 3) + 1);
+            uint4 x0, x1;
+            if (fwd) x0 = __ldg(b16 + (c >> 3)), x1 = __ldg(b16 + (c >> 3) + 1);
+            else x0 = __ldcg(hsl + (size_t)(c >> 3) * 128), x1 = __ldcg(hsl + (size_t)((c >> 3) + 1) * 128);
             tmem_ld_wait();
-            const uint32_t bv[8] = {bc0.x, bc0.y, bc0.z, bc0.w, bc1.x, bc1.y, bc1.z, bc1.w};
-            uint32_t o[8];
-#pragma unroll
-            for (int i2 = 0; i2 < 8; ++i2) {
-              const uint32_t z = h2_add(pack_f16x2(__uint_as_float(v[2 * i2]), __uint_as_float(v[2 * i2 + 1])), bv[i2]);
-              const uint32_t e = h2_ex2(h2_min(z, kZero));
-              o[i2] = elu ? h2_max(z, h2_fma(e, kL, kNegL)) : z;
-            }
-            const int col8 = c >> 3;
-            const uint4 ch0 = make_uint4(o[0], o[1], o[2], o[3]), ch1 = make_uint4(o[4], o[5], o[6], o[7]);
-            *reinterpret_cast<uint4*>(smem + kOffA + panel_off(dst_base + col8, r)) = ch0;
-            *reinterpret_cast<uint4*>(smem + kOffA + panel_off(dst_base + col8 + 1, r)) = ch1;
-            if (hsl) {
-              hsl[(size_t)col8 * 128 + r] = ch0;
-              hsl[(size_t)(col8 + 1) * 128 + r] = ch1;
-            }
+            uint4 o0, o1;
+            if (fwd) fwd16(v, x0, x1, elu, o0, o1);
+            else bwd16(v, x0, x1, o0, o1);
+            if (epi == kEpiFwdHid) hsl[(size_t)(c >> 3) * 128] = o0, hsl[(size_t)((c >> 3) + 1) * 128] = o1;
+            *reinterpret_cast<uint4*>(smem + kOffA + panel_off(dst_base + (c >> 3), r)) = o0;
+            *reinterpret_cast<uint4*>(smem + kOffA + panel_off(dst_base + (c >> 3) + 1, r)) = o1;
           }
           step_done();
         } else if (epi == kEpiSmOut) {
-          // last 64 -> 64 layer of smooth_net, then ELU and row 0 of the output layer: S_raw (solution.py:231-254)
+          // last 64 -> 64 layer of smooth_net, then ELU and row 0 of the output layer: S_raw (solution.py:231-254);
+          // 16 columns per part, partials added in part order
           const uint32_t* b32 = A.bias16[si];
+          float* sp = reinterpret_cast<float*>(smem + kOffA + kOffSrawPart);
           float acc = 0.f;
-#pragma unroll 1
-          for (int c = c0; c < c1; c += 16) {
+          {
             uint32_t v[16];
-            tmem_ld16(trow + (uint32_t)(acc0 + c), v);
+            tmem_ld16(trow + (uint32_t)(acc0 + c0), v);
             tmem_ld_wait();
 #pragma unroll
             for (int i2 = 0; i2 < 8; ++i2) {
-              const float2 b = h2_unpack(__ldg(b32 + ((c >> 1) + i2)));
+              const float2 b = h2_unpack(__ldg(b32 + ((c0 >> 1) + i2)));
               const float z0 = __uint_as_float(v[2 * i2]) + b.x, z1 = __uint_as_float(v[2 * i2 + 1]) + b.y;  // log2e-scaled
               const float h0 = z0 > 0.f ? z0 : kLog2e * (exp2f(z0) - 1.f), h1 = z1 > 0.f ? z1 : kLog2e * (exp2f(z1) - 1.f);
-              acc = fmaf(__ldg(A.sm_w0 + c + 2 * i2), h0, acc);
-              acc = fmaf(__ldg(A.sm_w0 + c + 2 * i2 + 1), h1, acc);
+              acc = fmaf(__ldg(A.sm_w0 + c0 + 2 * i2), h0, acc);
+              acc = fmaf(__ldg(A.sm_w0 + c0 + 2 * i2 + 1), h1, acc);
             }
           }
-          if (hh == 0) sraw_s[r] = acc;
-          named_bar_sync(1 + q, 64);
-          if (hh == 1) sraw_s[r] += acc + A.sm_b0;
+          sp[part * 128 + r] = acc;
+          named_bar_sync(1 + q, 32 * kParts);
+          if (part == 0) sraw_s[r] = ((sp[r] + sp[128 + r]) + (sp[256 + r] + sp[384 + r])) + A.sm_b0;
           step_done();
         } else if (epi == kEpiFwdOut) {
           // n = ln2 acc + b (unscaled) -> scratch; cotangent X (unscaled, fp16) -> panels 0, 1.  (u = S <n, x> + (1 - S) g
@@ -386,40 +475,15 @@ hjb_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ Args
             }
           }
           step_done();
-        } else if (epi == kEpiBwdHid) {
-          // c = acc . ELU'(z_l), ELU' recovered from the stored activation: min(1, 1 + ln2 h').  The activations come
-          // back from L2: the loads of the next 16 columns are in flight under the arithmetic of the current ones.
-          const uint4* hsl = hs + (size_t)S.layer * (A.H / 8) * 128 + r;
-          uint4 hn0 = __ldcg(hsl + (size_t)(c0 >> 3) * 128), hn1 = __ldcg(hsl + (size_t)((c0 >> 3) + 1) * 128);
-#pragma unroll 1
-          for (int c = c0; c < c1; c += 16) {
-            uint32_t v[16];
-            tmem_ld16(trow + (uint32_t)(acc0 + c), v);
-            const uint4 h0 = hn0, h1 = hn1;
-            if (c + 16 < c1) {
-              hn0 = __ldcg(hsl + (size_t)((c + 16) >> 3) * 128);
-              hn1 = __ldcg(hsl + (size_t)(((c + 16) >> 3) + 1) * 128);
-            }
-            tmem_ld_wait();
-            const uint32_t hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-            uint32_t o[8];
-#pragma unroll
-            for (int i2 = 0; i2 < 8; ++i2) {
-              const uint32_t e = h2_min(h2_fma(hv[i2], kLn2h, kOne), kOne);
-              o[i2] = h2_mul(pack_f16x2(__uint_as_float(v[2 * i2]), __uint_as_float(v[2 * i2 + 1])), e);
-            }
-            *reinterpret_cast<uint4*>(smem + kOffA + panel_off(c >> 3, r)) = make_uint4(o[0], o[1], o[2], o[3]);
-            *reinterpret_cast<uint4*>(smem + kOffA + panel_off((c >> 3) + 1, r)) = make_uint4(o[4], o[5], o[6], o[7]);
-          }
-          step_done();
         } else {
           // ---------------- FINAL: jtx in TMEM columns [0, 128); grad_x u, f, Bismut sums ----------------
-          // this thread: row r, columns [64 hh, 64 hh + 64).  The A region is free: Zs [col][129], the per-row exchange
-          // and the GMM constants live there for the duration of this step.
+          // this thread: row r, columns [32 part, 32 part + 32).  The A region is free: Zs [col][129], the per-row
+          // exchange and the GMM constants live there for the duration of this step.  Cross-part sums are added in part
+          // order by one thread per row: no atomics, fixed order.
           float* Zs = reinterpret_cast<float*>(smem + kOffA + kFinZ);
           float* rows_s = reinterpret_cast<float*>(smem + kOffA + kFinRow);
-          float* rowx = rows_s + r * 12;
-          float* gm = rows_s + 128 * 12;        // [K][128] mixture means
+          float* rowx = rows_s + r * kRowF;  // [k][part] at 4 k + part; dfg at 32 + part; gg at 36 + part; coef 40; dTf 41
+          float* gm = rows_s + 128 * kRowF;     // [K][128] mixture means
           float* gi = gm + kMaxOuK * 128;       // [K][128] inverse variances (0 for padded dims)
           const float Ssm = sraw_s[r] - A.S0;
           const float gamma = __expf(-0.5f * lam);
@@ -429,18 +493,14 @@ hjb_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ Args
             gm[i] = (jj < d) ? __ldg(P.ou_mean + k * d + jj) : 0.f;
             gi[i] = (jj < d) ? __ldg(P.ou_ivar + k * d + jj) : 0.f;
           }
-          if (hh == 0) {
-#pragma unroll
-            for (int i = 0; i < 12; ++i) rowx[i] = 0.f;
-          }
           named_bar_sync(9, kEpiWarps * 32);
           // pass 1: increments -> Zs, mixture quadratic forms at y = gamma X (utils.py:852-880)
           float qk[kMaxOuK];
 #pragma unroll
           for (int k = 0; k < kMaxOuK; ++k) qk[k] = 0.f;
 #pragma unroll 1
-          for (int g = 0; g < 8; ++g) {
-            const int o = 8 * hh + g;
+          for (int g = 0; g < 4; ++g) {
+            const int o = 4 * part + g;
             float z[8];
             row_z8(A, R, o, z);
 #pragma unroll
@@ -457,13 +517,13 @@ hjb_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ Args
             }
           }
 #pragma unroll
-          for (int k = 0; k < kMaxOuK; ++k)
-            if (k < K) atomicAdd(&rowx[k], qk[k]);  // two addends onto 0: order-independent
-          named_bar_sync(1 + q, 64);
+          for (int k = 0; k < kMaxOuK; ++k) rowx[4 * k + part] = qk[k];
+          named_bar_sync(1 + q, 32 * kParts);
           float l[kMaxOuK], mx = -INFINITY;
 #pragma unroll
           for (int k = 0; k < kMaxOuK; ++k) {
-            l[k] = (k < K) ? P.ou_lognorm[k] - 0.5f * rowx[k] : -INFINITY;
+            const float Q = (rowx[4 * k] + rowx[4 * k + 1]) + (rowx[4 * k + 2] + rowx[4 * k + 3]);
+            l[k] = (k < K) ? P.ou_lognorm[k] - 0.5f * Q : -INFINITY;
             mx = fmaxf(mx, l[k]);
           }
           float se = 0.f;
@@ -478,7 +538,7 @@ hjb_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ Args
           // pass 2: grad_j = S (n_j + jtx_j) + (1 - S) gamma g_x(gamma X)_j  (utils.py:882-915), f's two sums
           float dfg = 0.f, gg = 0.f;
 #pragma unroll 1
-          for (int c = 64 * hh; c < 64 * hh + 64; c += 16) {
+          for (int c = 32 * part; c < 32 * part + 32; c += 16) {
             uint32_t v[16];
             tmem_ld16(trow + (uint32_t)(acc0 + c), v);
             float4 nn[4];
@@ -502,18 +562,19 @@ hjb_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ Args
               }
             }
           }
-          atomicAdd(&rowx[8], dfg);
-          atomicAdd(&rowx[9], gg);
-          named_bar_sync(1 + q, 64);
-          if (hh == 0) {
+          rowx[32 + part] = dfg;
+          rowx[36 + part] = gg;
+          named_bar_sync(1 + q, 32 * kParts);
+          if (part == 0) {
             // f = ff(s, X, u, grad) (equations.py:657-666); u itself does not enter f for this equation
-            const float f = -rowx[8] - 0.5f * P.alpha * rowx[9] - (float)d * P.ou_theta;
+            const float sdfg = (rowx[32] + rowx[33]) + (rowx[34] + rowx[35]), sgg = (rowx[36] + rowx[37]) + (rowx[38] + rowx[39]);
+            const float f = -sdfg - 0.5f * P.alpha * sgg - (float)d * P.ou_theta;
             if (A.baseline) {
               if (R.valid) A.fb_out[R.p] = f;
             } else {
               const float fb = __ldg(A.fb_in + R.p);
-              rowx[10] = R.valid ? dT * (f - fb) / a : 0.f;  // Bismut coefficient
-              rowx[11] = R.valid ? dT * f : 0.f;
+              rowx[40] = R.valid ? dT * (f - fb) / a : 0.f;  // Bismut coefficient
+              rowx[41] = R.valid ? dT * f : 0.f;
             }
           }
           tc_fence_before();
@@ -524,11 +585,11 @@ hjb_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ Args
             if (jt < d) {
               float Gj = 0.f;
 #pragma unroll 4
-              for (int rr = 0; rr < 128; ++rr) Gj = fmaf(rows_s[rr * 12 + 10], Zs[jt * 129 + rr], Gj);
+              for (int rr = 0; rr < 128; ++rr) Gj = fmaf(rows_s[rr * kRowF + 40], Zs[jt * 129 + rr], Gj);
               out[1 + jt] = Gj;
             } else if (jt == 128) {
               float fs = 0.f;
-              for (int rr = 0; rr < 128; ++rr) fs += rows_s[rr * 12 + 11];
+              for (int rr = 0; rr < 128; ++rr) fs += rows_s[rr * kRowF + 41];
               out[0] = fs;
             }
           }
@@ -593,7 +654,7 @@ bool hjb_tc_eligible(const PisDev& N, int d) {
   const int L = N.n_main;
   if (L < 3 || L > 6 || d > 128 || N.n_t_encoder != 2 || N.n_smooth != L + 1) return false;
   const int H = N.main[0].n_out;
-  if (H % 128 != 0 || H > 512) return false;
+  if (H != 128 && H != 256 && H != 512) return false;  // the half-layer split of the epilogue wants H / 128 a power of two
   for (int l = 0; l < L - 1; ++l)
     if (N.main[l].n_out != H) return false;
   for (int l = 1; l < N.n_smooth - 1; ++l)

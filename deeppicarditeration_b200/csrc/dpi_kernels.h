@@ -154,7 +154,7 @@ int launch_hjb_eval(const ProblemDev& P, const PisDev& net, const float* tx, int
 
 // ---- fused tcgen05 PISGradNet path (dpi_hjb_tc.cu): fp16 operands, activations on chip, weights streamed from L2 ----
 struct HjbTcNet;
-// packs the network when its shape qualifies (equal hidden widths, multiple of 128, <= 512; d <= 128); *out = null otherwise
+// packs the network when its shape qualifies (equal hidden widths of 128, 256 or 512; d <= 128); *out = null otherwise
 int hjb_tc_pack(const PisDev& net, int d, std::vector<void*>& owner, HjbTcNet** out, int64_t* launches, cudaStream_t st);
 void hjb_tc_free(HjbTcNet* net);
 int64_t hjb_tc_part_floats(int64_t n, int M_I, int d);

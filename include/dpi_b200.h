@@ -65,8 +65,8 @@ typedef enum { DPI_NET_ZERO = 0, DPI_NET_MLP = 1, DPI_NET_PISGRAD = 2 } dpi_netw
  * DPI_PREC_BF16 (bf16 operands: fp32's range, 8 mantissa bits) is NOT built: it is a distinct value that every entry
  * point rejects with DPI_ERR_UNSUPPORTED, so a caller asking for bf16's range is never silently given fp16's.
  * Which paths DPI_PREC_F16 selects: Cha with the MLP [1+d,128,128,128,128,1], d <= 1024 (chunked first layer above 128);
- * GBM/SDGD with hidden width 64, v <= 127 (fp16 2-jets); PISGradNet/OU with equal hidden widths (multiple of 128,
- * <= 512) and nx <= 128: the fused kernel of dpi_hjb_tc.cu (fp16 operands, activations on chip, weights streamed from
+ * GBM/SDGD with hidden width 64, v <= 127 (fp16 2-jets); PISGradNet/OU with equal hidden widths of 128, 256
+ * or 512 and nx <= 128: the fused kernel of dpi_hjb_tc.cu (fp16 operands, activations on chip, weights streamed from
  * L2).  DPI_PREC_TF32 (PISGradNet only): the layer-by-layer pipeline with its wide GEMMs on the tensor cores in TF32
  * (fp32 operands in memory, 10-bit mantissa in the multiply, fp32 accumulate; also what DPI_PREC_F16 falls back to for
  * PISGradNet shapes the fused kernel does not take).  Anything else: DPI_ERR_UNSUPPORTED. */
