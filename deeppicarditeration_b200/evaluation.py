@@ -53,21 +53,22 @@ def compute_at_t(engine: LabelEngine, t: torch.Tensor, equation, maximal_batch_s
 
 def error_metrics(u, u_exact, u_x=None, u_x_exact=None, u_xx=None, u_xx_exact=None) -> Dict[str, float]:
     """The metric block of EvalCallback (picard/utils.py:405-474): sums, not means, in the relative norms."""
-    err = np.abs(u - u_exact)
-    m = {"MSE": float(np.sqrt((err ** 2).mean())), "rRMSE": float(np.sqrt((err ** 2).sum()) / np.sqrt((u_exact ** 2).sum())),
-         "rMAE": float(err.sum() / np.abs(u_exact).sum()), "MArE": float((err / np.abs(u_exact)).mean())}
+    m: Dict[str, float] = {}
 
-    def per_dim(val, exact, suffix):
+    def block(val, exact, suffix, axis):
         e = np.abs(val - exact)
-        m["MSE" + suffix] = float(np.sqrt((e ** 2).mean(0)).mean())
-        m["rRMSE" + suffix] = float((np.sqrt((e ** 2).sum(0)) / np.sqrt((exact ** 2).sum(0))).mean())
-        m["rMAE" + suffix] = float((e.sum(0) / np.abs(exact).sum(0)).mean())
-        m["MArE" + suffix] = float((e / np.abs(exact)).mean())
+        norm = lambda a, p: (np.abs(a) ** p).sum(axis) ** (1.0 / p)
+        m["MSE" + suffix] = float(np.sqrt((e ** 2).mean(axis)).mean())
+        m["rRMSE" + suffix] = float((norm(e, 2) / norm(exact, 2)).mean())
+        m["rMAE" + suffix] = float((norm(e, 1) / norm(exact, 1)).mean())
+        m["MArE" + suffix] = float((e / np.abs(exact)).mean())  # inf when an exact value is 0 (e.g. t = 0, x = 0), as upstream
 
-    if u_x is not None:
-        per_dim(u_x, u_x_exact, "g")
-    if u_xx is not None:
-        per_dim(u_xx, u_xx_exact, "h")
+    with np.errstate(divide="ignore", invalid="ignore"):
+        block(u, u_exact, "", None)  # the value metrics pool all points
+        if u_x is not None:
+            block(u_x, u_x_exact, "g", 0)  # the derivative metrics are per dimension, then averaged
+        if u_xx is not None:
+            block(u_xx, u_xx_exact, "h", 0)
     return m
 
 

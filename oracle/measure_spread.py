@@ -108,8 +108,13 @@ def main():
     ap.add_argument("--seeds", type=int, nargs="+", default=[0, 1, 2])
     ap.add_argument("--iterations", type=int, default=8)
     ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r02_spread_reference.json"))
+    ap.add_argument("--data-size", type=int, default=CONFIG["data_size"])
+    ap.add_argument("--mc", type=int, default=CONFIG["M"])
+    ap.add_argument("--batch-size", type=int, default=CONFIG["batch_size"])
+    ap.add_argument("--threads", type=int, default=max(1, (os.cpu_count() or 2) - 1))
     a = ap.parse_args()
-    torch.set_num_threads(max(1, (os.cpu_count() or 2) - 1))
+    CONFIG.update(data_size=a.data_size, M=a.mc, batch_size=a.batch_size)
+    torch.set_num_threads(a.threads)
     out = dict(config=CONFIG, iterations=a.iterations, impl="reference (unmodified picard/ behind oracle/ref_shim.py, CPU fp64)", runs={})
     for s in a.seeds:
         out["runs"][str(s)] = run(s, a.iterations)

@@ -4,8 +4,9 @@ the reference's; `python tools/spread_repo.py table` prints the side-by-side tab
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-REF = os.path.join(ROOT, "profiles", "r02_spread_reference.json")
-OUT = os.path.join(ROOT, "profiles", "r02_spread_repo.json")
+TAG = os.environ.get("SPREAD_TAG", "")  # e.g. "_ds4096": a second config next to the default one
+REF = os.path.join(ROOT, "profiles", f"r02_spread_reference{TAG}.json")
+OUT = os.path.join(ROOT, "profiles", f"r02_spread_repo{TAG}.json")
 
 
 def table():
