@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -653,6 +654,17 @@ static int label_gen_body(dpi_handle* h, const float* tx, int64_t n, const dpi_l
     if (cfg->precision != DPI_PREC_FP32) {
       // 16-bit tensor-core path: hidden layers of the 2-jets as tcgen05 GEMMs (u_k == 0 has no network to evaluate)
       if (h->net_kind == DPI_NET_MLP) {
+        static const bool force_v1 = getenv("DPI_GBM_TC_V1") != nullptr;  // developer switch: the bulk-synchronous kernel
+        if (!force_v1 && gbm_tc2_eligible(P, h->mlp)) {
+          if (draws && !draws->idx) {
+            set_error("deterministic mode with SDGD needs the idx draws");
+            return DPI_ERR_INVALID;
+          }
+          rc = launch_gbm_tc2(P, h->mlp, tx, n, cfg->M_I, cfg->seed, cfg->point_index_base, draws ? draws->u_s : nullptr,
+                              draws ? draws->zS : nullptr, draws ? draws->idx : nullptr, bound, y, st);
+          if (!rc) h->launches += 1;
+          return rc;
+        }
         rc = launch_gbm_tc(P, h->mlp, tx, n, cfg->M_I, cfg->seed, cfg->point_index_base, draws ? draws->u_s : nullptr,
                            draws ? draws->zS : nullptr, draws ? draws->idx : nullptr, bound, y, st);
         if (!rc) h->launches += 1;

@@ -55,6 +55,11 @@ int launch_mlp_hess_diag(const ProblemDev& P, const MlpDev& net, const float* tx
 int launch_gbm_tc(const ProblemDev& P, const MlpDev& net, const float* tx, int64_t n, int M_I, uint64_t seed, int64_t base,
                   const float* u_s, const float* zS, const int32_t* idx, float bound, float* y, cudaStream_t st);
 
+// warp-specialised version (dpi_gbm_tc2.cu): value chain on a prep team, two path rows in flight; nx, v <= 128, <= 3 hidden GEMM layers
+bool gbm_tc2_eligible(const ProblemDev& P, const MlpDev& net);
+int launch_gbm_tc2(const ProblemDev& P, const MlpDev& net, const float* tx, int64_t n, int M_I, uint64_t seed, int64_t base,
+                   const float* u_s, const float* zS, const int32_t* idx, float bound, float* y, cudaStream_t st);
+
 // ---- 16-bit tcgen05 path (dpi_mlp_tc.cu): fp16 operands, fp32 accumulation ---------------------------------------------------------------
 #ifndef DPI_TC_GROUP_TILES
 #define DPI_TC_GROUP_TILES 16
