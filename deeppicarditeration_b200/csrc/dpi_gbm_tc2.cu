@@ -48,7 +48,7 @@ struct Smem {
   float c0[kH], wt[kH], wout[kH];
   uint32_t wout_h[kH / 2];
   RowCtx ctx[kNCtx];
-  float hbuf[2][2][kH];                           // prep: activation vector, [half][ping-pong]
+  alignas(16) float hbuf[2][2][kH];               // prep: activation vector, [half][ping-pong]
   float xs[128], diag[128];
   float gw[kMaxGbmNodes][128], gw2[kMaxGbmNodes];  // GBM w_k[1+j]; sum_j w_kj^2
   float w0[kMaxGbmNodes];
@@ -252,12 +252,17 @@ gbm_tc2_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ Mlp
       }
       // ---- value chain: thread k owns hidden unit k of every layer ----
       {
+        // the increments (and below the activations) are read four at a time: one broadcast LDS.128 instead of four LDS.32
         float z0 = 0.f, z1 = 0.f;
-        for (int j = 0; j + 1 < d; j += 2) {
-          z0 = fmaf(S.W1t[j][k], C.zs[j], z0);
-          z1 = fmaf(S.W1t[j + 1][k], C.zs[j + 1], z1);
+        int j = 0;
+        for (; j + 3 < d; j += 4) {
+          const float4 zz = *reinterpret_cast<const float4*>(&C.zs[j]);
+          z0 = fmaf(S.W1t[j][k], zz.x, z0);
+          z1 = fmaf(S.W1t[j + 1][k], zz.y, z1);
+          z0 = fmaf(S.W1t[j + 2][k], zz.z, z0);
+          z1 = fmaf(S.W1t[j + 3][k], zz.w, z1);
         }
-        if (d & 1) z0 = fmaf(S.W1t[d - 1][k], C.zs[d - 1], z0);
+        for (; j < d; ++j) z0 = fmaf(S.W1t[j][k], C.zs[j], z0);
         float z = S.c0[k] + s * S.wt[k] + a * (z0 + z1);
         int pp = 0;
         for (int l = 0;; ++l) {
@@ -269,10 +274,13 @@ gbm_tc2_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ Mlp
           S.hbuf[h][pp][k] = pos ? z : e - 1.f;
           named_bar_sync(10 + h, 64);
           float y0 = 0.f, y1 = 0.f;
-#pragma unroll 8
-          for (int kk = 0; kk < kH; kk += 2) {
-            y0 = fmaf(S.Wht[l][kk][k], S.hbuf[h][pp][kk], y0);
-            y1 = fmaf(S.Wht[l][kk + 1][k], S.hbuf[h][pp][kk + 1], y1);
+#pragma unroll 4
+          for (int kk = 0; kk < kH; kk += 4) {
+            const float4 hh = *reinterpret_cast<const float4*>(&S.hbuf[h][pp][kk]);
+            y0 = fmaf(S.Wht[l][kk][k], hh.x, y0);
+            y1 = fmaf(S.Wht[l][kk + 1][k], hh.y, y1);
+            y0 = fmaf(S.Wht[l][kk + 2][k], hh.z, y0);
+            y1 = fmaf(S.Wht[l][kk + 3][k], hh.w, y1);
           }
           z = S.bh[l][k] + (y0 + y1);
           pp ^= 1;
