@@ -8,7 +8,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libdpi_b200.so")
-SOURCES = ["dpi_api.cu", "dpi_terminal.cu", "dpi_mlp_simt.cu", "dpi_mlp_tc.cu", "dpi_gbm_simt.cu", "dpi_gbm_tc.cu", "dpi_hjb.cu", "dpi_gemm_tc.cu", "dpi_train.cu", "dpi_draws.cu", "dpi_hjb_tc.cu", "dpi_gbm_tc2.cu"]
+SOURCES = ["dpi_api.cu", "dpi_terminal.cu", "dpi_mlp_simt.cu", "dpi_mlp_tc.cu", "dpi_gbm_simt.cu", "dpi_gbm_tc.cu", "dpi_hjb.cu", "dpi_gemm_tc.cu", "dpi_train.cu", "dpi_draws.cu", "dpi_hjb_tc.cu", "dpi_gbm_tc2.cu", "dpi_gbm_tc3.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "--use_fast_math",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v",

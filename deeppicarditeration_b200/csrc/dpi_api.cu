@@ -655,6 +655,17 @@ static int label_gen_body(dpi_handle* h, const float* tx, int64_t n, const dpi_l
       // 16-bit tensor-core path: hidden layers of the 2-jets as tcgen05 GEMMs (u_k == 0 has no network to evaluate)
       if (h->net_kind == DPI_NET_MLP) {
         static const bool force_v1 = getenv("DPI_GBM_TC_V1") != nullptr;  // developer switch: the bulk-synchronous kernel
+        static const bool force_v2 = getenv("DPI_GBM_TC_V2") != nullptr;  // developer switch: gathered directions, value chain from shared memory
+        if (!force_v1 && !force_v2 && gbm_tc3_eligible(P, h->mlp)) {
+          if (draws && !draws->idx) {
+            set_error("deterministic mode with SDGD needs the idx draws");
+            return DPI_ERR_INVALID;
+          }
+          rc = launch_gbm_tc3(P, h->mlp, tx, n, cfg->M_I, cfg->seed, cfg->point_index_base, draws ? draws->u_s : nullptr,
+                              draws ? draws->zS : nullptr, draws ? draws->idx : nullptr, bound, y, st);
+          if (!rc) h->launches += 1;
+          return rc;
+        }
         if (!force_v1 && gbm_tc2_eligible(P, h->mlp)) {
           if (draws && !draws->idx) {
             set_error("deterministic mode with SDGD needs the idx draws");

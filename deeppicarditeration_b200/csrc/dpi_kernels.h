@@ -60,6 +60,11 @@ bool gbm_tc2_eligible(const ProblemDev& P, const MlpDev& net);
 int launch_gbm_tc2(const ProblemDev& P, const MlpDev& net, const float* tx, int64_t n, int M_I, uint64_t seed, int64_t base,
                    const float* u_s, const float* zS, const int32_t* idx, float bound, float* y, cudaStream_t st);
 
+// directions in natural order, value-chain weights in registers, four path rows in flight (dpi_gbm_tc3.cu); nx, v <= 128, 4 v >= nx
+bool gbm_tc3_eligible(const ProblemDev& P, const MlpDev& net);
+int launch_gbm_tc3(const ProblemDev& P, const MlpDev& net, const float* tx, int64_t n, int M_I, uint64_t seed, int64_t base,
+                   const float* u_s, const float* zS, const int32_t* idx, float bound, float* y, cudaStream_t st);
+
 // ---- 16-bit tcgen05 path (dpi_mlp_tc.cu): fp16 operands, fp32 accumulation ---------------------------------------------------------------
 #ifndef DPI_TC_GROUP_TILES
 #define DPI_TC_GROUP_TILES 16

@@ -102,7 +102,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
   // One asm loop: try_wait (hardware sleep up to the hint, woken by barrier traffic), retry counter, trap.  The
   // retry path is 5 instructions; the C++ loop with a timer read was 17, and ncu's source view attributed 45 % of
   // all executed warp instructions of the integral kernel to the waiting warps -- issue slots taken from the
-  // epilogue warps of the same sub-partition.  2^26 retries of >= 60 ns each: the watchdog fires after >= 4 s.
+  // epilogue warps of the same sub-partition.  2^22 retries of 60 ns (woken early) to 20 us (the hint) each: the watchdog fires after 0.25 .. 84 s.
   (void)tag;
   asm volatile(
       "{\n"
@@ -113,7 +113,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
       "@p bra.uni DONE_%=;\n"
       "add.u32 c, c, 1;\n"
-      "setp.lt.u32 q, c, 0x4000000;\n"
+      "setp.lt.u32 q, c, 0x400000;\n"
       "@q bra.uni WAIT_%=;\n"
       "trap;\n"
       "DONE_%=:\n"
@@ -273,6 +273,13 @@ __device__ __forceinline__ uint32_t h2_mul(uint32_t a, uint32_t b) {
 __device__ __forceinline__ uint32_t h2_fma(uint32_t a, uint32_t b, uint32_t c) {
   uint32_t r;
   asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+__device__ __forceinline__ uint32_t h2_abs(uint32_t a) { return a & 0x7FFF7FFFu; }
+// max(-a, 0) per half
+__device__ __forceinline__ uint32_t h2_negrelu(uint32_t a) {
+  uint32_t r;
+  asm("{\n.reg .b32 n;\nneg.f16x2 n, %1;\nmax.f16x2 %0, n, %2;\n}" : "=r"(r) : "r"(a), "r"(0u));
   return r;
 }
 __device__ __forceinline__ uint32_t h2_min(uint32_t a, uint32_t b) {
