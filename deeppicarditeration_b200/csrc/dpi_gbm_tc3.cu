@@ -31,6 +31,16 @@ constexpr int kH = 64, kMaxHid = 3, kNCtx = 8;
 constexpr int kSlots = DPI_GBM3_SLOTS;  // path rows in flight on the jet team
 constexpr int kJetWarps = 8, kPrepWarp0 = 8, kPrepWarps = 8, kSrcWarp0 = 16, kSrcWarps = 3, kMmaWarp = 19, kThreads = 32 * 20;
 constexpr int kPrepThreads = 32 * kPrepWarps;
+// Register split (setmaxnreg, per warpgroup; a sub-partition holds one warp of each of the five warpgroups, 5 x 96
+// registers per lane at launch): jet team 2 x kJetRegs, prep team 2 x 96, source-term + MMA warps kAuxRegs.
+#ifndef DPI_GBM3_JET_REGS
+#define DPI_GBM3_JET_REGS 120
+#endif
+#ifndef DPI_GBM3_AUX_REGS
+#define DPI_GBM3_AUX_REGS 40
+#endif
+constexpr int kJetRegs = DPI_GBM3_JET_REGS, kAuxRegs = DPI_GBM3_AUX_REGS;
+static_assert(2 * kJetRegs + 2 * 96 + kAuxRegs <= 480, "register split exceeds the launch allocation");
 constexpr uint32_t kOpBytes = 128 * 128;  // one [128 rows x 64 k] fp16 operand image
 
 // a prep thread reads a quarter of a vector with 16-byte loads; four quarters 128 bytes apart would share their banks,
@@ -128,6 +138,8 @@ gbm_tc3_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ Mlp
   __syncthreads();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(&S.tmem_ptr);
 
+  if (warp >= kSrcWarp0) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kAuxRegs));
   if (warp == kMmaWarp) {
     // =================================== MMA issuer ===================================
     const uint32_t leader = elect_one();
@@ -152,14 +164,14 @@ gbm_tc3_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ Mlp
         }
     }
     __syncwarp();
-  } else if (warp >= kSrcWarp0 && warp < kSrcWarp0 + kSrcWarps) {
+  } else {
     // =================================== source term ===================================
     // f of the exact solution at (s, X = x + a Z) (equations.py:457-466); warp w takes rows w, w + 3, ...
     // (one warp needs about two row times for it: the dot products, sin / cos of every node, the |.| sum over d)
     for (int r = warp - kSrcWarp0; r < R; r += kSrcWarps) {
       const int cs = r & (kNCtx - 1);
       RowCtx& C = S.ctx[cs];
-      mbar_wait(bar(&S.bar_draws[cs]), (uint32_t)(r / kNCtx) & 1u, 5);  // the slot's (r / kNCtx)-th use
+      mbar_wait_relaxed(bar(&S.bar_draws[cs]), (uint32_t)(r / kNCtx) & 1u);  // the slot's (r / kNCtx)-th use
       const float s = C.s, a = C.a;
       float pk[kMaxGbmNodes];
 #pragma unroll
@@ -175,8 +187,11 @@ gbm_tc3_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ Mlp
         sn[q] = 0.f;
         if (q < P.gbm_nodes) {
           const float ak = warp_sum(pk[q]) + S.w0[q] * s;
+          // two-constant reduction to [-pi, pi], then the MUFU sine / cosine (absolute error ~1e-6: this is the 16-bit path)
+          const float kq = rintf(ak * 0.15915494309189535f);
+          const float ar = fmaf(kq, 1.7484555e-7f, fmaf(kq, -6.2831854820251465f, ak));
           float cs_;
-          sincosf(ak, &sn[q], &cs_);
+          __sincosf(ar, &sn[q], &cs_);
           ut = fmaf(P.gbm_v[q] * S.w0[q], cs_, ut);
           lap = fmaf(-P.gbm_v[q] * S.gw2[q], sn[q], lap);
         }
@@ -194,7 +209,9 @@ gbm_tc3_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ Mlp
         mbar_arrive(bar(&S.bar_ctx_full[cs]));
       }
     }
+  }
   } else if (warp >= kPrepWarp0) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(96));
     // =================================== PREP team ===================================
     // thread (k, q): hidden unit k of every layer, quarter q of every reduction; rows r0, r0 + 1 together
     const int pt = tid - 32 * kPrepWarp0, k = pt >> 2, q = pt & 3;
@@ -223,7 +240,7 @@ gbm_tc3_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ Mlp
       for (int rr = 0; rr < npair; ++rr) {
         const int cs = (r0 + rr) & (kNCtx - 1);
         if (used & (1u << cs)) {
-          mbar_wait(bar(&S.bar_ctx_empty[cs]), (ph_empty >> cs) & 1u, 2);
+          mbar_wait_relaxed(bar(&S.bar_ctx_empty[cs]), (ph_empty >> cs) & 1u);
           ph_empty ^= 1u << cs;
         }
         used |= 1u << cs;
@@ -343,6 +360,7 @@ gbm_tc3_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ Mlp
     }
   } else {
     // =================================== JET team ===================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kJetRegs));
     const int row = (warp & 3) * 32 + lane, hf = warp >> 2;  // direction row = TMEM lane = coordinate; this warp's 32 columns
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(hf * 32);
     uint32_t w1r[16];  // W1[hf*32 .. hf*32+31][1 + row] as fp16x2: the first-layer jet of direction `row` before ELU'
@@ -352,8 +370,14 @@ gbm_tc3_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ Mlp
     uint32_t woh[16];  // the output weights of this warp's columns
 #pragma unroll
     for (int i = 0; i < 16; ++i) woh[i] = pack_f16x2(N.wout[hf * 32 + 2 * i], N.wout[hf * 32 + 2 * i + 1]);
+    // shared addresses of this thread's four 16-byte operand chunks (logical chunk hf*4 + c of operand row `row`)
+    const uint32_t sA = smem_u32(&S.A[0][0][0]), sCtx = smem_u32(&S.ctx[0]);
+    uint32_t poff[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) poff[c] = sA + (uint32_t)row * 128u + ((((uint32_t)(hf * 4 + c)) ^ ((uint32_t)row & 7u)) << 4);
+    constexpr uint32_t kEsOff = (uint32_t)offsetof(RowCtx, es);
     uint32_t ph_ctx = 0u, ph_acc = 0u;
-    float G = 0.f, fsum = 0.f, diag = 0.f;
+    float G = 0.f, facc = 0.f, srcsum = 0.f, diag = 0.f;
     const float alpha_term = 0.5f * (1.f - P.alpha) * (float)d, abs_term = 0.25f * (float)d, inv_v = 1.f / (float)v;
     float src_b = 0.f;
     for (int r0 = 0; r0 < R; r0 += kSlots) {
@@ -361,21 +385,21 @@ gbm_tc3_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ Mlp
       // ---- first-layer jets: dh = e1 w, ddh = e2 w^2 ----
       for (int sl = 0; sl < nrow; ++sl) {
         const int cs = (r0 + sl) & (kNCtx - 1);
-        const RowCtx& C = S.ctx[cs];
         mbar_wait(bar(&S.bar_ctx_full[cs]), (ph_ctx >> cs) & 1u, 3);
         ph_ctx ^= 1u << cs;
+        const uint32_t sEs = sCtx + (uint32_t)cs * (uint32_t)sizeof(RowCtx) + kEsOff + (uint32_t)hf * 64u;
+        const uint32_t sSlot = (uint32_t)sl * 2u * kOpBytes;
 #pragma unroll
         for (int c8 = 0; c8 < 4; ++c8) {
-          const int k0 = hf * 32 + c8 * 8;
-          const uint4 es = *reinterpret_cast<const uint4*>(&C.es[0][k0]);
+          const uint4 es = lds128(sEs + 16u * c8);
           const uint4 e1 = make_uint4(h2_abs(es.x), h2_abs(es.y), h2_abs(es.z), h2_abs(es.w));
           const uint4 e2 = make_uint4(h2_negrelu(es.x), h2_negrelu(es.y), h2_negrelu(es.z), h2_negrelu(es.w));
           const uint32_t* w = &w1r[4 * c8];
           const uint4 wd = make_uint4(h2_mul(e1.x, w[0]), h2_mul(e1.y, w[1]), h2_mul(e1.z, w[2]), h2_mul(e1.w, w[3]));
           const uint4 wdd = make_uint4(h2_mul(h2_mul(e2.x, w[0]), w[0]), h2_mul(h2_mul(e2.y, w[1]), w[1]),
                                        h2_mul(h2_mul(e2.z, w[2]), w[2]), h2_mul(h2_mul(e2.w, w[3]), w[3]));
-          *reinterpret_cast<uint4*>(&S.A[sl][0][0] + a_off(row, k0)) = wd;
-          *reinterpret_cast<uint4*>(&S.A[sl][1][0] + a_off(row, k0)) = wdd;
+          sts128(poff[c8] + sSlot, wd.x, wd.y, wd.z, wd.w);
+          sts128(poff[c8] + sSlot + kOpBytes, wdd.x, wdd.y, wdd.z, wdd.w);
         }
         fence_proxy_async();
         __syncwarp();
@@ -385,36 +409,43 @@ gbm_tc3_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ Mlp
 #pragma unroll
       for (int l = 0; l < NH; ++l)
         for (int sl = 0; sl < nrow; ++sl) {
-          const RowCtx& C = S.ctx[(r0 + sl) & (kNCtx - 1)];
+          const uint32_t sEs = sCtx + (uint32_t)((r0 + sl) & (kNCtx - 1)) * (uint32_t)sizeof(RowCtx) + kEsOff +
+                               (uint32_t)(l + 1) * (uint32_t)(kH * 2) + (uint32_t)hf * 64u;
+          const uint32_t sSlot = (uint32_t)sl * 2u * kOpBytes;
           mbar_wait(bar(&S.bar_acc[sl]), (ph_acc >> sl) & 1u, 4);
           ph_acc ^= 1u << sl;
           tc_fence_after();
           const bool last = l == NH - 1;
           uint32_t accu = 0u;
           float pj = 0.f;
+          // all four accumulator loads of the row are in flight before the first conversion
+          uint32_t dz[2][16], ddz[2][16];
+          tmem_ld16(trow + (uint32_t)(sl * 128), dz[0]);
+          tmem_ld16(trow + (uint32_t)(sl * 128 + 64), ddz[0]);
+          tmem_ld16(trow + (uint32_t)(sl * 128 + 16), dz[1]);
+          tmem_ld16(trow + (uint32_t)(sl * 128 + 64 + 16), ddz[1]);
+          uint4 ev[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) ev[c] = lds128(sEs + 16u * c);
+          tmem_ld_wait();
 #pragma unroll
           for (int c16 = 0; c16 < 2; ++c16) {
-            uint32_t dz[16], ddz[16];
-            tmem_ld16(trow + (uint32_t)(sl * 128 + c16 * 16), dz);
-            tmem_ld16(trow + (uint32_t)(sl * 128 + 64 + c16 * 16), ddz);
-            const int k0 = hf * 32 + c16 * 16;
-            const uint4 ea = *reinterpret_cast<const uint4*>(&C.es[l + 1][k0]), eb = *reinterpret_cast<const uint4*>(&C.es[l + 1][k0 + 8]);
-            const uint32_t esv[8] = {ea.x, ea.y, ea.z, ea.w, eb.x, eb.y, eb.z, eb.w};
-            tmem_ld_wait();
+            const uint32_t esv[8] = {ev[2 * c16].x, ev[2 * c16].y, ev[2 * c16].z, ev[2 * c16].w,
+                                     ev[2 * c16 + 1].x, ev[2 * c16 + 1].y, ev[2 * c16 + 1].z, ev[2 * c16 + 1].w};
             uint32_t od[8], odd[8];
 #pragma unroll
             for (int i2 = 0; i2 < 8; ++i2) {
-              const uint32_t z2 = pack_f16x2(__uint_as_float(dz[2 * i2]), __uint_as_float(dz[2 * i2 + 1]));
-              const uint32_t zz2 = pack_f16x2(__uint_as_float(ddz[2 * i2]), __uint_as_float(ddz[2 * i2 + 1]));
+              const uint32_t z2 = pack_f16x2(__uint_as_float(dz[c16][2 * i2]), __uint_as_float(dz[c16][2 * i2 + 1]));
+              const uint32_t zz2 = pack_f16x2(__uint_as_float(ddz[c16][2 * i2]), __uint_as_float(ddz[c16][2 * i2 + 1]));
               const uint32_t e1 = h2_abs(esv[i2]), e2 = h2_negrelu(esv[i2]);
               od[i2] = h2_mul(e1, z2);
               odd[i2] = h2_fma(h2_mul(e2, z2), z2, h2_mul(e1, zz2));
             }
             if (!last) {
-              *reinterpret_cast<uint4*>(&S.A[sl][0][0] + a_off(row, k0)) = make_uint4(od[0], od[1], od[2], od[3]);
-              *reinterpret_cast<uint4*>(&S.A[sl][0][0] + a_off(row, k0 + 8)) = make_uint4(od[4], od[5], od[6], od[7]);
-              *reinterpret_cast<uint4*>(&S.A[sl][1][0] + a_off(row, k0)) = make_uint4(odd[0], odd[1], odd[2], odd[3]);
-              *reinterpret_cast<uint4*>(&S.A[sl][1][0] + a_off(row, k0 + 8)) = make_uint4(odd[4], odd[5], odd[6], odd[7]);
+              sts128(poff[2 * c16] + sSlot, od[0], od[1], od[2], od[3]);
+              sts128(poff[2 * c16 + 1] + sSlot, od[4], od[5], od[6], od[7]);
+              sts128(poff[2 * c16] + sSlot + kOpBytes, odd[0], odd[1], odd[2], odd[3]);
+              sts128(poff[2 * c16 + 1] + sSlot + kOpBytes, odd[4], odd[5], odd[6], odd[7]);
             } else {
               // u_jj = w_out . ddh over this warp's columns (fp16x2 partial sums, flushed to fp32 every 16 columns)
 #pragma unroll
@@ -435,6 +466,9 @@ gbm_tc3_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ Mlp
           }
         }
       // ---- the rows' f, control variate, Bismut sums (jet team barriers 1, 2: 256 threads) ----
+      // f - f_baseline = sum_j cnt_j [alpha_term (u_jj - diag_j) + abs_term (|u_jj| - |diag_j|)] / v + src - src_b needs
+      // ONE sum over the directions per row; the sum of f over the rows is linear in the per-direction terms and is
+      // reduced once, at the end of the kernel
       named_bar_sync(1, kJetWarps * 32);
       if (hf == 0) {
         for (int sl = 0; sl < nrow; ++sl) {
@@ -445,11 +479,12 @@ gbm_tc3_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ Mlp
             diag = ujj;
             continue;
           }
-          const float c = (float)C.cnt[row];
+          const float c = (float)C.cnt[row] * inv_v;
           C.cnt[row] = 0;  // the context comes back to the prep team with its histogram cleared
-          float a1 = c * ujj, a2 = c * fabsf(ujj), b1 = c * diag, b2 = c * fabsf(diag);
-          a1 = warp_sum(a1), a2 = warp_sum(a2), b1 = warp_sum(b1), b2 = warp_sum(b2);
-          if (lane == 0) S.sums[sl][warp][0] = a1, S.sums[sl][warp][1] = a2, S.sums[sl][warp][2] = b1, S.sums[sl][warp][3] = b2;
+          const float fu = alpha_term * ujj + abs_term * fabsf(ujj), fb = alpha_term * diag + abs_term * fabsf(diag);
+          facc = fmaf(c, fu, facc);
+          const float w = warp_sum(c * (fu - fb));
+          if (lane == 0) S.sums[sl][warp][0] = w;
         }
       }
       if (r0 == 0) src_b = S.ctx[0].src;
@@ -458,19 +493,21 @@ gbm_tc3_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ Mlp
         const int r = r0 + sl;
         const RowCtx& C = S.ctx[r & (kNCtx - 1)];
         if (r > 0) {
-          float a1 = 0.f, a2 = 0.f, b1 = 0.f, b2 = 0.f;
-#pragma unroll
-          for (int w = 0; w < 4; ++w) a1 += S.sums[sl][w][0], a2 += S.sums[sl][w][1], b1 += S.sums[sl][w][2], b2 += S.sums[sl][w][3];
-          const float f = alpha_term * (a1 * inv_v) + abs_term * (a2 * inv_v) + C.src;
-          const float fbv = alpha_term * (b1 * inv_v) + abs_term * (b2 * inv_v) + src_b;
-          fsum += dT * f;
-          const float coef = dT * (f - fbv) / C.a;
+          const float src = C.src;
+          const float df = (S.sums[sl][0][0] + S.sums[sl][1][0]) + (S.sums[sl][2][0] + S.sums[sl][3][0]) + (src - src_b);
+          srcsum += src;
+          const float coef = dT * df / C.a;
           if (hf == 0 && row < d) G = fmaf(coef, C.zs[zi(row)], G);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(&S.bar_ctx_empty[r & (kNCtx - 1)]));  // the context slot may be refilled
       }
     }
+    // sum of f over the rows: the per-direction terms of the hf == 0 threads plus the source terms
+    facc = warp_sum(facc);
+    if (hf == 0 && lane == 0) S.sums[0][warp][1] = facc;
+    named_bar_sync(1, kJetWarps * 32);
+    const float fsum = dT * ((S.sums[0][0][1] + S.sums[0][1][1]) + (S.sums[0][2][1] + S.sums[0][3][1]) + srcsum);
     // ---- y += integral part; clip (data.py:222) ----
     float* yp = y + p * (int64_t)(1 + d);
     const float invM = 1.f / (float)M_I;

@@ -135,6 +135,28 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
   }
 #endif
 }
+// Wait of a warp that runs well AHEAD of its consumer (ring producers): poll at most every ~0.4 us.  mbar_wait's
+// try_wait is woken by every barrier event of the CTA (measured: one retry per ~150 cycles per waiting warp, 7
+// instructions each -- a fifth of all issued instructions of the SDGD kernel); a producer with rows of slack does
+// not need that reaction time.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(400);
+    if (++spins > (1u << 23)) __trap();  // > 3 s
+  }
+}
+
+// 16-byte shared-memory accesses by 32-bit shared address (no generic-pointer arithmetic in the hot loops)
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 // make generic-proxy shared-memory writes visible to the async proxy (UMMA operand reads)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
