@@ -209,16 +209,27 @@ class OUProcessEquation(Equation):
         return (-(F * z).sum(-1, keepdim=True) - self.alpha / 2 * (z ** 2).sum(-1, keepdim=True)
                 - self.d * self.theta * torch.ones_like(y))
 
-    def exact_solution(self, t, x):  # equations.py:625-655: the GMM pushed through the OU flow, row by row
-        out = []
-        for i in range(t.shape[0]):
-            lam = self.T - t[i]
-            e1, e2 = torch.exp(-self.theta * lam), torch.exp(-2 * self.theta * lam)
-            mean_t = self.mu + (self.mean.to(x) - self.mu) * e1
-            var_t = self.diagvar.to(x) * e2 + (self.alpha / (2 * self.theta)) * (1 - e2)
-            lp, _ = self._log_terms(x[i:i + 1], mean_t, var_t)
-            out.append(-torch.logsumexp(lp, dim=1, keepdim=True))
-        return torch.cat(out, 0)
+    def exact_solution(self, t, x):  # equations.py:625-655: the GMM pushed through the OU flow (all rows at once)
+        lam = (self.T - t).reshape(-1, 1, 1)                                    # [b,1,1]
+        e1, e2 = torch.exp(-self.theta * lam), torch.exp(-2 * self.theta * lam)
+        mean_t = self.mu + (self.mean.to(x).unsqueeze(0) - self.mu) * e1         # [b,K,n]
+        var_t = self.diagvar.to(x).unsqueeze(0) * e2 + (self.alpha / (2 * self.theta)) * (1 - e2)
+        diff = x.unsqueeze(1) - mean_t
+        expo = -0.5 * (diff ** 2 / var_t).sum(-1)
+        norm = -0.5 * (self.nx * math.log(2.0 * math.pi) + torch.log(var_t).sum(-1))
+        lp = torch.log(self.pi.to(x)).unsqueeze(0) + norm + expo
+        return -torch.logsumexp(lp, dim=1, keepdim=True)
+
+    def u_x(self, t, x, retain_graph=False):  # equations.py:675-686: by automatic differentiation, as upstream
+        with torch.enable_grad():
+            xr = x.detach().clone().requires_grad_(True)
+            tt = t if t.shape[0] == xr.shape[0] else t.expand(xr.shape[0], -1)
+            u = self.exact_solution(tt, xr)
+            (ux,) = torch.autograd.grad(u.sum(), xr)
+        return ux
+
+    def u_u_x(self, t, x):  # equations.py:697-700
+        return self.exact_solution(t, x), self.u_x(t, x)
 
     def sample_x0(self, n: int):  # equations.py:710-711, utils.py:785-789
         return torch.sqrt(self.alpha_init) * torch.randn(n, self.nx, device=self._device)

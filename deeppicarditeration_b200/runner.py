@@ -31,7 +31,7 @@ from .data import OnlineDataGenerator
 from .dataset import CacheToMemoryWrapper
 from .evaluation import EvalCallback
 from .sharding import shard_range
-from .trainer import RegressionTrainer
+from .trainer import AutogradRegressionTrainer, RegressionTrainer
 
 
 def _dist():
@@ -109,10 +109,7 @@ class PicardRunner:
     def _new_solution(self):
         torch.manual_seed(self.seed)  # identical initial weights on every rank
         net = sols.PicardSolution(self.equation, self.cfg.NETWORK).float().to(self.device)
-        if self.cfg.NETWORK.PISGRADNET:
-            raise NotImplementedError("the regression step for PISGradNet is not built: the HJB config can be labelled "
-                                      "(OnlineDataGenerator) but not trained by this runner")
-        return net
+        return net  # (PISGradNet trains through AutogradRegressionTrainer, the library path: trainer.py)
 
     def state_dict_for_ckpt(self) -> Dict[str, torch.Tensor]:
         """Key layout of the reference's checkpoints: `model.<idx>.weight` under PicardSolution, prefixed `solution.`
@@ -141,11 +138,16 @@ class PicardRunner:
             if cfg.TRAIN.OPTIMIZER.cls != "Adam" or cfg.TRAIN.OPTIMIZER.SCHEDULER.cls is not None:
                 raise NotImplementedError("only Adam without a scheduler is built (what every BASELINE config uses)")
             scaler = cfg.TRAIN.LOSS.SCALER
-            if scaler.cls not in (None, "FixedLossScaler"):
-                raise NotImplementedError(f"loss scaler {scaler.cls} is not built (FixedLossScaler is)")
+            if scaler.cls not in (None, "FixedLossScaler", "SimpleLossScaler", "DimensionLossScaler"):
+                raise NotImplementedError(f"loss scaler {scaler.cls} is not built")
             fw = float(dict(scaler.kwargs).get("fixed_weight", 1.0)) if scaler.cls else 1.0
-            self.trainer = RegressionTrainer(self.model, lr=lr, loss_beta=float(cfg.TRAIN.LOSS.beta), fixed_weight=fw,
-                                             max_batch=int(cfg.TRAIN.BATCH_SIZE), device=self.device)
+            if cfg.NETWORK.PISGRADNET or scaler.cls not in (None, "FixedLossScaler"):
+                # what the native step does not cover runs on torch autograd (same loss, same optimiser)
+                self.trainer = AutogradRegressionTrainer(self.model, lr=lr, loss_beta=float(cfg.TRAIN.LOSS.beta),
+                                                         scaler=scaler.cls, fixed_weight=fw, device=self.device)
+            else:
+                self.trainer = RegressionTrainer(self.model, lr=lr, loss_beta=float(cfg.TRAIN.LOSS.beta), fixed_weight=fw,
+                                                 max_batch=int(cfg.TRAIN.BATCH_SIZE), device=self.device)
         elif not cfg.NETWORK.RELOAD:
             # a fresh network per iteration unless RELOAD (picard_iteration.py:242,249-251): re-initialise in place
             fresh = self._new_solution()

@@ -11,6 +11,12 @@ the gradient all-reduce happens INSIDE the optimiser kernel over NVLink peer mem
 every rank sums the peers' gradients in rank order, so the replicas of `u_k` stay bitwise identical without a
 broadcast.  `step()` (one mini-batch from Python) keeps the plain NCCL all-reduce between `dpi_train_grad` and
 `dpi_train_adam`.
+
+`AutogradRegressionTrainer` is the LIBRARY path for what the native step does not cover -- PISGradNet (the HJB
+config: `jacrev` through the network inside the loss, solution_jac.py:167-213) and the `SimpleLossScaler` /
+`DimensionLossScaler` weightings (solution_jac.py:40-68): same loss and optimiser, evaluated by torch autograd
+(double backward) and `torch.optim.Adam`.  It exists so that every BASELINE config can be SOLVED end to end on the
+label kernels; it is not a kernel of this repository and is not counted as one.
 """
 from __future__ import annotations
 
@@ -140,3 +146,79 @@ class RegressionTrainer:
             for i in range(0, n, batch_size):
                 last = self.step(tx[i:i + batch_size], y[i:i + batch_size])
         return last
+
+
+
+class AutogradRegressionTrainer:
+    """Same interface as `RegressionTrainer` (reset_optimizer / step / fit / close, losses = [total, value, gradient]),
+    any scalar-output torch module, loss of `PicardSolutionGradientWrapper.training_step` (solution_jac.py:167-213) with
+    `scaler` in {"FixedLossScaler", "SimpleLossScaler", "DimensionLossScaler"} (solution_jac.py:40-78)."""
+
+    def __init__(self, solution, *, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, loss_beta: float = 0.0,
+                 scaler: Optional[str] = "FixedLossScaler", fixed_weight: float = 1.0, device="cuda", process_group=None):
+        if scaler not in (None, "FixedLossScaler", "SimpleLossScaler", "DimensionLossScaler"):
+            raise NotImplementedError(f"loss scaler {scaler}")
+        self.solution, self.device = solution, torch.device(device)
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.beta, self.scaler, self.fixed_weight = float(loss_beta), scaler or "FixedLossScaler", float(fixed_weight)
+        self.pg = process_group
+        self.losses = torch.zeros(3, device=self.device, dtype=torch.float32)
+        self.step_count = 0
+        self.reset_optimizer()
+
+    def _world(self) -> int:
+        d = torch.distributed
+        return d.get_world_size(self.pg) if d.is_available() and d.is_initialized() else 1
+
+    def reset_optimizer(self):
+        self.opt = torch.optim.Adam([p for p in self.solution.parameters() if p.requires_grad], lr=self.lr,
+                                    betas=self.betas, eps=self.eps)
+        self.step_count = 0
+
+    def loss_terms(self, tx: torch.Tensor, y: torch.Tensor):
+        """v_loss [1], gd_loss_multi_dim [nx] and the scaled total (solution_jac.py:167-213)."""
+        tx = tx.detach().clone().requires_grad_(True)
+        u = self.solution(tx).reshape(-1, 1)
+        (du,) = torch.autograd.grad(u.sum(), tx, create_graph=True)  # rows are independent: the row-wise jacrev
+        w = torch.exp(tx[:, 0:1].detach() * self.beta)
+        v_loss = torch.mean(w * (u - y[:, 0:1]) ** 2, dim=0)
+        gd = torch.mean(w * (du[:, 1:] - y[:, 1:]) ** 2, dim=0)
+        if self.scaler == "FixedLossScaler":
+            g = gd.sum(-1, keepdim=True)
+            total = v_loss + self.fixed_weight * g
+        elif self.scaler == "SimpleLossScaler":
+            # as upstream (solution_jac.py:42-47): the summed gradient loss is formed under no_grad, so this scaler's
+            # second term shifts the reported loss but contributes nothing to the parameter gradient
+            g = gd.sum(-1, keepdim=True).detach()
+            a = torch.clamp(v_loss.detach() / g, min=0.0, max=1e3)
+            total = v_loss + a * g
+        else:  # DimensionLossScaler
+            a = torch.clamp((v_loss / gd).detach(), min=0.0, max=1e3)
+            g = (a * gd).sum(-1, keepdim=True)
+            total = v_loss + g
+        return total, v_loss, g
+
+    def step(self, tx: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        p0 = next(self.solution.parameters())
+        tx, y = tx.to(self.device, p0.dtype), y.to(self.device, p0.dtype)
+        self.opt.zero_grad(set_to_none=True)
+        total, v, g = self.loss_terms(tx, y)
+        total.sum().backward()
+        if self._world() > 1:
+            for p in self.solution.parameters():
+                if p.grad is not None:
+                    torch.distributed.all_reduce(p.grad, op=torch.distributed.ReduceOp.AVG, group=self.pg)
+        self.opt.step()
+        self.step_count += 1
+        self.losses = torch.stack([total.detach().sum(), v.detach().sum(), g.detach().sum()]).float()
+        return self.losses
+
+    def fit(self, tx: torch.Tensor, y: torch.Tensor, batch_size: int, n_epochs: int) -> Optional[torch.Tensor]:
+        last = None
+        for _ in range(n_epochs):
+            for i in range(0, tx.shape[0], batch_size):
+                last = self.step(tx[i:i + batch_size], y[i:i + batch_size])
+        return last
+
+    def close(self):
+        pass

@@ -160,3 +160,42 @@ EVAL: {L2_N_POINTS: 1000, FREQ: 8, TEST_GRAD: true}
         finally:
             os.chdir(cwd)
             torch.set_default_dtype(torch.float32)
+
+
+def test_picard_train_hjb_pisgradnet_end_to_end(tmp_path):
+    """The HJB config shape (OUProcessEquation + PISGradNet) through `picard train`: labels from the PISGradNet label
+    kernels, regression by the library path (AutogradRegressionTrainer), evaluation by dpi_net_eval."""
+    (tmp_path / "hjb.yaml").write_text("""
+NAME: hjb_small
+EQUATION:
+  cls: OUProcessEquation
+  kwargs: {nx: 20, alpha: 1.0, T: 1.0, num_components: 3, mean_scale: 1.0, var_scale: 2.0, alpha_scale: 4.0}
+PICARD: {N: 3}
+FORCE: true
+DATA:
+  FLOAT: double
+  DATA_SIZE: 1024
+  PREFETCH_FACTOR: None
+  kwargs: {t_always_uniform: true, n_estimate_terminal: 512, n_estimate_integral: 256}
+TRAIN:
+  N_EPOCHS: 8
+  BATCH_SIZE: 256
+  LOSS: {SCALER: {cls: FixedLossScaler, kwargs: {fixed_weight: 0.1}}}
+  OPTIMIZER: {kwargs: {lr: 0.001}}
+NETWORK: {NEURONS: [128, 128], ACTIVATIONS: [ELU, ELU], BOUND: None, RELOAD: true, PISGRADNET: true}
+EVAL: {L2_N_POINTS: 500, FREQ: 8, TEST_GRAD: true}
+""")
+    from deeppicarditeration_b200.main import train
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        hist = train("hjb.yaml", [])
+    finally:
+        os.chdir(cwd)
+        torch.set_default_dtype(torch.float32)
+    assert len(hist) == 3
+    assert all(np.isfinite(h["rRMSE"]) and np.isfinite(h["rRMSEg"]) and np.isfinite(h["loss"]) for h in hist)
+    sd = torch.load(tmp_path / "hjb_small" / "model_3.ckpt")["state_dict"]
+    assert "solution.model.timestep_phase" in sd and sd["solution.model.nn_module.0.weight"].shape == (128, 20 + 64)
+    # the network starts at its residual g(e^{-lambda/2} x), so iteration 1 is already close; the iteration must not diverge
+    assert hist[-1]["rRMSE"] < 0.5 and hist[-1]["rRMSE"] <= 1.5 * hist[0]["rRMSE"]

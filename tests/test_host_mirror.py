@@ -86,6 +86,14 @@ def test_gbm_and_ou_mirror_match_oracle():
                           h.eq.ff(None, xx, torch.zeros(xx.shape[0], 1, dtype=xx.dtype), zz), rtol=1e-10)
     d = o.descriptor()
     assert d["kind"] == "OU" and d["ou_mean"].shape == (5, 100) and abs(d["ou_alpha_init"] - 4.0) < 1e-12
+    # exact solution (all rows at once) and its x-gradient by autograd against the oracle's row-by-row restatement
+    tt = torch.rand(xx.shape[0], 1, dtype=xx.dtype)
+    assert torch.allclose(o.exact_solution(tt, xx), h.eq.exact_solution(tt, xx), rtol=1e-10, atol=1e-12)
+    xr = xx.clone().requires_grad_(True)
+    (gx,) = torch.autograd.grad(h.eq.exact_solution(tt, xr).sum(), xr)
+    assert torch.allclose(o.u_x(tt, xx), gx, rtol=1e-9, atol=1e-12)
+    u2, ux2 = o.u_u_x(tt, xx)
+    assert torch.allclose(ux2, gx, rtol=1e-9, atol=1e-12) and u2.shape == (xx.shape[0], 1)
 
 
 def test_describe_solution_layouts():
