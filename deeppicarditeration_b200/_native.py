@@ -61,7 +61,7 @@ class dpi_draws(C.Structure):
 class dpi_label_config(C.Structure):
     _fields_ = [
         ("M_T", C.c_int32), ("M_I", C.c_int32), ("precision", C.c_int32), ("sample_bound", C.c_float),
-        ("seed", C.c_uint64), ("point_index_base", C.c_int64),
+        ("seed", C.c_uint64), ("point_index_base", C.c_int64), ("estimate_delta_t", C.c_float), ("reserved0", C.c_int32),
     ]
 
 

@@ -55,6 +55,8 @@ struct dpi_handle {
   // activations of one chunk of rows of the batched-GEMM (PISGradNet) path
   float* hjb_scratch = nullptr;
   int64_t hjb_scratch_floats = 0;
+  void* td_scratch = nullptr;  // TD estimator: path-end rows and their u_k values of one chunk of points
+  int64_t td_scratch_bytes = 0;
   std::vector<void*> prob_bufs;  // device allocations owned by the problem
   std::vector<void*> net_bufs;   // device allocations owned by the packed network
   // per-point scratch: control variate f_b [n], first-layer constant c0 [n][HP]
@@ -246,6 +248,7 @@ int dpi_destroy(dpi_handle* h) {
   if (h->partF) cudaFree(h->partF);
   if (h->hjb_scratch) cudaFree(h->hjb_scratch);
   if (h->hjb_part) cudaFree(h->hjb_part);
+  if (h->td_scratch) cudaFree(h->td_scratch);
   if (h->hjb_tc) hjb_tc_free(h->hjb_tc);
   if (h->nonfinite_flag) cudaFree(h->nonfinite_flag);
   if (h->train_m) cudaFree(h->train_m);
@@ -628,6 +631,11 @@ static int label_gen_body(dpi_handle* h, const float* tx, int64_t n, const dpi_l
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   DPI_CUDA_CHECK(cudaSetDevice(h->device));
+  if (!(cfg->estimate_delta_t >= 0.f)) {
+    set_error("dpi_label_gen: estimate_delta_t must be >= 0");
+    return DPI_ERR_INVALID;
+  }
+  h->P.td_delta = cfg->estimate_delta_t;  // the horizon of both estimators (dpi_common.cuh: horizon)
   const ProblemDev& P = h->P;
   const float bound = cfg->sample_bound;
   int rc;
@@ -635,12 +643,44 @@ static int label_gen_body(dpi_handle* h, const float* tx, int64_t n, const dpi_l
   for (int s = 0; s < DPI_STAGE_COUNT; ++s) h->ev_valid[s] = false;
 
   // 1) terminal estimator -> y
-  {
+  if (cfg->estimate_delta_t > 0.f) {
+    // TD form (data.py:928-952): u_k at the path ends of every point, chunk by chunk -- rows, value pass of the frozen
+    // network, then the terminal kernel reading those values where the step ends before T.  Not a tuned path (no
+    // BASELINE config sets ESTIMATE_DELTA_T): the rows go through HBM.
+    if (P.eq == DPI_EQ_GBM) {
+      set_error("dpi_label_gen: ESTIMATE_DELTA_T > 0 is defined for Cha and OUProcessEquation (data.py:533)");
+      return DPI_ERR_UNSUPPORTED;
+    }
+    StageTimer tm(h, DPI_STAGE_TERMINAL, st);
+    const int d1 = 1 + P.nx;
+    const int64_t per_point = (int64_t)cfg->M_T * (d1 + 1) * (int64_t)sizeof(float);
+    const int64_t cp = std::max<int64_t>(1, std::min<int64_t>(n, (256LL << 20) / per_point));
+    const int64_t need = cp * per_point;
+    if (h->td_scratch_bytes < need) {
+      if (h->td_scratch) cudaFree(h->td_scratch);
+      h->td_scratch = nullptr, h->td_scratch_bytes = 0;
+      DPI_CUDA_CHECK(cudaMalloc(&h->td_scratch, (size_t)need));
+      h->td_scratch_bytes = need;
+    }
+    float* rows = reinterpret_cast<float*>(h->td_scratch);
+    float* uvals = rows + cp * cfg->M_T * d1;
+    for (int64_t p0 = 0; p0 < n; p0 += cp) {
+      const int64_t np = std::min(cp, n - p0);
+      const float* zTc = draws ? draws->zT + p0 * cfg->M_T * (int64_t)P.nx : nullptr;
+      rc = launch_td_rows(P, tx + p0 * d1, np, cfg->M_T, cfg->seed, cfg->point_index_base + p0, zTc, rows, st);
+      if (rc) return rc;
+      rc = dpi_net_eval(h, rows, np * cfg->M_T, uvals, nullptr, stream);
+      if (rc) return rc;
+      rc = launch_terminal(P, tx + p0 * d1, np, cfg->M_T, cfg->seed, cfg->point_index_base + p0, zTc, y + p0 * d1, st, uvals);
+      if (rc) return rc;
+      h->launches += 2;
+    }
+  } else {
     StageTimer tm(h, DPI_STAGE_TERMINAL, st);
     rc = launch_terminal(P, tx, n, cfg->M_T, cfg->seed, cfg->point_index_base, draws ? draws->zT : nullptr, y, st);
+    if (rc) return rc;
+    h->launches += 1;
   }
-  if (rc) return rc;
-  h->launches += 1;
 
   // 2) integral estimator: y += ..., then clip
   if (P.eq == DPI_EQ_GBM && (h->net_kind == DPI_NET_ZERO || h->net_kind == DPI_NET_MLP)) {
@@ -746,6 +786,7 @@ static int label_gen_body(dpi_handle* h, const float* tx, int64_t n, const dpi_l
       const int64_t pf = hjb_tc_part_floats(n, cfg->M_I, P.nx);
       if (pf > h->hjb_part_floats) {
         if (h->hjb_part) cudaFree(h->hjb_part);
+  if (h->td_scratch) cudaFree(h->td_scratch);
         h->hjb_part = nullptr, h->hjb_part_floats = 0;
         DPI_CUDA_CHECK(cudaMalloc((void**)&h->hjb_part, sizeof(float) * pf));
         h->hjb_part_floats = pf;

@@ -40,7 +40,15 @@ struct ProblemDev {
   float ou_lognorm[kMaxOuK];
   float ou_theta, ou_mu, ou_x0_std;
   int sdgd_v;
+  // DATA.ESTIMATE_DELTA_T (data.py:529-575, :928-952): > 0 replaces the horizon T - t of both estimators by
+  // min(t + td_delta, T) - t; set per call from dpi_label_config
+  float td_delta;
 };
+
+// length of the time interval the estimators of a point at time t integrate over
+__host__ __device__ __forceinline__ float horizon(const ProblemDev& P, float t) {
+  return P.td_delta > 0.f ? fminf(t + P.td_delta, P.T) - t : P.T - t;
+}
 
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al. 2011), counter-based: every (point, stream, sample, dim-block) has its own

@@ -231,7 +231,7 @@ gbm_simt_kernel(const ProblemDev P, const MlpDev N, const float* __restrict__ tx
   const uint64_t gp = (uint64_t)(point_base + p);
   const bool det = zS != nullptr;
   const float* txp = tx + p * (int64_t)(1 + d);
-  const float t = __ldg(txp), dT = P.T - t;
+  const float t = __ldg(txp), dT = horizon(P, t);
   const float fd = (float)d;
   float bout = 0.f;
 

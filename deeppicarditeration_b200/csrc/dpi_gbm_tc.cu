@@ -258,7 +258,7 @@ gbm_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ MlpD
   const int64_t p = blockIdx.x;
   const uint64_t gp = (uint64_t)(point_base + p);
   const float* txp = tx + p * (int64_t)(1 + d);
-  const float t = __ldg(txp), dT = P.T - t;
+  const float t = __ldg(txp), dT = horizon(P, t);
   const float fd = (float)d;
   const int n_hidden = N.n_linear - 2;
 

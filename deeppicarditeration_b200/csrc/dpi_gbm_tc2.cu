@@ -78,7 +78,7 @@ gbm_tc2_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ Mlp
   const int64_t p = blockIdx.x;
   const uint64_t gp = (uint64_t)(point_base + p);
   const float* txp = tx + p * (int64_t)(1 + d);
-  const float t = __ldg(txp), dT = P.T - t;
+  const float t = __ldg(txp), dT = horizon(P, t);
   const int n_hid = N.n_linear - 2;  // hidden GEMM layers
   const int R = M_I + 1;             // row 0 = the baseline pseudo-row (t, x) with all d directions; row 1 + m = sample m
   auto bar = [&](const uint64_t* b) -> uint32_t { return smem_u32(b); };

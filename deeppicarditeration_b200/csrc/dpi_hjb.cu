@@ -361,8 +361,8 @@ hjb_rows_kernel(const ProblemDev P, const float* __restrict__ tx, int64_t np, in
     if (path) {
       const uint64_t gp = (uint64_t)(point_base + p);
       const float uu = zS ? __ldg(u_s + p * M_I + m) : u01(philox_at(seed, gp, kStreamS, (uint32_t)m, 0u).x);
-      s = uu * (P.T - t) + t;
-      a = sqrtf(uu * (P.T - t)) * P.sigma;
+      s = uu * horizon(P, t) + t;
+      a = sqrtf(uu * horizon(P, t)) * P.sigma;
       const bool vec_ok = (d & 3) == 0;
       for (int j0 = 4 * lane; j0 < d; j0 += 128) {
         float4 z;
@@ -497,7 +497,7 @@ hjb_reduce_kernel(const ProblemDev P, const float* __restrict__ tx, int M_I, con
   const int slice = blockIdx.y;
   const int d = P.nx, rpp = M_I + 1;
   const int gq = threadIdx.x >> 7, tj = threadIdx.x & 127;
-  const float dT = P.T - __ldg(tx + p * (int64_t)(1 + d));
+  const float dT = horizon(P, __ldg(tx + p * (int64_t)(1 + d)));
   const int64_t rb = p * rpp;
   const float fb = __ldg(f + rb + M_I);
   float G[8], fs = 0.f;  // components tj + 128 k (d <= 1024)
@@ -551,7 +551,7 @@ hjb_reduce_finish_kernel(const ProblemDev P, const float* __restrict__ tx, int M
                          float bound, float* __restrict__ y) {
   const int64_t p = blockIdx.x;
   const int d = P.nx;
-  const float dT = P.T - __ldg(tx + p * (int64_t)(1 + d));
+  const float dT = horizon(P, __ldg(tx + p * (int64_t)(1 + d)));
   const float invM = 1.f / (float)M_I;
   const bool clip = bound > 0.f && isfinite(bound);
   float* yp = y + p * (int64_t)(1 + d);

@@ -265,7 +265,7 @@ hjb_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ Args
       const int64_t tile = blockIdx.x + it * (int64_t)gridDim.x;
       const RowId R = row_of(A, tile, r);
       const float* txp = A.tx + R.p * (int64_t)(1 + d);
-      const float t = __ldg(txp), dT = P.T - t;
+      const float t = __ldg(txp), dT = horizon(P, t);
       float uu = 0.5f;
       if (A.baseline) {
         uu = 0.f;

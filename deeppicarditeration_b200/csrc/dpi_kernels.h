@@ -26,8 +26,12 @@ struct MlpDev {
 // n_factors = 0: t = (T - 2 eps)(1 - U) + eps (data.py:161-167); n_factors >= 1: t = T (1 - prod of n_factors uniforms) (data.py:149-159)
 int launch_sample_tx(const ProblemDev& P, int64_t n, int64_t base, uint64_t seed, float eps, int n_factors, float* tx,
                      cudaStream_t st);
+// u_td (nullable): [n * M_T] values u_k(t + delta, X) for the TD estimator (used by the points whose step ends before T)
 int launch_terminal(const ProblemDev& P, const float* tx, int64_t n, int M_T, uint64_t seed, int64_t base,
-                    const float* zT, float* y, cudaStream_t st);
+                    const float* zT, float* y, cudaStream_t st, const float* u_td = nullptr);
+// rows [np * M_T][1 + nx] = (t_next, x + sqrt(t_next - t) sigma Z): the inputs of those values
+int launch_td_rows(const ProblemDev& P, const float* tx, int64_t np, int M_T, uint64_t seed, int64_t base, const float* zT,
+                   float* rows, cudaStream_t st);
 
 // Pack torch-layout weights into MlpDev buffers (buffers preallocated by the handle; `bout` read back by caller).
 int launch_pack_mlp(const dpi_network& net, int nx, int HP, int d_pad, float* Wt1, float* wt, float* b1, float* wsum,

@@ -81,7 +81,7 @@ cha_simt_kernel(const ProblemDev P, const MlpDev N, const float* __restrict__ tx
   int ntiles = 1;
   if (mode == kModePath) {
     t = __ldg(tx + p * (int64_t)(1 + d));
-    dT = P.T - t;
+    dT = horizon(P, t);
     fbp = __ldg(fb_in + p);
     ntiles = (M_I + G::RT - 1) / G::RT;
   }
@@ -425,7 +425,7 @@ __global__ void finish_zero_kernel(const ProblemDev P, const float* __restrict__
   const int64_t p = i / ld;
   const int c = (int)(i - p * ld);
   float v = y[i];
-  if (c == 0 && P.eq == DPI_EQ_OU) v += -(P.T - tx[p * ld]) * (float)P.nx * P.ou_theta;
+  if (c == 0 && P.eq == DPI_EQ_OU) v += -horizon(P, tx[p * ld]) * (float)P.nx * P.ou_theta;
   if (bound > 0.f && isfinite(bound)) v = fminf(fmaxf(v, -bound), bound);
   y[i] = v;
 }

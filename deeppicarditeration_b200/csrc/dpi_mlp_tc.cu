@@ -536,7 +536,7 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
       const int g = (int)(u % UP);
       const int tiles = min(kTcGroupTiles, A.tiles_per_point - g * kTcGroupTiles);
       const float t = t_n, fbp = fb_n;
-      const float dT = P.T - t;
+      const float dT = horizon(P, t);
       const float* c0g = A.c0 + p * 128;  // already scaled by log2e (baseline pass)
       u_n = feed.get(k + 1u);  // published when the TMA warp started on unit k
       if (u_n < A.n_units) {

@@ -96,7 +96,7 @@ struct Payoff<DPI_EQ_OU> {
 template <int EQ, int NSLOT, bool DET>
 __global__ void __launch_bounds__(kTermThreads, (NSLOT >= DPI_TERM_WIDE_SLOTS) ? 2 : DPI_TERM_MINBLOCKS)
 terminal_kernel(const ProblemDev P, const float* __restrict__ tx, int M_T, const PhiloxKeys keys, int64_t point_base,
-                const float* __restrict__ zT, float* __restrict__ y) {
+                const float* __restrict__ zT, const float* __restrict__ u_td, float* __restrict__ y) {
   using PO = Payoff<EQ>;
   constexpr int NS = PO::NS;
   constexpr int LDC = NSLOT * 128;  // padded dim count
@@ -111,8 +111,10 @@ terminal_kernel(const ProblemDev P, const float* __restrict__ tx, int M_T, const
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float* txp = tx + p * (int64_t)(1 + d);
   const float t = __ldg(txp);
-  const float a = sqrtf(P.T - t) * P.sigma;
+  const float a = sqrtf(horizon(P, t)) * P.sigma;
   const bool vec_ok = (d & 3) == 0;
+  // TD estimator (data.py:928-952): a point whose step ends before T takes u_k(t + delta, X) in place of g(X)
+  const bool td_interior = u_td != nullptr && P.td_delta > 0.f && t + P.td_delta < P.T;
 
   // ---- per-point constants -----------------------------------------------------------------
   for (int i = threadIdx.x; i < PO::NCH * LDC; i += kTermThreads) {
@@ -203,7 +205,8 @@ terminal_kernel(const ProblemDev P, const float* __restrict__ tx, int M_T, const
 #pragma unroll
       for (int o = 8; o > 0; o >>= 1) st[k] += __shfl_xor_sync(0xffffffffu, st[k], o);  // over the 16 lanes of a sample
     }
-    const float dg = live ? PO::eval(P, st, base, a) - g0 : 0.f;
+    float dg = 0.f;
+    if (live) dg = (td_interior ? __ldg(u_td + p * M_T + m) : PO::eval(P, st, base, a)) - g0;
     if (hl == 0) acc_v += dg;
 #pragma unroll
     for (int q = 0; q < NSLOT; ++q)
@@ -287,9 +290,39 @@ sample_tx_kernel(const ProblemDev P, int64_t n, int64_t point_base, uint64_t see
   }
 }
 
+// TD estimator: the path ends (t_next, x + sqrt(t_next - t) sigma Z) of `np` points as network input rows
+// [np * M_T][1 + d], with the terminal stream's increments (one thread per row and octet of dims)
+__global__ void __launch_bounds__(256)
+td_rows_kernel(const ProblemDev P, const float* __restrict__ tx, int64_t np, int M_T, const PhiloxKeys keys,
+               int64_t point_base, const float* __restrict__ zT, float* __restrict__ rows) {
+  const int d = P.nx, no = (d + 7) / 8;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= np * M_T * no) return;
+  const int o = (int)(i % no);
+  const int64_t r = i / no, p = r / M_T;
+  const int m = (int)(r - p * M_T);
+  const float* txp = tx + p * (int64_t)(1 + d);
+  const float t = __ldg(txp), hz = horizon(P, t), a = sqrtf(hz) * P.sigma;
+  float4 za, zb;
+  if (zT) {
+    za = load_row4(zT + r * d, 8 * o, d, (d & 3) == 0);
+    zb = load_row4(zT + r * d, 8 * o + 4, d, (d & 3) == 0);
+  } else {
+    normal8(keys, (uint64_t)(point_base + p), kStreamTerminal, (uint32_t)m, (uint32_t)o, za, zb);
+  }
+  float* row = rows + r * (int64_t)(1 + d);
+  if (o == 0) row[0] = t + hz;
+  const float z[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int j = 8 * o + q;
+    if (j < d) row[1 + j] = fmaf(a, z[q], __ldg(txp + 1 + j));
+  }
+}
+
 template <int EQ, int NSLOT>
 int launch_terminal_t(const ProblemDev& P, const float* tx, int64_t n, int M_T, uint64_t seed, int64_t base,
-                      const float* zT, float* y, cudaStream_t st) {
+                      const float* zT, const float* u_td, float* y, cudaStream_t st) {
   using PO = Payoff<EQ>;
   constexpr int LDC = NSLOT * 128;
   const size_t smem = sizeof(float) * (PO::NCH * LDC + 2 * kTermWarps * (LDC + 8));
@@ -300,21 +333,21 @@ int launch_terminal_t(const ProblemDev& P, const float* tx, int64_t n, int M_T, 
     DPI_CUDA_CHECK(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   if (zT)
-    kd<<<(unsigned)n, kTermThreads, smem, st>>>(P, tx, M_T, make_philox_keys(seed), base, zT, y);
+    kd<<<(unsigned)n, kTermThreads, smem, st>>>(P, tx, M_T, make_philox_keys(seed), base, zT, u_td, y);
   else
-    kp<<<(unsigned)n, kTermThreads, smem, st>>>(P, tx, M_T, make_philox_keys(seed), base, nullptr, y);
+    kp<<<(unsigned)n, kTermThreads, smem, st>>>(P, tx, M_T, make_philox_keys(seed), base, nullptr, u_td, y);
   DPI_CUDA_CHECK(cudaGetLastError());
   return DPI_OK;
 }
 
 template <int EQ>
 int launch_terminal_eq(const ProblemDev& P, const float* tx, int64_t n, int M_T, uint64_t seed, int64_t base,
-                       const float* zT, float* y, cudaStream_t st) {
+                       const float* zT, const float* u_td, float* y, cudaStream_t st) {
   const int d = P.nx;
-  if (d <= 128) return launch_terminal_t<EQ, 1>(P, tx, n, M_T, seed, base, zT, y, st);
-  if (d <= 256) return launch_terminal_t<EQ, 2>(P, tx, n, M_T, seed, base, zT, y, st);
-  if (d <= 512) return launch_terminal_t<EQ, 4>(P, tx, n, M_T, seed, base, zT, y, st);
-  if (d <= 1024) return launch_terminal_t<EQ, 8>(P, tx, n, M_T, seed, base, zT, y, st);
+  if (d <= 128) return launch_terminal_t<EQ, 1>(P, tx, n, M_T, seed, base, zT, u_td, y, st);
+  if (d <= 256) return launch_terminal_t<EQ, 2>(P, tx, n, M_T, seed, base, zT, u_td, y, st);
+  if (d <= 512) return launch_terminal_t<EQ, 4>(P, tx, n, M_T, seed, base, zT, u_td, y, st);
+  if (d <= 1024) return launch_terminal_t<EQ, 8>(P, tx, n, M_T, seed, base, zT, u_td, y, st);
   set_error("nx=%d > 1024 is not supported by the terminal kernel", d);
   return DPI_ERR_UNSUPPORTED;
 }
@@ -322,12 +355,12 @@ int launch_terminal_eq(const ProblemDev& P, const float* tx, int64_t n, int M_T,
 }  // namespace
 
 int launch_terminal(const ProblemDev& P, const float* tx, int64_t n, int M_T, uint64_t seed, int64_t base,
-                    const float* zT, float* y, cudaStream_t st) {
+                    const float* zT, float* y, cudaStream_t st, const float* u_td) {
   if (n <= 0) return DPI_OK;
   switch (P.eq) {
-    case DPI_EQ_CHA: return launch_terminal_eq<DPI_EQ_CHA>(P, tx, n, M_T, seed, base, zT, y, st);
-    case DPI_EQ_GBM: return launch_terminal_eq<DPI_EQ_GBM>(P, tx, n, M_T, seed, base, zT, y, st);
-    case DPI_EQ_OU: return launch_terminal_eq<DPI_EQ_OU>(P, tx, n, M_T, seed, base, zT, y, st);
+    case DPI_EQ_CHA: return launch_terminal_eq<DPI_EQ_CHA>(P, tx, n, M_T, seed, base, zT, u_td, y, st);
+    case DPI_EQ_GBM: return launch_terminal_eq<DPI_EQ_GBM>(P, tx, n, M_T, seed, base, zT, u_td, y, st);
+    case DPI_EQ_OU: return launch_terminal_eq<DPI_EQ_OU>(P, tx, n, M_T, seed, base, zT, u_td, y, st);
   }
   set_error("unknown equation kind %d", P.eq);
   return DPI_ERR_INVALID;
@@ -338,6 +371,15 @@ int launch_sample_tx(const ProblemDev& P, int64_t n, int64_t base, uint64_t seed
   if (n <= 0) return DPI_OK;
   const int wpb = 8;
   sample_tx_kernel<<<(unsigned)((n + wpb - 1) / wpb), wpb * 32, 0, st>>>(P, n, base, seed, eps, n_factors, tx);
+  DPI_CUDA_CHECK(cudaGetLastError());
+  return DPI_OK;
+}
+
+int launch_td_rows(const ProblemDev& P, const float* tx, int64_t np, int M_T, uint64_t seed, int64_t base, const float* zT,
+                   float* rows, cudaStream_t st) {
+  if (np <= 0) return DPI_OK;
+  const int64_t total = np * M_T * ((P.nx + 7) / 8);
+  td_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(P, tx, np, M_T, make_philox_keys(seed), base, zT, rows);
   DPI_CUDA_CHECK(cudaGetLastError());
   return DPI_OK;
 }

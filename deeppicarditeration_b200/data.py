@@ -57,8 +57,13 @@ class OnlineDataGenerator(DataGenerator):
         # data.py:108-111: t_always_uniform selects U[eps, T - eps]; otherwise t = T (1 - prod of N - i + 1 uniforms)
         self.t_always_uniform = bool(t_always_uniform)
         self._t_factors = 0 if self.t_always_uniform else max(1, int(N) - int(i) + 1)
-        if estimate_delta_t and estimate_delta_t > 0:
-            raise NotImplementedError("ESTIMATE_DELTA_T > 0 (TD estimators, data.py:529-575,928-952) is not built yet")
+        # data.py:529-575, :928-952: > 0 selects the temporal-difference estimators (both integrate to min(t + delta, T),
+        # the terminal one takes u_k there); upstream asserts SimpleDiffusionEquation or OUProcessEquation
+        self.estimate_delta_t = float(estimate_delta_t or 0.0)
+        if self.estimate_delta_t < 0:
+            raise ValueError("estimate_delta_t must be >= 0")
+        if self.estimate_delta_t > 0 and getattr(equation, "has_hessian_term", False):
+            raise AssertionError("ESTIMATE_DELTA_T > 0 is defined for SimpleDiffusionEquation / OUProcessEquation only")
         method = getattr(hessian_approximation, "method", None) if hessian_approximation is not None else None
         self.sdgd_v = 0
         if method is not None:  # data.py:113-121
@@ -136,7 +141,7 @@ class OnlineDataGenerator(DataGenerator):
         y = torch.ops.picard_b200.label_gen(
             tx.to(self._device, torch.float32).contiguous(), self._engine.id, self.n_estimate_terminal,
             self.n_estimate_integral, self.precision, float(bound) if math.isfinite(bound) else 0.0, self.seed, int(base),
-            d.get("zT"), d.get("u_s"), d.get("zS"), d.get("idx"))
+            d.get("zT"), d.get("u_s"), d.get("zS"), d.get("idx"), self.estimate_delta_t)
         self._engine.check_labels()  # raises FloatingPointError instead of handing out inf / NaN labels
         return y
 

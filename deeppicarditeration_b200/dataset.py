@@ -76,6 +76,8 @@ class LabelStore:
         arrays = {name: col.detach().cpu().numpy() for name, col in zip(labels, self.columns)}
         try:
             import h5py  # noqa: WPS433 (optional dependency, absent from the build image)
+            if not hasattr(h5py, "Dataset"):  # an inert stand-in registered by a test harness, not the library
+                raise ImportError("h5py stand-in")
         except ImportError:
             import numpy as np
 

@@ -130,8 +130,9 @@ class LabelEngine:
         return tx
 
     @staticmethod
-    def _cfg(M_T, M_I, precision, bound, seed, base):
+    def _cfg(M_T, M_I, precision, bound, seed, base, delta_t=0.0):
         cfg = nat.dpi_label_config()
+        cfg.estimate_delta_t = float(delta_t or 0.0)
         cfg.M_T, cfg.M_I = int(M_T), int(M_I)
         # "tf32": PISGradNet's layer-by-layer pipeline with TF32 tensor-core GEMMs; "bf16" maps to the distinct
         # DPI_PREC_BF16 value, which the library rejects (bf16 operands are not built) instead of aliasing fp16
@@ -144,14 +145,15 @@ class LabelEngine:
 
     def label_gen(self, tx: torch.Tensor, M_T: int, M_I: int, *, precision: str = "fp32", sample_bound=None,
                   seed: int = 0, point_index_base: int = 0, draws: Optional[dict] = None,
-                  check: bool = False) -> torch.Tensor:
-        """dpi_label_gen on device tensors (asynchronous).  check=True additionally synchronises and raises
+                  check: bool = False, estimate_delta_t: float = 0.0) -> torch.Tensor:
+        """dpi_label_gen on device tensors (asynchronous).  estimate_delta_t > 0 selects the TD estimators
+        (data.py:529-575, :928-952).  check=True additionally synchronises and raises
         FloatingPointError if a label is inf / NaN (dpi_check_labels), e.g. a network outside fp16's range."""
         tx = _f32c(tx, self.device)
         n = tx.shape[0]
         assert tx.shape[1] == 1 + self.nx
         y = torch.empty_like(tx)
-        cfg = self._cfg(M_T, M_I, precision, sample_bound, seed, point_index_base)
+        cfg = self._cfg(M_T, M_I, precision, sample_bound, seed, point_index_base, estimate_delta_t)
         dr = None
         keep = []
         if draws is not None:
@@ -266,15 +268,17 @@ class LabelEngine:
 @torch.library.custom_op("picard_b200::label_gen", mutates_args=(), device_types="cuda")
 def label_gen_op(tx: torch.Tensor, engine_id: int, M_T: int, M_I: int, precision: str, sample_bound: float, seed: int,
                  point_index_base: int, zT: Optional[torch.Tensor] = None, u_s: Optional[torch.Tensor] = None,
-                 zS: Optional[torch.Tensor] = None, idx: Optional[torch.Tensor] = None) -> torch.Tensor:
+                 zS: Optional[torch.Tensor] = None, idx: Optional[torch.Tensor] = None,
+                 estimate_delta_t: float = 0.0) -> torch.Tensor:
     """`torch.ops.picard_b200.label_gen`: what `OnlineDataGenerator.generate_with_gradients` calls.  `engine_id` names
     the LabelEngine (handle with the packed equation and frozen u_k); the body is the C-ABI call, nothing else."""
     eng = _ENGINES[engine_id]
     draws = None if zT is None else {"zT": zT, "u_s": u_s, "zS": zS, "idx": idx}
     return eng.label_gen(tx, M_T, M_I, precision=precision, sample_bound=sample_bound, seed=seed,
-                         point_index_base=point_index_base, draws=draws)
+                         point_index_base=point_index_base, draws=draws, estimate_delta_t=estimate_delta_t)
 
 
 @label_gen_op.register_fake
-def _(tx, engine_id, M_T, M_I, precision, sample_bound, seed, point_index_base, zT=None, u_s=None, zS=None, idx=None):
+def _(tx, engine_id, M_T, M_I, precision, sample_bound, seed, point_index_base, zT=None, u_s=None, zS=None, idx=None,
+      estimate_delta_t=0.0):
     return torch.empty_like(tx, dtype=torch.float32)

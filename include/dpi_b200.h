@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define DPI_B200_VERSION 100 /* major*10000 + minor*100 + patch */
+#define DPI_B200_VERSION 101 /* major*10000 + minor*100 + patch; 101: dpi_label_config.estimate_delta_t */
 #define DPI_MAX_LINEAR 8     /* Linear layers per chain */
 
 typedef struct dpi_handle dpi_handle;
@@ -137,6 +137,11 @@ typedef struct {
   int64_t point_index_base; /* global index of tx row 0: Philox counters are keyed by the GLOBAL point
                                index so labels do not depend on the shard size or GPU count;
                                0 <= point_index_base, point_index_base + n <= 2^48 */
+  float estimate_delta_t;   /* DATA.ESTIMATE_DELTA_T (data.py:529-575, :928-952): 0 = the estimators integrate to T;
+                               > 0 = temporal-difference form: both integrate to t_next = min(t + delta, T) and the
+                               terminal estimator takes u_k(t_next, X) in place of g(X) where t_next < T.  Cha and
+                               OUProcessEquation only (as upstream asserts) */
+  int32_t reserved0;
 } dpi_label_config;
 
 int dpi_version(void);

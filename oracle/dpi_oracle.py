@@ -464,11 +464,55 @@ def estimate_integral_with_gradients(eq, net, tx: Tensor, u_s: Tensor, zS: Tenso
     return integral.view(n, M_I, -1).sum(1) / M_I
 
 
+def estimate_terminal_with_gradients_td(eq, net, tx: Tensor, zT: Tensor, M_T: int, delta_t: float) -> Tensor:
+    """data.py:928-952: the step ends at t_next = min(t + delta, T); u_k(t_next, X) replaces g(X) where t_next < T."""
+    n = tx.shape[0]
+    t = tx[:, :1].repeat_interleave(M_T, 0)
+    x = tx[:, 1:].repeat_interleave(M_T, 0)
+    t_next = torch.clip(t + delta_t, max=eq.T)
+    XT = x + torch.sqrt(t_next - t) * eq.alpha_sqrt * zT
+    if net.kind == "zero":
+        u_next = torch.zeros_like(t)
+    else:
+        u_next = _net_forward(eq, net, torch.cat([t_next, XT], dim=1)).detach()
+    gT = torch.where(t_next == eq.T, eq.g(XT), u_next)
+    Y = zT / torch.sqrt(t_next - t) / eq.alpha_sqrt
+    eY = torch.cat([torch.ones_like(gT), Y], dim=-1)
+    g_single = eq.g(tx[:, 1:])
+    term = (gT - g_single.repeat_interleave(M_T, 0)) * eY
+    term = term.view(n, M_T, -1).sum(1) / M_T
+    term[:, 0:1] = term[:, 0:1] + g_single
+    return term
+
+
+def estimate_integral_with_gradients_td(eq, net, tx: Tensor, u_s: Tensor, zS: Tensor, idx: Optional[Tensor], M_I: int,
+                                        delta_t: float, mode: str = "closed") -> Tensor:
+    """data.py:529-575: the integral estimator over [t, t_next]."""
+    assert eq.name in ("Cha", "OU")  # data.py:533
+    n = tx.shape[0]
+    t = tx[:, :1].repeat_interleave(M_I, 0)
+    x = tx[:, 1:].repeat_interleave(M_I, 0)
+    t_next = torch.clip(t + delta_t, max=eq.T)
+    s = u_s * (t_next - t) + t
+    Xs = x + torch.sqrt(s - t) * eq.alpha_sqrt * zS
+    f = get_f(eq, net, s, Xs, idx, None, mode)
+    f_b = get_f(eq, net, tx[:, :1], tx[:, 1:], idx, M_I, mode)
+    Ys = zS / torch.sqrt(s - t) / eq.alpha_sqrt
+    eYs = torch.cat([torch.ones_like(s), Ys], dim=-1)
+    integral = (t_next - t) * (f - f_b) * eYs
+    integral[:, 0:1] = integral[:, 0:1] + f_b * (t_next - t)
+    return integral.view(n, M_I, -1).sum(1) / M_I
+
+
 def generate_with_gradients(eq, net, tx: Tensor, d: Draws, M_T: int, M_I: int, mode: str = "closed",
-                            sample_bound: float = float("inf")) -> Tensor:
-    """data.py:1208-1218 (non-TD branch) followed by the clip of data.py:222."""
-    y = (estimate_terminal_with_gradients(eq, tx, d.zT, M_T)
-         + estimate_integral_with_gradients(eq, net, tx, d.u_s, d.zS, d.idx, M_I, mode))
+                            sample_bound: float = float("inf"), delta_t: float = 0.0) -> Tensor:
+    """data.py:1208-1218 (TD branch when delta_t > 0) followed by the clip of data.py:222."""
+    if delta_t > 0:
+        y = (estimate_terminal_with_gradients_td(eq, net, tx, d.zT, M_T, delta_t)
+             + estimate_integral_with_gradients_td(eq, net, tx, d.u_s, d.zS, d.idx, M_I, delta_t, mode))
+    else:
+        y = (estimate_terminal_with_gradients(eq, tx, d.zT, M_T)
+             + estimate_integral_with_gradients(eq, net, tx, d.u_s, d.zS, d.idx, M_I, mode))
     return torch.clip(y.detach(), -sample_bound, sample_bound)
 
 

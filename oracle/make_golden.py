@@ -130,7 +130,7 @@ def _net_arrays(net):
     return out
 
 
-def make_case(name, eq_name, eq_kwargs, net_spec, n, M_T, M_I, v=None, seed=0):
+def make_case(name, eq_name, eq_kwargs, net_spec, n, M_T, M_I, v=None, seed=0, delta_t=0.0):
     ref_shim.install()
     import picard.data as rdata
     import picard.equations as reqs
@@ -183,7 +183,7 @@ def make_case(name, eq_name, eq_kwargs, net_spec, n, M_T, M_I, v=None, seed=0):
         gen = rdata.OnlineDataGenerator(
             req, rnet, N=40, i=2, device="cpu", t_always_uniform=True, n_estimate_terminal=M_T,
             n_estimate_integral=M_I, hessian_approximation=hess, sample_bound=None,
-            estimate_terminal="OU_ByGx", estimate_integral="OU_Simple", estimate_delta_t=0.0)
+            estimate_terminal="OU_ByGx", estimate_integral="OU_Simple", estimate_delta_t=delta_t)
 
         g = torch.Generator().manual_seed(seed)
         d = orc.draw(oeq, n, M_T, M_I, v, g, round_fp32=True)
@@ -191,14 +191,17 @@ def make_case(name, eq_name, eq_kwargs, net_spec, n, M_T, M_I, v=None, seed=0):
             tx, y = gen.sample_with_gradients(n)
         tx = tx.detach()
         with Replay(_queue(d, "terminal")):
-            yT = gen.estimate_terminal_with_gradients(tx.clone()).detach()
+            yT = (gen.estimate_terminal_with_gradients_td(tx.clone()) if delta_t > 0
+                  else gen.estimate_terminal_with_gradients(tx.clone())).detach()
         with Replay(_queue(d, "integral")):
-            yI = gen.estimate_integral_with_gradients(tx.clone()).detach()
+            yI = (gen.estimate_integral_with_gradients_td(tx.clone()) if delta_t > 0
+                  else gen.estimate_integral_with_gradients(tx.clone())).detach()
         assert torch.allclose(yT + yI, y, rtol=0, atol=1e-12)
 
         arrays = dict(
             eq_name=np.array(eq_name), nx=np.array(nx), alpha=np.array(eq_kwargs["alpha"]), T=np.array(eq_kwargs["T"]),
             k=np.array(eq_kwargs.get("k", 0.0)), M_T=np.array(M_T), M_I=np.array(M_I), v=np.array(v or 0), n=np.array(n),
+            delta_t=np.array(float(delta_t)),
             u_t=d.u_t.numpy().astype(np.float32), z_x=d.z_x.numpy().astype(np.float32),
             zT=d.zT.numpy().astype(np.float32), u_s=d.u_s.numpy().astype(np.float32),
             zS=d.zS.numpy().astype(np.float32),
@@ -237,14 +240,24 @@ CASES = [
     dict(name="hjb_100d_zero", eq_name="OUProcessEquation",
          eq_kwargs=dict(nx=100, alpha=1.0, T=1.0, num_components=5, mean_scale=1.0, var_scale=2.0, alpha_scale=4.0),
          net_spec=dict(kind="zero"), n=4, M_T=12, M_I=12, seed=16),
+    # temporal-difference estimators (DATA.ESTIMATE_DELTA_T = 0.3: about a third of the points end their step at T)
+    dict(name="burgers_100d_mlp128_td", eq_name="Cha", eq_kwargs=dict(nx=100, alpha=1.0, k=5.0, T=1.0),
+         net_spec=dict(kind="mlp", hidden=[128] * 4), n=8, M_T=24, M_I=24, seed=17, delta_t=0.3),
+    dict(name="burgers_10d_zero_td", eq_name="Cha", eq_kwargs=dict(nx=10, alpha=0.7, k=2.0, T=1.5),
+         net_spec=dict(kind="zero"), n=8, M_T=17, M_I=5, seed=18, delta_t=0.4),
+    dict(name="hjb_100d_pisgrad_td", eq_name="OUProcessEquation",
+         eq_kwargs=dict(nx=100, alpha=1.0, T=1.0, num_components=5, mean_scale=1.0, var_scale=2.0, alpha_scale=4.0),
+         net_spec=dict(kind="pisgrad", hidden=[96, 64, 80]), n=6, M_T=12, M_I=12, seed=19, delta_t=0.3),
 ]
 
 
 def main():
     if not ref_shim.reference_available():
         raise SystemExit("reference not mounted; fixtures can only be generated in the build container")
+    only = set(sys.argv[1:])
     for c in CASES:
-        make_case(**c)
+        if not only or c["name"] in only:
+            make_case(**c)
 
 
 if __name__ == "__main__":

@@ -28,6 +28,7 @@ class Golden:
         self.eq_name = str(z["eq_name"])
         self.nx, self.M_T, self.M_I, self.v, self.n = (int(z[k]) for k in ("nx", "M_T", "M_I", "v", "n"))
         self.alpha, self.T, self.k = float(z["alpha"]), float(z["T"]), float(z["k"])
+        self.delta_t = float(z["delta_t"]) if "delta_t" in z else 0.0  # DATA.ESTIMATE_DELTA_T of the generating run
         if self.eq_name == "Cha":
             self.eq = orc.Cha(self.nx, self.alpha, self.k, self.T)
         elif self.eq_name == "GBMEquationComplexExact":

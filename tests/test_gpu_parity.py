@@ -25,7 +25,8 @@ def test_labels_match_reference_fp32(name):
     from tests.gpu_util import draws_dict
     g = Golden(name)
     e = _engine(g)
-    y = e.label_gen(g.tx, g.M_T, g.M_I, precision="fp32", draws=draws_dict(g.draws)).double().cpu()
+    y = e.label_gen(g.tx, g.M_T, g.M_I, precision="fp32", draws=draws_dict(g.draws),
+                    estimate_delta_t=g.delta_t).double().cpu()  # delta_t > 0: the TD fixtures (data.py:529-575, :928-952)
     assert torch.isfinite(y).all()
     assert orc.rel_l2(y, g.y) < TOL_FP32
     # gradient columns on their own (the value column dominates the norm otherwise)
@@ -41,7 +42,7 @@ def test_terminal_only_matches_reference(name):
     from tests.gpu_util import draws_dict
     g = Golden(name)
     e = _engine(g)
-    y = e.label_gen(g.tx, g.M_T, g.M_I, draws=draws_dict(g.draws)).double().cpu()
+    y = e.label_gen(g.tx, g.M_T, g.M_I, draws=draws_dict(g.draws), estimate_delta_t=g.delta_t).double().cpu()
     assert orc.rel_l2(y, g.y) < 1e-5
     e.close()
 
@@ -202,7 +203,7 @@ def test_umma_selftest_matches_bf16_matmul():
     e.close()
 
 
-TC_GOLDEN = ["burgers_100d_mlp128", "gbm_100d_mlp64_sdgd"]
+TC_GOLDEN = ["burgers_100d_mlp128", "gbm_100d_mlp64_sdgd", "burgers_100d_mlp128_td"]
 
 
 @pytest.mark.parametrize("name", TC_GOLDEN)
@@ -210,7 +211,7 @@ def test_labels_match_reference_bf16(name):
     from tests.gpu_util import draws_dict
     g = Golden(name)
     e = _engine(g)
-    y = e.label_gen(g.tx, g.M_T, g.M_I, precision="f16", draws=draws_dict(g.draws)).double().cpu()
+    y = e.label_gen(g.tx, g.M_T, g.M_I, precision="f16", draws=draws_dict(g.draws), estimate_delta_t=g.delta_t).double().cpu()
     assert torch.isfinite(y).all()
     assert orc.rel_l2(y, g.y) < TOL_BF16
     assert orc.rel_l2(y[:, 1:], g.y[:, 1:]) < TOL_BF16
@@ -300,3 +301,46 @@ def test_bf16_rejects_unsupported_network_loudly():
     with pytest.raises(NotImplementedError):
         e.label_gen(tx, 16, 16, precision="f16")
     e.close()
+
+
+def test_td_estimators_philox_mode_and_generator_keyword():
+    """ESTIMATE_DELTA_T through the host mirror in Philox mode: statistically the same labels as the oracle's TD
+    estimators on its own draws (M = 4096), shard invariant, and rejected for the Hessian equation as upstream asserts."""
+    from deeppicarditeration_b200 import equations as eqs
+    from deeppicarditeration_b200 import solution as sol
+    from deeppicarditeration_b200.data import OnlineDataGenerator
+    from tests.gpu_util import engine_for
+
+    class HA:
+        method, kwargs = None, {}
+
+    class Cfg:
+        TYPE, PISGRADNET, NEURONS, ACTIVATIONS, BOUND = "Value", False, [64, 64], ["ELU", "ELU"], None
+
+    torch.manual_seed(0)
+    eq = eqs.Cha(nx=20, alpha=1.0, k=5.0, T=1.0)
+    net = sol.PicardSolution(eq, Cfg).float().cuda()
+    gen = OnlineDataGenerator(eq, net, 40, 2, device="cuda", t_always_uniform=True, n_estimate_terminal=4096,
+                              n_estimate_integral=4096, hessian_approximation=HA(), estimate_delta_t=0.25, seed=3)
+    tx, y = gen.sample_with_gradients(24)
+    assert torch.isfinite(y).all() and bool((tx[:, 0] + 0.25 < 1.0).any()) and bool((tx[:, 0] + 0.25 >= 1.0).any())
+    # oracle on its own draws at the same points
+    oeq = orc.Cha(20, 1.0, 5.0, 1.0)
+    lin = [m for m in net.model if isinstance(m, torch.nn.Linear)]
+    onet = orc.MLP([m.weight.detach().double().cpu() for m in lin], [m.bias.detach().double().cpu() for m in lin])
+    g = torch.Generator().manual_seed(5)
+    d = orc.draw(oeq, 24, 4096, 4096, None, g)
+    yo = orc.generate_with_gradients(oeq, onet, tx.double().cpu(), d, 4096, 4096, delta_t=0.25)
+    assert orc.rel_l2(y[:, :1].double().cpu(), yo[:, :1]) < 2e-2  # value labels: MC error ~ 1/sqrt(4096)
+    # bitwise shard invariance of the TD path
+    e = gen.engine
+    ya = e.label_gen(tx, 64, 96, seed=9, estimate_delta_t=0.25)
+    yb = torch.cat([e.label_gen(tx[:10], 64, 96, seed=9, estimate_delta_t=0.25),
+                    e.label_gen(tx[10:], 64, 96, seed=9, point_index_base=10, estimate_delta_t=0.25)])
+    assert torch.equal(ya, yb)
+    e.close()
+    gg = Golden("gbm_100d_mlp64_sdgd")
+    eg = engine_for(gg.eq, gg.net, gg.v)
+    with pytest.raises(Exception):
+        eg.label_gen(gg.tx, 8, 8, estimate_delta_t=0.2)
+    eg.close()

@@ -29,7 +29,7 @@ def test_c_abi_exports_every_declared_symbol():
     assert declared >= {"dpi_create", "dpi_label_gen", "dpi_label_gen_host", "dpi_sample_tx", "dpi_set_network"}
     assert declared == set(nat.EXPORTED_SYMBOLS)
     lib = nat.load()  # dlopen; raises AttributeError if a declared symbol is missing
-    assert lib.dpi_version() == 100
+    assert lib.dpi_version() == 101
     for name in declared:
         assert hasattr(lib, name)
 

@@ -22,7 +22,10 @@ def test_sample_tx_matches_reference(name):
 @pytest.mark.parametrize("name", golden_names())
 def test_terminal_matches_reference(name):
     g = Golden(name)
-    yT = orc.estimate_terminal_with_gradients(g.eq, g.tx, g.draws.zT, g.M_T)
+    if g.delta_t > 0:  # TD estimators (data.py:928-952)
+        yT = orc.estimate_terminal_with_gradients_td(g.eq, g.net, g.tx, g.draws.zT, g.M_T, g.delta_t)
+    else:
+        yT = orc.estimate_terminal_with_gradients(g.eq, g.tx, g.draws.zT, g.M_T)
     assert orc.rel_l2(yT, g.y_terminal) < TOL
 
 
@@ -30,19 +33,29 @@ def test_terminal_matches_reference(name):
 @pytest.mark.parametrize("name", golden_names())
 def test_integral_and_labels_match_reference(name, mode):
     g = Golden(name)
-    yI = orc.estimate_integral_with_gradients(g.eq, g.net, g.tx, g.draws.u_s, g.draws.zS, g.draws.idx, g.M_I, mode)
+    if g.delta_t > 0:  # data.py:529-575
+        yI = orc.estimate_integral_with_gradients_td(g.eq, g.net, g.tx, g.draws.u_s, g.draws.zS, g.draws.idx, g.M_I,
+                                                     g.delta_t, mode)
+    else:
+        yI = orc.estimate_integral_with_gradients(g.eq, g.net, g.tx, g.draws.u_s, g.draws.zS, g.draws.idx, g.M_I, mode)
     if float(g.y_integral.norm()) > 0:
         assert orc.rel_l2(yI, g.y_integral) < 1e-10  # cancellation in (f-f_b)/sqrt(s-t) costs a few digits
     else:
         assert float(yI.abs().max()) == 0.0
-    y = orc.generate_with_gradients(g.eq, g.net, g.tx, g.draws, g.M_T, g.M_I, mode)
+    y = orc.generate_with_gradients(g.eq, g.net, g.tx, g.draws, g.M_T, g.M_I, mode, delta_t=g.delta_t)
     assert orc.rel_l2(y, g.y) < TOL * 10
 
 
 def test_fixture_count_and_coverage():
     names = golden_names()
     assert {"burgers_100d_mlp128", "burgers_100d_zero", "burgers_10d_ragged", "gbm_100d_mlp64_sdgd",
-            "gbm_100d_zero_sdgd", "hjb_100d_pisgrad", "hjb_100d_zero"} <= set(names)
+            "gbm_100d_zero_sdgd", "hjb_100d_pisgrad", "hjb_100d_zero", "burgers_100d_mlp128_td", "burgers_10d_zero_td",
+            "hjb_100d_pisgrad_td"} <= set(names)
+    # the TD fixtures exercise both branches of `where(t_next == T, g, u_k)`
+    for n in ("burgers_100d_mlp128_td", "hjb_100d_pisgrad_td"):
+        g = Golden(n)
+        at_T = (g.tx[:, 0] + g.delta_t >= g.T)
+        assert bool(at_T.any()) and bool((~at_T).any()), n
 
 
 def test_exact_solution_is_picard_fixed_point_statistically():
