@@ -95,9 +95,13 @@ def test_unreachable_paths_raise_like_the_reference():
     from deeppicarditeration_b200 import equations as eqs, solution as sol
     from deeppicarditeration_b200.data import OnlineDataGenerator
     eq = eqs.Cha(nx=10, alpha=1.0, k=5.0)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):
         OnlineDataGenerator(eq, sol.ZeroSolution(), 10, 1, device="cuda", t_always_uniform=True,
-                            hessian_approximation=_HA(), estimate_delta_t=0.1)
+                            hessian_approximation=_HA(), estimate_delta_t=-0.1)
+    td = OnlineDataGenerator(eq, sol.ZeroSolution(), 10, 1, device="cuda", t_always_uniform=True, n_estimate_terminal=32,
+                             n_estimate_integral=32, hessian_approximation=_HA(), estimate_delta_t=0.1)
+    assert torch.isfinite(td.sample_with_gradients(8)[1]).all()  # the TD estimators are built (tests/test_gpu_parity.py)
+    td.engine.close()
     with pytest.raises(AssertionError):
         OnlineDataGenerator(eq, sol.ZeroSolution(), 10, 1, device="cuda", t_always_uniform=True,
                             hessian_approximation=_HA("SDGD", 10))  # Cha does not support SDGD (data.py:119-121)
