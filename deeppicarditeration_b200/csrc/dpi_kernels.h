@@ -79,6 +79,7 @@ constexpr int kTcGroupTiles = DPI_TC_GROUP_TILES;
 // per-column fp32 constants of the network, passed to the kernel by value (constant bank)
 struct alignas(16) TcConsts {
   float wt[128];            // log2e W1[:,0]                time column (fp32: multiplies the per-row time)
+  uint32_t wt16[64];        // the same as fp16x2 pairs (fp16-accumulator path)
   uint32_t wsum16[64];      // fp16x2 pairs: log2e sum_j W1[:,1+j]   first-layer tangent along (0,1,...,1)
   uint32_t b16[3][64];      // fp16x2 pairs: log2e biases of the three hidden GEMM layers
   uint32_t wout16[64];      // fp16x2 pairs: ln2 w_out

@@ -152,12 +152,23 @@ constexpr int kEpiUnroll = DPI_EPI_UNROLL;  // chunks per loop iteration of an e
 #define DPI_EPI_DB 0
 #endif
 #ifndef DPI_EPI_POLY
-#define DPI_EPI_POLY 0x0
+#define DPI_EPI_POLY 0x1
 #endif
 // which of the four column pairs of every 8-column group take the FMA-pipe exponential (h2_ex2_poly) instead of MUFU
 constexpr int kEpiPolyMask = DPI_EPI_POLY;
 constexpr int kEpiCW = DPI_EPI_CW;       // accumulator columns per tcgen05.ld (8 or 16)
 constexpr bool kEpiDB = DPI_EPI_DB != 0; // prefetch the next chunk under the arithmetic of the current one
+// fp16 accumulators in TMEM (see make_idesc_f16_acc16): the epilogue reads packed pairs and skips the fp32 -> fp16
+// conversions (2 of its ~8.5 instructions per column pair); the first layer of the chunked d > 128 path keeps fp32
+// accumulators (its sums run over up to 1024 inputs)
+#ifndef DPI_TC_ACC16
+#define DPI_TC_ACC16 1
+#endif
+constexpr bool kAcc16 = DPI_TC_ACC16 != 0;
+#ifndef DPI_TC_ACC16_FIRST
+#define DPI_TC_ACC16_FIRST DPI_TC_ACC16
+#endif
+constexpr bool kAcc16First = DPI_TC_ACC16_FIRST != 0;  // the first layer too (its epilogue then runs in packed fp16)
 static_assert(kEpiCW == 8 || kEpiCW == 16 || kEpiCW == 32, "chunk width");
 
 template <int N>
@@ -166,8 +177,14 @@ __device__ __forceinline__ void tmem_ldN(uint32_t taddr, uint32_t (&r)[N]) {
   else if constexpr (N == 16) tmem_ld16(taddr, r);
   else tmem_ld32(taddr, r);
 }
+template <int N>  // N registers = 2 N columns of fp16 accumulators
+__device__ __forceinline__ void tmem_ldN_pack(uint32_t taddr, uint32_t (&r)[N]) {
+  if constexpr (N == 4) tmem_ld4_pack(taddr, r);
+  else if constexpr (N == 8) tmem_ld8_pack(taddr, r);
+  else tmem_ld16_pack(taddr, r);
+}
 
-template <int MODE>
+template <int MODE, bool ACC16 = false>
 __device__ __forceinline__ void epi_pass(const TcConsts& C, uint32_t tacc, uint8_t* hv_row, uint8_t* ht_row,
                                          uint32_t rx, int half, const float* __restrict__ c0_s, int layer, float s2,
                                          float a2, float& pu, float& pD) {
@@ -175,11 +192,18 @@ __device__ __forceinline__ void epi_pass(const TcConsts& C, uint32_t tacc, uint8
   // constants in global memory (512 B per point, read by every tile of the point: L1 hits)
   constexpr int NB = kEpiDB ? 2 : 1, NCH = 64 / kEpiCW, G = kEpiCW / 8;
   const int ch0 = half * NCH;
-  uint32_t v[NB][kEpiCW], tv[NB][kEpiCW];
+  constexpr int NR = ACC16 ? kEpiCW / 2 : kEpiCW;  // registers per chunk and accumulator row
+  uint32_t v[NB][NR], tv[NB][NR];
   float4 cc[NB][2 * G];  // first pass: c0 of the current / next chunk (prefetched like the accumulators)
+  const uint32_t a2h = pack_f16x2(a2, a2), s2h = pack_f16x2(s2, s2);
   auto fetch = [&](int ch, int b) {
-    tmem_ldN<kEpiCW>(tacc + (uint32_t)(ch * kEpiCW), v[b]);
-    if (MODE != kPassFirst) tmem_ldN<kEpiCW>(tacc + 128u + (uint32_t)(ch * kEpiCW), tv[b]);
+    if constexpr (ACC16) {
+      tmem_ldN_pack<NR>(tacc + (uint32_t)(ch * kEpiCW), v[b]);
+      if (MODE != kPassFirst) tmem_ldN_pack<NR>(tacc + 128u + (uint32_t)(ch * kEpiCW), tv[b]);
+    } else {
+      tmem_ldN<kEpiCW>(tacc + (uint32_t)(ch * kEpiCW), v[b]);
+      if (MODE != kPassFirst) tmem_ldN<kEpiCW>(tacc + 128u + (uint32_t)(ch * kEpiCW), tv[b]);
+    }
     if (MODE == kPassFirst) {
 #pragma unroll
       for (int i = 0; i < 2 * G; ++i) cc[b][i] = __ldg(reinterpret_cast<const float4*>(&c0_s[ch * kEpiCW + 4 * i]));
@@ -200,8 +224,8 @@ __device__ __forceinline__ void epi_pass(const TcConsts& C, uint32_t tacc, uint8
     if (kEpiDB && ci + 1 < NCH) fetch(ch + 1, (ci + 1) & 1);
 #pragma unroll
     for (int g = 0; g < G; ++g) {  // groups of 8 columns = one 16-byte operand chunk of the value and tangent rows
-      const uint32_t* vv = &v[b][8 * g];
-      const uint32_t* tt = &tv[b][8 * g];
+      const uint32_t* vv = &v[b][(ACC16 ? 4 : 8) * g];
+      const uint32_t* tt = &tv[b][(ACC16 ? 4 : 8) * g];
       const int c8 = ch * G + g;   // 16-byte chunk index 0..15
       uint32_t hv[4], ht[4];
 #pragma unroll
@@ -211,9 +235,15 @@ __device__ __forceinline__ void epi_pass(const TcConsts& C, uint32_t tacc, uint8
         if (MODE == kPassFirst) {
           const float4 c0 = cc[b][2 * g + k2 / 4];
           const float c0a = (k2 & 2) ? c0.z : c0.x, c0b = (k2 & 2) ? c0.w : c0.y;
-          z = pack_f16x2(fmaf(a2, __uint_as_float(vv[k2]), fmaf(s2, C.wt[col], c0a)),
-                         fmaf(a2, __uint_as_float(vv[k2 + 1]), fmaf(s2, C.wt[col + 1], c0b)));
+          if constexpr (ACC16)  // packed: z' = a' acc + (s' w_t' + c0')
+            z = h2_fma(vv[k2 / 2], a2h, h2_fma(s2h, C.wt16[col / 2], pack_f16x2(c0a, c0b)));
+          else
+            z = pack_f16x2(fmaf(a2, __uint_as_float(vv[k2]), fmaf(s2, C.wt[col], c0a)),
+                           fmaf(a2, __uint_as_float(vv[k2 + 1]), fmaf(s2, C.wt[col + 1], c0b)));
           tg = C.wsum16[col / 2];
+        } else if constexpr (ACC16) {
+          z = h2_add(vv[k2 / 2], MODE == kPassHidden ? bias[col / 2] : C.b16[2][col / 2]);
+          tg = tt[k2 / 2];
         } else {
           z = h2_add(pack_f16x2(__uint_as_float(vv[k2]), __uint_as_float(vv[k2 + 1])),
                      MODE == kPassHidden ? bias[col / 2] : C.b16[2][col / 2]);
@@ -355,7 +385,9 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
       if (lane != 0) trace_p = nullptr;
 #endif
       mbar_wait(bar(kBarW), 0, 0);
-      constexpr uint32_t idesc = make_idesc_f16(128, 128);
+      // accumulator type per layer: fp16 (kAcc16) except the chunked first layer of the d > 128 path
+      constexpr uint32_t idesc = kAcc16 ? make_idesc_f16_acc16(128, 128) : make_idesc_f16(128, 128);
+      constexpr uint32_t idesc1 = (kAcc16First && !MULTI) ? make_idesc_f16_acc16(128, 128) : make_idesc_f16(128, 128);
       TileCursor cur;
       cur.init(A, feed);
       int lay0 = 0, lay1 = 0, slt0 = 0, slt1 = 0;  // two in-flight tiles: next layer to issue (0 = none) and slot
@@ -387,7 +419,7 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
 #pragma unroll
               for (int ks = 0; ks < 8; ++ks) {
                 const uint64_t o = (uint64_t)((ks >> 2) * 1024 + (ks & 3) * 2);
-                umma_bf16_p(acc, dV + o, dT + o, idesc, (uint32_t)((cch | ks) != 0), leader);
+                umma_bf16_p(acc, dV + o, dT + o, idesc1, (uint32_t)((cch | ks) != 0), leader);
               }
               if (cch + 1 < nch) tc_commit_p(bar(kBarSlotFree + s), leader);  // hV / hT may take the next chunk
             }
@@ -402,7 +434,7 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
             for (int ks = 0; ks < 8; ++ks) {
               if (ks < A.ksteps1) {
                 const uint64_t o = (uint64_t)((ks >> 2) * 1024 + (ks & 3) * 2);
-                umma_bf16_p(acc, dV + o, dT + o, idesc, ks > 0, leader);
+                umma_bf16_p(acc, dV + o, dT + o, idesc1, ks > 0, leader);
               }
             }
           }
@@ -571,7 +603,7 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
             wait_acc(s);
             TRACE(2, s, j + s, 1);
             uint8_t* const hv = hv_row0 + (uint32_t)s * kSlotBytes;
-            epi_pass<kPassFirst>(C, tacc0 + (uint32_t)s * 256u, hv, hv + kOperandBytes, rx, h, c0g, 0, s2_[s],
+            epi_pass<kPassFirst, kAcc16First && !MULTI>(C, tacc0 + (uint32_t)s * 256u, hv, hv + kOperandBytes, rx, h, c0g, 0, s2_[s],
                                  a_[s] * kLog2e, pu, pD);
             pass_done(s);
             TRACE(2, s, j + s, 2);
@@ -586,7 +618,7 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
               wait_acc(s);
               TRACE(2, s, j + s, (l + 1) * 10 + 1);
               uint8_t* const hv = hv_row0 + (uint32_t)s * kSlotBytes;
-              epi_pass<kPassHidden>(C, tacc0 + (uint32_t)s * 256u, hv, hv + kOperandBytes, rx, h, c0g, l, 0.f, 0.f, pu,
+              epi_pass<kPassHidden, kAcc16>(C, tacc0 + (uint32_t)s * 256u, hv, hv + kOperandBytes, rx, h, c0g, l, 0.f, 0.f, pu,
                                     pD);
               pass_done(s);
               TRACE(2, s, j + s, (l + 1) * 10 + 2);
@@ -603,7 +635,7 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
             TRACE(2, s, j + s, 31);
             pu = pD = 0.f;
             uint8_t* const hv = hv_row0 + (uint32_t)s * kSlotBytes;
-            epi_pass<kPassOut>(C, tacc0 + (uint32_t)s * 256u, hv, hv + kOperandBytes, rx, h, c0g, 2, 0.f, 0.f, pu, pD);
+            epi_pass<kPassOut, kAcc16>(C, tacc0 + (uint32_t)s * 256u, hv, hv + kOperandBytes, rx, h, c0g, 2, 0.f, 0.f, pu, pD);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(kBarAReady + s));  // accumulators of the slot are free for the next tile
@@ -996,8 +1028,11 @@ __global__ void pack_sw128_kernel(const float* __restrict__ W, int ld, int col_o
 }
 
 // ---- UMMA self-test: D[128x128] = A[128x128] . B[128x128]^T through the same descriptors / layouts -------------
+// mode 0: fp32 accumulators; mode 1: fp16 accumulators (instruction descriptor c_format = 0) read back as raw 32-bit
+// TMEM cells; mode 2: fp16 accumulators read back with tcgen05.ld ... .pack::16b (two adjacent columns per register)
 __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const uint8_t* __restrict__ Aimg,
-                                                               const uint8_t* __restrict__ Bimg, float* __restrict__ D) {
+                                                               const uint8_t* __restrict__ Bimg, float* __restrict__ D,
+                                                               int mode) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const uint32_t barW = sbase + 2 * kOperandBytes, barD = barW + 8, tptr = barW + 16;
@@ -1019,19 +1054,33 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const uint8_t* __
     bulk_g2s(sbase + kOperandBytes, Bimg, kOperandBytes, barW);
     mbar_wait(barW, 0, 100);
     tc_fence_after();
+    const uint32_t idesc = mode == 0 ? make_idesc_f16(128, 128) : (make_idesc_f16(128, 128) & ~(3u << 4));
     for (int ks = 0; ks < 8; ++ks)
-      umma_bf16(tmem, desc_kstep(sbase, ks), desc_kstep(sbase + kOperandBytes, ks), make_idesc_f16(128, 128), ks > 0);
+      umma_bf16(tmem, desc_kstep(sbase, ks), desc_kstep(sbase + kOperandBytes, ks), idesc, ks > 0);
     tc_commit(barD);
   }
   __syncwarp();
   mbar_wait(barD, 0, 101);
   tc_fence_after();
   const int r = warp * 32 + lane;
-  for (int col0 = 0; col0 < 128; col0 += 32) {
-    uint32_t v[32];
-    tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + col0, v);
-    tmem_ld_wait();
-    for (int i = 0; i < 32; ++i) D[r * 128 + col0 + i] = __uint_as_float(v[i]);
+  if (mode == 2) {
+    for (int col0 = 0; col0 < 128; col0 += 32) {
+      uint32_t v[16];
+      tmem_ld16_pack(tmem + ((uint32_t)(warp * 32) << 16) + col0, v);  // 32 columns -> 16 registers of two halves
+      tmem_ld_wait();
+      for (int i = 0; i < 16; ++i) {
+        const float2 f = h2_unpack(v[i]);
+        D[r * 128 + col0 + 2 * i] = f.x;
+        D[r * 128 + col0 + 2 * i + 1] = f.y;
+      }
+    }
+  } else {
+    for (int col0 = 0; col0 < 128; col0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + col0, v);
+      tmem_ld_wait();
+      for (int i = 0; i < 32; ++i) D[r * 128 + col0 + i] = __uint_as_float(v[i]);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -1083,6 +1132,7 @@ int tc_pack_network(const dpi_network& net, const ProblemDev& P, const MlpDev& M
   for (int i = 0; i < 128; ++i) T.consts.wt[i] = wt[i] * kLog2e;
   for (int i = 0; i < 64; ++i) {
     T.consts.wsum16[i] = h2_const(wsum[2 * i] * kLog2e, wsum[2 * i + 1] * kLog2e);
+    T.consts.wt16[i] = h2_const(wt[2 * i] * kLog2e, wt[2 * i + 1] * kLog2e);
     T.consts.wout16[i] = h2_const(wout[2 * i] * 0.6931471805599453f, wout[2 * i + 1] * 0.6931471805599453f);
   }
   for (int l = 0; l < 3; ++l) {
@@ -1224,7 +1274,8 @@ int tc_umma_selftest(const float* A, const float* B, float* D, cudaStream_t st) 
   const int smem = 2 * tc::kOperandBytes + 64;
   cudaError_t e = cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e == cudaSuccess) {
-    umma_selftest_kernel<<<1, 128, smem, st>>>(img, img + tc::kOperandBytes, D);
+    const char* m = getenv("DPI_SELFTEST_MODE");  // developer switch: see the kernel comment
+    umma_selftest_kernel<<<1, 128, smem, st>>>(img, img + tc::kOperandBytes, D, m ? atoi(m) : 0);
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);

@@ -30,6 +30,12 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// the same with fp16 ACCUMULATORS (c_format = 0): one half per 32-bit TMEM cell, read back two columns per register by
+// tcgen05.ld ... .pack::16b (checked by the UMMA self-test, modes 1 and 2: 4.4e-4 from the fp32-accumulated product
+// at K = 128, against 2.8e-4 for rounding an fp32 accumulator to fp16 -- which every epilogue pass does anyway)
+__host__ __device__ constexpr uint32_t make_idesc_f16_acc16(int M, int N) {
+  return ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 
 // kind::tf32: fp32 words in shared memory read as TF32 (format code 2 for A and B), K = 8 per instruction
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
@@ -269,6 +275,29 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
+}
+// 32 lanes x 32 columns of 16-bit accumulators (c_format = F16: one half per 32-bit TMEM cell), adjacent columns packed
+// two per register: thread i of warp w reads lane 32*(w%4)+i, columns [c, c+32) -> r[j] = {col c+2j, col c+2j+1}
+__device__ __forceinline__ void tmem_ld16_pack(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.pack::16b.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld8_pack(uint32_t taddr, uint32_t (&r)[8]) {  // 16 columns -> 8 registers
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.pack::16b.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld4_pack(uint32_t taddr, uint32_t (&r)[4]) {  // 8 columns -> 4 registers
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.pack::16b.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 

@@ -31,3 +31,6 @@ else:
         r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "quick_bench.py"), "f16", n, M], env=env,
                            capture_output=True, text=True, timeout=300)
         print(lib, (r.stdout.strip().splitlines() or [r.stderr[-300:]])[-1])
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "acc16_check.py")], env=env, capture_output=True,
+                           text=True, timeout=300)
+        print("   ", " | ".join(r.stdout.strip().splitlines()[-2:]))
