@@ -143,7 +143,8 @@ gbm_tc3_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ Mlp
   if (warp == kMmaWarp) {
     // =================================== MMA issuer ===================================
     const uint32_t leader = elect_one();
-    constexpr uint32_t idesc = make_idesc_f16(128, 64);
+    // fp16 accumulators (one half per TMEM cell, read back two columns per register): the jet team converts nothing
+    constexpr uint32_t idesc = make_idesc_f16_acc16(128, 64);
     uint32_t ph = 0u;
     for (int r0 = 0; r0 < R; r0 += kSlots) {
       const int nrow = min(kSlots, R - r0);
@@ -419,11 +420,11 @@ gbm_tc3_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ Mlp
           uint32_t accu = 0u;
           float pj = 0.f;
           // all four accumulator loads of the row are in flight before the first conversion
-          uint32_t dz[2][16], ddz[2][16];
-          tmem_ld16(trow + (uint32_t)(sl * 128), dz[0]);
-          tmem_ld16(trow + (uint32_t)(sl * 128 + 64), ddz[0]);
-          tmem_ld16(trow + (uint32_t)(sl * 128 + 16), dz[1]);
-          tmem_ld16(trow + (uint32_t)(sl * 128 + 64 + 16), ddz[1]);
+          uint32_t dz[2][8], ddz[2][8];  // packed fp16x2 pairs of adjacent columns
+          tmem_ld8_pack(trow + (uint32_t)(sl * 128), dz[0]);
+          tmem_ld8_pack(trow + (uint32_t)(sl * 128 + 64), ddz[0]);
+          tmem_ld8_pack(trow + (uint32_t)(sl * 128 + 16), dz[1]);
+          tmem_ld8_pack(trow + (uint32_t)(sl * 128 + 64 + 16), ddz[1]);
           uint4 ev[4];
 #pragma unroll
           for (int c = 0; c < 4; ++c) ev[c] = lds128(sEs + 16u * c);
@@ -435,8 +436,7 @@ gbm_tc3_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ Mlp
             uint32_t od[8], odd[8];
 #pragma unroll
             for (int i2 = 0; i2 < 8; ++i2) {
-              const uint32_t z2 = pack_f16x2(__uint_as_float(dz[c16][2 * i2]), __uint_as_float(dz[c16][2 * i2 + 1]));
-              const uint32_t zz2 = pack_f16x2(__uint_as_float(ddz[c16][2 * i2]), __uint_as_float(ddz[c16][2 * i2 + 1]));
+              const uint32_t z2 = dz[c16][i2], zz2 = ddz[c16][i2];
               const uint32_t e1 = h2_abs(esv[i2]), e2 = h2_negrelu(esv[i2]);
               od[i2] = h2_mul(e1, z2);
               odd[i2] = h2_fma(h2_mul(e2, z2), z2, h2_mul(e1, zz2));
