@@ -184,7 +184,7 @@ __device__ __forceinline__ void tmem_ldN_pack(uint32_t taddr, uint32_t (&r)[N]) 
   else tmem_ld16_pack(taddr, r);
 }
 
-template <int MODE, bool ACC16 = false>
+template <int MODE, bool ACC16 = false, int POLY = kEpiPolyMask>
 __device__ __forceinline__ void epi_pass(const TcConsts& C, uint32_t tacc, uint8_t* hv_row, uint8_t* ht_row,
                                          uint32_t rx, int half, const float* __restrict__ c0_s, int layer, float s2,
                                          float a2, float& pu, float& pD) {
@@ -250,7 +250,7 @@ __device__ __forceinline__ void epi_pass(const TcConsts& C, uint32_t tacc, uint8
           tg = pack_f16x2(__uint_as_float(tt[k2]), __uint_as_float(tt[k2 + 1]));
         }
         const uint32_t zneg = h2_min(z, kZero);
-        const uint32_t e = ((kEpiPolyMask >> (k2 / 2)) & 1) ? h2_ex2_poly(zneg) : h2_ex2(zneg);  // ELU'(z) = 2^min(z',0)
+        const uint32_t e = ((POLY >> (k2 / 2)) & 1) ? h2_ex2_poly(zneg) : h2_ex2(zneg);  // ELU'(z) = 2^min(z',0)
         const uint32_t h = h2_max(z, h2_fma(e, kL, kNegL));    // log2e ELU(z)
         const uint32_t dh = h2_mul(e, tg);
         if (MODE == kPassOut) {
@@ -535,6 +535,8 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
     const uint32_t tacc0 = tmem + ((uint32_t)(q * 32) << 16);
     uint8_t* const hv_row0 = smem + kOffSlot + (uint32_t)r * 128u;
     const uint32_t rx = (uint32_t)(r & 7) << 4;
+    // the chunked d > 128 path is bound by its generator (issue slots), not by the XU pipe: all exponentials on MUFU there
+    constexpr int kPoly = MULTI ? 0 : kEpiPolyMask;
     float2* exch = reinterpret_cast<float2*>(smem + kOffExch);  // [128] output-layer partial sums of the other half
     float* coef_s = reinterpret_cast<float*>(smem + kOffCoef);
     uint32_t ph_acc = 0, j = 0;  // ph_acc bit s = slot s
@@ -603,7 +605,7 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
             wait_acc(s);
             TRACE(2, s, j + s, 1);
             uint8_t* const hv = hv_row0 + (uint32_t)s * kSlotBytes;
-            epi_pass<kPassFirst, kAcc16First && !MULTI>(C, tacc0 + (uint32_t)s * 256u, hv, hv + kOperandBytes, rx, h, c0g, 0, s2_[s],
+            epi_pass<kPassFirst, kAcc16First && !MULTI, kPoly>(C, tacc0 + (uint32_t)s * 256u, hv, hv + kOperandBytes, rx, h, c0g, 0, s2_[s],
                                  a_[s] * kLog2e, pu, pD);
             pass_done(s);
             TRACE(2, s, j + s, 2);
@@ -618,7 +620,7 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
               wait_acc(s);
               TRACE(2, s, j + s, (l + 1) * 10 + 1);
               uint8_t* const hv = hv_row0 + (uint32_t)s * kSlotBytes;
-              epi_pass<kPassHidden, kAcc16>(C, tacc0 + (uint32_t)s * 256u, hv, hv + kOperandBytes, rx, h, c0g, l, 0.f, 0.f, pu,
+              epi_pass<kPassHidden, kAcc16, kPoly>(C, tacc0 + (uint32_t)s * 256u, hv, hv + kOperandBytes, rx, h, c0g, l, 0.f, 0.f, pu,
                                     pD);
               pass_done(s);
               TRACE(2, s, j + s, (l + 1) * 10 + 2);
@@ -635,7 +637,7 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
             TRACE(2, s, j + s, 31);
             pu = pD = 0.f;
             uint8_t* const hv = hv_row0 + (uint32_t)s * kSlotBytes;
-            epi_pass<kPassOut, kAcc16>(C, tacc0 + (uint32_t)s * 256u, hv, hv + kOperandBytes, rx, h, c0g, 2, 0.f, 0.f, pu, pD);
+            epi_pass<kPassOut, kAcc16, kPoly>(C, tacc0 + (uint32_t)s * 256u, hv, hv + kOperandBytes, rx, h, c0g, 2, 0.f, 0.f, pu, pD);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(kBarAReady + s));  // accumulators of the slot are free for the next tile
