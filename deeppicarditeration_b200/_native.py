@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = (
     "dpi_sample_tx", "dpi_label_gen", "dpi_label_gen_host", "dpi_net_eval", "dpi_launch_count",
     "dpi_set_stage_timing", "dpi_stage_ms", "dpi_selftest_umma",
     "dpi_train_init", "dpi_train_param_count", "dpi_train_grad", "dpi_train_adam", "dpi_train_fit", "dpi_train_reset",
-    "dpi_check_labels", "dpi_export_draws", "dpi_sample_tx_ex", "dpi_net_hessian_diag",
+    "dpi_check_labels", "dpi_export_draws", "dpi_sample_tx_ex", "dpi_net_hessian_diag", "dpi_net_hessian",
     "dpi_train_dp_export", "dpi_train_dp_connect",
 )
 
@@ -97,6 +97,7 @@ def load() -> C.CDLL:
                                        C.c_void_p]
     lib.dpi_sample_tx_ex.argtypes = [H, C.c_int64, C.c_int64, C.c_uint64, C.c_int32, C.c_float, C.c_void_p, C.c_void_p]
     lib.dpi_net_hessian_diag.argtypes = [H, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    lib.dpi_net_hessian.argtypes = [H, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     lib.dpi_train_dp_export.argtypes = [H, C.c_void_p]
     lib.dpi_train_dp_connect.argtypes = [H, C.c_int32, C.c_int32, C.c_void_p]
     lib.dpi_check_labels.argtypes = [H, C.c_void_p]

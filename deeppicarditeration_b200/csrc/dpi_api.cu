@@ -903,6 +903,31 @@ int dpi_net_hessian_diag(dpi_handle* h, const float* tx, int64_t n, float* d2u, 
   return rc;
 }
 
+int dpi_net_hessian(dpi_handle* h, const float* tx, int64_t n, float* d2u, void* stream) {
+  if (!h || !h->has_problem || !h->has_net) {
+    set_error("dpi_net_hessian: problem/network not set");
+    return DPI_ERR_STATE;
+  }
+  if (n <= 0) return DPI_OK;
+  if (!tx || !d2u) {
+    set_error("dpi_net_hessian: NULL buffer");
+    return DPI_ERR_INVALID;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  DPI_CUDA_CHECK(cudaSetDevice(h->device));
+  if (h->net_kind == DPI_NET_ZERO) {
+    DPI_CUDA_CHECK(cudaMemsetAsync(d2u, 0, sizeof(float) * n * h->P.nx * h->P.nx, st));
+    return DPI_OK;
+  }
+  if (h->net_kind != DPI_NET_MLP) {
+    set_error("dpi_net_hessian: built for plain MLPs (the fully nonlinear config)");
+    return DPI_ERR_UNSUPPORTED;
+  }
+  int rc = launch_mlp_hess_full(h->P, h->mlp, tx, n, d2u, st);
+  if (!rc) h->launches += 1;
+  return rc;
+}
+
 int dpi_train_init(dpi_handle* h, const dpi_network* net, int64_t max_batch, void* stream) {
   if (!h || !net || max_batch < 1) {
     set_error("dpi_train_init: bad arguments");

@@ -39,6 +39,7 @@ struct GbmSmem {
   float gw[kMaxGbmNodes][128];       // GBM w_k[1+j]
   float part[4][kH];
   int idx[kDirs];
+  int idx2[kDirs];                   // pair directions e_i + e_j (full Hessian): second coordinate, -1 = none
   float scal[16];
 };
 
@@ -86,7 +87,8 @@ __device__ float forward_row(GbmSmem& S, const MlpDev& N, int d, float s, float 
 }
 
 // second derivatives u_jj for the directions idx[0..ndir): result in S.red[0][i]
-__device__ void jet_tile(GbmSmem& S, const MlpDev& N, int ndir) {
+// (pairs: direction i is e_idx[i] + e_idx2[i] where idx2[i] >= 0 -- polarisation for the mixed derivatives)
+__device__ void jet_tile(GbmSmem& S, const MlpDev& N, int ndir, bool pairs = false) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ty = lane, txg = warp;  // 32 row groups (8 GEMM rows = 4 directions), 8 column groups (8 columns)
   const int n_hidden = N.n_linear - 2;
@@ -95,7 +97,8 @@ __device__ void jet_tile(GbmSmem& S, const MlpDev& N, int ndir) {
     const int i = tid & 127, k0 = tid >> 7;
     const int j = (i < ndir) ? S.idx[i] : -1;
     for (int k = k0; k < kH; k += 2) {
-      const float w = (j >= 0) ? S.Wt1[j * kLDW1 + k] : 0.f;
+      float w = (j >= 0) ? S.Wt1[j * kLDW1 + k] : 0.f;
+      if (pairs && j >= 0 && S.idx2[i] >= 0) w += S.Wt1[S.idx2[i] * kLDW1 + k];
       *reinterpret_cast<float2*>(&S.act[k * kLDA + 2 * i]) = make_float2(S.e1[0][k] * w, S.e2[0][k] * w * w);
     }
   }
@@ -409,6 +412,77 @@ mlp_hess_diag_kernel(const ProblemDev P, const MlpDev N, const float* __restrict
   if (tid < d) diag[p * (int64_t)d + tid] = S.red[0][tid];
 }
 
+// Full Hessian of u_k in x (EvalCallback with TEST_HESSIAN, picard/utils.py:198-200,579-591: d backward passes upstream).
+// One CTA per point: the value chain once, the d coordinate directions (diagonal), then the d (d - 1) / 2 pair directions
+// e_i + e_j in tiles of 128 jets; H_ij = (D2[e_i + e_j] - H_ii - H_jj) / 2.  H [n][d][d], symmetric.
+__global__ void __launch_bounds__(kThreads, 1)
+mlp_hess_full_kernel(const ProblemDev P, const MlpDev N, const float* __restrict__ tx, float* __restrict__ H) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  GbmSmem& S = *reinterpret_cast<GbmSmem*>(smem_raw);
+  const int tid = threadIdx.x, d = P.nx;
+  const int64_t p = blockIdx.x;
+  const float* txp = tx + p * (int64_t)(1 + d);
+  const float t = __ldg(txp);
+  for (int i = tid; i < 128; i += kThreads) {
+    S.xs[i] = (i < d) ? __ldg(txp + 1 + i) : 0.f;
+    S.zs[i] = 0.f;
+  }
+  const int n_hidden = N.n_linear - 2;
+  for (int i = tid; i < 128 * kH; i += kThreads) {
+    const int j = i / kH, h = i - j * kH;
+    S.Wt1[j * kLDW1 + h] = N.Wt1[i];
+  }
+  for (int l = 0; l < n_hidden; ++l) {
+    for (int i = tid; i < kH * kH; i += kThreads) S.Wh[l][i] = N.Wth[l][i];
+    if (tid < kH) S.bh[l][tid] = N.bh[l][tid];
+  }
+  if (tid < kH) {
+    S.wt[tid] = N.wt[tid];
+    S.wout[tid] = N.wout[tid];
+  }
+  const float bout = __ldg(N.bout);
+  __syncthreads();
+  {
+    const int col = tid & 63, part = tid >> 6;
+    float acc = 0.f;
+    for (int j = part; j < d; j += 4) acc = fmaf(S.Wt1[j * kLDW1 + col], S.xs[j], acc);
+    S.part[part][col] = acc;
+    __syncthreads();
+    if (tid < kH) S.c0[tid] = N.b1[tid] + S.part[0][tid] + S.part[1][tid] + S.part[2][tid] + S.part[3][tid];
+    __syncthreads();
+  }
+  if (tid < kDirs) S.idx[tid] = tid, S.idx2[tid] = -1;
+  forward_row(S, N, d, t, 0.f, bout, false);
+  jet_tile(S, N, d, true);
+  float* Hp = H + p * (int64_t)d * d;
+  if (tid < d) {
+    S.diag[tid] = S.red[0][tid];
+    Hp[tid * d + tid] = S.red[0][tid];
+  }
+  __syncthreads();
+  const int npairs = d * (d - 1) / 2;
+  for (int q0 = 0; q0 < npairs; q0 += kDirs) {
+    // pair q = (i, j), i < j, enumerated row by row: q = i d - i (i + 1) / 2 + (j - i - 1)
+    int pi = -1, pj = -1;
+    if (tid < kDirs && q0 + tid < npairs) {
+      const int q = q0 + tid;
+      int i = (int)floorf(((2.f * d - 1.f) - sqrtf((2.f * d - 1.f) * (2.f * d - 1.f) - 8.f * (float)q)) * 0.5f);
+      while (i > 0 && i * d - i * (i + 1) / 2 > q) --i;                      // (guards the float estimate)
+      while ((i + 1) * d - (i + 1) * (i + 2) / 2 <= q) ++i;
+      pi = i, pj = q - (i * d - i * (i + 1) / 2) + i + 1;
+    }
+    if (tid < kDirs) S.idx[tid] = pi, S.idx2[tid] = pj;
+    __syncthreads();
+    jet_tile(S, N, min(kDirs, npairs - q0), true);
+    if (tid < kDirs && pi >= 0) {
+      const float hij = 0.5f * (S.red[0][tid] - S.diag[pi] - S.diag[pj]);
+      Hp[pi * d + pj] = hij;
+      Hp[pj * d + pi] = hij;
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace
 
 int launch_gbm_simt(const ProblemDev& P, const MlpDev& N, bool zero_net, const float* tx, int64_t n, int M_I,
@@ -443,6 +517,19 @@ int launch_gbm_simt(const ProblemDev& P, const MlpDev& N, bool zero_net, const f
 }  // namespace dpi
 
 namespace dpi {
+int launch_mlp_hess_full(const ProblemDev& P, const MlpDev& N, const float* tx, int64_t n, float* H, cudaStream_t st) {
+  if (n <= 0) return DPI_OK;
+  if (P.nx > 128 || N.HP != 64 || N.n_linear - 2 > kMaxHidden || N.n_linear < 3 || N.d_pad != 128) {
+    set_error("dpi_net_hessian: needs nx <= 128 and an MLP with 1..%d hidden GEMM layers of width <= 64", kMaxHidden);
+    return DPI_ERR_UNSUPPORTED;
+  }
+  const size_t smem = sizeof(GbmSmem);
+  DPI_CUDA_CHECK(cudaFuncSetAttribute(mlp_hess_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mlp_hess_full_kernel<<<(unsigned)n, kThreads, smem, st>>>(P, N, tx, H);
+  DPI_CUDA_CHECK(cudaGetLastError());
+  return DPI_OK;
+}
+
 int launch_mlp_hess_diag(const ProblemDev& P, const MlpDev& N, const float* tx, int64_t n, float* diag, cudaStream_t st) {
   if (n <= 0) return DPI_OK;
   if (P.nx > 128 || N.HP != 64 || N.n_linear - 2 > kMaxHidden || N.n_linear < 3 || N.d_pad != 128) {

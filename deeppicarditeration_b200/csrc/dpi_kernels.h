@@ -54,6 +54,8 @@ int launch_gbm_simt(const ProblemDev& P, const MlpDev& net, bool zero_net, const
 
 // Hessian diagonal [n, nx] of the MLP at the rows of tx (hidden width <= 64, nx <= 128)
 int launch_mlp_hess_diag(const ProblemDev& P, const MlpDev& net, const float* tx, int64_t n, float* diag, cudaStream_t st);
+// the full Hessian [n][nx][nx] (coordinate and pair directions, polarisation)
+int launch_mlp_hess_full(const ProblemDev& P, const MlpDev& net, const float* tx, int64_t n, float* H, cudaStream_t st);
 
 // same on the tensor cores (dpi_gbm_tc.cu): fp16 jets through the hidden layers, nx <= 127, v <= 127
 int launch_gbm_tc(const ProblemDev& P, const MlpDev& net, const float* tx, int64_t n, int M_I, uint64_t seed, int64_t base,

@@ -237,6 +237,14 @@ class LabelEngine:
                       "dpi_net_hessian_diag")
         return d2
 
+    def net_hessian(self, tx: torch.Tensor) -> torch.Tensor:
+        """The full Hessian of u_k in x at the rows of tx: [n, nx, nx] (dpi_net_hessian)."""
+        tx = _f32c(tx, self.device)
+        H = torch.empty(tx.shape[0], self.nx, self.nx, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            nat.check(self.lib.dpi_net_hessian(self.h, _ptr(tx), tx.shape[0], _ptr(H), self._stream()), "dpi_net_hessian")
+        return H
+
     def launch_count(self) -> int:
         return int(self.lib.dpi_launch_count(self.h))
 

@@ -146,6 +146,12 @@ class GBMEquationComplexExact(SimpleDiffusionEquation):
     def hessian_diagonal(self, t, x):  # diagonal of equations.py:445-450
         return -torch.sin(self._arg(t, x)) @ (self.v * self.w[:, 1:] ** 2).to(x)
 
+    def u_hessian(self, t, x):  # equations.py:445-450: -sum_k v_k sin(a_k) w_k w_k^T, [n, nx, nx]
+        sin_term = -torch.sin(self._arg(t, x))
+        wx = self.w[:, 1:].to(x)
+        weights = self.v.to(x).unsqueeze(-1) * (wx.unsqueeze(2) * wx.unsqueeze(1))
+        return torch.einsum("ij,jkl->ikl", sin_term, weights)
+
     def ffi(self, t, x, u, u_ii):  # equations.py:457-466
         hd = self.hessian_diagonal(t, x)
         src = -self.u_t(t, x) - 0.5 * hd.sum(-1, keepdim=True) - 0.25 * hd.abs().sum(-1, keepdim=True)

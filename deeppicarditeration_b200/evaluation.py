@@ -8,9 +8,12 @@ The reference evaluates every EVAL.FREQ steps on L2_N_POINTS points `t = linspac
     u, grad_x u      dpi_net_eval           value chain + one VJP (plain MLP, PISGradNet closed form, ZeroSolution)
     diag Hess_x u    dpi_net_hessian_diag   forward 2-jets along the coordinate directions (the SDGD kernel's baseline tile)
 
+    Hess_x u         dpi_net_hessian        the same jets along the pairs e_i + e_j (polarisation): all d x d entries
+
 and the metrics are the reference's, name for name (MSE, rRMSE, rMAE, MArE, and the *g / *h variants computed per
-dimension and then averaged, picard/utils.py:405-474).  The Hessian metrics cover the DIAGONAL (what the SDGD label path
-itself consumes); the reference's TEST_HESSIAN compares all d x d entries.
+dimension / per Hessian entry and then averaged, picard/utils.py:405-474).  With TEST_HESSIAN the *h metrics compare
+all d x d entries against `equation.u_hessian` like upstream (picard/utils.py:198-200,461-470); an equation that only
+offers `hessian_diagonal` is compared on the diagonal.
 
 Exact solutions and the point sampler are the host mirror's torch code (equations.py): evaluation is not the hot path.
 """
@@ -45,8 +48,12 @@ def compute_at_t(engine: LabelEngine, t: torch.Tensor, equation, maximal_batch_s
             outs["g"].append(du.double())
             outs["ge"].append(eq.u_x(tb.double(), xb.double()))
         if eval_hessian:
-            outs["h"].append(engine.net_hessian_diag(tx).double())
-            outs["he"].append(eq.hessian_diagonal(tb.double(), xb.double()))
+            if hasattr(eq, "u_hessian"):  # the reference's comparison: every entry of the Hessian
+                outs["h"].append(engine.net_hessian(tx).double())
+                outs["he"].append(eq.u_hessian(tb.double(), xb.double()))
+            else:
+                outs["h"].append(engine.net_hessian_diag(tx).double())
+                outs["he"].append(eq.hessian_diagonal(tb.double(), xb.double()))
     cat = lambda k: torch.cat(outs[k]).cpu().numpy() if outs[k] else None
     return cat("u"), cat("ue"), cat("g"), cat("ge"), cat("h"), cat("he")
 
@@ -84,7 +91,7 @@ class EvalCallback:
         self.eval_gradient = bool(get("TEST_GRAD", False))
         self.eval_hessian = bool(get("TEST_HESSIAN", False))
         self.equation, self.writer, self.iter, self.seed = equation, writer, iter, seed
-        if self.eval_hessian and not hasattr(equation, "hessian_diagonal"):
+        if self.eval_hessian and not (hasattr(equation, "u_hessian") or hasattr(equation, "hessian_diagonal")):
             raise NotImplementedError(f"{type(equation).__name__} has no exact Hessian diagonal to compare against")
 
     def __call__(self, engine: LabelEngine) -> Dict[str, float]:

@@ -195,6 +195,10 @@ int dpi_net_eval(dpi_handle* h, const float* tx, int64_t n, float* u, float* du,
  * directions, the construction the SDGD label kernel uses).  For the evaluation callback's Hessian metric
  * (picard/utils.py:329-478 with get_hessian :579-591, restricted to the diagonal).  Plain MLPs, hidden width <= 64. */
 int dpi_net_hessian_diag(dpi_handle* h, const float* tx, int64_t n, float* d2u, void* stream);
+/* The full Hessian of u_k in x at the rows of tx: d2u [n, nx, nx] (symmetric), what EvalCallback's TEST_HESSIAN compares
+ * (picard/utils.py:198-200, get_hessian :579-591: nx backward passes upstream; here forward 2-jets along the
+ * coordinate directions and the pairs e_i + e_j).  Plain MLPs of the fully nonlinear config's shape. */
+int dpi_net_hessian(dpi_handle* h, const float* tx, int64_t n, float* d2u, void* stream);
 
 /* ---- regression step (the trainer's inner loop) -------------------------------------------
  *   dpi_train_init  <- PicardSolutionGradientWrapper.__init__ + configure_optimizers   picard/solution_jac.py:125-146,

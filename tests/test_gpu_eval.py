@@ -38,6 +38,28 @@ def test_hessian_diagonal_matches_oracle_jets():
     e.close()
 
 
+def test_full_hessian_matches_autograd():
+    """dpi_net_hessian (2-jets along e_i and e_i + e_j, polarisation) vs the fp64 Hessian of the same MLP by autograd --
+    what the reference's get_hessian computes with d backward passes (picard/utils.py:579-591)."""
+    from tests.gpu_util import engine_for
+    g = Golden("gbm_100d_mlp64_sdgd")
+    for nx, hidden in ((100, [64] * 3), (17, [48, 32])):
+        net = orc.make_mlp(1 + nx, hidden, seed=43, gain=1.6)
+        eq = g.eq if nx == 100 else orc.Cha(nx, 1.0, 2.0, 1.0)
+        e = engine_for(eq, net, nx if nx == 100 else 0)
+        gen = torch.Generator().manual_seed(4)
+        n = 9
+        tx = torch.cat([torch.rand(n, 1, generator=gen, dtype=torch.float64),
+                        torch.randn(n, nx, generator=gen, dtype=torch.float64)], 1).float().double()
+        H = e.net_hessian(tx).double().cpu()
+        assert tuple(H.shape) == (n, nx, nx) and torch.equal(H, H.transpose(1, 2))
+        ref = torch.stack([torch.autograd.functional.hessian(lambda v: net.forward(v.unsqueeze(0)).sum(), tx[i])[1:, 1:]
+                           for i in range(n)])
+        assert orc.rel_l2(H, ref) < 1e-4
+        assert orc.rel_l2(torch.diagonal(H, dim1=1, dim2=2), e.net_hessian_diag(tx).double().cpu()) < 1e-6
+        e.close()
+
+
 def test_eval_callback_metrics_match_a_host_restatement():
     """EvalCallback on the label kernels (value, gradient, Hessian diagonal) vs the same metrics computed on the host
     from the oracle network with autograd, on the callback's own points (utils.py:362-474)."""
@@ -65,6 +87,11 @@ def test_eval_callback_metrics_match_a_host_restatement():
     t = torch.linspace(0.0, 1.0, 500, device="cuda").reshape(-1, 1)
     u, ue, gx, gxe, hx, hxe = compute_at_t(e, t, eq, 200, True, True, gen)
     assert abs(error_metrics(u, ue, gx, gxe, hx, hxe)["rRMSE"] - m["rRMSE"]) < 1e-12
+    assert hx.shape == (500, 100, 100) and hxe.shape == (500, 100, 100)  # TEST_HESSIAN compares ALL entries, as upstream
+    # the *h block is the reference's arithmetic on those arrays (picard/utils.py:461-470)
+    err = np.abs(hx - hxe)
+    assert abs(m["rRMSEh"] - float((np.sqrt((err ** 2).sum(0)) / np.sqrt((hxe ** 2).sum(0))).mean())) < 1e-12
+    assert abs(m["MSEh"] - float(np.sqrt((err ** 2).mean(0)).mean())) < 1e-12
     # network side of those arrays vs autograd of the oracle net at the same points is covered by the net_eval tests;
     # here: the exact side must be the closed forms of equations.py
     # (MArE divides by |u_exact|, which is 0 at the point t = 0, x = 0 of the linspace grid: inf there, as upstream)

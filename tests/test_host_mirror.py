@@ -75,6 +75,12 @@ def test_gbm_and_ou_mirror_match_oracle():
     uii = torch.randn(x.shape[0], 7, dtype=torch.float64)
     assert torch.allclose(e.ffi(t, x, None, uii), g.eq.ffi(t, x, None, uii), rtol=1e-9, atol=1e-12)
     assert e.supported_approximate_methods == ("SDGD",) and e.has_hessian_term
+    # exact Hessian (equations.py:445-450) against autograd of the exact solution; its diagonal is hessian_diagonal
+    Hx = e.u_hessian(t[:3], x[:3])
+    for i in range(3):
+        ref = torch.autograd.functional.hessian(lambda v: e.exact_solution(t[i:i + 1], v.unsqueeze(0)).sum(), x[i])
+        assert torch.allclose(Hx[i], ref, rtol=1e-9, atol=1e-12)
+    assert torch.allclose(torch.diagonal(Hx, dim1=1, dim2=2), e.hessian_diagonal(t[:3], x[:3]), rtol=1e-12)
     h = Golden("hjb_100d_zero")
     var = torch.diag_embed(h.eq.diagvar)
     o = eqs.OUProcessEquation(nx=100, T=1.0, num_components=5, mean=h.eq.mean, var=var, pi=h.eq.pi)
