@@ -154,3 +154,23 @@ def test_gbm_and_hjb_zero_network_iterations_are_shard_invariant():
         y_b = torch.cat([e.label_gen(tx[:13], 256, 256, seed=8), e.label_gen(tx[13:], 256, 256, seed=8, point_index_base=13)])
         assert torch.equal(y, y_b) and torch.isfinite(y).all()
         e.close()
+
+
+def test_hjb_narrow_network_with_a_single_integral_sample():
+    """PISGradNet path at the constructor default n_estimate_integral = 1 with a narrow nn_module: the MC reduction's
+    slice partials live in their own scratch (they used to overrun the activation buffer when
+    8 (1 + d) > (M_I + 1) hmax); checked against the oracle on replayed draws, fp32 and tf32."""
+    from tests.golden_util import Golden
+    from tests.gpu_util import draws_dict
+    g = Golden("hjb_100d_pisgrad")
+    net = orc.make_pisgrad(100, [64, 64], T=1.0, seed=5, phase_scale=0.3)
+    e = _eng(g.eq, net)
+    gen = torch.Generator().manual_seed(8)
+    for M_T, M_I, n in ((7, 1, 9), (3, 2, 33)):
+        d = orc.draw(g.eq, n, M_T, M_I, None, gen, round_fp32=True)
+        tx = orc.sample_tx(g.eq, d)
+        ref = orc.generate_with_gradients(g.eq, net, tx, d, M_T, M_I)
+        for prec, tol in (("fp32", 1e-4), ("tf32", 1e-2)):
+            y = e.label_gen(tx, M_T, M_I, precision=prec, draws=draws_dict(d)).double().cpu()
+            assert torch.isfinite(y).all() and orc.rel_l2(y, ref) < tol, (prec, M_T, M_I, orc.rel_l2(y, ref))
+    e.close()
