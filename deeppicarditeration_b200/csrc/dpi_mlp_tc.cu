@@ -1,4 +1,5 @@
-// 16-bit (fp16 operands, fp32 accumulation) tcgen05 integral estimator for the Burgers-type equation `Cha` (u_k = MLP [1+d,128,128,128,128,1], d <= 128).
+// 16-bit (fp16 operands, fp16 accumulators in TMEM; fp32 accumulators for the chunked first layer of d > 128) tcgen05
+// integral estimator for the Burgers-type equation `Cha` (u_k = MLP [1+d,128,128,128,128,1], d <= 1024).
 //
 // Same mathematics as dpi_mlp_simt.cu (picard/data.py:471-527,350-366,1226-1325; equations.py:297-302;
 // solution.py:123-135) with the first-layer GEMM and the three hidden 128x128 GEMMs (value and tangent) on the
@@ -11,14 +12,15 @@
 //     each slot owns an hV and an hT buffer (value rows / tangent rows of the next A operand, 2 x 32 KB).  For layer 1
 //     the slot's hV holds the increments Z (A operand) and its hT receives the W1 image (B operand) by TMA bulk copy
 //     from L2 for every tile -- that is what makes room for the second tile in 227 KB;
-//   * TMEM: 512 columns = 2 slots x (value 128 + tangent 128) fp32 accumulator columns;
+//   * TMEM: 512 columns = 2 slots x (value 128 + tangent 128) accumulator columns (fp16 accumulators keep one half per
+//     32-bit cell and are read back two columns per register, tcgen05.ld ... .pack::16b: no conversions in the epilogue);
 //   * 8 producer warps draw the Brownian increments with Philox4x32-10 + Box-Muller in registers, round them to fp16,
 //     store the [128 x d] A-operand tile when the slot frees up, and KEEP them in registers: once the tile's Bismut
 //     coefficients are known they accumulate G_j += coef_m Z_mj there, so increments never leave the SM;
 //   * one thread issues tcgen05.mma for both slots in a fixed round-robin order (one issuing warp per slot was
 //     measured 5 % slower), one thread issues the TMA copies and pulls the CTA's next work unit from a global counter;
-//   * 4 epilogue warps per slot (thread = sample row) read the accumulators with tcgen05.ld, apply bias/ELU/ELU' in
-//     packed fp16x2 arithmetic (two columns per instruction; its absolute error stays below the rounding of the
+//   * 8 epilogue warps (thread = sample row x column half) serve both slots in turn: they read the accumulators with
+//     tcgen05.ld, apply bias/ELU/ELU' in packed fp16x2 arithmetic (two columns per instruction; its absolute error stays below the rounding of the
 //     16-bit operands it produces) and write the next layer's A operands straight into the swizzled shared-memory
 //     layout; the last layer is a dot product in the epilogue, followed by f, the Bismut coefficient and the
 //     value-label partial sum in fp32.
@@ -40,7 +42,7 @@ namespace {
 using namespace tc;
 
 // ---- roles ---------------------------------------------------------------------------------------------------
-// warps 0-3: epilogue of tile slot 0, warps 4-7: epilogue of tile slot 1 (warp & 3 = TMEM lane quarter),
+// warps 0-7: epilogue (warp & 3 = TMEM lane quarter, warp >> 2 = column half; both tile slots alternately),
 // warps 8-15: increment producers, warp 16: MMA issuer (one thread), warp 17: TMA issuer (one thread) and unit
 // hand-out, warps 18-19: idle.
 // The register file is per SM sub-partition (512 registers per lane, warp w lives on sub-partition w % 4), so each
