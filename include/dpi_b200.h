@@ -57,7 +57,10 @@ typedef enum {
 typedef enum { DPI_EQ_CHA = 0, DPI_EQ_GBM = 1, DPI_EQ_OU = 2 } dpi_equation_kind;
 typedef enum { DPI_NET_ZERO = 0, DPI_NET_MLP = 1, DPI_NET_PISGRAD = 2 } dpi_network_kind;
 /* arithmetic of the u_k GEMM chain: fp32 FMA (labels within 1e-4 rel of the fp64 reference) or the 16-bit tcgen05
- * tensor-core path with fp32 accumulation (within 1e-2 rel; measured 6e-5).  The tensor-core operands are IEEE fp16,
+ * tensor-core path (within 1e-2 rel; measured 6e-5).  Accumulation: the Cha and GBM kernels keep fp16 accumulators in
+ * TMEM for their hidden layers (K <= 128 per sum: 4.4e-4 from an fp32-accumulated product, against 2.8e-4 for the
+ * rounding to fp16 that the next layer's operand needs anyway), fp32 for first layers that sum over more than 128
+ * inputs and everywhere in the PISGradNet kernel.  The tensor-core operands are IEEE fp16,
  * not bf16: three more mantissa bits at the same operand width, and the bias/ELU/ELU' epilogue runs in packed
  * fp16x2.  Its range limit is |log2(e) x pre-activation| < 6.5e4, far above anything a trained u_k produces; a network
  * that does leave it yields inf / NaN, which the label kernels' final pass records in a status word:
