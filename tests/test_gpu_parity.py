@@ -344,3 +344,20 @@ def test_td_estimators_philox_mode_and_generator_keyword():
     with pytest.raises(Exception):
         eg.label_gen(gg.tx, 8, 8, estimate_delta_t=0.2)
     eg.close()
+
+
+def test_td_estimators_on_the_fused_pisgradnet_kernel():
+    """ESTIMATE_DELTA_T on the fused fp16 PISGradNet kernel (its horizon comes from the same helper as every other
+    estimator kernel): same Philox draws, fp32 pipeline as the reference; both branches of t_next present."""
+    from tests.gpu_util import engine_for
+    g = Golden("hjb_100d_pisgrad")
+    net = orc.make_pisgrad(100, [128, 128], T=1.0, seed=9, phase_scale=0.3)
+    e = engine_for(g.eq, net)
+    tx = e.sample_tx(40, seed=2)
+    assert bool((tx[:, 0] + 0.3 < 1.0).any()) and bool((tx[:, 0] + 0.3 >= 1.0).any())
+    y32 = e.label_gen(tx, 256, 512, precision="fp32", seed=4, estimate_delta_t=0.3).double().cpu()
+    y16 = e.label_gen(tx, 256, 512, precision="f16", seed=4, estimate_delta_t=0.3).double().cpu()
+    y0 = e.label_gen(tx, 256, 512, precision="f16", seed=4).double().cpu()
+    assert torch.isfinite(y16).all() and orc.rel_l2(y16, y32) < 1e-2
+    assert orc.rel_l2(y0, y32) > 1e-2  # (the TD labels differ from the plain ones: the keyword reaches the kernel)
+    e.close()
