@@ -278,3 +278,27 @@ def test_describe_accepts_live_reference_objects():
     mlp = rsol.construct_mlp(101, 1, [128] * 4, ["ELU"] * 4, None)
     assert sol.describe_solution(mlp)["kind"] == "mlp"
     assert sol.describe_solution(rsol.ZeroSolution())["kind"] == "zero"
+
+
+def test_ctypes_structures_match_the_c_header_layout(tmp_path):
+    """sizeof / offsetof of every structure that crosses the C ABI, as gcc lays out include/dpi_b200.h, against the
+    ctypes mirrors in _native.py (a silent mismatch would shift every field after it)."""
+    import ctypes as C
+    import subprocess
+    structs = {"dpi_linear": nat.dpi_linear, "dpi_network": nat.dpi_network, "dpi_problem": nat.dpi_problem,
+               "dpi_draws": nat.dpi_draws, "dpi_label_config": nat.dpi_label_config, "dpi_train_config": nat.dpi_train_config}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "dpi_b200.h"', 'int main(void) {']
+    for name, cls in structs.items():
+        lines.append(f'  printf("{name} %zu\\n", sizeof({name}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{name}.{fname} %zu\\n", offsetof({name}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for name, cls in structs.items():
+        assert int(got[name]) == C.sizeof(cls), name
+        for fname, _ in cls._fields_:
+            assert int(got[f"{name}.{fname}"]) == getattr(cls, fname).offset, f"{name}.{fname}"
