@@ -21,6 +21,7 @@ label kernels; it is not a kernel of this repository and is not counted as one.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import torch
@@ -159,6 +160,9 @@ class AutogradRegressionTrainer:
         if scaler not in (None, "FixedLossScaler", "SimpleLossScaler", "DimensionLossScaler"):
             raise NotImplementedError(f"loss scaler {scaler}")
         self.solution, self.device = solution, torch.device(device)
+        eq = getattr(solution, "equation", None)
+        if eq is not None and hasattr(eq, "to"):
+            eq.to(self.device)  # PISGradNet's residual g0 = equation.g reads the equation's tensors on every forward
         self.lr, self.betas, self.eps = lr, betas, eps
         self.beta, self.scaler, self.fixed_weight = float(loss_beta), scaler or "FixedLossScaler", float(fixed_weight)
         self.pg = process_group
@@ -171,8 +175,17 @@ class AutogradRegressionTrainer:
         return d.get_world_size(self.pg) if d.is_available() and d.is_initialized() else 1
 
     def reset_optimizer(self):
-        self.opt = torch.optim.Adam([p for p in self.solution.parameters() if p.requires_grad], lr=self.lr,
-                                    betas=self.betas, eps=self.eps)
+        """Fresh Adam state, weights kept.  Once a step graph has been captured the state is cleared IN PLACE (the graph
+        holds the state tensors), otherwise a new optimiser is built."""
+        if getattr(self, "_graph", None) is not None:
+            for st in self.opt.state.values():
+                for v in st.values():
+                    if torch.is_tensor(v):
+                        v.zero_()
+        else:
+            params = [p for p in self.solution.parameters() if p.requires_grad]
+            cuda = self.device.type == "cuda"
+            self.opt = torch.optim.Adam(params, lr=self.lr, betas=self.betas, eps=self.eps, capturable=cuda)
         self.step_count = 0
 
     def loss_terms(self, tx: torch.Tensor, y: torch.Tensor):
@@ -213,12 +226,40 @@ class AutogradRegressionTrainer:
         self.losses = torch.stack([total.detach().sum(), v.detach().sum(), g.detach().sum()]).float()
         return self.losses
 
+    def _capture(self, tx: torch.Tensor, y: torch.Tensor) -> None:
+        """One optimiser step (loss, double backward, Adam) as a CUDA graph on static batch buffers: the step is a few
+        hundred small autograd kernels, launch-bound when run eagerly."""
+        self._gtx, self._gy = tx.clone(), y.clone()
+        self._graph = torch.cuda.CUDAGraph()
+        self.opt.zero_grad(set_to_none=True)
+        with torch.cuda.graph(self._graph):
+            total, v, g = self.loss_terms(self._gtx, self._gy)
+            total.sum().backward()
+            self.opt.step()
+            self._glosses = torch.stack([total.detach().sum(), v.detach().sum(), g.detach().sum()]).float()
+
     def fit(self, tx: torch.Tensor, y: torch.Tensor, batch_size: int, n_epochs: int) -> Optional[torch.Tensor]:
         last = None
+        n = tx.shape[0]
+        graphable = (self.device.type == "cuda" and self._world() == 1 and n % batch_size == 0
+                     and os.environ.get("DPI_AUTOGRAD_NO_GRAPH") is None)
+        p0 = next(self.solution.parameters())
         for _ in range(n_epochs):
-            for i in range(0, tx.shape[0], batch_size):
-                last = self.step(tx[i:i + batch_size], y[i:i + batch_size])
+            for i in range(0, n, batch_size):
+                xb, yb = tx[i:i + batch_size], y[i:i + batch_size]
+                g = getattr(self, "_graph", None)
+                if graphable and g is not None and tuple(self._gtx.shape) == tuple(xb.shape):
+                    self._gtx.copy_(xb)
+                    self._gy.copy_(yb)
+                    g.replay()
+                    self.step_count += 1
+                    last = self.losses = self._glosses
+                    continue
+                last = self.step(xb, yb)
+                if graphable and g is None and self.step_count >= 3:  # three eager steps first (allocator / autotune warm-up)
+                    torch.cuda.synchronize(self.device)
+                    self._capture(xb.to(self.device, p0.dtype), yb.to(self.device, p0.dtype))
         return last
 
     def close(self):
-        pass
+        self._graph = None

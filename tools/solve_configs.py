@@ -91,9 +91,8 @@ def instance_files(name, d):
 
 
 def main():
-    args = [a for a in sys.argv[1:] if not a.startswith("--")]
-    names = args or ["burgers", "hjb", "gbm"]
     n_it = int(sys.argv[sys.argv.index("--iterations") + 1]) if "--iterations" in sys.argv else None
+    names = [a for a in sys.argv[1:] if a in CFG] or ["burgers", "hjb", "gbm"]
     from deeppicarditeration_b200.main import train
     out_dir = os.path.join(ROOT, "gpurun_out")
     os.makedirs(out_dir, exist_ok=True)
