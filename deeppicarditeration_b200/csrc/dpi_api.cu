@@ -786,7 +786,6 @@ static int label_gen_body(dpi_handle* h, const float* tx, int64_t n, const dpi_l
       const int64_t pf = hjb_tc_part_floats(n, cfg->M_I, P.nx);
       if (pf > h->hjb_part_floats) {
         if (h->hjb_part) cudaFree(h->hjb_part);
-  if (h->td_scratch) cudaFree(h->td_scratch);
         h->hjb_part = nullptr, h->hjb_part_floats = 0;
         DPI_CUDA_CHECK(cudaMalloc((void**)&h->hjb_part, sizeof(float) * pf));
         h->hjb_part_floats = pf;
