@@ -62,6 +62,16 @@ WORKLOADS = {
 }
 
 
+# what "dtype" stands for on each tensor-core path (include/dpi_b200.h; labels stay within the 16-bit tolerance 1e-2 of
+# the fp64 oracle, measured 6e-6 .. 3e-4 at these sizes: tests/test_gpu_baseline_sizes.py)
+ARITHMETIC = {
+    ("Cha", "f16"): "fp16 operands; fp16 accumulators in TMEM for the 128-wide layers (fp32 for a chunked first layer, "
+                    "d > 128); packed fp16 ELU epilogue; f, Bismut sums and MC means in fp32",
+    ("GBM", "f16"): "fp16 2-jet operands, fp16 accumulators in TMEM; value chain, f and MC sums in fp32",
+    ("OU", "f16"): "fp16 operands, fp32 accumulators in TMEM; packed fp16 ELU epilogue; F, Bismut sums and MC means in fp32",
+}
+
+
 def flops_per_point(wl, M_I: int) -> float:
     """F_point = (M_I + 1) * F_row, 2 flops per MAC, un-padded dims.
     Cha: forward + one tangent (the first-layer tangent along a fixed direction is a constant vector: 0 flops);
@@ -386,6 +396,7 @@ def run_b200(args, wl):
                 "rng": "on-device Philox4x32-10 keyed by global point index",
                 "l2": "256 MiB buffer written between timed iterations",
                 "weights": "nn.Linear default init, seed 0",
+                "arithmetic": ARITHMETIC.get((wl["eq"], dt), dt),
                 "instance": "Cha closed form" if wl["eq"] == "Cha" else "reference's shipped tensors (tests/golden fixture)"})
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": args.warmup,

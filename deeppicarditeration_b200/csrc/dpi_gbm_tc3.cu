@@ -12,7 +12,9 @@
 //     reduction (32 inputs of layer 1, 16 of every hidden layer), two path rows at a time, partial sums combined by two
 //     shuffles; what it reads from shared memory are broadcast 16-byte loads of the increments / activations;
 //   * the source term of the exact solution moved to three warps of its own (one row each, round robin);
-//   * FOUR path rows in flight on the jet team (TMEM 4 x 128 columns) instead of two.
+//   * FOUR path rows in flight on the jet team (TMEM 4 x 128 columns) instead of two;
+//   * fp16 ACCUMULATORS (one half per TMEM cell, read back two columns per register): the jet team converts nothing,
+//     and ELU' / ELU'' of a unit travel in one fp16 (+1 or -e^z) instead of two vectors.
 // One CTA per collocation point, rows in a fixed order: labels do not depend on the launch geometry.
 #include <cstdio>
 
