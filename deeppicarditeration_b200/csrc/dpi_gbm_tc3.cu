@@ -370,6 +370,9 @@ gbm_tc3_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ Mlp
 #pragma unroll
     for (int i = 0; i < 16; ++i)
       w1r[i] = (row < d) ? pack_f16x2(N.Wt1[row * kH + hf * 32 + 2 * i], N.Wt1[row * kH + hf * 32 + 2 * i + 1]) : 0u;
+    uint32_t w2r[16];  // their squares (the first-layer ddh = ELU'' w^2)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) w2r[i] = h2_mul(w1r[i], w1r[i]);
     uint32_t woh[16];  // the output weights of this warp's columns
 #pragma unroll
     for (int i = 0; i < 16; ++i) woh[i] = pack_f16x2(N.wout[hf * 32 + 2 * i], N.wout[hf * 32 + 2 * i + 1]);
@@ -399,8 +402,8 @@ gbm_tc3_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ Mlp
           const uint4 e2 = make_uint4(h2_negrelu(es.x), h2_negrelu(es.y), h2_negrelu(es.z), h2_negrelu(es.w));
           const uint32_t* w = &w1r[4 * c8];
           const uint4 wd = make_uint4(h2_mul(e1.x, w[0]), h2_mul(e1.y, w[1]), h2_mul(e1.z, w[2]), h2_mul(e1.w, w[3]));
-          const uint4 wdd = make_uint4(h2_mul(h2_mul(e2.x, w[0]), w[0]), h2_mul(h2_mul(e2.y, w[1]), w[1]),
-                                       h2_mul(h2_mul(e2.z, w[2]), w[2]), h2_mul(h2_mul(e2.w, w[3]), w[3]));
+          const uint32_t* w2 = &w2r[4 * c8];
+          const uint4 wdd = make_uint4(h2_mul(e2.x, w2[0]), h2_mul(e2.y, w2[1]), h2_mul(e2.z, w2[2]), h2_mul(e2.w, w2[3]));
           sts128(poff[c8] + sSlot, wd.x, wd.y, wd.z, wd.w);
           sts128(poff[c8] + sSlot + kOpBytes, wdd.x, wdd.y, wdd.z, wdd.w);
         }
