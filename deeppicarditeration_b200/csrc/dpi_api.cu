@@ -404,7 +404,9 @@ int dpi_set_network(dpi_handle* h, const dpi_network* net, void* stream) {
     MlpDev M{};
     M.n_linear = L;
     M.nx = nx;
-    M.HP = maxw <= 64 ? 64 : 128;
+    // five-layer Cha networks keep the 128-wide layout whatever their widths: the tensor-core path (tc_pack_network)
+    // pads narrower layers with zeros and reads the baseline pass's per-point rows with that stride
+    M.HP = (maxw <= 64 && !(L == 5 && h->P.eq == DPI_EQ_CHA)) ? 64 : 128;
     M.d_pad = round_up(nx, 128);
     float *Wt1, *wt, *b1, *wsum, *wout, *bout;
     float* Wth[DPI_MAX_LINEAR] = {nullptr};

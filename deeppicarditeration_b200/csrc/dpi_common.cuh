@@ -60,10 +60,15 @@ __device__ __forceinline__ uint4 philox_round(uint4 c, uint32_t kx, uint32_t ky)
   const uint64_t p0 = (uint64_t)M0 * c.x, p1 = (uint64_t)M1 * c.z;
   return make_uint4((uint32_t)(p1 >> 32) ^ c.y ^ kx, (uint32_t)p1, (uint32_t)(p0 >> 32) ^ c.w ^ ky, (uint32_t)p0);
 }
+// Rounds of the bijection.  10 is the Random123 / cuRAND default; DPI_PHILOX_ROUNDS exists for sensitivity builds
+// (tools/variants.py), nothing shipped changes it.
+#ifndef DPI_PHILOX_ROUNDS
+#define DPI_PHILOX_ROUNDS 10
+#endif
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
   constexpr uint32_t W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < DPI_PHILOX_ROUNDS; ++r) {
     c = philox_round(c, k.x, k.y);
     k.x += W0;
     k.y += W1;
@@ -87,7 +92,7 @@ inline PhiloxKeys make_philox_keys(uint64_t seed) {
 }
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, const PhiloxKeys& K) {
 #pragma unroll
-  for (int r = 0; r < 10; ++r) c = philox_round(c, K.kx[r], K.ky[r]);
+  for (int r = 0; r < DPI_PHILOX_ROUNDS; ++r) c = philox_round(c, K.kx[r], K.ky[r]);
   return c;
 }
 

@@ -723,20 +723,28 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
         if (pw < nch && 8 * oct < d) {
           const float* cf_s = coef_s + cbuf * 128u;
           const uint4* zr = zring + ((size_t)(jt & 3u) * nch + pw) * 2048 + bo;
-#pragma unroll 4
-          for (int i = 0; i < 64; ++i) {
-            const int rr = rh + 2 * i;
-            const float cf = cf_s[rr];
-            const uint4 z = __ldcg(zr + rr * 16);
-            const float2 p0 = h2_unpack(z.x), p1 = h2_unpack(z.y), p2 = h2_unpack(z.z), p3 = h2_unpack(z.w);
-            Ga.x = fmaf(cf, p0.x, Ga.x);
-            Ga.y = fmaf(cf, p0.y, Ga.y);
-            Ga.z = fmaf(cf, p1.x, Ga.z);
-            Ga.w = fmaf(cf, p1.y, Ga.w);
-            Gb.x = fmaf(cf, p2.x, Gb.x);
-            Gb.y = fmaf(cf, p2.y, Gb.y);
-            Gb.z = fmaf(cf, p3.x, Gb.z);
-            Gb.w = fmaf(cf, p3.y, Gb.w);
+          // The ring is larger than L2 (4 tiles x nch x 32 KB per CTA), so a read-back is a DRAM round trip: kBisBatch
+          // independent 16-byte loads are issued before the first is consumed (4 in flight made the read-back half of
+          // the producers' time in ncu's stall samples), on top of the L2 prefetch issued a tile earlier.
+          constexpr int kBisBatch = 16;
+          for (int i0 = 0; i0 < 64; i0 += kBisBatch) {
+            uint4 zb[kBisBatch];
+#pragma unroll
+            for (int i = 0; i < kBisBatch; ++i) zb[i] = __ldcg(zr + (rh + 2 * (i0 + i)) * 16);
+#pragma unroll
+            for (int i = 0; i < kBisBatch; ++i) {
+              const float cf = cf_s[rh + 2 * (i0 + i)];
+              const uint4 z = zb[i];
+              const float2 p0 = h2_unpack(z.x), p1 = h2_unpack(z.y), p2 = h2_unpack(z.z), p3 = h2_unpack(z.w);
+              Ga.x = fmaf(cf, p0.x, Ga.x);
+              Ga.y = fmaf(cf, p0.y, Ga.y);
+              Ga.z = fmaf(cf, p1.x, Ga.z);
+              Ga.w = fmaf(cf, p1.y, Ga.w);
+              Gb.x = fmaf(cf, p2.x, Gb.x);
+              Gb.y = fmaf(cf, p2.y, Gb.y);
+              Gb.z = fmaf(cf, p3.x, Gb.z);
+              Gb.w = fmaf(cf, p3.y, Gb.w);
+            }
           }
         }
         (void)mt0;
@@ -761,6 +769,15 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
           const int s = tl & 1;
           const uint32_t bit = 1u << s;
           uint8_t* const zdst = smem + kOffSlot + (uint32_t)s * kSlotBytes;
+#ifndef DPI_MULTI_NO_PREFETCH
+          if (pending == 2 && pw < nch) {
+            // the chunk this warp sums once this tile is generated (32 KB, contiguous): pull it towards L2 now
+            const char* pf = reinterpret_cast<const char*>(zring + ((size_t)(j2 & 3u) * nch + pw) * 2048);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + (size_t)(lane + 32 * i) * 128));
+          }
+#endif
           for (int cch = 0; cch < nch; ++cch) {
             const int oct = 16 * cch + o;
             const bool col_ok = 8 * oct < d;
@@ -1109,19 +1126,24 @@ int tc_pack_network(const dpi_network& net, const ProblemDev& P, const MlpDev& M
                     TcNetDev* out, bool* ready, int64_t* launches, cudaStream_t st) {
   *ready = false;
   const int L = net.n_main;
-  if (L != 5 || P.nx > 1024) return DPI_OK;  // this kernel: Linear(1+d,128), 3 x Linear(128,128), Linear(128,1)
+  // this kernel: Linear(1+d,H1), Linear(H1,H2), Linear(H2,H3), Linear(H3,H4), Linear(H4,1) with every H_l <= 128.
+  // Narrower layers are zero-padded to the 128 x 128 operand images: a padded unit has zero weights and bias, so its
+  // activation, ELU' * tangent and output weight are all exactly zero.  (M.HP == 128 is what the baseline pass and the
+  // per-point c0 rows are laid out for; dpi_set_network picks it for every five-layer Cha network.)
+  if (L != 5 || P.nx > 1024 || M.HP != 128) return DPI_OK;
   const int nch = (P.nx + 127) / 128;        // first-layer K chunks of 128 input dims
   for (int l = 0; l < L - 1; ++l)
-    if (net.main[l].n_out != 128) return DPI_OK;
+    if (net.main[l].n_out > 128) return DPI_OK;
   void* img = nullptr;
   DPI_CUDA_CHECK(cudaMalloc(&img, (size_t)(nch + 3) * tc::kOperandBytes));
   owner.push_back(img);
   uint8_t* base = reinterpret_cast<uint8_t*>(img);
   for (int cch = 0; cch < nch; ++cch)  // W1 x-columns [128 cch, 128 cch + 128)
-    pack_sw128_kernel<<<64, 256, 0, st>>>(net.main[0].W, 1 + P.nx, 1 + 128 * cch, 128, std::min(128, P.nx - 128 * cch),
-                                          base + (size_t)cch * tc::kOperandBytes);
+    pack_sw128_kernel<<<64, 256, 0, st>>>(net.main[0].W, 1 + P.nx, 1 + 128 * cch, net.main[0].n_out,
+                                          std::min(128, P.nx - 128 * cch), base + (size_t)cch * tc::kOperandBytes);
   for (int l = 1; l <= 3; ++l)
-    pack_sw128_kernel<<<64, 256, 0, st>>>(net.main[l].W, 128, 0, 128, 128, base + (size_t)(nch - 1 + l) * tc::kOperandBytes);
+    pack_sw128_kernel<<<64, 256, 0, st>>>(net.main[l].W, net.main[l].n_in, 0, net.main[l].n_out, net.main[l].n_in,
+                                          base + (size_t)(nch - 1 + l) * tc::kOperandBytes);
   DPI_CUDA_CHECK(cudaGetLastError());
   *launches += nch + 3;
   // per-column fp32 constants travel as kernel parameters (constant bank): copy the packed vectors back once

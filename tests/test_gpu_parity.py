@@ -293,6 +293,34 @@ def test_bf16_shard_invariance_and_determinism():
     e.close()
 
 
+@pytest.mark.parametrize("nx,hidden", [(100, [96, 64, 128, 32]), (37, [64, 64, 64, 64]), (200, [120, 128, 72, 8])])
+def test_tensor_core_path_takes_narrower_hidden_layers(nx, hidden):
+    """The tcgen05 kernel is written for 128-wide operand images; hidden layers narrower than that are zero-padded at
+    dpi_set_network (a padded unit contributes exactly zero), so four-hidden-layer networks of any widths <= 128 take
+    the 16-bit path.  Checked against the pinned oracle in deterministic mode and against the fp32 kernel on the same
+    Philox draws."""
+    from tests.gpu_util import draws_dict, engine_for
+    eq = orc.Cha(nx, 1.0, 5.0, 1.0)
+    net = orc.make_mlp(1 + nx, hidden, seed=11, gain=1.5)
+    n, M_T, M_I = 5, 64, 300
+    d = orc.draw(eq, n, M_T, M_I, None, torch.Generator().manual_seed(7), round_fp32=True)
+    tx = orc.sample_tx(eq, d).float().double()
+    yT = orc.estimate_terminal_with_gradients(eq, tx, d.zT, M_T)
+    y_ref = (yT + orc.estimate_integral_with_gradients(eq, net, tx, d.u_s, d.zS, d.idx, M_I, mode="closed")).detach()
+    e = engine_for(eq, net)
+    y16 = e.label_gen(tx, M_T, M_I, precision="f16", draws=draws_dict(d), check=True).double().cpu()
+    assert orc.rel_l2(y16, y_ref) < TOL_BF16
+    assert orc.rel_l2(y16 - yT, y_ref - yT) < TOL_BF16
+    y32 = e.label_gen(tx, M_T, M_I, precision="fp32", draws=draws_dict(d), check=True).double().cpu()
+    assert orc.rel_l2(y32, y_ref) < 1e-4
+    txp = e.sample_tx(9, seed=3)
+    p32 = e.label_gen(txp, 64, 1100, precision="fp32", seed=5).double().cpu()
+    p16 = e.label_gen(txp, 64, 1100, precision="f16", seed=5).double().cpu()
+    assert torch.isfinite(p16).all()
+    assert orc.rel_l2(p16, p32) < TOL_BF16
+    e.close()
+
+
 def test_bf16_rejects_unsupported_network_loudly():
     from tests.gpu_util import engine_for
     eq = orc.Cha(100, 1.0, 5.0, 1.0)
