@@ -24,8 +24,10 @@ Prints ONE JSON line (rank 0).  `value` is device-resident throughput; `e2e` goe
 (`dpi_label_gen_host`: pinned host tx -> H2D -> kernels -> D2H y -> sync -> label check); `roofline` is the integral
 (u_k over paths) stage timed by CUDA events on its own stream inside the same run, against the MEASURED bf16 peak:
 burst when the SM clock stayed at its maximum through the timed region, sustained otherwise (both fractions are
-printed); `cpu_baseline` is the CPU restatement of the reference's torch path (oracle/dpi_oracle.py,
-mode="autograd" = the ops the reference executes, fp64) on this box's host cores on a bounded sample.
+printed); `cpu_baseline` is the reference's OWN implementation of the path on this box's host cores on a bounded
+sample (`kind: "reference"`: the unmodified `picard/` package staged into the git-ignored `oracle/_ref/` by
+`oracle/build_ref.py`, imported behind `oracle/ref_shim.py`, fp64 as `DATA.FLOAT: double` says), or -- only when that
+staged copy is absent -- the CPU restatement `oracle/dpi_oracle.py` (`kind: "port"`, mode="autograd").
 `--impl reference` times only that CPU arm.
 """
 from __future__ import annotations
@@ -213,15 +215,26 @@ def describe(wl, M):
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the restatement of the reference's torch path (oracle), all host threads, fp64
+# CPU arm: the reference's own code (oracle/_ref) when staged, else the restatement (oracle/dpi_oracle.py); all host threads, fp64
 # ------------------------------------------------------------------------------------------------
 def cpu_arm(wl, net, M: int, n_sample: int, steps: int, warmup: int):
     import torch
     from oracle import dpi_oracle as orc
+    from oracle import ref_arm
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     inst = problem_instance(wl)
+    if ref_arm.available() and not os.environ.get("DPI_BENCH_CPU_PORT"):
+        # the reference's own code (unmodified picard/ staged by oracle/build_ref.py), all host threads, fp64
+        r = ref_arm.time_reference(wl, net, inst, M, n_sample, steps, warmup, cores)
+        return dict(value=r["value"], unit=UNIT, cores=r["cores"], kind="reference",
+                    sample=f"{n_sample} points/step x {r['steps']} steps (+{warmup} warm-up), fp64 (DATA.FLOAT: double), "
+                           f"M_T=M_I={M}, picard.data.OnlineDataGenerator.sample_with_gradients of the unmodified "
+                           f"reference on CPU (oracle/_ref behind oracle/ref_shim.py)",
+                    note="the reference's own implementation of the path, same weights and problem instance as the GPU "
+                         "arm; a bounded sample of the workload (a per-point rate)",
+                    ms_per_step=r["ms_per_step"])
     dd = lambda lins: [(W.double(), b.double()) for W, b in lins]
     if wl["eq"] == "Cha":
         eq = orc.Cha(wl["nx"], 1.0, wl["cha_k"], 1.0)

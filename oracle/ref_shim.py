@@ -2,10 +2,11 @@
 
 TEST INFRASTRUCTURE ONLY.  Nothing in the product path imports this file.  It is used in
 the build container (where `/root/reference` is mounted) by `oracle/make_golden.py` to
-generate the committed fixtures under `tests/golden/`, and by the `not gpu` test that
+generate the committed fixtures under `tests/golden/`, by the `not gpu` test that
 re-checks the CPU restatement (`oracle/dpi_oracle.py`) against the live reference when the
-mount is present.  `/root/reference` does not exist on the GPU box, so nothing that runs
-there may import this module.
+mount is present, and by `oracle/ref_arm.py` (the CPU legs of `bench.py`).  `/root/reference`
+does not exist on the GPU box: there the shim resolves to `oracle/_ref/`, the byte-identical
+staged copy made by `oracle/build_ref.py` (git-ignored, shipped by gpurun).
 
 Why a shim: `import picard` pulls lightning / yacs / h5py / tensorboardX / matplotlib
 (`picard/__init__.py:1-6`, `picard/data.py:8,12-13,24`, `picard/solution.py:6,18-19`,
@@ -21,7 +22,17 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("DPI_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")  # oracle/build_ref.py (travels to the GPU box)
+
+
+def _default_root() -> str:
+    """The mount in the build container; on the GPU box (no mount) the byte-identical staged copy."""
+    if os.path.isdir("/root/reference/picard"):
+        return "/root/reference"
+    return _STAGED
+
+
+REFERENCE_ROOT = os.environ.get("DPI_REFERENCE_ROOT") or _default_root()
 
 
 def reference_available() -> bool:

@@ -302,3 +302,37 @@ def test_ctypes_structures_match_the_c_header_layout(tmp_path):
         assert int(got[name]) == C.sizeof(cls), name
         for fname, _ in cls._fields_:
             assert int(got[f"{name}.{fname}"]) == getattr(cls, fname).offset, f"{name}.{fname}"
+
+
+@pytest.mark.skipif(not ref_shim.reference_available(), reason="neither /root/reference nor oracle/_ref present")
+def test_reference_cpu_arm_builds_the_same_network_and_instance():
+    """bench.py's CPU arm (oracle/ref_arm.py) drives the UNMODIFIED reference: its network must carry the bench's
+    weights (same function as the oracle's network on random inputs) and its generator must run for every equation."""
+    import bench
+    from oracle import build_ref, ref_arm
+
+    if os.path.isdir("/root/reference/picard"):
+        assert build_ref.build_ref() and build_ref.verify_ref()
+    prev = torch.get_default_dtype()
+    try:
+        for name, M in (("burgers100d", 8), ("gbm100d", 6), ("hjb100d", 6)):
+            wl = dict(bench.WORKLOADS[name])
+            if name == "hjb100d":
+                wl["hidden"] = [48, 40]  # same architecture family, CPU-sized
+            net, inst = bench.make_network(wl), bench.problem_instance(wl)
+            gen = ref_arm.build_generator(wl, net, inst, M)
+            tx, y = gen.sample_with_gradients(3)
+            assert tuple(y.shape) == (3, 1 + wl["nx"]) and torch.isfinite(y).all()
+            dd = lambda lins: [(W.double(), b.double()) for W, b in lins]
+            if net["kind"] == "mlp":
+                onet = orc.MLP([W.double() for W, _ in net["main"]], [b.double() for _, b in net["main"]])
+            else:
+                onet = orc.PISGradNet(net["phase"].double(), net["coeff"].double(), dd(net["t_encoder"]),
+                                      dd(net["smooth_net"]), dd(net["main"]), 1.0)
+            txr = torch.rand(5, 1 + wl["nx"], dtype=torch.float64)
+            u_ref = gen.solution(txr).detach()
+            if net["kind"] == "mlp":
+                u_orc = onet.forward(txr).reshape_as(u_ref)
+                assert torch.allclose(u_ref, u_orc, rtol=1e-12, atol=1e-12)
+    finally:
+        torch.set_default_dtype(prev)
