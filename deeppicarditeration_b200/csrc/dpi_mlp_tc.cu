@@ -71,9 +71,9 @@ constexpr uint32_t kSlotBytes = 2 * kOperandBytes;
 constexpr uint32_t kOffExch = kOffSlot + 2 * kSlotBytes;   // [128] float2: output-layer partials handed between the halves
 constexpr uint32_t kOffCoef = kOffExch + 1024;              // [3][128] Bismut coefficients (ring over tiles)
 constexpr uint32_t kOffBars = kOffCoef + 1536;             // 20 mbarriers
-constexpr uint32_t kOffTmemPtr = kOffBars + 160;
+constexpr uint32_t kOffTmemPtr = kOffBars + 224;           // 26 mbarriers (8 B each) + padding
 constexpr uint32_t kOffUnits = kOffTmemPtr + 16;           // [4] ring of unit ids handed out by the global counter
-constexpr uint32_t kTcSmemBytes = kOffUnits + 16;          // 232,128 B <= 232,448 B
+constexpr uint32_t kTcSmemBytes = kOffUnits + 16;          // 232,192 B <= 232,448 B
 
 enum Bar : int {
   kBarW = 0,         // W2..W4 landed (TMA)
@@ -83,8 +83,20 @@ enum Bar : int {
   kBarAccFull = 7,   // [2] a layer's accumulators are complete (tcgen05.commit, 4 per tile)
   kBarAReady = 9,    // [2] an epilogue pass is done: next A operand written, accumulators read (8 epilogue warps)
   kBarCoef = 11,     // [3] Bismut coefficients of a tile written (4 epilogue warps)
-  kBarUnit = 14      // [4] the CTA's k-th unit id is in ring entry k % 4 (TMA warp)
+  kBarUnit = 14,     // [4] the CTA's k-th unit id is in ring entry k % 4 (TMA warp)
+  kBarRingFull = 18, // [4] MULTI: every chunk of tile j is in ring slot j % 4 of the global increment ring (8 producer warps)
+  kBarRingFree = 22  // [4] MULTI: the Bismut sums of the tile in ring slot j % 4 are done (8 epilogue warps)
 };
+
+// d > 128: the Bismut sums G_j += coef_m Z_mj of a tile are taken by the EPILOGUE warps right after the tile's output
+// pass (warp e owns first-layer chunk e), reading the tile's increments back from the global ring.  The producers used
+// to do it two tiles later (DPI_MULTI_PROD_BISMUT restores that): ring write + read-back + sums sat on the producers'
+// critical path, which is what bounds this kernel, while the epilogue warps idle for most of a tile.
+#ifdef DPI_MULTI_PROD_BISMUT
+constexpr bool kMultiEpiBismut = false;
+#else
+constexpr bool kMultiEpiBismut = true;
+#endif
 
 struct TcArgs {
   const void* W;  // 4 consecutive operand images: W1 (x columns), W2, W3, W4
@@ -355,6 +367,10 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
     }
     for (int b = 0; b < 3; ++b) mbar_init(bar(kBarCoef + b), 4);
     for (int b = 0; b < 4; ++b) mbar_init(bar(kBarUnit + b), 1);
+    for (int b = 0; b < 4; ++b) {
+      mbar_init(bar(kBarRingFull + b), 8);
+      mbar_init(bar(kBarRingFree + b), 8);
+    }
     fence_barrier_init();
   }
   // The layer-1 MMA reads K = 16 ceil(d/16) columns of the slot's hV buffer; the producers write the first d of them
@@ -542,6 +558,46 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
     float2* exch = reinterpret_cast<float2*>(smem + kOffExch);  // [128] output-layer partial sums of the other half
     float* coef_s = reinterpret_cast<float*>(smem + kOffCoef);
     uint32_t ph_acc = 0, j = 0;  // ph_acc bit s = slot s
+    // MULTI: Bismut sums of first-layer chunk `ew` (lane = octet x row parity), see kMultiEpiBismut
+    [[maybe_unused]] float4 Ga = make_float4(0.f, 0.f, 0.f, 0.f), Gb = make_float4(0.f, 0.f, 0.f, 0.f);
+    [[maybe_unused]] uint32_t ph_coef_e = 0, ph_full = 0;
+    [[maybe_unused]] const int ew = warp - kEpiWarp0;
+    [[maybe_unused]] auto epi_bismut = [&](uint32_t jt) {
+      const uint32_t cbuf = jt % 3u, rs = jt & 3u;
+      mbar_wait(bar(kBarCoef + (int)cbuf), (ph_coef_e >> cbuf) & 1u, 42);
+      ph_coef_e ^= 1u << cbuf;
+      mbar_wait(bar(kBarRingFull + (int)rs), (ph_full >> rs) & 1u, 43);  // (acquire: the producers' ring stores)
+      ph_full ^= 1u << rs;
+      const int bo = lane & 15, rh = lane >> 4, oct = 16 * ew + bo;
+      if (ew < A.nchunks && 8 * oct < d) {
+        const float* cf_s = coef_s + cbuf * 128u;
+        const uint4* zr = A.zring + (size_t)blockIdx.x * ((size_t)4 * A.nchunks * 2048) +
+                          ((size_t)rs * A.nchunks + ew) * 2048 + bo;
+        constexpr int kBatch = 16;  // independent 16-byte loads in flight (L2, or DRAM when the ring was evicted)
+#pragma unroll 1
+        for (int i0 = 0; i0 < 64; i0 += kBatch) {
+          uint4 zb[kBatch];
+#pragma unroll
+          for (int i = 0; i < kBatch; ++i) zb[i] = __ldcg(zr + (rh + 2 * (i0 + i)) * 16);
+#pragma unroll
+          for (int i = 0; i < kBatch; ++i) {
+            const float cf = cf_s[rh + 2 * (i0 + i)];
+            const uint4 z = zb[i];
+            const float2 p0 = h2_unpack(z.x), p1 = h2_unpack(z.y), p2 = h2_unpack(z.z), p3 = h2_unpack(z.w);
+            Ga.x = fmaf(cf, p0.x, Ga.x);
+            Ga.y = fmaf(cf, p0.y, Ga.y);
+            Ga.z = fmaf(cf, p1.x, Ga.z);
+            Ga.w = fmaf(cf, p1.y, Ga.w);
+            Gb.x = fmaf(cf, p2.x, Gb.x);
+            Gb.y = fmaf(cf, p2.y, Gb.y);
+            Gb.z = fmaf(cf, p3.x, Gb.z);
+            Gb.w = fmaf(cf, p3.y, Gb.w);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(kBarRingFree + (int)rs));  // the producers may overwrite the ring slot
+    };
     TRACE_DECL(1 + h);
 #ifdef DPI_TC_TRACE
     if (q != 0 || lane != 0) trace_p = nullptr;
@@ -663,7 +719,19 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
             TRACE(2, s, j + s, 32);
           }
         }
+        if constexpr (MULTI && kMultiEpiBismut) {
+          epi_bismut(j);
+          if (hasB) epi_bismut(j + 1u);
+        }
         j += hasB ? 2u : 1u;
+      }
+      if constexpr (MULTI && kMultiEpiBismut) {  // unit partial: [chunk][row parity][128]
+        if (ew < A.nchunks) {
+          float* gp_ = A.partG + u * kTcPartGFloatsPerUnit + (int64_t)(ew * 2 + (lane >> 4)) * 128 + 8 * (lane & 15);
+          *reinterpret_cast<float4*>(gp_) = Ga;
+          *reinterpret_cast<float4*>(gp_ + 4) = Gb;
+        }
+        Ga = Gb = make_float4(0.f, 0.f, 0.f, 0.f);
       }
       const float ws = warp_sum(fsum);
       if (lane == 0) A.partF[u * kTcPartFFloatsPerUnit + h * 4 + q] = ws;
@@ -687,6 +755,7 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
       const float* coef_s = reinterpret_cast<const float*>(smem + kOffCoef);
       float4 Ga = make_float4(0.f, 0.f, 0.f, 0.f), Gb = make_float4(0.f, 0.f, 0.f, 0.f);
       uint32_t ph_free = 0, used = 0, ph_coef = 0, j = 0;
+      [[maybe_unused]] uint32_t ph_ring = 0;
       int pending = 0;
       int64_t u1 = 0, u2 = 0;  // units of the pending tiles (1 = newer, 2 = older)
       int m1 = 0, m2 = 0;      // their first samples
@@ -783,8 +852,15 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
           const int s = tl & 1;
           const uint32_t bit = 1u << s;
           uint8_t* const zdst = smem + kOffSlot + (uint32_t)s * kSlotBytes;
+          if constexpr (kMultiEpiBismut) {
+            if (j >= 4u) {  // the epilogue warps are done with the tile that used this ring slot
+              const uint32_t rs = j & 3u;
+              mbar_wait(bar(kBarRingFree + (int)rs), (ph_ring >> rs) & 1u, 44);
+              ph_ring ^= 1u << rs;
+            }
+          }
 #ifndef DPI_MULTI_NO_PREFETCH
-          if (pending == 2 && pw < nch) {
+          if (!kMultiEpiBismut && pending == 2 && pw < nch) {
             // the chunk this warp sums once this tile is generated (32 KB, contiguous): pull it towards L2 now
             const char* pf = reinterpret_cast<const char*>(zring + ((size_t)(j2 & 3u) * nch + pw) * 2048);
 #pragma unroll
@@ -820,14 +896,21 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
             }
           }
           __threadfence_block();
-          if (pending == 2) bismut(j2, u2, m2, last2);
-          j2 = j1, u2 = u1, m2 = m1, last2 = last1;
-          j1 = j, u1 = u, m1 = m0, last1 = (tl == tiles - 1);
-          if (pending < 2) ++pending;
+          if constexpr (kMultiEpiBismut) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(kBarRingFull + (int)(j & 3u)));  // (release: the warp's ring stores of tile j)
+          } else {
+            if (pending == 2) bismut(j2, u2, m2, last2);
+            j2 = j1, u2 = u1, m2 = m1, last2 = last1;
+            j1 = j, u1 = u, m1 = m0, last1 = (tl == tiles - 1);
+            if (pending < 2) ++pending;
+          }
         }
       }
-      if (pending == 2) bismut(j2, u2, m2, last2);
-      if (pending >= 1) bismut(j1, u1, m1, last1);
+      if constexpr (!kMultiEpiBismut) {
+        if (pending == 2) bismut(j2, u2, m2, last2);
+        if (pending >= 1) bismut(j1, u1, m1, last1);
+      }
     } else {
     // All 8 warps draw every tile: thread (o, c) owns the 8 dims [8o, 8o+8) -- one Philox block, one 16-byte operand
     // chunk -- of the rows r = c + cls i.  A tile's increments are generated into registers (no dependence on shared
