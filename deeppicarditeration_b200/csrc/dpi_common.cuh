@@ -181,6 +181,29 @@ __device__ __forceinline__ void normal8(const PhiloxKeys& K, uint64_t point, uin
   box_muller16<LOP3>(r.w, zb.z, zb.w);
 }
 
+// Two blocks at once -- same (point, stream, dim block), samples m0 and m1 -- with the Philox rounds of the two
+// counters written in lock-step.  One block is a chain of ten dependent rounds (2 wide multiplies + 2 XORs each, ~10
+// cycles per round); a producer role with two warps per scheduler cannot hide that chain, and the compiler does not
+// interleave separate calls on its own (it serialises them to save registers).  Bit-identical to two normal8 calls.
+template <bool LOP3 = kBmLop3Default>
+__device__ __forceinline__ void normal8x2(const PhiloxKeys& K, uint64_t point, uint32_t stream, uint32_t m0, uint32_t m1,
+                                          uint32_t block8, float4& za0, float4& zb0, float4& za1, float4& zb1) {
+  uint4 a = philox_counter(point, stream, m0, block8), b = philox_counter(point, stream, m1, block8);
+#pragma unroll
+  for (int r = 0; r < DPI_PHILOX_ROUNDS; ++r) {
+    a = philox_round(a, K.kx[r], K.ky[r]);
+    b = philox_round(b, K.kx[r], K.ky[r]);
+  }
+  box_muller16<LOP3>(a.x, za0.x, za0.y);
+  box_muller16<LOP3>(b.x, za1.x, za1.y);
+  box_muller16<LOP3>(a.y, za0.z, za0.w);
+  box_muller16<LOP3>(b.y, za1.z, za1.w);
+  box_muller16<LOP3>(a.z, zb0.x, zb0.y);
+  box_muller16<LOP3>(b.z, zb1.x, zb1.y);
+  box_muller16<LOP3>(a.w, zb0.z, zb0.w);
+  box_muller16<LOP3>(b.w, zb1.z, zb1.w);
+}
+
 // normals of dims [4 q, 4 q + 4): half of a normal8 block.  For the kernels that are not bound by the generator and
 // keep a lane <-> 4 dims layout (they draw the block twice); the terminal and tensor-core kernels consume all eight.
 __device__ __forceinline__ float4 normal4(uint64_t seed, uint64_t point, uint32_t stream, uint32_t sample,

@@ -872,10 +872,26 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
             const int oct = 16 * cch + o;
             const bool col_ok = 8 * oct < d;
             uint4 zc[8];
+#if !defined(DPI_NO_PHILOX_X2) && !defined(DPI_DBG_NO_RNG)
+            if (!DET && col_ok && nvalid == 128) {  // full tile: two rows per step, Philox rounds interleaved
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int rr = c + 16 * i;
-              zc[i] = draw8(p, m0 + rr, oct, col_ok && rr < nvalid);
+              for (int i = 0; i < 8; i += 2) {
+                float4 za0, zb0, za1, zb1;
+                normal8x2<true>(A.keys, (uint64_t)(A.point_base + p), kStreamIntegral, (uint32_t)(m0 + c + 16 * i),
+                                (uint32_t)(m0 + c + 16 * (i + 1)), (uint32_t)oct, za0, zb0, za1, zb1);
+                zc[i] = make_uint4(pack_f16x2(za0.x, za0.y), pack_f16x2(za0.z, za0.w), pack_f16x2(zb0.x, zb0.y),
+                                   pack_f16x2(zb0.z, zb0.w));
+                zc[i + 1] = make_uint4(pack_f16x2(za1.x, za1.y), pack_f16x2(za1.z, za1.w), pack_f16x2(zb1.x, zb1.y),
+                                       pack_f16x2(zb1.z, zb1.w));
+              }
+            } else
+#endif
+            {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int rr = c + 16 * i;
+                zc[i] = draw8(p, m0 + rr, oct, col_ok && rr < nvalid);
+              }
             }
             if (used & bit) {
               mbar_wait(bar(kBarSlotFree + s), (ph_free >> s) & 1u, 41);  // previous chunk / tile has left hV / hT
@@ -983,7 +999,31 @@ cha_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ TcCo
         const int m0 = (g * kTcGroupTiles + tl) * 128;
         const int nvalid = min(128, M_I - m0);
         TRACE(3, tl & 1, j, 0);
-        if (active) {
+        // (measured: -3.7 % on the d > 128 kernel, whose producers are latency bound; +0.5 % here, where the epilogue
+        // warps want the same issue slots -- so this path keeps one block at a time unless DPI_PHILOX_X2_ALL is set)
+#if defined(DPI_PHILOX_X2_ALL) && !defined(DPI_DBG_NO_RNG)
+        constexpr bool kX2 = !DET;
+#else
+        constexpr bool kX2 = false;
+#endif
+        if (kX2 && active && nvalid == 128) {  // full tile: two rows per step, Philox rounds interleaved (normal8x2)
+          auto pk = [](const float4& za, const float4& zb) {
+            return make_uint4(pack_f16x2(za.x, za.y), pack_f16x2(za.z, za.w), pack_f16x2(zb.x, zb.y), pack_f16x2(zb.z, zb.w));
+          };
+#pragma unroll
+          for (int i = 0; i + 1 < ITEMS; i += 2) {
+            float4 za0, zb0, za1, zb1;
+            normal8x2(A.keys, gp, kStreamIntegral, (uint32_t)(m0 + c + cls * i), (uint32_t)(m0 + c + cls * (i + 1)),
+                      (uint32_t)o, za0, zb0, za1, zb1);
+            zc[i] = pk(za0, zb0);  // a row >= 128 of the last items is drawn like any other and never stored
+            zc[i + 1] = pk(za1, zb1);
+          }
+          if constexpr (ITEMS & 1) {
+            float4 za, zb;
+            normal8(A.keys, gp, kStreamIntegral, (uint32_t)(m0 + c + cls * (ITEMS - 1)), (uint32_t)o, za, zb);
+            zc[ITEMS - 1] = pk(za, zb);
+          }
+        } else if (active) {
 #pragma unroll
           for (int i = 0; i < ITEMS; ++i) {
             const int rr = c + cls * i;
