@@ -74,6 +74,9 @@ struct dpi_handle {
   float* stage_tx = nullptr;
   float* stage_y = nullptr;
   int64_t stage_floats = 0;
+  // copy streams + events of the pipelined host path (dpi_label_gen_host on large calls), created on first use
+  cudaStream_t host_in = nullptr, host_out = nullptr;
+  std::vector<cudaEvent_t> host_ev;
   int64_t launches = 0;
   int* nonfinite_flag = nullptr;  // device: set by the label kernels' final check when a label is inf / NaN
   // optional per-stage timing (dpi_set_stage_timing)
@@ -243,6 +246,9 @@ int dpi_destroy(dpi_handle* h) {
   if (h->c0) cudaFree(h->c0);
   if (h->stage_tx) cudaFree(h->stage_tx);
   if (h->stage_y) cudaFree(h->stage_y);
+  if (h->host_in) cudaStreamDestroy(h->host_in);
+  if (h->host_out) cudaStreamDestroy(h->host_out);
+  for (cudaEvent_t e : h->host_ev) cudaEventDestroy(e);
   if (h->partG) cudaFree(h->partG);
   if (h->tc_zring) cudaFree(h->tc_zring);
   if (h->partF) cudaFree(h->partF);
@@ -826,6 +832,52 @@ int dpi_label_gen_host(dpi_handle* h, const float* tx_in_host, int64_t n, const 
   const int64_t floats = n * (1 + h->P.nx);
   int rc = ensure_stage(h, floats);
   if (rc) return rc;
+  // Large calls (the 2^20-point sweep moves 4.2 GB each way) are pipelined: the points go through in chunks of
+  // ~kHostPipeChunkBytes, chunk k's kernels on `stream` overlapping the H2D copy of chunk k + 1 and the D2H copy of
+  // chunk k - 1 on two copy streams of the handle.  Labels do not depend on how a call is split (Philox counters are
+  // keyed by the global point index), so the result is bitwise the one-shot result.
+  constexpr int64_t kHostPipeChunkBytes = 64ll << 20, kHostPipeMinBytes = 256ll << 20;
+  if ((int64_t)sizeof(float) * floats >= kHostPipeMinBytes && !h->timing) {
+    const int64_t ld = 1 + h->P.nx;
+    const int64_t cp = std::max<int64_t>(1024, kHostPipeChunkBytes / ((int64_t)sizeof(float) * ld));
+    const int64_t nchunk = (n + cp - 1) / cp;
+    if (!h->host_in) DPI_CUDA_CHECK(cudaStreamCreateWithFlags(&h->host_in, cudaStreamNonBlocking));
+    if (!h->host_out) DPI_CUDA_CHECK(cudaStreamCreateWithFlags(&h->host_out, cudaStreamNonBlocking));
+    while ((int64_t)h->host_ev.size() < 2 * nchunk + 2) {
+      cudaEvent_t e;
+      DPI_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      h->host_ev.push_back(e);
+    }
+    cudaEvent_t ev_start = h->host_ev[2 * nchunk], ev_done = h->host_ev[2 * nchunk + 1];
+    DPI_CUDA_CHECK(cudaEventRecord(ev_start, st));  // the staging buffers are free once earlier work on `stream` is done
+    DPI_CUDA_CHECK(cudaStreamWaitEvent(h->host_in, ev_start, 0));
+    DPI_CUDA_CHECK(cudaStreamWaitEvent(h->host_out, ev_start, 0));
+    if (!tx_in_host) {
+      rc = dpi_sample_tx(h, n, cfg->point_index_base, cfg->seed, h->stage_tx, stream);
+      if (rc) return rc;
+    }
+    for (int64_t k = 0; k < nchunk; ++k) {
+      const int64_t p0 = k * cp, np = std::min(cp, n - p0);
+      const size_t off = (size_t)(p0 * ld), bytes = sizeof(float) * (size_t)(np * ld);
+      if (tx_in_host) {
+        DPI_CUDA_CHECK(cudaMemcpyAsync(h->stage_tx + off, tx_in_host + off, bytes, cudaMemcpyHostToDevice, h->host_in));
+        DPI_CUDA_CHECK(cudaEventRecord(h->host_ev[2 * k], h->host_in));
+        DPI_CUDA_CHECK(cudaStreamWaitEvent(st, h->host_ev[2 * k], 0));
+      }
+      dpi_label_config ck = *cfg;
+      ck.point_index_base = cfg->point_index_base + p0;
+      rc = dpi_label_gen(h, h->stage_tx + off, np, &ck, nullptr, h->stage_y + off, stream);
+      if (rc) return rc;
+      DPI_CUDA_CHECK(cudaEventRecord(h->host_ev[2 * k + 1], st));
+      DPI_CUDA_CHECK(cudaStreamWaitEvent(h->host_out, h->host_ev[2 * k + 1], 0));
+      DPI_CUDA_CHECK(cudaMemcpyAsync(y_host + off, h->stage_y + off, bytes, cudaMemcpyDeviceToHost, h->host_out));
+      if (tx_out_host)
+        DPI_CUDA_CHECK(cudaMemcpyAsync(tx_out_host + off, h->stage_tx + off, bytes, cudaMemcpyDeviceToHost, h->host_out));
+    }
+    DPI_CUDA_CHECK(cudaEventRecord(ev_done, h->host_out));
+    DPI_CUDA_CHECK(cudaStreamWaitEvent(st, ev_done, 0));  // `stream` (synchronised below) covers the last copies
+    return dpi_check_labels(h, stream);
+  }
   if (tx_in_host) {
     DPI_CUDA_CHECK(cudaMemcpyAsync(h->stage_tx, tx_in_host, sizeof(float) * floats, cudaMemcpyHostToDevice, st));
   } else {

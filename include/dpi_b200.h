@@ -187,7 +187,9 @@ int dpi_export_draws(dpi_handle* h, int64_t n, const dpi_label_config* cfg, floa
 
 /* Same, with HOST buffers (pinned for full speed): copies tx in, y out, synchronises, and checks the labels
  * (DPI_ERR_NONFINITE). If tx_in_host is NULL the points are drawn on the device (dpi_sample_tx) and returned in
- * tx_out_host. */
+ * tx_out_host.  Calls of 256 MB or more per direction are pipelined in ~64 MB chunks of points (H2D of chunk k + 1 and
+ * D2H of chunk k - 1 on two copy streams of the handle under the kernels of chunk k); the labels are bitwise those of
+ * the one-shot call, because Philox counters are keyed by the global point index. */
 int dpi_label_gen_host(dpi_handle* h, const float* tx_in_host, int64_t n, const dpi_label_config* cfg,
                        float* tx_out_host /* nullable */, float* y_host, void* stream);
 

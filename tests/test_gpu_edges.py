@@ -174,3 +174,26 @@ def test_hjb_narrow_network_with_a_single_integral_sample():
             y = e.label_gen(tx, M_T, M_I, precision=prec, draws=draws_dict(d)).double().cpu()
             assert torch.isfinite(y).all() and orc.rel_l2(y, ref) < tol, (prec, M_T, M_I, orc.rel_l2(y, ref))
     e.close()
+
+
+@pytest.mark.parametrize("with_tx", [True, False])
+def test_large_host_call_is_pipelined_and_bitwise_the_device_result(with_tx):
+    """dpi_label_gen_host splits calls of >= 256 MB into ~64 MB chunks (copies on two handle streams overlapping the
+    kernels).  Labels are keyed by the global point index, so the pipelined call must reproduce the one-shot
+    device-buffer call bit for bit -- with caller-supplied points and with points sampled on the device."""
+    from tests.gpu_util import engine_for
+    nx, n, M = 1000, 70000, 4  # 70000 x 1001 x 4 B = 280 MB each way, 5 chunks
+    eq = orc.Cha(nx, 1.0, 5.0, 1.0)
+    e = engine_for(eq, orc.make_mlp(1 + nx, [128] * 4, seed=3))
+    if with_tx:
+        tx = e.sample_tx(n, seed=4, point_index_base=11)
+        tx_host = tx.cpu().pin_memory()
+        _, y_host = e.label_gen_host(n, M, M, tx_host=tx_host, precision="f16", seed=9, point_index_base=11)
+    else:
+        tx_host, y_host = e.label_gen_host(n, M, M, precision="f16", seed=9, point_index_base=11)
+        tx = e.sample_tx(n, seed=9, point_index_base=11)
+        assert torch.equal(tx.cpu(), tx_host)
+    y = e.label_gen(tx, M, M, precision="f16", seed=9, point_index_base=11)
+    assert torch.isfinite(y_host).all()
+    assert torch.equal(y.cpu(), y_host)
+    e.close()
