@@ -867,7 +867,12 @@ int dpi_label_gen_host(dpi_handle* h, const float* tx_in_host, int64_t n, const 
       dpi_label_config ck = *cfg;
       ck.point_index_base = cfg->point_index_base + p0;
       rc = dpi_label_gen(h, h->stage_tx + off, np, &ck, nullptr, h->stage_y + off, stream);
-      if (rc) return rc;
+      if (rc) {  // nothing of this call may still be writing the caller's buffers when the error is reported
+        cudaStreamSynchronize(h->host_in);
+        cudaStreamSynchronize(st);
+        cudaStreamSynchronize(h->host_out);
+        return rc;
+      }
       DPI_CUDA_CHECK(cudaEventRecord(h->host_ev[2 * k + 1], st));
       DPI_CUDA_CHECK(cudaStreamWaitEvent(h->host_out, h->host_ev[2 * k + 1], 0));
       DPI_CUDA_CHECK(cudaMemcpyAsync(y_host + off, h->stage_y + off, bytes, cudaMemcpyDeviceToHost, h->host_out));
