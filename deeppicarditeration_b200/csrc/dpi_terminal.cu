@@ -30,7 +30,7 @@ template <>
 struct Payoff<DPI_EQ_CHA> {
   static constexpr int NS = 1;
   static constexpr int NCH = 1;  // per-dim constant channels in shared memory: 1 for j < d, 0 for the padded dims
-  __device__ static void accumulate(float (&st)[NS], const float4 z, const float* cst, int ldc, int j0, float a) {
+  __device__ static void accumulate(float (&st)[NS], const float4 z, const float* cst, int ldc, int j0, float a, int) {
     const float4 w = *reinterpret_cast<const float4*>(cst + j0);
     st[0] += (w.x * z.x + w.y * z.y) + (w.z * z.z + w.w * z.w);
   }
@@ -43,7 +43,7 @@ template <>
 struct Payoff<DPI_EQ_GBM> {
   static constexpr int NS = kMaxGbmNodes;
   static constexpr int NCH = kMaxGbmNodes;  // w_k[j]
-  __device__ static void accumulate(float (&st)[NS], const float4 z, const float* cst, int ldc, int j0, float a) {
+  __device__ static void accumulate(float (&st)[NS], const float4 z, const float* cst, int ldc, int j0, float a, int) {
 #pragma unroll
     for (int k = 0; k < NS; ++k) {
       const float4 w = *reinterpret_cast<const float4*>(cst + k * ldc + j0);
@@ -63,13 +63,17 @@ template <>
 struct Payoff<DPI_EQ_OU> {
   static constexpr int NS = kMaxOuK;
   static constexpr int NCH = 2 * kMaxOuK;  // (x - m_k)[j], ivar_k[j]
-  __device__ static void accumulate(float (&st)[NS], const float4 z, const float* cst, int ldc, int j0, float a) {
+  // K = the mixture's component count (warp-uniform): the statistics of the unused components up to kMaxOuK are
+  // skipped by uniform branches (K = 5 in the shipped instance: 3/8 of this loop and of the shuffle reductions)
+  __device__ static void accumulate(float (&st)[NS], const float4 z, const float* cst, int ldc, int j0, float a, int K) {
 #pragma unroll
     for (int k = 0; k < NS; ++k) {
-      const float4 dm = *reinterpret_cast<const float4*>(cst + (2 * k) * ldc + j0);
-      const float4 iv = *reinterpret_cast<const float4*>(cst + (2 * k + 1) * ldc + j0);
-      const float e0 = dm.x + a * z.x, e1 = dm.y + a * z.y, e2 = dm.z + a * z.z, e3 = dm.w + a * z.w;
-      st[k] += (e0 * e0 * iv.x + e1 * e1 * iv.y) + (e2 * e2 * iv.z + e3 * e3 * iv.w);
+      if (k < K) {
+        const float4 dm = *reinterpret_cast<const float4*>(cst + (2 * k) * ldc + j0);
+        const float4 iv = *reinterpret_cast<const float4*>(cst + (2 * k + 1) * ldc + j0);
+        const float e0 = dm.x + a * z.x, e1 = dm.y + a * z.y, e2 = dm.z + a * z.z, e3 = dm.w + a * z.w;
+        st[k] += (e0 * e0 * iv.x + e1 * e1 * iv.y) + (e2 * e2 * iv.z + e3 * e3 * iv.w);
+      }
     }
   }
   __device__ static float eval(const ProblemDev& P, const float (&st)[NS], const float* base, float a) {
@@ -81,7 +85,8 @@ struct Payoff<DPI_EQ_OU> {
     }
     float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < NS; ++k) s += __expf(l[k] - mx);
+    for (int k = 0; k < NS; ++k)
+      if (k < P.ou_K) s += __expf(l[k] - mx);
     return -(mx + __logf(s));
   }
 };
@@ -149,6 +154,7 @@ terminal_kernel(const ProblemDev P, const float* __restrict__ tx, int M_T, const
   }
   __syncthreads();
 
+  const int klive = (EQ == DPI_EQ_OU) ? P.ou_K : NS;  // statistics in use (warp-uniform)
   // g(x): the same payoff with zero increments
   float g0;
   {
@@ -157,7 +163,7 @@ terminal_kernel(const ProblemDev P, const float* __restrict__ tx, int M_T, const
     for (int k = 0; k < NS; ++k) st[k] = 0.f;
     if (EQ == DPI_EQ_OU) {
 #pragma unroll
-      for (int q = 0; q < NSLOT; ++q) PO::accumulate(st, make_float4(0.f, 0.f, 0.f, 0.f), cst, LDC, 4 * lane + 128 * q, 0.f);
+      for (int q = 0; q < NSLOT; ++q) PO::accumulate(st, make_float4(0.f, 0.f, 0.f, 0.f), cst, LDC, 4 * lane + 128 * q, 0.f, klive);
 #pragma unroll
       for (int k = 0; k < NS; ++k) st[k] = warp_sum(st[k]);
     }
@@ -192,18 +198,20 @@ terminal_kernel(const ProblemDev P, const float* __restrict__ tx, int M_T, const
           // dims >= d of the last octet stay as drawn: every payoff statistic weights them with a zero constant and
           // their Bismut sums are never written out
         }
-        PO::accumulate(st, z[q][0], cst, LDC, j0, a);
-        PO::accumulate(st, z[q][1], cst, LDC, j0 + 4, a);
+        PO::accumulate(st, z[q][0], cst, LDC, j0, a, klive);
+        PO::accumulate(st, z[q][1], cst, LDC, j0 + 4, a, klive);
       } else if (EQ == DPI_EQ_OU) {
         // padded dims contribute 0 (ivar = 0); dims of a dead sample are discarded below
-        PO::accumulate(st, z[q][0], cst, LDC, j0, a);
-        PO::accumulate(st, z[q][1], cst, LDC, j0 + 4, a);
+        PO::accumulate(st, z[q][0], cst, LDC, j0, a, klive);
+        PO::accumulate(st, z[q][1], cst, LDC, j0 + 4, a, klive);
       }
     }
 #pragma unroll
     for (int k = 0; k < NS; ++k) {
+      if (k < klive) {
 #pragma unroll
-      for (int o = 8; o > 0; o >>= 1) st[k] += __shfl_xor_sync(0xffffffffu, st[k], o);  // over the 16 lanes of a sample
+        for (int o = 8; o > 0; o >>= 1) st[k] += __shfl_xor_sync(0xffffffffu, st[k], o);  // over the 16 lanes of a sample
+      }
     }
     float dg = 0.f;
     if (live) dg = (td_interior ? __ldg(u_td + p * M_T + m) : PO::eval(P, st, base, a)) - g0;
