@@ -135,7 +135,12 @@ terminal_kernel(const ProblemDev P, const float* __restrict__ tx, int M_T, const
         if (k < P.ou_K) v = (ch & 1) ? P.ou_ivar[k * d + j] : (__ldg(txp + 1 + j) - P.ou_mean[k * d + j]);
       }
     }
-    cst[i] = v;
+    // Stored PERMUTED inside each 128-dim slot: the MC loop reads a lane's 8 dims as two float4 (dims 8 hl .. 8 hl + 3
+    // and 8 hl + 4 .. 8 hl + 7); in natural order those are 32 bytes apart from lane to lane and the 16-byte loads of a
+    // quarter-warp hit every bank twice.  With [half][lane][4] every load is one contiguous 128 bytes per quarter-warp
+    // (the OU payoff issues 2 K of these loads per float4 of increments: its estimator was shared-memory bound).
+    const int jq = j >> 7, jr = j & 127;
+    cst[ch * LDC + (jq << 7) + (((jr >> 2) & 1) << 6) + ((jr >> 3) << 2) + (jr & 3)] = v;
   }
   if (warp == 0) {
     if (EQ == DPI_EQ_CHA) {
@@ -198,12 +203,12 @@ terminal_kernel(const ProblemDev P, const float* __restrict__ tx, int M_T, const
           // dims >= d of the last octet stay as drawn: every payoff statistic weights them with a zero constant and
           // their Bismut sums are never written out
         }
-        PO::accumulate(st, z[q][0], cst, LDC, j0, a, klive);
-        PO::accumulate(st, z[q][1], cst, LDC, j0 + 4, a, klive);
+        PO::accumulate(st, z[q][0], cst, LDC, 128 * q + 4 * hl, a, klive);       // permuted layout: see the fill loop
+        PO::accumulate(st, z[q][1], cst, LDC, 128 * q + 64 + 4 * hl, a, klive);
       } else if (EQ == DPI_EQ_OU) {
         // padded dims contribute 0 (ivar = 0); dims of a dead sample are discarded below
-        PO::accumulate(st, z[q][0], cst, LDC, j0, a, klive);
-        PO::accumulate(st, z[q][1], cst, LDC, j0 + 4, a, klive);
+        PO::accumulate(st, z[q][0], cst, LDC, 128 * q + 4 * hl, a, klive);       // permuted layout: see the fill loop
+        PO::accumulate(st, z[q][1], cst, LDC, 128 * q + 64 + 4 * hl, a, klive);
       }
     }
 #pragma unroll
