@@ -67,7 +67,7 @@ def test_burgers_1000d_sweep_shape_matches_oracle_on_replayed_draws():
     e.close()
 
 
-@pytest.mark.parametrize("nx", [200, 1000, 1024])
+@pytest.mark.parametrize("nx", [130, 200, 520, 777, 1000, 1024])  # 2, 2, 5, 7, 8, 8 chunks; 130 and 777: ragged last octet
 def test_chunked_tensor_core_path_tracks_fp32_on_the_same_philox_draws(nx):
     """128 < d <= 1024 on tcgen05: the first layer is accumulated over ceil(d/128) chunks and the increments wait for
     their Bismut coefficients in a per-CTA ring in global memory.  Same Philox counters as the fp32 kernel, so the two
