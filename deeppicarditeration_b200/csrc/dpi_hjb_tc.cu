@@ -38,8 +38,13 @@ using namespace tc;
 
 // warps 0-15: set-up + epilogue (warp = TMEM lane quarter x one of four column parts), warp 16: MMA issuer, warp 17: TMA issuer
 constexpr int kEpiWarps = 16, kMmaWarp = 16, kTmaWarp = 17, kThreads = 32 * 18, kParts = 4;
-constexpr int kSlots = 6;
-constexpr uint32_t kSlotBytes = 16384;
+// weight ring: 3 slots of one [256 n x 64 k] tile (32 KB) each.  The 512-wide layers run as N = 256 MMAs: per k-step a
+// 128 x N x 16 MMA reads 4 KB of A and N x 32 B of B from shared memory and the TMA stream writes the same N x 32 B
+// (every weight tile is used once), i.e. 192 B/cycle at N = 128 against 160 B/cycle at N = 256 -- both above the
+// 128 B/cycle the shared memory sustains, so the wide layers are shared-memory bound and the wider tile is the faster
+// one (DPI_HJB_N128 restores N = 128).
+constexpr int kSlots = 3;
+constexpr uint32_t kSlotBytes = 32768;
 constexpr uint32_t kOffA = 0;                             // 8 panels x 16 KB: the current A operand
 constexpr uint32_t kOffRing = 8 * kPanelBytes;            // weight ring
 constexpr uint32_t kOffMisc = kOffRing + kSlots * kSlotBytes;  // S_raw [128]
@@ -670,6 +675,10 @@ int hjb_tc_pack(const PisDev& N, int d, std::vector<void*>& owner, HjbTcNet** ou
   const int L = N.n_main, H = N.main[0].n_out, nh = H / 128, n_hid = L - 1, n_sm_hid = N.n_smooth - 2;
   A.H = H, A.nh = nh, A.n_hid = n_hid, A.d = d, A.no = (d + 7) / 8;
   const int k0_panels = (64 + d + 63) / 64;
+  // output-column tile of the nn_module hidden layers (forward and VJP): 256 at H = 512 (two tiles, so the half-layer
+  // overlap of the epilogue keeps its split point), 128 otherwise
+  static const bool n128 = getenv("DPI_HJB_N128") != nullptr;
+  const int wt = (H == 512 && !n128) ? 256 : 128, nw = H / wt;
   // ---- steps ----
   int ns = 0;
   auto add = [&](int a0, int nkp, int nch, int width, int acc0, int epi, int layer, int dstp) {
@@ -679,11 +688,11 @@ int hjb_tc_pack(const PisDev& N, int d, std::vector<void*>& owner, HjbTcNet** ou
   add(4, 1, 1, 64, 0, kEpiTemb, 0, 0);                                      // t_encoder.1 -> t_emb' in panel 0
   for (int l = 0; l < n_sm_hid; ++l)                                        // smooth_net 64 -> 64 layers, ping-pong 5 -> 4 -> 5 ..
     add((l & 1) ? 4 : 5, 1, 1, 64, 0, l + 1 < n_sm_hid ? kEpiSmHid : kEpiSmOut, l, (l & 1) ? 5 : 4);
-  add(0, k0_panels, nh, 128, 0, kEpiFwdHid, 0, 0);                           // nn_module layer 1
-  for (int l = 1; l < n_hid; ++l) add(0, H / 64, nh, 128, 0, kEpiFwdHid, l, 0);
+  add(0, k0_panels, nw, wt, 0, kEpiFwdHid, 0, 0);                            // nn_module layer 1
+  for (int l = 1; l < n_hid; ++l) add(0, H / 64, nw, wt, 0, kEpiFwdHid, l, 0);
   add(0, H / 64, 1, 128, 0, kEpiFwdOut, 0, 0);                               // output layer -> n
-  add(0, 2, nh, 128, 0, kEpiBwdHid, n_hid - 1, 0);                           // c = (x W_L) . e_{n_hid}
-  for (int l = n_hid - 1; l >= 1; --l) add(0, H / 64, nh, 128, 0, kEpiBwdHid, l - 1, 0);
+  add(0, 2, nw, wt, 0, kEpiBwdHid, n_hid - 1, 0);                            // c = (x W_L) . e_{n_hid}
+  for (int l = n_hid - 1; l >= 1; --l) add(0, H / 64, nw, wt, 0, kEpiBwdHid, l - 1, 0);
   add(0, H / 64, 1, 128, 0, kEpiFinal, 0, 0);                                // jtx = c_1 W_1[:, 64:]
   A.n_steps = ns;
   // ---- weight tiles in consumption order ----
@@ -719,11 +728,11 @@ int hjb_tc_pack(const PisDev& N, int d, std::vector<void*>& owner, HjbTcNet** ou
     }
     pack_layer(N.t_encoder[1], false, 0, 64, 64, 64, 1, 1);
     for (int l = 0; l < n_sm_hid; ++l) pack_layer(N.smooth_net[1 + l], false, 0, 64, 64, 64, 1, 1);
-    pack_layer(N.main[0], false, 0, H, 64 + d, 128, nh, k0_panels);
-    for (int l = 1; l < n_hid; ++l) pack_layer(N.main[l], false, 0, H, H, 128, nh, H / 64);
+    pack_layer(N.main[0], false, 0, H, 64 + d, wt, nw, k0_panels);
+    for (int l = 1; l < n_hid; ++l) pack_layer(N.main[l], false, 0, H, H, wt, nw, H / 64);
     pack_layer(N.main[L - 1], false, 0, d, H, 128, 1, H / 64);
-    pack_layer(N.main[L - 1], true, 0, H, d, 128, nh, 2);                    // B[n = hidden][k = output j] = W_L[j][n]
-    for (int l = n_hid - 1; l >= 1; --l) pack_layer(N.main[l], true, 0, H, H, 128, nh, H / 64);
+    pack_layer(N.main[L - 1], true, 0, H, d, wt, nw, 2);                     // B[n = hidden][k = output j] = W_L[j][n]
+    for (int l = n_hid - 1; l >= 1; --l) pack_layer(N.main[l], true, 0, H, H, wt, nw, H / 64);
     pack_layer(N.main[0], true, 64, d, H, 128, 1, H / 64);                   // x columns of W_1
   }
   if ((size_t)(cur - W) != total) {
