@@ -63,11 +63,12 @@ constexpr int kEpiWarps = 16, kMmaWarp = 16, kTmaWarp = 17, kThreads = 32 * 18, 
 // (every weight tile is used once), i.e. 192 B/cycle at N = 128 against 160 B/cycle at N = 256 -- both above the
 // 128 B/cycle the shared memory sustains, so the wide layers are shared-memory bound and the wider tile is the faster
 // one (DPI_HJB_N128 restores N = 128).
-constexpr int kSlots = 3;
-constexpr uint32_t kSlotBytes = 32768;
+// (Networks whose widest tile is 128 columns keep six slots of 16 KB: Args::n_slots / slot_bytes.)
+constexpr int kSlots = 6;                       // barrier pairs reserved (the most slots a network uses)
+constexpr uint32_t kRingBytes = 6 * 16384;      // 96 KB: 3 x 32 KB or 6 x 16 KB
 constexpr uint32_t kOffA = 0;                             // 8 panels x 16 KB: the current A operand
 constexpr uint32_t kOffRing = 8 * kPanelBytes;            // weight ring
-constexpr uint32_t kOffMisc = kOffRing + kSlots * kSlotBytes;  // S_raw [128]
+constexpr uint32_t kOffMisc = kOffRing + kRingBytes;           // S_raw [128]
 constexpr uint32_t kOffBars = kOffMisc + 1024;
 constexpr uint32_t kOffTmemPtr = kOffBars + 8 * (2 * kSlots + 3);
 constexpr uint32_t kSmemBytes = kOffTmemPtr + 16;
@@ -90,6 +91,8 @@ struct Args {
   Step steps[kMaxSteps];
   int n_steps;
   int H, nh, n_hid;            // hidden width, H / 128, number of hidden layers
+  int n_slots;                 // weight ring: 3 slots of 32 KB when a layer runs as N = 256 tiles, else 6 of 16 KB
+  uint32_t slot_bytes;
   int d, no;                   // nx, ceil(d / 8)
   const uint8_t* W;            // packed weight tiles in consumption order
   uint32_t tile_bytes_total;   // bytes of one pass over the tile stream
@@ -203,9 +206,9 @@ hjb_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ Args
           if (used & (1u << slot)) ph ^= 1u << slot;
           used |= 1u << slot;
           mbar_arrive_expect_tx_p(bar_full(slot), bytes, leader);
-          bulk_g2s_p(sbase + kOffRing + slot * kSlotBytes, src, bytes, bar_full(slot), leader);
+          bulk_g2s_p(sbase + kOffRing + slot * A.slot_bytes, src, bytes, bar_full(slot), leader);
           src += bytes;
-          slot = (slot + 1 == kSlots) ? 0 : slot + 1;
+          slot = (slot + 1 == (uint32_t)A.n_slots) ? 0 : slot + 1;
         }
       }
     }
@@ -229,13 +232,13 @@ hjb_tc_kernel(const __grid_constant__ ProblemDev P, const __grid_constant__ Args
             ph_full ^= 1u << slot;
             tc_fence_after();
             const uint32_t a_base = sbase + kOffA + (uint32_t)(S.a_panel0 + kp) * kPanelBytes;
-            const uint32_t b_base = sbase + kOffRing + slot * kSlotBytes;
+            const uint32_t b_base = sbase + kOffRing + slot * A.slot_bytes;
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
               umma_bf16_p(acc, make_desc_sw128(a_base + ks * 32u), make_desc_sw128(b_base + ks * 32u), idesc,
                           (uint32_t)((kp | ks) != 0), leader);
             tc_commit_p(bar_empty(slot), leader);  // the slot may be refilled once these MMAs have read it
-            slot = (slot + 1 == kSlots) ? 0 : slot + 1;
+            slot = (slot + 1 == (uint32_t)A.n_slots) ? 0 : slot + 1;
           }
           // wide layers: the first half of the output columns is complete -> its epilogue arithmetic starts while
           // the tensor pipe works on the second half
@@ -703,6 +706,7 @@ int hjb_tc_pack(const PisDev& N, int d, std::vector<void*>& owner, HjbTcNet** ou
   // overlap of the epilogue keeps its split point), 128 otherwise
   static const bool n128 = getenv("DPI_HJB_N128") != nullptr;
   const int wt = (H == 512 && !n128) ? 256 : 128, nw = H / wt;
+  A.n_slots = wt == 256 ? 3 : 6, A.slot_bytes = wt == 256 ? 32768u : 16384u;
   // ---- steps ----
   int ns = 0;
   auto add = [&](int a0, int nkp, int nch, int width, int acc0, int epi, int layer, int dstp) {
